@@ -1,0 +1,183 @@
+/*
+ * pttools_b200 -- C ABI of the B200-native hot path of PTtools (fluid-shell solve + Sound Shell Model spectrum).
+ *
+ * Every entry point is a batched, array-in/array-out replacement of one reference operator; the reference
+ * interface it replaces is cited (paths relative to the reference repository).  Conventions:
+ *   - plain pointers and sizes only; all floating point data is FP64, indices/status codes are int32;
+ *   - `mem` says where the caller's buffers live: PTT_MEM_HOST (the library stages them through device memory
+ *     and returns after the results are back on the host) or PTT_MEM_DEVICE (pointers are device pointers on the
+ *     current CUDA device; the work is enqueued on `stream` (a cudaStream_t, NULL = default stream) and the call
+ *     returns without synchronising);
+ *   - the return value is 0 on success or a negative PTT_E_* code for launch/argument errors
+ *     (ptt_last_error() gives the message); numerical failures are reported PER POINT in `status[]`
+ *     (PTT_ST_*), with NaN-filled outputs where the reference returns nan_arr / raises;
+ *   - all output buffers are caller-owned.
+ */
+#ifndef PTTOOLS_B200_H
+#define PTTOOLS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTT_MEM_HOST 0
+#define PTT_MEM_DEVICE 1
+
+/* return codes */
+#define PTT_OK 0
+#define PTT_E_ARG (-1)
+#define PTT_E_CUDA (-2)
+#define PTT_E_NOMEM (-3)
+
+/* per-point status (mirrors the reference's flags: Bubble.solver_failed / no_solution_found, nan_arr returns,
+ * RuntimeError("Integration failed"); pttools/bubble/bubble.py:123-131, fluid_bag.py:61-73, integrate.py:133) */
+#define PTT_ST_OK 0
+#define PTT_ST_NO_SOLUTION 1
+#define PTT_ST_INTEGRATION_FAILED 2
+#define PTT_ST_ROOT_NOT_CONVERGED 3
+#define PTT_ST_INVALID_INPUT 4
+#define PTT_ST_SOLVER_FAILED 5
+
+/* solution types (pttools/bubble/boundary.py:37-62) */
+#define PTT_SOL_SUB_DEF 0
+#define PTT_SOL_HYBRID 1
+#define PTT_SOL_DETON 2
+#define PTT_SOL_ERROR (-1)
+
+/* Equation of state.  Replaces the C function pointer `double cs2(double w, double phase)` that the reference
+ * compiles per model (pttools/type_hints.py:33-37, models/model.py:620-639): both in-scope models have a
+ * piecewise-constant sound speed, so a POD is enough.  p(w,phase) = w/mu - V,  e(w,phase) = (1-1/mu) w + V,
+ * mu = 1 + 1/cs2  (models/bag.py, models/const_cs.py:585-621). */
+typedef struct ptt_eos {
+    int32_t kind;      /* 0 = BagModel, 1 = ConstCSModel */
+    int32_t reserved;
+    double css2, csb2; /* sound speed squared, symmetric / broken phase */
+    double a_s, a_b;   /* pressure prefactors */
+    double V_s, V_b;   /* potentials */
+    double T_ref;
+} ptt_eos_t;
+
+const char* ptt_last_error(void);
+int ptt_version(void);
+/* capacity (in doubles) of one profile row for a given n_xi; the assembled shell is row[off .. off+npts) */
+int ptt_profile_row_capacity(int n_xi);
+
+/* --- Seam A: integrator plug-in ------------------------------------------------------------------------------
+ * fluid_integrate_param(v0, w0, xi0, phase, t_end, n_xi, df_dtau_ptr, method)   pttools/bubble/integrate.py:81-135
+ * Batched: lane i integrates from (v0[i], w0[i], xi0[i]) over t = linspace(0, t_end[i], n_xi);
+ * outputs are [n, n_xi] row-major.  status[i] = PTT_ST_INTEGRATION_FAILED where the reference raises. */
+int ptt_integrate_batch(int n, const double* v0, const double* w0, const double* xi0, const double* phase,
+                        const double* t_end, int n_xi, const ptt_eos_t* eos,
+                        double* out_v, double* out_w, double* out_xi, int32_t* status, int mem, void* stream);
+
+/* --- Seam B: bag-model shell operators -----------------------------------------------------------------------
+ * alpha_n_max_deflagration_bag(v_wall)                                           pttools/bubble/alpha.py:44-50,71 */
+int ptt_bag_alpha_n_max(int n, const double* v_wall, double* out, int32_t* status, int mem, void* stream);
+
+/* identify_solution_type_bag + find_alpha_plus_bag                 transition.py:19-44, alpha.py:305-331,361-388
+ * an_max may be NULL (then it is computed per point).  Outputs: alpha_plus[n], sol_type[n], status[n]. */
+int ptt_bag_find_alpha_plus(int n, const double* v_wall, const double* alpha_n, int n_xi, const double* an_max,
+                            double* alpha_plus, int32_t* sol_type, int32_t* status, int mem, void* stream);
+
+/* sound_shell_alpha_plus(v_wall, alpha_plus, sol_type, n_xi, w_n)                       fluid_bag.py:83-222
+ * rows_*: [n, row_stride] with row_stride >= ptt_profile_row_capacity(n_xi); shell i is
+ * rows_*[i*row_stride + off[i] .. + npts[i]).  scalars[n,4] = {xi_shock, w_n_raw, n_wall, reserved}. */
+int ptt_bag_profiles(int n, const double* v_wall, const double* alpha_plus, const int32_t* sol_type, int n_xi,
+                     const double* w_n, double* rows_v, double* rows_w, double* rows_xi, int64_t row_stride,
+                     int32_t* off, int32_t* npts, double* scalars, int32_t* status, int mem, void* stream);
+
+/* sound_shell_bag(v_wall, alpha_n, n_xi) for a whole sweep                                fluid_bag.py:33-79
+ * = alpha_n_max (once per distinct v_wall is the caller's business: pass an_max or NULL) + root + profile. */
+int ptt_sweep_shells_bag(int n, const double* v_wall, const double* alpha_n, int n_xi, const double* an_max,
+                         double* rows_v, double* rows_w, double* rows_xi, int64_t row_stride,
+                         int32_t* off, int32_t* npts, double* alpha_plus, int32_t* sol_type, double* scalars,
+                         int32_t* status, int mem, void* stream);
+
+/* --- Seam C: Sound Shell Model array operators (all pointers DEVICE pointers, enqueued on `stream`) -----------
+ * Grids that depend only on (y, cs, nt, ...) are built once per sweep by the host mirror (numpy expressions
+ * identical to the reference's) and passed in; the kernels do the per-profile arithmetic. */
+
+/* sin_transform(z, xi, f, z_st_thresh)                                     pttools/ssmtools/calculators.py:119-190
+ * Batched over P ragged profiles: profile p is xi/f[p*stride + off[p] .. + npts[p]).
+ * frac[n_z]: 0 = exact trapezoid only, 1 = asymptotic formula only, in between = cubic blend weight
+ * (calculators.py:136-153; depends only on z, so the host computes it).  out[P, n_z]. */
+int ptt_sin_transform_batch(int P, const double* xi, const double* f, int64_t stride, const int32_t* off,
+                            const int32_t* npts, int n_z, const double* z, const double* frac,
+                            double* out, void* stream);
+
+typedef struct ptt_a2_plan {
+    int32_t n_z;          /* total number of wavenumbers (all lookup grids concatenated) */
+    int32_t n_seg;        /* number of grids; gradients never cross a grid boundary */
+    const int32_t* seg;   /* [n_seg+1] start index of each grid in z */
+    const double* z;      /* [n_z] */
+    const double* frac;   /* [n_z] blend fraction, see ptt_sin_transform_batch */
+    int32_t nxi;          /* resampling size for lambda (ssm.py:40, default 2000) */
+    int32_t phase_rule;   /* 0: xi < v_wall (boundary.get_phase, old bag path); 1: props.find_phase (Bubble path) */
+    const double* xi_re;  /* [nxi] = linspace(0, 1-1/nxi, nxi) */
+} ptt_a2_plan_t;
+
+/* a2_e_conserving / a2_e_conserving_bag                                       pttools/ssmtools/ssm.py:35-140
+ * per-point params pp[P,8] = {v_wall, cs, e_coef_s, e_coef_b, V_s, V_b, 0, 0} with e(w,phase) = e_coef*w + V.
+ * work: [P, 2*row_cap + 2*nxi + 32] doubles of scratch.  Outputs a2/fp2_2/lam2: [P, n_z] (the last two may be NULL). */
+int ptt_a2_batch(const ptt_a2_plan_t* plan, int P, const double* rows_v, const double* rows_w, const double* rows_xi,
+                 int64_t row_stride, const int32_t* off, const int32_t* npts, const double* pp,
+                 double* work, int64_t work_stride, double* a2, double* fp2_2, double* lam2, void* stream);
+
+typedef struct ptt_sdv_plan {
+    int32_t n_q;          /* size of qT_lookup */
+    int32_t n_z;          /* evaluation points */
+    int32_t nt;           /* T-tilde samples */
+    int32_t z_tile;       /* evaluation points per CTA (host-chosen so that the lookup window fits in shared memory) */
+    const double* qT;     /* [n_q]  10**arange(...)   spectrum.py:515 */
+    const double* z;      /* [n_z] */
+    const double* zterm;  /* [n_z]  (log10 z - log10 qT[0]) / dlog10 */
+    const double* T;      /* [nt]   logspace(log10 0.01, log10 20, nt)  spectrum.py:473 */
+    const double* LT;     /* [nt]   log10(T) / dlog10 */
+    const double* W;      /* [nt]   trapezoid weight * T^6 * nu(T) */
+    double inv_dlog;      /* 1 / dlog10z */
+    int32_t smem_bytes;   /* dynamic shared memory per CTA */
+    int32_t reserved;
+} ptt_sdv_plan_t;
+
+/* spec_den_v core                                                        pttools/ssmtools/spectrum.py:451-486
+ * a2: [P, a2_stride] lookup values on qT; out: [P, n_z]. */
+int ptt_spec_den_v_batch(const ptt_sdv_plan_t* plan, int P, const double* a2, int64_t a2_stride,
+                         const double* v_wall, double* out, int64_t out_stride, void* stream);
+
+typedef struct ptt_gw_plan {
+    int32_t n_zl;         /* size of z_lookup */
+    int32_t n_y;
+    int32_t n_int;        /* integration samples per y (nz_int) */
+    int32_t y_tile;
+    const double* z_lookup;  /* [n_zl] log-uniform */
+    const double* y;      /* [n_y] */
+    const double* yterm;  /* [n_y]  (log10 y - log10 z_lookup[0]) / dlog10 */
+    const double* L1;     /* [n_int] log10(zeta_k) / dlog10 */
+    const double* L2;     /* [n_int] log10(zeta_+ + zeta_- - zeta_k) / dlog10 */
+    const double* Z1;     /* [n_int] zeta_k */
+    const double* Z2;     /* [n_int] zeta_+ + zeta_- - zeta_k */
+    const double* G;      /* [n_int] trapezoid weight * integrand kernel */
+    double prefactor;     /* 0.75 Gamma^2 ((1-cs^2)/cs^2)^2 / (4 pi cs) */
+    int32_t smem_bytes;
+    int32_t reserved;
+} ptt_gw_plan_t;
+
+/* spec_den_gw_scaled core + pow_spec                                    spectrum.py:327-368, 230-240
+ * pv: [P, pv_stride] P_v on z_lookup; slf[P] source lifetime factor; scale[P] = r_star * F_gw0 * suppression
+ * (omgw0_ssm.py:123-131) or NULL.  Outputs [P, n_y]: sd_gw (may be NULL), pow_gw, omgw0 (NULL if scale NULL). */
+int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const double* pv, int64_t pv_stride, const double* slf,
+                          const double* scale, double* sd_gw, double* pow_gw, double* omgw0, void* stream);
+
+/* pow_spec(z, spec_den) = z^3/(2 pi^2) spec_den, row-wise                         spectrum.py:230-240 */
+int ptt_pow_spec_batch(int P, int n_z, const double* z, const double* spec_den, int64_t stride, double* out,
+                       void* stream);
+
+/* FP64 FMA throughput probe used by bench.py for the roofline denominator (not part of the reference). */
+int ptt_fp64_peak_probe(int iters, double* out_flops_per_s, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

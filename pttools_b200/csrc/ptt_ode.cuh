@@ -1,0 +1,241 @@
+// Batched FP64 adaptive Runge-Kutta core for the self-similar fluid equations.
+//
+// Replaces scipy.integrate.odeint (ODEPACK LSODA) at the reference call site pttools/bubble/integrate.py:180 and
+// the RHS built at integrate.py:38-74.  One parameter point per thread: every lane owns its own step-size control.
+// The output semantics are those of the reference: the solution is sampled on t = linspace(0, t_end, n) and events
+// (shock, sound-speed crossing) are located BY GRID INDEX, not by root finding (trim.py:50-56, :94-99).
+//
+// The code is host/device portable (PTT_HD) so the same source can be compiled with g++ into a test-only emulation
+// library (tests/hostemu); the product only ever runs the nvcc build.
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PTT_HD __host__ __device__ __forceinline__
+#else
+#define PTT_HD inline
+#endif
+
+namespace ptt {
+
+// Equation of state seen by the fluid equations: both in-scope models have a piecewise-constant sound speed,
+// cs2(w, phase) = phase*csb2 + (1-phase)*css2  (models/bag.py:21-27, models/const_cs.py:553-557).
+struct Eos {
+    double css2;   // symmetric phase (ahead of the wall)
+    double csb2;   // broken phase (behind the wall)
+};
+
+struct State {
+    double v, w, xi;
+};
+
+PTT_HD void rhs(const double cs2, const State& y, State& d) {
+    // integrate.py:62-73
+    const double xiv = y.xi * y.v;
+    const double xi_v = y.xi - y.v;
+    const double v2 = y.v * y.v;
+    const double one_xiv = 1.0 - xiv;
+    d.v = 2.0 * y.v * cs2 * (1.0 - v2) * one_xiv;
+    d.w = (y.w / (1.0 - v2)) * (xi_v / one_xiv) * (1.0 / cs2 + 1.0) * d.v;
+    d.xi = y.xi * (xi_v * xi_v - cs2 * one_xiv * one_xiv);
+}
+
+// numpy.linspace(0, t_end, n)[i]: i*step with the last sample forced to the end point.
+PTT_HD double grid_time(const double t_end, const int n, const int i) {
+    if (i >= n - 1) return t_end;
+    return (double)i * (t_end / (double)(n - 1));
+}
+
+// Dormand-Prince 5(4) with the 4th-order continuous extension (Hairer, Norsett & Wanner, "dopri5").
+// Tolerances are far tighter than LSODA's 1.5e-8 defaults so that index decisions agree with the reference
+// except on razor edges.
+struct Dopri5 {
+    static constexpr double RTOL = 1e-10;
+    static constexpr double ATOL = 1e-13;
+
+    double cs2;
+    double t, h, t_end;
+    State y, k1;                 // current state and its derivative (FSAL)
+    // dense-output data of the last accepted step [t0, t0 + hd]
+    double t0, hd;
+    State r1, r2, r3, r4, r5;
+    int nsteps, nrej;
+    bool failed;
+
+    PTT_HD void init(const double cs2_, const State& y0, const double t_end_) {
+        cs2 = cs2_;
+        t = 0.0;
+        t_end = t_end_;
+        y = y0;
+        rhs(cs2, y, k1);
+        nsteps = 0;
+        nrej = 0;
+        failed = false;
+        // Initial step: small fraction of the interval, bounded by the local time scale.
+        const double sc_v = ATOL + RTOL * fabs(y.v), sc_w = ATOL + RTOL * fabs(y.w), sc_x = ATOL + RTOL * fabs(y.xi);
+        const double d0 = sqrt((y.v * y.v / (sc_v * sc_v) + y.w * y.w / (sc_w * sc_w) + y.xi * y.xi / (sc_x * sc_x)) / 3.0);
+        const double d1 = sqrt((k1.v * k1.v / (sc_v * sc_v) + k1.w * k1.w / (sc_w * sc_w) + k1.xi * k1.xi / (sc_x * sc_x)) / 3.0);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        const double span = fabs(t_end);
+        if (h0 > span) h0 = span;
+        if (h0 < 1e-12 * span) h0 = 1e-12 * span;
+        h = (t_end < 0.0) ? -h0 : h0;
+        t0 = 0.0;
+        hd = 0.0;
+    }
+
+    PTT_HD bool done() const { return failed || t == t_end; }
+
+    // One accepted step (internally retries rejected ones). Returns false on failure.
+    PTT_HD bool step() {
+        const double c2 = 0.2, c3 = 0.3, c4 = 0.8, c5 = 8.0 / 9.0;
+        const double a21 = 0.2;
+        const double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
+        const double a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0;
+        const double a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0, a54 = -212.0 / 729.0;
+        const double a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0, a64 = 49.0 / 176.0,
+                     a65 = -5103.0 / 18656.0;
+        const double a71 = 35.0 / 384.0, a73 = 500.0 / 1113.0, a74 = 125.0 / 192.0, a75 = -2187.0 / 6784.0,
+                     a76 = 11.0 / 84.0;
+        const double e1 = 71.0 / 57600.0, e3 = -71.0 / 16695.0, e4 = 71.0 / 1920.0, e5 = -17253.0 / 339200.0,
+                     e6 = 22.0 / 525.0, e7 = -1.0 / 40.0;
+        const double d1 = -12715105075.0 / 11282082432.0, d3 = 87487479700.0 / 32700410799.0,
+                     d4 = -10690763975.0 / 1880347072.0, d5 = 701980252875.0 / 199316789632.0,
+                     d6 = -1453857185.0 / 822651844.0, d7 = 69997945.0 / 29380423.0;
+        (void)c2; (void)c3; (void)c4; (void)c5;   // autonomous system: stage times are not needed
+
+        for (int attempt = 0; attempt < 60; ++attempt) {
+            bool last = false;
+            double hs = h;
+            if ((t + 1.01 * hs - t_end) * ((t_end < 0.0) ? -1.0 : 1.0) >= 0.0) {
+                hs = t_end - t;
+                last = true;
+            }
+            State k2, k3, k4, k5, k6, k7, yt, y1;
+            yt.v = y.v + hs * a21 * k1.v; yt.w = y.w + hs * a21 * k1.w; yt.xi = y.xi + hs * a21 * k1.xi;
+            rhs(cs2, yt, k2);
+            yt.v = y.v + hs * (a31 * k1.v + a32 * k2.v);
+            yt.w = y.w + hs * (a31 * k1.w + a32 * k2.w);
+            yt.xi = y.xi + hs * (a31 * k1.xi + a32 * k2.xi);
+            rhs(cs2, yt, k3);
+            yt.v = y.v + hs * (a41 * k1.v + a42 * k2.v + a43 * k3.v);
+            yt.w = y.w + hs * (a41 * k1.w + a42 * k2.w + a43 * k3.w);
+            yt.xi = y.xi + hs * (a41 * k1.xi + a42 * k2.xi + a43 * k3.xi);
+            rhs(cs2, yt, k4);
+            yt.v = y.v + hs * (a51 * k1.v + a52 * k2.v + a53 * k3.v + a54 * k4.v);
+            yt.w = y.w + hs * (a51 * k1.w + a52 * k2.w + a53 * k3.w + a54 * k4.w);
+            yt.xi = y.xi + hs * (a51 * k1.xi + a52 * k2.xi + a53 * k3.xi + a54 * k4.xi);
+            rhs(cs2, yt, k5);
+            yt.v = y.v + hs * (a61 * k1.v + a62 * k2.v + a63 * k3.v + a64 * k4.v + a65 * k5.v);
+            yt.w = y.w + hs * (a61 * k1.w + a62 * k2.w + a63 * k3.w + a64 * k4.w + a65 * k5.w);
+            yt.xi = y.xi + hs * (a61 * k1.xi + a62 * k2.xi + a63 * k3.xi + a64 * k4.xi + a65 * k5.xi);
+            rhs(cs2, yt, k6);
+            y1.v = y.v + hs * (a71 * k1.v + a73 * k3.v + a74 * k4.v + a75 * k5.v + a76 * k6.v);
+            y1.w = y.w + hs * (a71 * k1.w + a73 * k3.w + a74 * k4.w + a75 * k5.w + a76 * k6.w);
+            y1.xi = y.xi + hs * (a71 * k1.xi + a73 * k3.xi + a74 * k4.xi + a75 * k5.xi + a76 * k6.xi);
+            rhs(cs2, y1, k7);
+
+            const double ev = hs * (e1 * k1.v + e3 * k3.v + e4 * k4.v + e5 * k5.v + e6 * k6.v + e7 * k7.v);
+            const double ew = hs * (e1 * k1.w + e3 * k3.w + e4 * k4.w + e5 * k5.w + e6 * k6.w + e7 * k7.w);
+            const double ex = hs * (e1 * k1.xi + e3 * k3.xi + e4 * k4.xi + e5 * k5.xi + e6 * k6.xi + e7 * k7.xi);
+            const double sv = ATOL + RTOL * fmax(fabs(y.v), fabs(y1.v));
+            const double sw = ATOL + RTOL * fmax(fabs(y.w), fabs(y1.w));
+            const double sx = ATOL + RTOL * fmax(fabs(y.xi), fabs(y1.xi));
+            const double err = sqrt(((ev / sv) * (ev / sv) + (ew / sw) * (ew / sw) + (ex / sx) * (ex / sx)) / 3.0);
+            if (!(err == err)) {           // NaN: the trajectory left the domain (v -> 1 or xi*v -> 1)
+                failed = true;
+                return false;
+            }
+            double fac = (err > 0.0) ? 0.9 * pow(err, -0.2) : 5.0;
+            if (fac < 0.2) fac = 0.2;
+            if (fac > 5.0) fac = 5.0;
+            if (err <= 1.0) {
+                // accept; build the continuous extension (Hairer's contd5)
+                t0 = t;
+                hd = hs;
+                r1 = y;
+                r2.v = y1.v - y.v; r2.w = y1.w - y.w; r2.xi = y1.xi - y.xi;
+                r3.v = hs * k1.v - r2.v; r3.w = hs * k1.w - r2.w; r3.xi = hs * k1.xi - r2.xi;
+                r4.v = r2.v - hs * k7.v - r3.v; r4.w = r2.w - hs * k7.w - r3.w; r4.xi = r2.xi - hs * k7.xi - r3.xi;
+                r5.v = hs * (d1 * k1.v + d3 * k3.v + d4 * k4.v + d5 * k5.v + d6 * k6.v + d7 * k7.v);
+                r5.w = hs * (d1 * k1.w + d3 * k3.w + d4 * k4.w + d5 * k5.w + d6 * k6.w + d7 * k7.w);
+                r5.xi = hs * (d1 * k1.xi + d3 * k3.xi + d4 * k4.xi + d5 * k5.xi + d6 * k6.xi + d7 * k7.xi);
+                y = y1;
+                k1 = k7;
+                t = last ? t_end : t + hs;
+                if (nrej > 0 && fac > 1.0) fac = 1.0;   // no growth right after a rejection
+                nrej = 0;
+                h = hs * fac;
+                ++nsteps;
+                return true;
+            }
+            // reject
+            ++nrej;
+            h = hs * fac;
+            if (fabs(h) < 1e-15 * fmax(1.0, fabs(t))) {
+                failed = true;
+                return false;
+            }
+        }
+        failed = true;
+        return false;
+    }
+
+    // Continuous extension inside the last accepted step.
+    PTT_HD State dense(const double tq) const {
+        const double th = (tq - t0) / hd;
+        const double th1 = 1.0 - th;
+        State o;
+        o.v = r1.v + th * (r2.v + th1 * (r3.v + th * (r4.v + th1 * r5.v)));
+        o.w = r1.w + th * (r2.w + th1 * (r3.w + th * (r4.w + th1 * r5.w)));
+        o.xi = r1.xi + th * (r2.xi + th1 * (r3.xi + th * (r4.xi + th1 * r5.xi)));
+        return o;
+    }
+};
+
+// Walks the tau-grid t_i = linspace(0, t_end, n)[i] in order and hands samples to a visitor:
+//   bool visit(int i, const State& y)   -- return false to stop early
+//   bool skip(const State& y_end)       -- true if no event can lie inside a step that ends in y_end; then only the
+//                                          LAST grid sample of that step is visited (so that the sample preceding an
+//                                          event in the next step is always known). Return false to see every sample.
+// Returns the number of grid samples covered, or -1 if the integrator failed
+// (the reference raises RuntimeError("Integration failed"), integrate.py:133).
+template <class Visitor>
+PTT_HD int integrate_grid(const double cs2, const State& y0, const double t_end, const int n, Visitor& visit) {
+    if (!visit.visit(0, y0)) return 1;
+    if (n < 2) return 1;
+    if (t_end == 0.0) {
+        for (int i = 1; i < n; ++i)
+            if (!visit.visit(i, y0)) return i + 1;
+        return n;
+    }
+    Dopri5 s;
+    s.init(cs2, y0, t_end);
+    const double sgn = (t_end < 0.0) ? -1.0 : 1.0;
+    const double dt = t_end / (double)(n - 1);
+    int i = 1;
+    while (i < n) {
+        if (!s.step()) return -1;
+        // last grid index inside (t0, t]
+        int i_hi;
+        if (s.t == t_end) {
+            i_hi = n - 1;
+        } else {
+            i_hi = (int)(s.t / dt);
+            if (i_hi > n - 1) i_hi = n - 1;
+            while (i_hi + 1 < n && (grid_time(t_end, n, i_hi + 1) - s.t) * sgn <= 0.0) ++i_hi;
+            while (i_hi >= i && (grid_time(t_end, n, i_hi) - s.t) * sgn > 0.0) --i_hi;
+        }
+        if (i_hi < i) continue;
+        if (i > 1 && i_hi > i && visit.skip(s.y)) i = i_hi;
+        for (; i <= i_hi; ++i) {
+            const double ti = grid_time(t_end, n, i);
+            const State yi = (ti == s.t) ? s.y : s.dense(ti);
+            if (!visit.visit(i, yi)) return i + 1;
+        }
+    }
+    return n;
+}
+
+}  // namespace ptt

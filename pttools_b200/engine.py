@@ -1,0 +1,501 @@
+"""Batched device operators: thin torch-tensor wrappers over the C ABI plus the sweep-level grid plans.
+
+torch is plumbing here (device memory, streams); all arithmetic on the hot path runs in the hand-written CUDA
+kernels of libpttools_b200.so.  The "plans" hold the grids that depend only on (y, cs, nt, ...): they are built
+with the same numpy expressions the reference uses (pttools/ssmtools/spectrum.py:169-186, 503-515, 473) so that
+the knots are bit-identical, and uploaded once per sweep.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import typing as tp
+
+import numpy as np
+
+from . import _lib
+from ._lib import A2Plan, Eos, GwPlan, SdvPlan
+
+N_XI_DEFAULT = 5000
+Z_ST_THRESH = 50.0
+DZ_ST_BLEND = np.pi
+T_TILDE_MIN, T_TILDE_MAX = 0.01, 20.0
+NXI_DEFAULT, NT_DEFAULT, NZ_LOOKUP_DEFAULT = 2000, 10000, 10000
+GAMMA_DEFAULT = 4.0 / 3.0
+CS0 = 1.0 / np.sqrt(3.0)
+
+SMEM_WINDOW_BYTES = 200 * 1024     # dynamic shared memory budget for the lookup windows (B200: 227 KB per CTA)
+
+
+def _torch():
+    return _lib.require_cuda()
+
+
+def _stream_ptr(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def dev_f64(a, device=None):
+    torch = _torch()
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device or "cuda", dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device or "cuda")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Shell operators
+# ---------------------------------------------------------------------------------------------------------------
+
+def integrate_batch(v0, w0, xi0, phase, t_end, n_xi, css2=1 / 3, csb2=1 / 3):
+    """Batched fluid_integrate_param (pttools/bubble/integrate.py:81-135). Returns v, w, xi [n, n_xi], status[n]."""
+    torch = _torch()
+    lib = _lib.load()
+    v0, w0, xi0, phase, t_end = (dev_f64(a) for a in (v0, w0, xi0, phase, t_end))
+    n = v0.numel()
+    out = [torch.empty((n, n_xi), dtype=torch.float64, device=v0.device) for _ in range(3)]
+    status = torch.empty(n, dtype=torch.int32, device=v0.device)
+    eos = Eos(kind=0, css2=css2, csb2=csb2, a_s=0, a_b=0, V_s=0, V_b=0, T_ref=1)
+    _lib.check(lib.ptt_integrate_batch(n, _ptr(v0), _ptr(w0), _ptr(xi0), _ptr(phase), _ptr(t_end), n_xi, C.byref(eos),
+                                       _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(status), _lib.MEM_DEVICE,
+                                       _stream_ptr(torch)), "ptt_integrate_batch")
+    return out[0], out[1], out[2], status
+
+
+def bag_alpha_n_max(v_wall):
+    """alpha_n_max_deflagration_bag for an array of wall speeds (pttools/bubble/alpha.py:44-50)."""
+    torch = _torch()
+    lib = _lib.load()
+    v_wall = dev_f64(v_wall)
+    out = torch.empty_like(v_wall)
+    status = torch.empty(v_wall.numel(), dtype=torch.int32, device=v_wall.device)
+    _lib.check(lib.ptt_bag_alpha_n_max(v_wall.numel(), _ptr(v_wall), _ptr(out), _ptr(status), _lib.MEM_DEVICE,
+                                       _stream_ptr(torch)), "ptt_bag_alpha_n_max")
+    return out, status
+
+
+def bag_alpha_n_max_unique(v_wall):
+    """Same, but evaluated once per distinct wall speed and broadcast (the quantity depends on v_wall only; the
+    reference recomputes it up to four times per point: transition.py:27, alpha.py:185,316, bubble.py:252)."""
+    torch = _torch()
+    v_wall = dev_f64(v_wall)
+    uniq, inv = torch.unique(v_wall, return_inverse=True)
+    am, st = bag_alpha_n_max(uniq)
+    return am[inv], st[inv]
+
+
+@dataclasses.dataclass
+class ShellBatch:
+    """Profiles of a batch of shells in device memory. Shell i is rows_*[i, off[i] : off[i] + npts[i]]."""
+    v_wall: tp.Any
+    alpha_n: tp.Any
+    alpha_plus: tp.Any
+    sol_type: tp.Any
+    status: tp.Any
+    rows_v: tp.Any
+    rows_w: tp.Any
+    rows_xi: tp.Any
+    off: tp.Any
+    npts: tp.Any
+    scalars: tp.Any
+    n_xi: int
+
+    def __len__(self):
+        return self.v_wall.numel()
+
+    def profile(self, i):
+        o, n = int(self.off[i]), int(self.npts[i])
+        return (self.rows_v[i, o:o + n].cpu().numpy(), self.rows_w[i, o:o + n].cpu().numpy(),
+                self.rows_xi[i, o:o + n].cpu().numpy())
+
+
+def sweep_shells_bag(v_wall, alpha_n, n_xi=N_XI_DEFAULT, an_max=None) -> ShellBatch:
+    """sound_shell_bag for a batch of points (pttools/bubble/fluid_bag.py:33-79)."""
+    torch = _torch()
+    lib = _lib.load()
+    v_wall, alpha_n = dev_f64(v_wall).reshape(-1), dev_f64(alpha_n).reshape(-1)
+    n = v_wall.numel()
+    if an_max is None:
+        an_max, _ = bag_alpha_n_max_unique(v_wall)
+    cap = lib.ptt_profile_row_capacity(n_xi)
+    dev = v_wall.device
+    rows = [torch.empty((n, cap), dtype=torch.float64, device=dev) for _ in range(3)]
+    off = torch.empty(n, dtype=torch.int32, device=dev)
+    npts = torch.empty(n, dtype=torch.int32, device=dev)
+    ap = torch.empty(n, dtype=torch.float64, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    scalars = torch.empty((n, 4), dtype=torch.float64, device=dev)
+    _lib.check(lib.ptt_sweep_shells_bag(n, _ptr(v_wall), _ptr(alpha_n), n_xi, _ptr(an_max), _ptr(rows[0]), _ptr(rows[1]),
+                                        _ptr(rows[2]), cap, _ptr(off), _ptr(npts), _ptr(ap), _ptr(st), _ptr(scalars),
+                                        _ptr(status), _lib.MEM_DEVICE, _stream_ptr(torch)), "ptt_sweep_shells_bag")
+    return ShellBatch(v_wall, alpha_n, ap, st, status, rows[0], rows[1], rows[2], off, npts, scalars, n_xi)
+
+
+def bag_find_alpha_plus(v_wall, alpha_n, n_xi=N_XI_DEFAULT, an_max=None):
+    torch = _torch()
+    lib = _lib.load()
+    v_wall, alpha_n = dev_f64(v_wall).reshape(-1), dev_f64(alpha_n).reshape(-1)
+    n = v_wall.numel()
+    if an_max is None:
+        an_max, _ = bag_alpha_n_max_unique(v_wall)
+    ap = torch.empty(n, dtype=torch.float64, device=v_wall.device)
+    st = torch.empty(n, dtype=torch.int32, device=v_wall.device)
+    status = torch.empty(n, dtype=torch.int32, device=v_wall.device)
+    _lib.check(lib.ptt_bag_find_alpha_plus(n, _ptr(v_wall), _ptr(alpha_n), n_xi, _ptr(an_max), _ptr(ap), _ptr(st),
+                                           _ptr(status), _lib.MEM_DEVICE, _stream_ptr(torch)), "ptt_bag_find_alpha_plus")
+    return ap, st, status
+
+
+def bag_profiles(v_wall, alpha_plus, sol_type, n_xi=N_XI_DEFAULT, w_n=None) -> ShellBatch:
+    """sound_shell_alpha_plus for a batch (pttools/bubble/fluid_bag.py:83-222)."""
+    torch = _torch()
+    lib = _lib.load()
+    v_wall, alpha_plus = dev_f64(v_wall).reshape(-1), dev_f64(alpha_plus).reshape(-1)
+    n = v_wall.numel()
+    dev = v_wall.device
+    sol_type = torch.as_tensor(sol_type, dtype=torch.int32, device=dev).reshape(-1).contiguous()
+    w_n_t = dev_f64(w_n).reshape(-1) if w_n is not None else None
+    cap = lib.ptt_profile_row_capacity(n_xi)
+    rows = [torch.empty((n, cap), dtype=torch.float64, device=dev) for _ in range(3)]
+    off = torch.empty(n, dtype=torch.int32, device=dev)
+    npts = torch.empty(n, dtype=torch.int32, device=dev)
+    status = torch.zeros(n, dtype=torch.int32, device=dev)
+    scalars = torch.empty((n, 4), dtype=torch.float64, device=dev)
+    _lib.check(lib.ptt_bag_profiles(n, _ptr(v_wall), _ptr(alpha_plus), _ptr(sol_type), n_xi, _ptr(w_n_t), _ptr(rows[0]),
+                                    _ptr(rows[1]), _ptr(rows[2]), cap, _ptr(off), _ptr(npts), _ptr(scalars), _ptr(status),
+                                    _lib.MEM_DEVICE, _stream_ptr(torch)), "ptt_bag_profiles")
+    return ShellBatch(v_wall, None, alpha_plus, sol_type, status, rows[0], rows[1], rows[2], off, npts, scalars, n_xi)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Spectrum plans (host: numpy, identical expressions to the reference; device: uploaded once)
+# ---------------------------------------------------------------------------------------------------------------
+
+def blend_fraction(z: np.ndarray, z_st_thresh: float = Z_ST_THRESH) -> np.ndarray:
+    """Per-wavenumber weight of the asymptotic formula in sin_transform (calculators.py:119-158):
+    0 = exact trapezoid only, 1 = asymptotic only, in between = cubic blend on (thresh - pi, thresh]."""
+    z = np.asarray(z, dtype=np.float64)
+    frac = np.zeros_like(z)
+    if z.size <= 1:
+        # scalar branch (calculators.py:104-116)
+        frac[z > z_st_thresh] = 1.0
+        return frac
+    frac[z > z_st_thresh] = 1.0
+    blend = (z > z_st_thresh - DZ_ST_BLEND) & (z <= z_st_thresh)
+    if np.any(blend):
+        zb = z[blend]
+        zmax, zmin = zb.max(), zb.min()
+        s = (zb - zmin) / (zmax - zmin) if zmax > zmin else 0.5 * np.ones_like(zb)
+        frac[blend] = 3 * s ** 2 - 2 * s ** 3
+    return frac
+
+
+def qt_lookup_grid(z: np.ndarray):
+    """qT_lookup of spec_den_v (spectrum.py:503-515) and its log-grid parameters (l0, dlog10)."""
+    lmin, lmax = np.log10(np.min(z)), np.log10(np.max(z))
+    dl = (lmax - lmin) / z.size
+    l0 = lmin + np.log10(T_TILDE_MIN)
+    return 10 ** np.arange(l0, lmax + np.log10(T_TILDE_MAX), dl), l0, dl
+
+
+def nu(t, nuc_type="exponential", a=1.0):
+    """Bubble lifetime distribution (spectrum.py:189-205)."""
+    if nuc_type == "simultaneous":
+        return 0.5 * a * (a * t) ** 2 * np.exp(-(a * t) ** 3 / 6)
+    if nuc_type == "exponential":
+        return a * np.exp(-a * t)
+    raise ValueError("Nucleation type not recognized")
+
+
+def _trapz_weights(x: np.ndarray) -> np.ndarray:
+    w = np.empty_like(x)
+    w[1:-1] = 0.5 * (x[2:] - x[:-2])
+    w[0] = 0.5 * (x[1] - x[0])
+    w[-1] = 0.5 * (x[-1] - x[-2])
+    return w
+
+
+class SdvPass:
+    """One spec_den_v evaluation: A^2 tabulated on qT_lookup(z), convolved with the lifetime distribution at z."""
+
+    def __init__(self, z: np.ndarray, nt: int, nuc_type: str, a: float):
+        z = np.asarray(z, dtype=np.float64)
+        if np.any(np.diff(z) < 0):
+            raise ValueError("z must be ascending")
+        self.z = z
+        self.qT, self.l0, self.dl = qt_lookup_grid(z)
+        self.nt = nt
+        lt = np.linspace(np.log10(T_TILDE_MIN), np.log10(T_TILDE_MAX), nt)
+        self.T = 10.0 ** lt
+        self.LT = lt / self.dl
+        self.W = _trapz_weights(self.T) * self.T ** 6 * nu(self.T, nuc_type, a)
+        self.zterm = (np.log10(z) - self.l0) / self.dl
+        # tile size: the lookup window of a tile must fit in shared memory
+        cap_entries = SMEM_WINDOW_BYTES // 16
+        t_span = self.LT[-1] - self.LT[0]
+        tile = 512
+        best = None
+        while True:
+            spans = self.zterm[np.minimum(np.arange(0, z.size, tile) + tile - 1, z.size - 1)] - self.zterm[::tile]
+            need = int(np.ceil(spans.max() + t_span)) + 6
+            if need <= cap_entries:
+                best = (tile, need)
+                if tile >= z.size:
+                    break
+                tile += 512
+            else:
+                break
+        if best is None:
+            raise ValueError("spec_den_v lookup window does not fit in shared memory; reduce nt range or z density")
+        self.z_tile, self.win_entries = best
+        self.smem_bytes = self.win_entries * 16
+
+
+class SsmPlan:
+    """Grids for a batch of SSM spectra that share (y, cs, sizes).
+
+    mode="ssm": the SSMSpectrum.compute chain (spectrum.py:96-115): pass A on z=y (gives pow_v and a2), z_lookup =
+    gen_lookup(y, cs, n_z_lookup, eps=1e-8), pass B on z_lookup, GW integral on (z_lookup, y).
+    mode="bag": power_gw_scaled_bag (spectrum.py:243-294): x = np.logspace(log10 xmin, log10 xmax, npt[2]),
+    one pass on x, GW integral on (x, z).
+    """
+
+    def __init__(self, y, cs=CS0, nt=NT_DEFAULT, n_z_lookup=NZ_LOOKUP_DEFAULT, nxi=NXI_DEFAULT,
+                 z_st_thresh=Z_ST_THRESH, nuc_type="exponential", a=1.0, gamma=GAMMA_DEFAULT, mode="ssm",
+                 phase_rule=None, nz_int=None):
+        torch = _torch()
+        y = np.asarray(y, dtype=np.float64)
+        if np.any(y <= 0.0):
+            raise ValueError("z values must all be positive.")
+        self.y, self.cs, self.nt, self.nxi, self.mode = y, float(cs), int(nt), int(nxi), mode
+        self.z_st_thresh, self.nuc_type, self.a, self.gamma = z_st_thresh, str(nuc_type), float(a), gamma
+        eps = 1e-8
+        lo = y.min() * 0.5 * (1.0 - cs) / cs - eps      # lookup_limits, spectrum.py:183-186
+        hi = y.max() * 0.5 * (1.0 + cs) / cs + eps
+        self.z_lookup = 10.0 ** np.linspace(np.log10(lo), np.log10(hi), n_z_lookup)
+        self.passes: tp.List[SdvPass] = []
+        if mode == "ssm":
+            self.passes.append(SdvPass(y, nt, self.nuc_type, self.a))
+            self.phase_rule = 1 if phase_rule is None else phase_rule
+        elif mode == "bag":
+            self.phase_rule = 0 if phase_rule is None else phase_rule
+        else:
+            raise ValueError(mode)
+        self.passes.append(SdvPass(self.z_lookup, nt, self.nuc_type, self.a))
+        self.lookup_pass = self.passes[-1]
+
+        # A^2 wavenumbers: all lookup grids concatenated
+        self.seg = np.cumsum([0] + [p.qT.size for p in self.passes]).astype(np.int32)
+        self.z_all = np.concatenate([p.qT for p in self.passes])
+        self.frac_all = np.concatenate([blend_fraction(p.qT, z_st_thresh) for p in self.passes])
+        self.xi_re = np.linspace(0, 1 - 1 / nxi, nxi)     # calculators.py:100
+
+        # GW integral (spectrum.py:327-368), z = y * zeta
+        n_int = self.z_lookup.size if nz_int is None else int(nz_int)
+        zpf, zmf = (1 + cs) / (2 * cs), (1 - cs) / (2 * cs)
+        lz = np.linspace(np.log10(zmf), np.log10(zpf), n_int)
+        zeta = 10.0 ** lz
+        zeta2 = zpf + zmf - zeta
+        lz0 = np.log10(lo)
+        dlz = (np.log10(hi) - np.log10(lo)) / (n_z_lookup - 1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            kern = ((zeta - zpf) ** 2 * (zeta - zmf) ** 2) / (zeta * zeta2)
+        self.gw = dict(
+            n_int=n_int, L1=lz / dlz, L2=np.log10(zeta2) / dlz, Z1=zeta, Z2=zeta2, G=_trapz_weights(zeta) * kern,
+            yterm=(np.log10(y) - lz0) / dlz,
+            prefactor=0.75 * gamma ** 2 * ((1 - cs ** 2) / cs ** 2) ** 2 / (4 * np.pi * cs))
+        y_tile = 128
+        span = (self.gw["yterm"][np.minimum(np.arange(0, y.size, y_tile) + y_tile - 1, y.size - 1)]
+                - self.gw["yterm"][::y_tile]).max()
+        lrange = max(self.gw["L1"].max(), self.gw["L2"].max()) - min(self.gw["L1"].min(), self.gw["L2"].min())
+        self.gw["y_tile"] = y_tile
+        self.gw["win_entries"] = int(np.ceil(span + lrange)) + 6
+        if self.gw["win_entries"] * 16 > SMEM_WINDOW_BYTES:
+            raise ValueError("spec_den_gw lookup window does not fit in shared memory")
+
+        # upload
+        self._t = {}
+        up = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device="cuda")
+        self._t["seg"] = up(self.seg, torch.int32)
+        for k in ("z_all", "frac_all", "xi_re", "z_lookup", "y"):
+            self._t[k] = up(getattr(self, k))
+        for i, p in enumerate(self.passes):
+            for k in ("qT", "z", "zterm", "T", "LT", "W"):
+                self._t[f"p{i}_{k}"] = up(getattr(p, k))
+        for k in ("L1", "L2", "Z1", "Z2", "G", "yterm"):
+            self._t["gw_" + k] = up(self.gw[k])
+
+        self.a2_plan = A2Plan(n_z=self.z_all.size, n_seg=len(self.passes), seg=self._t["seg"].data_ptr(),
+                              z=self._t["z_all"].data_ptr(), frac=self._t["frac_all"].data_ptr(), nxi=self.nxi,
+                              phase_rule=self.phase_rule, xi_re=self._t["xi_re"].data_ptr())
+        self.sdv_plans = []
+        for i, p in enumerate(self.passes):
+            self.sdv_plans.append(SdvPlan(
+                n_q=p.qT.size, n_z=p.z.size, nt=p.nt, z_tile=p.z_tile, qT=self._t[f"p{i}_qT"].data_ptr(),
+                z=self._t[f"p{i}_z"].data_ptr(), zterm=self._t[f"p{i}_zterm"].data_ptr(),
+                T=self._t[f"p{i}_T"].data_ptr(), LT=self._t[f"p{i}_LT"].data_ptr(), W=self._t[f"p{i}_W"].data_ptr(),
+                inv_dlog=1.0 / p.dl, smem_bytes=p.smem_bytes))
+        g = self.gw
+        self.gw_plan = GwPlan(n_zl=self.z_lookup.size, n_y=y.size, n_int=g["n_int"], y_tile=g["y_tile"],
+                              z_lookup=self._t["z_lookup"].data_ptr(), y=self._t["y"].data_ptr(),
+                              yterm=self._t["gw_yterm"].data_ptr(), L1=self._t["gw_L1"].data_ptr(),
+                              L2=self._t["gw_L2"].data_ptr(), Z1=self._t["gw_Z1"].data_ptr(),
+                              Z2=self._t["gw_Z2"].data_ptr(), G=self._t["gw_G"].data_ptr(),
+                              prefactor=g["prefactor"], smem_bytes=g["win_entries"] * 16)
+
+    @property
+    def n_a2(self):
+        return int(self.z_all.size)
+
+
+class A2OnlyPlan:
+    """Plan for a2_e_conserving on one arbitrary ascending z grid (ssm.py:35-140)."""
+
+    def __init__(self, z, nxi=NXI_DEFAULT, z_st_thresh=Z_ST_THRESH, phase_rule=1):
+        torch = _torch()
+        z = np.asarray(z, dtype=np.float64)
+        self.nxi = int(nxi)
+        self.z_all = z
+        self.seg = np.array([0, z.size], dtype=np.int32)
+        self.xi_re = np.linspace(0, 1 - 1 / nxi, nxi)
+        up = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device="cuda")
+        self._t = {"seg": up(self.seg, torch.int32), "z": up(z), "frac": up(blend_fraction(z, z_st_thresh)),
+                   "xi_re": up(self.xi_re)}
+        self.a2_plan = A2Plan(n_z=z.size, n_seg=1, seg=self._t["seg"].data_ptr(), z=self._t["z"].data_ptr(),
+                              frac=self._t["frac"].data_ptr(), nxi=self.nxi, phase_rule=phase_rule,
+                              xi_re=self._t["xi_re"].data_ptr())
+
+    @property
+    def n_a2(self):
+        return int(self.z_all.size)
+
+
+@dataclasses.dataclass
+class SpectrumBatch:
+    y: np.ndarray
+    pow_gw: tp.Any
+    sd_gw: tp.Any
+    omgw0: tp.Any = None
+    pow_v: tp.Any = None
+    sd_v: tp.Any = None
+    a2: tp.Any = None          # A^2 on the first pass' qT_lookup (SSMSpectrum.a2)
+    sd_v_lookup: tp.Any = None
+
+
+def point_params(v_wall, cs, e_coef_s, e_coef_b, V_s, V_b):
+    """pp[P,8] rows of ptt_a2_batch."""
+    torch = _torch()
+    v_wall = dev_f64(v_wall).reshape(-1)
+    n = v_wall.numel()
+    pp = torch.zeros((n, 8), dtype=torch.float64, device=v_wall.device)
+    pp[:, 0] = v_wall
+    for j, val in enumerate((cs, e_coef_s, e_coef_b, V_s, V_b), start=1):
+        pp[:, j] = dev_f64(val) if not np.isscalar(val) else float(val)
+    return pp
+
+
+def a2_batch(plan: SsmPlan, shells: ShellBatch, pp, want_parts=False):
+    """A^2 on all lookup grids of the plan for a batch of shells (ssm.py:35-140). Returns [P, plan.n_a2]."""
+    torch = _torch()
+    lib = _lib.load()
+    P = len(shells)
+    cap = shells.rows_v.shape[1]
+    ws = lib.ptt_a2_work_stride(cap, plan.nxi, plan.n_a2)
+    dev = shells.rows_v.device
+    work = torch.empty((P, ws), dtype=torch.float64, device=dev)
+    a2 = torch.empty((P, plan.n_a2), dtype=torch.float64, device=dev)
+    fp = torch.empty_like(a2) if want_parts else None
+    l2 = torch.empty_like(a2) if want_parts else None
+    _lib.check(lib.ptt_a2_batch(C.byref(plan.a2_plan), P, _ptr(shells.rows_v), _ptr(shells.rows_w), _ptr(shells.rows_xi),
+                                cap, _ptr(shells.off), _ptr(shells.npts), _ptr(pp), _ptr(work), ws, _ptr(a2), _ptr(fp),
+                                _ptr(l2), _stream_ptr(torch)), "ptt_a2_batch")
+    if want_parts:
+        return a2, fp, l2
+    return a2
+
+
+def spec_den_v_batch(plan: SsmPlan, ipass: int, a2, v_wall):
+    """_spec_den_v_core for pass `ipass` (spectrum.py:451-486); a2 is the full [P, n_a2] table."""
+    torch = _torch()
+    lib = _lib.load()
+    P = a2.shape[0]
+    sp = plan.sdv_plans[ipass]
+    out = torch.empty((P, sp.n_z), dtype=torch.float64, device=a2.device)
+    a2_view_ptr = C.c_void_p(a2.data_ptr() + 8 * int(plan.seg[ipass]))
+    _lib.check(lib.ptt_spec_den_v_batch(C.byref(sp), P, a2_view_ptr, a2.shape[1], _ptr(v_wall), _ptr(out), sp.n_z,
+                                        _stream_ptr(torch)), "ptt_spec_den_v_batch")
+    return out
+
+
+def spec_den_gw_batch(plan: SsmPlan, pv, slf=None, scale=None, want_sd=True):
+    torch = _torch()
+    lib = _lib.load()
+    P = pv.shape[0]
+    dev = pv.device
+    n_y = plan.y.size
+    slf_t = torch.ones(P, dtype=torch.float64, device=dev) if slf is None else dev_f64(slf).reshape(-1)
+    scale_t = None if scale is None else dev_f64(scale).reshape(-1)
+    sd = torch.empty((P, n_y), dtype=torch.float64, device=dev) if want_sd else None
+    pw = torch.empty((P, n_y), dtype=torch.float64, device=dev)
+    om = torch.empty((P, n_y), dtype=torch.float64, device=dev) if scale_t is not None else None
+    _lib.check(lib.ptt_spec_den_gw_batch(C.byref(plan.gw_plan), P, _ptr(pv), pv.shape[1], _ptr(slf_t), _ptr(scale_t),
+                                         _ptr(sd), _ptr(pw), _ptr(om), _stream_ptr(torch)), "ptt_spec_den_gw_batch")
+    return sd, pw, om
+
+
+def pow_spec_batch(z_dev, sd):
+    torch = _torch()
+    lib = _lib.load()
+    out = torch.empty_like(sd)
+    _lib.check(lib.ptt_pow_spec_batch(sd.shape[0], sd.shape[1], _ptr(z_dev), _ptr(sd), sd.shape[1], _ptr(out),
+                                      _stream_ptr(torch)), "ptt_pow_spec_batch")
+    return out
+
+
+def spectra_from_shells(plan: SsmPlan, shells: ShellBatch, pp, slf=None, scale=None, keep=False) -> SpectrumBatch:
+    """Shell profiles -> A^2 -> spec_den_v -> spec_den_gw -> pow_gw (-> omgw0), all on the device."""
+    a2 = a2_batch(plan, shells, pp)
+    res = SpectrumBatch(y=plan.y, pow_gw=None, sd_gw=None)
+    v_wall = pp[:, 0].contiguous()
+    if plan.mode == "ssm":
+        sdv_y = spec_den_v_batch(plan, 0, a2, v_wall)
+        res.sd_v = sdv_y
+        res.pow_v = pow_spec_batch(plan._t["y"], sdv_y)
+        if keep:
+            res.a2 = a2[:, : int(plan.seg[1])]
+    sdv_l = spec_den_v_batch(plan, len(plan.passes) - 1, a2, v_wall)
+    if keep:
+        res.sd_v_lookup = sdv_l
+    res.sd_gw, res.pow_gw, res.omgw0 = spec_den_gw_batch(plan, sdv_l, slf, scale)
+    return res
+
+
+def sin_transform_batch(z, xi, f, off, npts, z_st_thresh=Z_ST_THRESH):
+    """Batched sin_transform over ragged profiles stored as rows (calculators.py:161-190)."""
+    torch = _torch()
+    lib = _lib.load()
+    zz = np.asarray(z, dtype=np.float64)
+    frac = dev_f64(blend_fraction(zz, z_st_thresh))
+    z_d = dev_f64(zz)
+    xi, f = dev_f64(xi), dev_f64(f)
+    if xi.dim() == 1:
+        xi, f = xi[None, :], f[None, :]
+    P, stride = xi.shape
+    off_t = torch.as_tensor(off, dtype=torch.int32, device=xi.device).reshape(-1).contiguous()
+    npts_t = torch.as_tensor(npts, dtype=torch.int32, device=xi.device).reshape(-1).contiguous()
+    out = torch.empty((P, zz.size), dtype=torch.float64, device=xi.device)
+    _lib.check(lib.ptt_sin_transform_batch(P, _ptr(xi), _ptr(f), stride, _ptr(off_t), _ptr(npts_t), zz.size, _ptr(z_d),
+                                           _ptr(frac), _ptr(out), _stream_ptr(torch)), "ptt_sin_transform_batch")
+    return out
+
+
+def fp64_peak_flops(iters=20000):
+    torch = _torch()
+    lib = _lib.load()
+    out = C.c_double(0.0)
+    _lib.check(lib.ptt_fp64_peak_probe(iters, C.byref(out), _stream_ptr(torch)), "ptt_fp64_peak_probe")
+    return out.value

@@ -1,0 +1,72 @@
+"""ctypes access to the TEST-ONLY host emulation of the device headers (see hostemu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libhostemu.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "hostemu.cpp")
+    hdrs = [os.path.join(_HERE, "..", "..", "pttools_b200", "csrc", h) for h in os.listdir(
+        os.path.join(_HERE, "..", "..", "pttools_b200", "csrc")) if h.endswith(".cuh")]
+    newest = max(os.path.getmtime(p) for p in [src] + hdrs)
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", _SO, src])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        d, i, pd, pi = C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)
+        _lib.emu_integrate.argtypes = [d, d, d, d, d, i, pd, pd, pd]
+        _lib.emu_anmax.argtypes = [d, pi]
+        _lib.emu_anmax.restype = d
+        _lib.emu_bag_forward.argtypes = [d, d, i, i, pd]
+        _lib.emu_bag_find_alpha_plus.argtypes = [d, d, i, d, pd, pi, pi]
+        _lib.emu_bag_profile.argtypes = [d, d, i, i, d, pd, pd, pd, pi, pi, pi]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def integrate(v0, w0, xi0, cs2, t_end, n):
+    v, w, xi = np.empty(n), np.empty(n), np.empty(n)
+    rc = lib().emu_integrate(v0, w0, xi0, cs2, t_end, n, _p(v), _p(w), _p(xi))
+    return rc, v, w, xi
+
+
+def anmax(v_wall):
+    st = C.c_int(0)
+    return lib().emu_anmax(v_wall, C.byref(st)), st.value
+
+
+def bag_forward(v_wall, ap, sol_type, n_xi):
+    out = np.empty(8)
+    st = lib().emu_bag_forward(v_wall, ap, sol_type, n_xi, _p(out))
+    return st, dict(i1=int(out[0]), t_end2=out[1], n_fwd=int(out[2]), v=out[3], w=out[4], xi=out[5], w1=out[6], wn_raw=out[7])
+
+
+def find_alpha_plus(v_wall, alpha_n, n_xi, an_max):
+    ap, st, it = C.c_double(0), C.c_int(0), C.c_int(0)
+    rc = lib().emu_bag_find_alpha_plus(v_wall, alpha_n, n_xi, an_max, C.byref(ap), C.byref(st), C.byref(it))
+    return rc, ap.value, st.value, it.value
+
+
+def bag_profile(v_wall, ap, sol_type, n_xi, w_n=1.0):
+    cap = lib().emu_row_capacity(n_xi)
+    v, w, xi = np.full(cap, np.nan), np.full(cap, np.nan), np.full(cap, np.nan)
+    off, npts, nw = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = lib().emu_bag_profile(v_wall, ap, sol_type, n_xi, w_n, _p(v), _p(w), _p(xi), C.byref(off), C.byref(npts), C.byref(nw))
+    s = slice(off.value, off.value + npts.value)
+    return rc, v[s].copy(), w[s].copy(), xi[s].copy(), nw.value

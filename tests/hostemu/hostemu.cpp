@@ -1,0 +1,51 @@
+// TEST-ONLY host emulation of the device algorithm headers (pttools_b200/csrc/*.cuh compiled with g++).
+// It exists so that the per-thread device logic can be unit-tested in a container without a GPU.
+// The product package never loads this library; it only ever runs the nvcc-built CUDA kernels.
+#include "../../pttools_b200/csrc/ptt_bag.cuh"
+
+using namespace ptt;
+
+namespace {
+struct ArrayEmitter {
+    double *v, *w, *xi;
+    bool skip(const State&) const { return false; }
+    bool visit(int i, const State& y) { v[i] = y.v; w[i] = y.w; xi[i] = y.xi; return true; }
+};
+}
+
+extern "C" {
+
+int emu_integrate(double v0, double w0, double xi0, double cs2, double t_end, int n,
+                  double* v, double* w, double* xi) {
+    State y0{v0, w0, xi0};
+    ArrayEmitter em{v, w, xi};
+    return integrate_grid(cs2, y0, t_end, n, em);
+}
+
+double emu_anmax(double v_wall, int* status) { return alpha_n_max_deflagration(v_wall, *status); }
+
+int emu_bag_forward(double v_wall, double ap, int sol_type, int n_xi, double* out) {
+    BagForward f = bag_forward(v_wall, ap, sol_type, n_xi);
+    out[0] = f.i1; out[1] = f.t_end2; out[2] = f.n_fwd; out[3] = f.last.v; out[4] = f.last.w; out[5] = f.last.xi;
+    out[6] = f.w1; out[7] = f.wn_raw;
+    return f.status;
+}
+
+int emu_bag_find_alpha_plus(double v_wall, double alpha_n, int n_xi, double anmax, double* ap, int* sol_type, int* iters) {
+    BagRoot r = bag_find_alpha_plus(v_wall, alpha_n, n_xi, anmax);
+    *ap = r.alpha_plus; *sol_type = r.sol_type; *iters = r.iters;
+    return r.status;
+}
+
+// rows must hold profile_row_capacity(n_xi) doubles each
+int emu_bag_profile(double v_wall, double ap, int sol_type, int n_xi, double w_n,
+                    double* v, double* w, double* xi, int* off, int* npts, int* n_wall) {
+    RowOut row{v, w, xi};
+    BagProfile p = bag_emit_profile(v_wall, ap, sol_type, n_xi, w_n, row);
+    *off = p.off; *npts = p.npts; *n_wall = p.n_wall;
+    return p.status;
+}
+
+int emu_row_capacity(int n_xi) { return profile_row_capacity(n_xi); }
+
+}

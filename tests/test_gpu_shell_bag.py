@@ -1,0 +1,97 @@
+"""GPU parity: bag fluid shell (CUDA through the C ABI) against the oracle on the same inputs."""
+import numpy as np
+import pytest
+
+from oracle import shell_bag as sb
+from util_compare import curve_errors
+
+pytestmark = pytest.mark.gpu
+
+PROFILE_RTOL = 1e-6     # north_star: velocity/enthalpy profiles within 1e-6 relative
+
+
+def test_integrate_batch_matches_tight_reference():
+    from scipy.integrate import solve_ivp
+    from pttools_b200 import engine
+    cases = [(0.2519, 1.0, 0.5, 0.0, -50.0), (0.42, 1.0, 0.7, 0.0, -50.0), (0.2058, 0.5376, 0.7, 1.0, -50.0),
+             (0.2519, 1.0, 0.5, 0.0, -3.3), (0.3, 1.0, 0.4, 0.0, 20.0)]
+    arr = np.array(cases)
+    n_xi = 1000
+    v, w, xi, st = engine.integrate_batch(arr[:, 0], arr[:, 1], arr[:, 2], arr[:, 3], arr[:, 4], n_xi)
+    v, w, xi, st = v.cpu().numpy(), w.cpu().numpy(), xi.cpu().numpy(), st.cpu().numpy()
+    for i, (v0, w0, xi0, ph, te) in enumerate(cases):
+        t = np.linspace(0, te, n_xi)
+        ref = solve_ivp(lambda t_, y_: sb.rhs(y_, t_, 1 / 3), (0, te), [v0, w0, xi0], method="DOP853",
+                        rtol=1e-13, atol=1e-15, t_eval=t)
+        if st[i] != 0:
+            assert not ref.success or np.any(~np.isfinite(ref.y))
+            continue
+        np.testing.assert_allclose(v[i], ref.y[0], rtol=0, atol=2e-9)
+        np.testing.assert_allclose(w[i], ref.y[1], rtol=2e-9, atol=0)
+        np.testing.assert_allclose(xi[i], ref.y[2], rtol=0, atol=2e-9)
+
+
+def test_integrate_batch_matches_odeint_at_lsoda_tolerance():
+    # the reference's own integrator (odeint defaults) is only good to ~1e-7: compare at that level
+    from pttools_b200 import engine
+    v0, w0, xi0 = 0.25190626980271985, 1.0, 0.5
+    v, w, xi, st = engine.integrate_batch([v0], [w0], [xi0], [0.0], [-50.0], 5000)
+    vo, wo, xio, _ = sb.integrate(v0, w0, xi0, 0.0, -50.0, 5000)
+    assert int(st[0]) == 0
+    np.testing.assert_allclose(v[0].cpu().numpy(), vo, atol=5e-7)
+    np.testing.assert_allclose(xi[0].cpu().numpy(), xio, atol=5e-7)
+
+
+def test_alpha_n_max_matches_oracle():
+    from pttools_b200 import engine
+    vws = np.array([0.05, 0.3, 0.5, 0.577, 0.58, 0.7, 0.9])
+    got, st = engine.bag_alpha_n_max(vws)
+    want = np.array([sb.alpha_n_max_deflagration(v) for v in vws])
+    assert np.all(st.cpu().numpy() == 0)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=5e-7)
+
+
+def test_alpha_plus_and_types_match_oracle():
+    from pttools_b200 import engine
+    rng = np.random.default_rng(2)
+    vw = rng.uniform(0.05, 0.95, 48)
+    an = rng.uniform(0.005, 0.5, 48)
+    ap, ty, st = engine.bag_find_alpha_plus(vw, an)
+    ap, ty, st = ap.cpu().numpy(), ty.cpu().numpy(), st.cpu().numpy()
+    for i in range(vw.size):
+        t_o = sb.identify_solution_type(vw[i], an[i])
+        assert ty[i] == t_o
+        if t_o == sb.ERROR:
+            assert st[i] == 1 and np.isnan(ap[i])
+            continue
+        assert st[i] == 0
+        np.testing.assert_allclose(ap[i], sb.find_alpha_plus(vw[i], an[i]), rtol=5e-7)
+
+
+@pytest.mark.parametrize("v_wall,alpha_n", [(0.5, 0.1), (0.7, 0.1), (0.9, 0.1), (0.3, 0.2), (0.44, 0.0046),
+                                            (0.7, 0.052), (0.58, 0.3), (0.92, 0.05), (0.731, 0.05)])
+def test_profile_matches_oracle(v_wall, alpha_n):
+    from pttools_b200 import engine
+    sh = engine.sweep_shells_bag([v_wall], [alpha_n])
+    assert int(sh.status[0]) == 0
+    v, w, xi = sh.profile(0)
+    vo, wo, xio = sb.sound_shell_bag(v_wall, alpha_n)
+    assert v.size == w.size == xi.size
+    assert xi[0] == 0.0 and xi[-1] == 1.0 and v[0] == 0.0 and v[-1] == 0.0
+    np.testing.assert_allclose(w[-1], 1.0, rtol=1e-14)
+    # shock position and centre enthalpy
+    np.testing.assert_allclose(xi[-2], xio[-2], rtol=PROFILE_RTOL)
+    np.testing.assert_allclose(w[0], wo[0], rtol=PROFILE_RTOL)
+    ev, ew = curve_errors(xi, v, w, xio, vo, wo, v_wall)
+    assert ev < PROFILE_RTOL and ew < PROFILE_RTOL
+
+
+def test_no_solution_and_invalid_points():
+    from pttools_b200 import engine
+    sh = engine.sweep_shells_bag([0.2, 0.5, 1.5], [0.45, 0.1, 0.1])
+    st = sh.status.cpu().numpy()
+    assert st[0] == 1          # alpha_n above alpha_n_max_deflagration: reference returns nan_arr
+    assert st[1] == 0
+    assert st[2] == 4
+    v, w, xi = sh.profile(0)
+    assert v.size == 1 and np.isnan(v[0])

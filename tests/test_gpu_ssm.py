@@ -1,0 +1,129 @@
+"""GPU parity: Sound Shell Model chain (CUDA through the C ABI) against the oracle and the reference-run fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import shell_bag as sb
+from oracle import ssm
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SPEC_RTOL = 1e-5      # north_star: spectra and omgw0 amplitudes within 1e-5 relative
+
+
+def _rows_from_profiles(profiles, torch):
+    cap = max(p[0].size for p in profiles)
+    P = len(profiles)
+    rows = [torch.zeros((P, cap), dtype=torch.float64, device="cuda") for _ in range(3)]
+    for i, prof in enumerate(profiles):
+        for r, a in zip(rows, prof):
+            r[i, : a.size] = torch.as_tensor(a, device="cuda")
+    off = torch.zeros(P, dtype=torch.int32, device="cuda")
+    npts = torch.as_tensor([p[0].size for p in profiles], dtype=torch.int32, device="cuda")
+    return rows, off, npts
+
+
+def test_sin_transform_reference_fixture():
+    import torch
+    from pttools_b200 import engine
+    d = np.load(os.path.join(GOLDEN, "ref_sin_transform.npz"))
+    f = d["f"]
+    P, n = f.shape
+    xi = np.tile(d["xi"], (P, 1))
+    out = engine.sin_transform_batch(d["z"], xi, f, np.zeros(P, dtype=np.int32), np.full(P, n, dtype=np.int32))
+    out = out.cpu().numpy()
+    for p in range(P):
+        want = d[f"st_{p}"]
+        np.testing.assert_allclose(out[p], want, rtol=1e-9, atol=1e-13 * np.abs(want).max())
+
+
+def test_sin_transform_ragged_and_edge_cases():
+    import torch
+    from pttools_b200 import engine
+    rng = np.random.default_rng(3)
+    profs, zs = [], np.logspace(-1, np.log10(49.0), 64)      # all-exact branch (no z above the threshold)
+    for n in (17, 130, 1025):
+        xi = np.sort(rng.uniform(0, 1, n))
+        f = np.where((xi > 0.2) & (xi < 0.8), rng.uniform(0.1, 1, n), 0.0)
+        profs.append((f, f, xi))
+    rows, off, npts = _rows_from_profiles(profs, torch)
+    out = engine.sin_transform_batch(zs, rows[2], rows[0], off, npts).cpu().numpy()
+    for p, (f, _, xi) in enumerate(profs):
+        np.testing.assert_allclose(out[p], ssm.sin_transform(zs, xi, f), rtol=1e-9, atol=1e-14)
+    # all-asymptotic branch
+    zs_hi = np.logspace(2, 3, 16)
+    out = engine.sin_transform_batch(zs_hi, rows[2], rows[0], off, npts).cpu().numpy()
+    for p, (f, _, xi) in enumerate(profs):
+        np.testing.assert_allclose(out[p], ssm.sin_transform(zs_hi, xi, f), rtol=1e-9, atol=1e-14)
+
+
+@pytest.mark.parametrize("mode", ["oracle_profiles", "gpu_profiles"])
+def test_a2_spec_den_and_gw_bag_chain(mode):
+    """power_gw_scaled_bag / power_v_bag / a2_e_conserving_bag at the fixture sizes (npt = 2000, 500, 1000)."""
+    import torch
+    from pttools_b200 import engine
+    d = np.load(os.path.join(GOLDEN, "ref_bag_spectra.npz"))
+    z, npt = d["z"], tuple(int(x) for x in d["npt"])
+    pts = d["points"]
+    vw, an = pts[:, 0], pts[:, 1]
+    if mode == "gpu_profiles":
+        shells = engine.sweep_shells_bag(vw, an, n_xi=npt[0])
+        assert np.all(shells.status.cpu().numpy() == 0)
+        tol = SPEC_RTOL
+    else:
+        # decouple spectrum parity from shell parity: feed the oracle's own profiles
+        profs = [sb.sound_shell_bag(a, b, npt[0]) for a, b in pts]
+        rows, off, npts_t = _rows_from_profiles(profs, torch)
+        shells = engine.ShellBatch(engine.dev_f64(vw), engine.dev_f64(an), None, None, None, rows[0], rows[1], rows[2],
+                                   off, npts_t, None, npt[0])
+        tol = 1e-8
+    theta_s = 0.75 * an          # e = 3/4 w + theta_s (1 - phase), w_n = 1  (quantities.py:38-54)
+    pp = engine.point_params(vw, sb.CS0, 0.75, 0.75, theta_s, 0.0)
+    for nuc in ("exponential", "simultaneous"):
+        plan = engine.SsmPlan(z, cs=sb.CS0, nt=npt[1], n_z_lookup=npt[2], nxi=npt[0], nuc_type=nuc, mode="bag")
+        res = engine.spectra_from_shells(plan, shells, pp, keep=True)
+        pow_gw = res.pow_gw.cpu().numpy()
+        for i in range(len(pts)):
+            np.testing.assert_allclose(pow_gw[i], d[f"pow_gw_{nuc[:3]}_{i}"], rtol=tol)
+    # power_v_bag: spec_den_v evaluated on z itself
+    plan = engine.SsmPlan(z, cs=sb.CS0, nt=npt[1], n_z_lookup=npt[2], nxi=npt[0], mode="ssm", phase_rule=0)
+    res = engine.spectra_from_shells(plan, shells, pp, keep=True)
+    pow_v = res.pow_v.cpu().numpy()
+    for i in range(len(pts)):
+        np.testing.assert_allclose(pow_v[i], d[f"pow_v_exp_{i}"], rtol=tol)
+
+
+def test_a2_parts_against_reference_fixture():
+    import torch
+    from pttools_b200 import engine, _lib
+    import ctypes as C
+    d = np.load(os.path.join(GOLDEN, "ref_bag_spectra.npz"))
+    npt = tuple(int(x) for x in d["npt"])
+    pts = d["points"]
+    profs = [sb.sound_shell_bag(a, b, npt[0]) for a, b in pts]
+    rows, off, npts_t = _rows_from_profiles(profs, torch)
+    shells = engine.ShellBatch(engine.dev_f64(pts[:, 0]), None, None, None, None, rows[0], rows[1], rows[2], off, npts_t,
+                               None, npt[0])
+    pp = engine.point_params(pts[:, 0], sb.CS0, 0.75, 0.75, 0.75 * pts[:, 1], 0.0)
+    # a plan whose single A^2 grid is the fixture's z_a2: build through the generic helper
+    zq = d["z_a2"]
+    plan = engine.A2OnlyPlan(zq, nxi=npt[0], phase_rule=0)
+    a2, fp2, lam2 = engine.a2_batch(plan, shells, pp, want_parts=True)
+    a2, fp2, lam2 = a2.cpu().numpy(), fp2.cpu().numpy(), lam2.cpu().numpy()
+    for i in range(len(pts)):
+        np.testing.assert_allclose(a2[i], d[f"a2_{i}"], rtol=1e-8, atol=1e-30)
+        np.testing.assert_allclose(fp2[i], d[f"fp2_{i}"], rtol=1e-8, atol=1e-30)
+        np.testing.assert_allclose(lam2[i], d[f"lam2_{i}"], rtol=1e-8, atol=1e-30)
+
+
+def test_failed_shell_gives_nan_spectrum():
+    from pttools_b200 import engine
+    z = np.logspace(-1, 3, 50)
+    shells = engine.sweep_shells_bag([0.2, 0.5], [0.45, 0.1], n_xi=500)
+    pp = engine.point_params([0.2, 0.5], sb.CS0, 0.75, 0.75, [0.75 * 0.45, 0.075], 0.0)
+    plan = engine.SsmPlan(z, nt=200, n_z_lookup=300, nxi=500, mode="bag")
+    res = engine.spectra_from_shells(plan, shells, pp)
+    pw = res.pow_gw.cpu().numpy()
+    assert np.all(np.isnan(pw[0]))
+    assert np.all(np.isfinite(pw[1])) and np.all(pw[1] > 0)
