@@ -174,6 +174,17 @@ int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const double* pv, in
 int ptt_pow_spec_batch(int P, int n_z, const double* z, const double* spec_den, int64_t stride, double* out,
                        void* stream);
 
+/* scratch size (doubles per profile) that ptt_a2_batch needs */
+int ptt_a2_work_stride(int row_stride, int nxi, int n_z);
+
+/* Thermodynamic integrals of a batch of shells (trapezoid rule over xi^3)        pttools/bubble/thermo.py:139-221
+ * pp2[P,12] = {v_wall, mu_s, mu_b, V_s, V_b, a_s, a_b, T_ref, phase_rule, 0, 0, 0}  (mu = 1 + 1/cs2)
+ * out[P,8]  = {int w v^2 gamma^2 dxi^3, int (theta - theta_n) dxi^3, int (w - w_n) dxi^3, int (s - s_n) dxi^3,
+ *              wbar, i_wall, n_broken, w[-1]};  device pointers, enqueued on `stream`. */
+int ptt_profile_integrals_batch(int P, const double* rows_v, const double* rows_w, const double* rows_xi,
+                                int64_t row_stride, const int32_t* off, const int32_t* npts, const double* pp2,
+                                double* out, void* stream);
+
 /* FP64 FMA throughput probe used by bench.py for the roofline denominator (not part of the reference). */
 int ptt_fp64_peak_probe(int iters, double* out_flops_per_s, void* stream);
 

@@ -37,6 +37,31 @@ def rhs(y, _t, cs2):
     return (dv, dw, dxi)
 
 
+_ODEINT_KW: dict = {}
+_ANMAX_CACHE: dict = {}
+
+
+class lsoda_tolerances:
+    """Context manager: run the oracle with explicit LSODA tolerances instead of scipy's defaults (1.49e-8).
+    Used by the parity tests to separate the reference's own integrator noise from implementation differences
+    (the tau-grid flips under 1e-8 perturbations)."""
+
+    def __init__(self, rtol, atol):
+        self.kw = {"rtol": rtol, "atol": atol}
+
+    def __enter__(self):
+        self.saved = dict(_ODEINT_KW)
+        _ODEINT_KW.update(self.kw)
+        _ANMAX_CACHE.clear()
+        return self
+
+    def __exit__(self, *exc):
+        _ODEINT_KW.clear()
+        _ODEINT_KW.update(self.saved)
+        _ANMAX_CACHE.clear()
+        return False
+
+
 def integrate(v0, w0, xi0, phase, t_end, n_xi, css2=CS0_2, csb2=CS0_2, **odeint_kw):
     """fluid_integrate_param with method="odeint"; integrate.py:81-135, 167-189.
 
@@ -45,7 +70,7 @@ def integrate(v0, w0, xi0, phase, t_end, n_xi, css2=CS0_2, csb2=CS0_2, **odeint_
     """
     t = np.linspace(0.0, t_end, n_xi)
     cs2 = phase * csb2 + (1.0 - phase) * css2
-    sol = odeint(rhs, np.array([v0, w0, xi0]), t, args=(cs2,), **odeint_kw)
+    sol = odeint(rhs, np.array([v0, w0, xi0]), t, args=(cs2,), **{**_ODEINT_KW, **odeint_kw})
     return sol[:, 0], sol[:, 1], sol[:, 2], t
 
 
@@ -241,9 +266,6 @@ def shell_alpha_plus(v_wall, alpha_plus, sol_type, n_xi=N_XI_DEFAULT, w_n=1.0):
 # ---------------------------------------------------------------------------------------------------------------
 # a4/a5: alpha_n <-> alpha_+, classification, full shell
 # ---------------------------------------------------------------------------------------------------------------
-
-_ANMAX_CACHE: dict = {}
-
 
 def alpha_n_max_deflagration(v_wall, n_xi=N_XI_DEFAULT):
     """alpha.py:44-50 (scalar).  Depends on v_wall only; memoised here because the reference recomputes it up to

@@ -254,7 +254,8 @@ constexpr int ST_TILE = 1024;
 
 __global__ void __launch_bounds__(ST_THREADS) sin_transform_kernel(
     const int n_z, const double* __restrict__ z_all, const double* __restrict__ frac_all,
-    const double* __restrict__ xiA_all, const double* __restrict__ gA_all, const long long strideA,
+    const double* __restrict__ xiA_all, const long long strideA, const double* __restrict__ gA_all,
+    const long long g_strideA, const int g_has_off,
     const int* __restrict__ off, const int* __restrict__ npts, const double* __restrict__ envA_all,
     const long long env_strideA, double* __restrict__ outA, const long long out_strideA,
     const int nB, const double* __restrict__ xiB, const double* __restrict__ gB_all, const long long strideB,
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(ST_THREADS) sin_transform_kernel(
     double accA = 0.0, accB = 0.0;
     if (need_exact) {
         const double* xi = xiA_all + (long long)p * strideA + off[p];
-        const double* g = gA_all + (long long)p * strideA + off[p];
+        const double* g = gA_all + (long long)p * g_strideA + (g_has_off ? off[p] : 0);
         for (int t0 = 0; t0 < N; t0 += ST_TILE) {
             const int m = min(ST_TILE, N - t0);
             for (int k = threadIdx.x; k < m; k += ST_THREADS) { s_x[k] = xi[t0 + k]; s_g[k] = g[t0 + k]; }
@@ -577,8 +578,8 @@ extern "C" int ptt_sin_transform_batch(int P, const double* xi, const double* f,
     if (e != cudaSuccess) { cudaFreeAsync(g, stream); return set_cuda_error("ptt_sin_transform_batch alloc", e); }
     st_prep_kernel<<<P, 256, 0, stream>>>(xi, f, stride, off, npts, g, env);
     dim3 grid((n_z + ST_THREADS - 1) / ST_THREADS, P);
-    sin_transform_kernel<<<grid, ST_THREADS, 0, stream>>>(n_z, z, frac, xi, g, stride, off, npts, env, ENV_SIZE, out, n_z,
-                                                          0, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, 0);
+    sin_transform_kernel<<<grid, ST_THREADS, 0, stream>>>(n_z, z, frac, xi, stride, g, stride, 1, off, npts, env, ENV_SIZE,
+                                                          out, n_z, 0, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, 0);
     const int rc = check_launch("sin_transform_kernel");
     cudaFreeAsync(g, stream);
     cudaFreeAsync(env, stream);
@@ -602,7 +603,8 @@ extern "C" int ptt_a2_batch(const ptt_a2_plan_t* plan, int P, const double* rows
                                           off, npts, pp, work, work_stride, lay);
     dim3 grid((plan->n_z + ST_THREADS - 1) / ST_THREADS, P);
     sin_transform_kernel<<<grid, ST_THREADS, 0, stream>>>(
-        plan->n_z, plan->z, plan->frac, rows_xi, work + lay.gv(), row_stride, off, npts, work + lay.env_v(), work_stride,
+        plan->n_z, plan->z, plan->frac, rows_xi, row_stride, work + lay.gv(), work_stride, 0, off, npts,
+        work + lay.env_v(), work_stride,
         work + lay.F(), work_stride, plan->nxi, plan->xi_re, work + lay.hl(), work_stride, work + lay.env_l(),
         work_stride, work + lay.L(), work_stride, 1);
     dim3 grid2((plan->n_z + 255) / 256, P);
@@ -626,7 +628,7 @@ extern "C" int ptt_spec_den_v_batch(const ptt_sdv_plan_t* plan, int P, const dou
     if (P == 0) return PTT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int smem = plan->smem_bytes;
-    if (smem > 48 * 1024) {
+    {   // static + dynamic shared memory may exceed the 48 KB default: always opt in
         const cudaError_t e = cudaFuncSetAttribute(spec_den_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return set_cuda_error("spec_den_v_kernel smem", e);
     }
@@ -645,7 +647,7 @@ extern "C" int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const dou
     if (P == 0) return PTT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int smem = plan->smem_bytes;
-    if (smem > 48 * 1024) {
+    {
         const cudaError_t e = cudaFuncSetAttribute(spec_den_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return set_cuda_error("spec_den_gw_kernel smem", e);
     }

@@ -31,6 +31,55 @@ def _torch():
     return _lib.require_cuda()
 
 
+class _Stages:
+    """Counts kernel launches and (when enabled) brackets every C-ABI call with CUDA events on the launching
+    stream, so that bench.py can report per-kernel device time measured inside its timed region."""
+
+    def __init__(self):
+        self.enabled = False
+        self.launches = 0
+        self._ev = []
+
+    def enable(self, on: bool):
+        self.enabled = on
+        self._ev = []
+
+    class _Ctx:
+        def __init__(self, outer, name, launches):
+            self.o, self.name, self.n = outer, name, launches
+
+        def __enter__(self):
+            self.o.launches += self.n
+            if self.o.enabled:
+                import torch
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.o.enabled:
+                self.b.record()
+                self.o._ev.append((self.name, self.a, self.b))
+            return False
+
+    def stage(self, name, launches=1):
+        return self._Ctx(self, name, launches)
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self._ev:
+            d = out.setdefault(name, {"ms": 0.0, "n": 0})
+            d["ms"] += a.elapsed_time(b)
+            d["n"] += 1
+        return out
+
+
+STAGES = _Stages()
+
+
 def _stream_ptr(torch):
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -72,8 +121,9 @@ def bag_alpha_n_max(v_wall):
     v_wall = dev_f64(v_wall)
     out = torch.empty_like(v_wall)
     status = torch.empty(v_wall.numel(), dtype=torch.int32, device=v_wall.device)
-    _lib.check(lib.ptt_bag_alpha_n_max(v_wall.numel(), _ptr(v_wall), _ptr(out), _ptr(status), _lib.MEM_DEVICE,
-                                       _stream_ptr(torch)), "ptt_bag_alpha_n_max")
+    with STAGES.stage("bag_alpha_n_max", 1):
+        _lib.check(lib.ptt_bag_alpha_n_max(v_wall.numel(), _ptr(v_wall), _ptr(out), _ptr(status), _lib.MEM_DEVICE,
+                                           _stream_ptr(torch)), "ptt_bag_alpha_n_max")
     return out, status
 
 
@@ -106,6 +156,13 @@ class ShellBatch:
     def __len__(self):
         return self.v_wall.numel()
 
+    def slice(self, a, b):
+        """Row-block view [a, b) of the batch (no copies)."""
+        f = lambda t: None if t is None else t[a:b]
+        return ShellBatch(f(self.v_wall), f(self.alpha_n), f(self.alpha_plus), f(self.sol_type), f(self.status),
+                          self.rows_v[a:b], self.rows_w[a:b], self.rows_xi[a:b], self.off[a:b], self.npts[a:b],
+                          f(self.scalars), self.n_xi)
+
     def profile(self, i):
         o, n = int(self.off[i]), int(self.npts[i])
         return (self.rows_v[i, o:o + n].cpu().numpy(), self.rows_w[i, o:o + n].cpu().numpy(),
@@ -129,9 +186,11 @@ def sweep_shells_bag(v_wall, alpha_n, n_xi=N_XI_DEFAULT, an_max=None) -> ShellBa
     st = torch.empty(n, dtype=torch.int32, device=dev)
     status = torch.empty(n, dtype=torch.int32, device=dev)
     scalars = torch.empty((n, 4), dtype=torch.float64, device=dev)
-    _lib.check(lib.ptt_sweep_shells_bag(n, _ptr(v_wall), _ptr(alpha_n), n_xi, _ptr(an_max), _ptr(rows[0]), _ptr(rows[1]),
-                                        _ptr(rows[2]), cap, _ptr(off), _ptr(npts), _ptr(ap), _ptr(st), _ptr(scalars),
-                                        _ptr(status), _lib.MEM_DEVICE, _stream_ptr(torch)), "ptt_sweep_shells_bag")
+    with STAGES.stage("shells_bag", 2):
+        _lib.check(lib.ptt_sweep_shells_bag(n, _ptr(v_wall), _ptr(alpha_n), n_xi, _ptr(an_max), _ptr(rows[0]),
+                                            _ptr(rows[1]), _ptr(rows[2]), cap, _ptr(off), _ptr(npts), _ptr(ap), _ptr(st),
+                                            _ptr(scalars), _ptr(status), _lib.MEM_DEVICE, _stream_ptr(torch)),
+                   "ptt_sweep_shells_bag")
     return ShellBatch(v_wall, alpha_n, ap, st, status, rows[0], rows[1], rows[2], off, npts, scalars, n_xi)
 
 
@@ -410,9 +469,10 @@ def a2_batch(plan: SsmPlan, shells: ShellBatch, pp, want_parts=False):
     a2 = torch.empty((P, plan.n_a2), dtype=torch.float64, device=dev)
     fp = torch.empty_like(a2) if want_parts else None
     l2 = torch.empty_like(a2) if want_parts else None
-    _lib.check(lib.ptt_a2_batch(C.byref(plan.a2_plan), P, _ptr(shells.rows_v), _ptr(shells.rows_w), _ptr(shells.rows_xi),
-                                cap, _ptr(shells.off), _ptr(shells.npts), _ptr(pp), _ptr(work), ws, _ptr(a2), _ptr(fp),
-                                _ptr(l2), _stream_ptr(torch)), "ptt_a2_batch")
+    with STAGES.stage("a2", 3):
+        _lib.check(lib.ptt_a2_batch(C.byref(plan.a2_plan), P, _ptr(shells.rows_v), _ptr(shells.rows_w),
+                                    _ptr(shells.rows_xi), cap, _ptr(shells.off), _ptr(shells.npts), _ptr(pp), _ptr(work),
+                                    ws, _ptr(a2), _ptr(fp), _ptr(l2), _stream_ptr(torch)), "ptt_a2_batch")
     if want_parts:
         return a2, fp, l2
     return a2
@@ -426,8 +486,9 @@ def spec_den_v_batch(plan: SsmPlan, ipass: int, a2, v_wall):
     sp = plan.sdv_plans[ipass]
     out = torch.empty((P, sp.n_z), dtype=torch.float64, device=a2.device)
     a2_view_ptr = C.c_void_p(a2.data_ptr() + 8 * int(plan.seg[ipass]))
-    _lib.check(lib.ptt_spec_den_v_batch(C.byref(sp), P, a2_view_ptr, a2.shape[1], _ptr(v_wall), _ptr(out), sp.n_z,
-                                        _stream_ptr(torch)), "ptt_spec_den_v_batch")
+    with STAGES.stage("spec_den_v" if ipass == len(plan.passes) - 1 else "spec_den_v_y", 1):
+        _lib.check(lib.ptt_spec_den_v_batch(C.byref(sp), P, a2_view_ptr, a2.shape[1], _ptr(v_wall), _ptr(out), sp.n_z,
+                                            _stream_ptr(torch)), "ptt_spec_den_v_batch")
     return out
 
 
@@ -442,8 +503,9 @@ def spec_den_gw_batch(plan: SsmPlan, pv, slf=None, scale=None, want_sd=True):
     sd = torch.empty((P, n_y), dtype=torch.float64, device=dev) if want_sd else None
     pw = torch.empty((P, n_y), dtype=torch.float64, device=dev)
     om = torch.empty((P, n_y), dtype=torch.float64, device=dev) if scale_t is not None else None
-    _lib.check(lib.ptt_spec_den_gw_batch(C.byref(plan.gw_plan), P, _ptr(pv), pv.shape[1], _ptr(slf_t), _ptr(scale_t),
-                                         _ptr(sd), _ptr(pw), _ptr(om), _stream_ptr(torch)), "ptt_spec_den_gw_batch")
+    with STAGES.stage("spec_den_gw", 1):
+        _lib.check(lib.ptt_spec_den_gw_batch(C.byref(plan.gw_plan), P, _ptr(pv), pv.shape[1], _ptr(slf_t), _ptr(scale_t),
+                                             _ptr(sd), _ptr(pw), _ptr(om), _stream_ptr(torch)), "ptt_spec_den_gw_batch")
     return sd, pw, om
 
 
@@ -451,8 +513,9 @@ def pow_spec_batch(z_dev, sd):
     torch = _torch()
     lib = _lib.load()
     out = torch.empty_like(sd)
-    _lib.check(lib.ptt_pow_spec_batch(sd.shape[0], sd.shape[1], _ptr(z_dev), _ptr(sd), sd.shape[1], _ptr(out),
-                                      _stream_ptr(torch)), "ptt_pow_spec_batch")
+    with STAGES.stage("pow_spec", 1):
+        _lib.check(lib.ptt_pow_spec_batch(sd.shape[0], sd.shape[1], _ptr(z_dev), _ptr(sd), sd.shape[1], _ptr(out),
+                                          _stream_ptr(torch)), "ptt_pow_spec_batch")
     return out
 
 
@@ -490,6 +553,19 @@ def sin_transform_batch(z, xi, f, off, npts, z_st_thresh=Z_ST_THRESH):
     out = torch.empty((P, zz.size), dtype=torch.float64, device=xi.device)
     _lib.check(lib.ptt_sin_transform_batch(P, _ptr(xi), _ptr(f), stride, _ptr(off_t), _ptr(npts_t), zz.size, _ptr(z_d),
                                            _ptr(frac), _ptr(out), _stream_ptr(torch)), "ptt_sin_transform_batch")
+    return out
+
+
+def profile_integrals(shells: ShellBatch, pp2):
+    """Raw trapezoid integrals over xi^3 per shell (pttools/bubble/thermo.py:139-221); see ptt_profile_integrals_batch."""
+    torch = _torch()
+    lib = _lib.load()
+    P = len(shells)
+    out = torch.empty((P, 8), dtype=torch.float64, device=shells.rows_v.device)
+    with STAGES.stage("profile_integrals", 1):
+        _lib.check(lib.ptt_profile_integrals_batch(P, _ptr(shells.rows_v), _ptr(shells.rows_w), _ptr(shells.rows_xi),
+                                                   shells.rows_v.shape[1], _ptr(shells.off), _ptr(shells.npts), _ptr(pp2),
+                                                   _ptr(out), _stream_ptr(torch)), "ptt_profile_integrals_batch")
     return out
 
 
