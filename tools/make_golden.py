@@ -91,6 +91,103 @@ def sin_transforms():
 
 TASKS = {"goldens": goldens, "bag_shells": bag_shells, "bag_spectra": bag_spectra, "sin_transforms": sin_transforms}
 
+# ---------------------------------------------------------------------------------------------------------------
+# Generic (model-independent) solver and SSMSpectrum / omgw0 fixtures
+# ---------------------------------------------------------------------------------------------------------------
+
+GENERIC_MODELS = {
+    # name: (class, kwargs)
+    "bag": ("BagModel", dict(a_s=1.1, a_b=1, V_s=1)),
+    "cs_quarter_third": ("ConstCSModel", dict(css2=1 / 4, csb2=1 / 3, a_s=1.5, a_b=1, V_s=1)),
+    "cs_third_quarter": ("ConstCSModel", dict(css2=1 / 3, csb2=1 / 4, a_s=5, a_b=1, V_s=1)),
+    "cs_032_third": ("ConstCSModel", dict(css2=1 / 3 - 0.01, csb2=1 / 3, a_s=1.5, a_b=1, V_s=1)),
+}
+# per-model points with alpha_n above the model's alpha_n_min (0, 0.173, 0.2755, 0.1194)
+GENERIC_POINTS = {
+    "bag": [(0.5, 0.1), (0.7, 0.1), (0.9, 0.1), (0.3, 0.05), (0.3, 0.2), (0.62, 0.15), (0.8, 0.3), (0.55, 0.2),
+            (0.44, 0.02), (0.95, 0.25)],
+    "cs_quarter_third": [(0.5, 0.2), (0.7, 0.2), (0.9, 0.2), (0.3, 0.25), (0.62, 0.3), (0.8, 0.3), (0.55, 0.2),
+                         (0.95, 0.25), (0.4, 0.35), (0.65, 0.18)],
+    "cs_third_quarter": [(0.3, 0.3), (0.45, 0.3), (0.55, 0.35), (0.7, 0.3), (0.8, 0.3), (0.9, 0.4), (0.62, 0.4),
+                         (0.95, 0.3)],
+    "cs_032_third": [(0.5, 0.15), (0.7, 0.15), (0.9, 0.15), (0.3, 0.2), (0.62, 0.15), (0.8, 0.3), (0.55, 0.2),
+                     (0.95, 0.25)],
+}
+SPECTRUM_POINTS = {"bag": [(0.5, 0.1), (0.7, 0.1), (0.9, 0.1)], "cs_quarter_third": [(0.5, 0.2), (0.8, 0.3)],
+                   "cs_third_quarter": [(0.45, 0.3), (0.7, 0.3)]}
+SCALARS = ["wn", "vp", "vm", "vp_tilde", "vm_tilde", "v_sh", "vm_sh", "vm_tilde_sh", "wp", "wm", "wm_sh", "v_cj",
+           "kappa", "omega", "kinetic_energy_fraction", "va_enthalpy_density", "ubarf2", "wbar", "ebar",
+           "va_kinetic_energy_density", "va_trace_anomaly_diff", "va_thermal_energy_density_diff",
+           "va_entropy_density_diff", "alpha_plus", "Tn"]
+
+
+def fluid_reference_table():
+    from pttools.bubble import fluid_reference
+    ref = fluid_reference.ref()
+    import numpy as np
+    raw = np.load(ref.path, allow_pickle=False)
+    d = {k: raw[k] for k in raw.files}
+    np.savez_compressed(os.path.join(OUT, "ref_fluid_reference.npz"), **d)
+    print("ref_fluid_reference.npz", list(d))
+
+
+def generic_bubbles():
+    import pttools.models as models
+    from pttools.bubble import Bubble
+    from pttools.bubble.boundary import SolutionType
+    codes = {SolutionType.SUB_DEF: 0, SolutionType.HYBRID: 1, SolutionType.DETON: 2}
+    d = {"scalar_names": np.array(SCALARS)}
+    for mname, (cls, kw) in GENERIC_MODELS.items():
+        model = getattr(models, cls)(**kw)
+        d[f"{mname}__model"] = np.array([getattr(model, "css2", 1 / 3), getattr(model, "csb2", 1 / 3), model.a_s, model.a_b,
+                                         model.V_s, model.V_b, model.T_ref, model.T_crit, model.w_crit, model.alpha_n_min])
+        d[f"{mname}__points"] = np.array(GENERIC_POINTS[mname])
+        for i, (vw, an) in enumerate(GENERIC_POINTS[mname]):
+            try:
+                b = Bubble(model, vw, an)
+            except Exception as e:  # invalid alpha_n for the model etc.
+                d[f"{mname}__err_{i}"] = np.array([1.0])
+                print(mname, vw, an, "ctor error", type(e).__name__, str(e)[:80])
+                continue
+            if not b.solved:
+                d[f"{mname}__err_{i}"] = np.array([2.0])
+                continue
+            d[f"{mname}__v_{i}"], d[f"{mname}__w_{i}"], d[f"{mname}__xi_{i}"] = b.v, b.w, b.xi
+            d[f"{mname}__phase_{i}"] = b.phase
+            d[f"{mname}__flags_{i}"] = np.array([codes[b.sol_type], b.solver_failed, b.no_solution_found,
+                                                 b.numerical_error, b.unphysical_alpha_plus, b.negative_entropy_flux,
+                                                 b.negative_net_entropy_change], dtype=float)
+            d[f"{mname}__scal_{i}"] = np.array([float(getattr(b, s)) for s in SCALARS])
+            print(mname, vw, an, b.sol_type.value, b.v.size, "failed" if b.solver_failed else "ok")
+    np.savez_compressed(os.path.join(OUT, "ref_generic_bubbles.npz"), **d)
+
+
+def generic_spectra():
+    import pttools.models as models
+    from pttools.bubble import Bubble
+    from pttools.omgw0 import Spectrum
+    d = {}
+    for mname, pts in SPECTRUM_POINTS.items():
+        cls, kw = GENERIC_MODELS[mname]
+        model = getattr(models, cls)(**kw)
+        d[f"{mname}__points"] = np.array(pts)
+        for i, (vw, an) in enumerate(pts):
+            b = Bubble(model, vw, an)
+            s = Spectrum(b, r_star=0.1)
+            d[f"{mname}__pow_v_{i}"], d[f"{mname}__pow_gw_{i}"] = s.pow_v, s.pow_gw
+            d[f"{mname}__omgw0_{i}"], d[f"{mname}__f_{i}"] = s.omgw0(), s.f()
+            d[f"{mname}__a2_{i}"] = s.a2
+            d[f"{mname}__misc_{i}"] = np.array([s.cs, s.source_lifetime_factor, s.F_gw0(), s.f_star0,
+                                                s.suppression_factor(), b.kinetic_energy_fraction])
+            print(mname, vw, an, "omgw0 peak", s.omgw0_peak())
+        d["y"] = s.y
+    np.savez_compressed(os.path.join(OUT, "ref_generic_spectra.npz"), **d)
+
+
+TASKS.update({"fluid_reference": fluid_reference_table, "generic_bubbles": generic_bubbles,
+              "generic_spectra": generic_spectra})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
