@@ -95,6 +95,28 @@ int ptt_sweep_shells_bag(int n, const double* v_wall, const double* alpha_n, int
                          int32_t* off, int32_t* npts, double* alpha_plus, int32_t* sol_type, double* scalars,
                          int32_t* status, int mem, void* stream);
 
+/* sound_shell_generic(model, v_wall, alpha_n, sol_type, wn, ...) for a whole sweep      pttools/bubble/fluid.py:848-1052
+ * One row of pg per point (models may differ from point to point):
+ *   pg[n,16] = {v_wall, alpha_n, sol_type, wn, v_cj, guess_vp, guess_vp_tilde, guess_wp, guess_wm,
+ *               css2, csb2, V_s, V_b, model_name_is_bag, 0, 0}
+ * (wn, v_cj and the solution type are closed-form host quantities of the model: models/bag.py:316, const_cs.py:633-737,
+ * chapman_jouguet.py:151-264; the guesses come from the fluid-reference table, fluid.py:925-949).
+ * Outputs: profile rows ([n,row_stride], row_stride >= ptt_generic_row_capacity(n_xi)), off/npts, and
+ *   scalars[n,16] = {vp, vm, vp_tilde, vm_tilde, v_sh, vm_sh, vm_tilde_sh, wp, wm, wm_sh, v_cj, wn, wn_estimate,
+ *                    solver_failed, 0, 0}  -- the reference's 17-tuple (fluid.py:1052).
+ * status[i] = PTT_ST_SOLVER_FAILED where the reference sets solver_failed. */
+int ptt_generic_row_capacity(int n_xi);
+int ptt_sweep_shells_generic(int n, const double* pg, int n_xi, double t_end, int thin_shell_limit, double wn_rtol,
+                             double* rows_v, double* rows_w, double* rows_xi, int64_t row_stride, int32_t* off,
+                             int32_t* npts, double* scalars, int32_t* status, int mem, void* stream);
+
+/* props.v_and_w_from_solution for a batch of bag shells (pttools/bubble/props.py:52-87): the entries of the
+ * fluid-reference starting-guess table (fluid_reference.py:166-196).  Device pointers.
+ * out[n,8] = {vp, vm, vp_tilde, vm_tilde, wp, wm, wn, 0}. */
+int ptt_shell_wall_values(int n, const double* rows_v, const double* rows_w, const double* rows_xi, int64_t row_stride,
+                          const int32_t* off, const int32_t* npts, const double* v_wall, const int32_t* sol_type,
+                          double* out, void* stream);
+
 /* --- Seam C: Sound Shell Model array operators (all pointers DEVICE pointers, enqueued on `stream`) -----------
  * Grids that depend only on (y, cs, nt, ...) are built once per sweep by the host mirror (numpy expressions
  * identical to the reference's) and passed in; the kernels do the per-profile arithmetic. */

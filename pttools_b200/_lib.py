@@ -70,6 +70,12 @@ SIGNATURES = {
     "ptt_spec_den_gw_batch": (C.c_int, [C.POINTER(GwPlan), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_pow_spec_batch": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ptt_generic_row_capacity": (C.c_int, [C.c_int]),
+    "ptt_sweep_shells_generic": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_void_p]),
+    "ptt_shell_wall_values": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_profile_integrals_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_fp64_peak_probe": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_void_p]),

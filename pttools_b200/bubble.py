@@ -1,0 +1,382 @@
+"""pttools.bubble call surface on top of the CUDA kernels.
+
+Batched operators (`sweep_bubbles`, `BubbleBatch`) are the product; the scalar functions and the `Bubble` class are
+one-point batches with the reference's names, arguments and error behaviour
+(pttools/bubble/{bubble,fluid,fluid_bag,alpha,transition,integrate}.py).
+"""
+from __future__ import annotations
+
+import dataclasses
+import logging
+import typing as tp
+
+import numpy as np
+
+from . import engine
+from . import fluid_reference
+from .models import CODE_SOL, SOL_CODE, Model, Phase, SolutionType
+
+logger = logging.getLogger(__name__)
+
+N_XI_DEFAULT = 5000                # pttools/bubble/const.py:12
+T_END_DEFAULT = 50.0               # const.py:18
+THIN_SHELL_T_POINTS_MIN = 100      # const.py:26
+CS0 = 1 / np.sqrt(3)
+CS0_2 = 1 / 3
+
+
+class NotYetSolvedError(RuntimeError):
+    """pttools/bubble/bubble.py:30-31."""
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Old bag-model API (fluid_bag.py, alpha.py, transition.py)
+# ---------------------------------------------------------------------------------------------------------------
+
+def alpha_n_max_deflagration_bag(v_wall, n_xi: int = N_XI_DEFAULT):
+    """alpha.py:71-88.  (As in the reference, the value does not depend on n_xi in practice: alpha.py:316.)"""
+    scalar = np.isscalar(v_wall)
+    vw = np.atleast_1d(np.asarray(v_wall, dtype=float))
+    if np.any(vw >= 1.0) or np.any(vw <= 0.0):
+        raise ValueError("Unphysical parameter(s): at least one value outside 0 < v_wall < 1.")
+    out = engine.bag_alpha_n_max(vw)[0].cpu().numpy()
+    return float(out[0]) if scalar else out
+
+
+alpha_n_max_bag = alpha_n_max_deflagration_bag
+
+
+def identify_solution_type_bag(v_wall: float, alpha_n: float, exit_on_error: bool = False) -> SolutionType:
+    """transition.py:19-44."""
+    from .models import BagModel
+    code = int(BagModel.solution_type_codes(None, np.asarray([v_wall]), np.asarray([alpha_n]))[0])
+    if code < 0 and exit_on_error:
+        raise RuntimeError("No solution for given v_wall, alpha_n")
+    return CODE_SOL[code]
+
+
+def find_alpha_plus_bag(v_wall, alpha_n_given: float, n_xi: int = N_XI_DEFAULT, **_):
+    """alpha.py:361-388: alpha_+ from alpha_n (NaN when alpha_n >= alpha_n_max_deflagration_bag)."""
+    scalar = np.isscalar(v_wall)
+    vw = np.atleast_1d(np.asarray(v_wall, dtype=float))
+    ap, _, _ = engine.bag_find_alpha_plus(vw, np.full_like(vw, alpha_n_given), n_xi)
+    ap = ap.cpu().numpy()
+    return float(ap[0]) if scalar else ap
+
+
+def sound_shell_bag(v_wall: float, alpha_n: float, n_xi: int = N_XI_DEFAULT, **_):
+    """fluid_bag.py:33-79: (v, w, xi); length-1 NaN arrays when there is no solution."""
+    if not 0.0 <= v_wall <= 1.0:
+        raise ValueError("Unphysical parameter: v_wall. See the log for details.")
+    sh = engine.sweep_shells_bag([v_wall], [alpha_n], n_xi=n_xi)
+    return sh.profile(0)
+
+
+def sound_shell_alpha_plus(v_wall: float, alpha_plus: float, sol_type=SolutionType.UNKNOWN, n_xi: int = N_XI_DEFAULT,
+                           w_n: float = 1.0, **_):
+    """fluid_bag.py:83-222."""
+    if not 0.0 <= v_wall <= 1.0:
+        raise ValueError("Unphysical parameter: v_wall. See the log for details.")
+    if isinstance(sol_type, SolutionType):
+        if sol_type == SolutionType.UNKNOWN:
+            sol_type = identify_solution_type_alpha_plus(v_wall, alpha_plus)
+        code = SOL_CODE[sol_type]
+    else:
+        code = int(sol_type)
+    sh = engine.bag_profiles([v_wall], [alpha_plus], [code], n_xi=n_xi, w_n=[w_n])
+    return sh.profile(0)
+
+
+def identify_solution_type_alpha_plus(v_wall: float, alpha_p: float) -> SolutionType:
+    """transition.py:97-124."""
+    if v_wall <= CS0:
+        sol = SolutionType.SUB_DEF
+    else:
+        ap_max_det = (1 - np.sqrt(3) * v_wall) ** 2 / (3 * (1 - v_wall ** 2))
+        sol = SolutionType.DETON if alpha_p < ap_max_det else SolutionType.HYBRID
+    if alpha_p > 1 / 3 and sol != SolutionType.DETON:
+        sol = SolutionType.ERROR
+    return sol
+
+
+fluid_shell_bag = sound_shell_bag
+fluid_shell_alpha_plus = sound_shell_alpha_plus
+
+
+def fluid_integrate_param(v0, w0, xi0, phase=-1., t_end=T_END_DEFAULT, n_xi=N_XI_DEFAULT, df_dtau_ptr=None,
+                          method: str = "cuda", cs2_s: float = CS0_2, cs2_b: float = CS0_2):
+    """integrate.py:81-135 as a one-lane batch.  `df_dtau_ptr` may be a Model (its sound speeds are used) or None
+    (bag); `method` is accepted for signature compatibility and ignored: there is one integrator, the CUDA one."""
+    if isinstance(df_dtau_ptr, Model):
+        cs2_s, cs2_b = df_dtau_ptr.css2, df_dtau_ptr.csb2
+    v, w, xi, st = engine.integrate_batch([v0], [w0], [xi0], [float(phase)], [t_end], n_xi, cs2_s, cs2_b)
+    if int(st[0]) != 0:
+        raise RuntimeError("Integration failed")
+    return v[0].cpu().numpy(), w[0].cpu().numpy(), xi[0].cpu().numpy(), np.linspace(0., t_end, n_xi)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Model-independent solver, batched
+# ---------------------------------------------------------------------------------------------------------------
+
+@dataclasses.dataclass
+class BubbleBatch:
+    """Solved bubbles of a sweep, all on the device.  `scal` holds the reference's per-bubble scalars
+    (fluid.py:1052 and the cached properties of bubble.py:377-632) as [n] tensors."""
+    model: tp.Union[Model, tp.Sequence[Model]]
+    shells: engine.ShellBatch
+    v_wall: tp.Any
+    alpha_n: tp.Any
+    wn: tp.Any
+    sol_type: tp.Any          # int32 codes
+    status: tp.Any
+    scal: tp.Dict[str, tp.Any]
+    pp: tp.Any                # [n,8] parameters of ptt_a2_batch
+    n_xi: int
+
+    def __len__(self):
+        return self.v_wall.numel()
+
+
+def _per_point(models, n, attr):
+    if isinstance(models, Model):
+        return np.full(n, getattr(models, attr), dtype=float)
+    return np.array([getattr(m, attr) for m in models], dtype=float)
+
+
+def sweep_bubbles(model, v_wall, alpha_n, sol_type=None, n_xi=N_XI_DEFAULT, t_end=T_END_DEFAULT,
+                  thin_shell_limit=THIN_SHELL_T_POINTS_MIN, wn_rtol=1e-4, thermo=True) -> BubbleBatch:
+    """Bubble(model, v_wall, alpha_n).solve() for every point of a sweep (bubble.py:232-352, fluid.py:848-1052).
+    `model` is one Model or a sequence with one Model per point."""
+    torch = engine._torch()
+    vw = np.asarray(v_wall, dtype=float).reshape(-1)
+    an = np.asarray(alpha_n, dtype=float).reshape(-1)
+    n = vw.size
+    single = isinstance(model, Model)
+    if single:
+        wn = np.asarray(model.wn(an), dtype=float).reshape(-1)
+        if sol_type is None:
+            codes = model.solution_type_codes(vw, an, wn)
+        else:
+            codes = np.asarray(sol_type, dtype=np.int32).reshape(-1)
+        v_cj = np.asarray(model.v_chapman_jouguet(an, wn), dtype=float).reshape(-1)
+    else:
+        wn = np.array([m.wn(a) for m, a in zip(model, an)], dtype=float)
+        codes = np.array([SOL_CODE[m.solution_type(v, a, w)] for m, v, a, w in zip(model, vw, an, wn)], dtype=np.int32) \
+            if sol_type is None else np.asarray(sol_type, dtype=np.int32).reshape(-1)
+        v_cj = np.array([m.v_chapman_jouguet(a, w) for m, a, w in zip(model, an, wn)], dtype=float)
+    guesses = fluid_reference.ref().get_batch(vw, an, codes)      # [n,6] vp, vm, vp_tilde, vm_tilde, wp, wm
+    pg = torch.zeros((n, 16), dtype=torch.float64, device="cuda")
+    wn_d = engine.dev_f64(wn)
+    pg[:, 0], pg[:, 1], pg[:, 2] = engine.dev_f64(vw), engine.dev_f64(an), engine.dev_f64(codes.astype(float))
+    pg[:, 3], pg[:, 4] = wn_d, engine.dev_f64(v_cj)
+    pg[:, 5], pg[:, 6] = guesses[:, 0], guesses[:, 2]
+    pg[:, 7] = guesses[:, 4] * wn_d                       # fluid.py:939-941
+    wm_g = guesses[:, 5] * wn_d
+    pg[:, 8] = torch.where(torch.isnan(wm_g), 0.3 * wn_d, wm_g)   # fluid.py:942-949
+    for col, attr in ((9, "css2"), (10, "csb2"), (11, "V_s"), (12, "V_b")):
+        pg[:, col] = engine.dev_f64(_per_point(model, n, attr))
+    pg[:, 13] = engine.dev_f64(np.array([1.0 if m.name == "bag" else 0.0 for m in ([model] * n if single else model)]))
+    shells = engine.sweep_shells_generic(pg, n_xi, t_end, thin_shell_limit, wn_rtol)
+    scal = {name: shells.scalars[:, k] for k, name in enumerate(engine.GEN_SCALARS)}
+    mu_s = engine.dev_f64(1 + 1 / _per_point(model, n, "css2"))
+    mu_b = engine.dev_f64(1 + 1 / _per_point(model, n, "csb2"))
+    V_s, V_b = pg[:, 11], pg[:, 12]
+    cs_b = torch.sqrt(pg[:, 10])
+    pp = engine.point_params(pg[:, 0], cs_b, 1 - 1 / mu_s, 1 - 1 / mu_b, V_s, V_b)
+    batch = BubbleBatch(model, shells, pg[:, 0].contiguous(), pg[:, 1].contiguous(), wn_d, shells.sol_type,
+                        shells.status, scal, pp, n_xi)
+    if thermo:
+        add_thermo(batch, mu_s, mu_b)
+    return batch
+
+
+def add_thermo(b: BubbleBatch, mu_s, mu_b):
+    """The volume-averaged thermodynamic quantities of thermo.py from the K4 integrals."""
+    torch = engine._torch()
+    n = len(b)
+    model = b.model
+    pp2 = torch.zeros((n, 12), dtype=torch.float64, device="cuda")
+    pp2[:, 0], pp2[:, 1], pp2[:, 2] = b.v_wall, mu_s, mu_b
+    pp2[:, 3], pp2[:, 4] = b.pp[:, 4], b.pp[:, 5]
+    pp2[:, 5] = engine.dev_f64(_per_point(model, n, "a_s"))
+    pp2[:, 6] = engine.dev_f64(_per_point(model, n, "a_b"))
+    pp2[:, 7] = engine.dev_f64(_per_point(model, n, "T_ref"))
+    pp2[:, 8] = 1.0                                               # props.find_phase
+    I = engine.profile_integrals(b.shells, pp2)
+    s = b.scal
+    four_pi_3 = 4 * np.pi / 3
+    vw3 = b.v_wall ** 3
+    wn = b.wn
+    s["va_kinetic_energy_density"] = four_pi_3 * I[:, 0]                                  # thermo.py:169-181
+    s["va_trace_anomaly_diff"] = four_pi_3 * I[:, 1]                                      # :213-221
+    s["va_thermal_energy_density_diff"] = four_pi_3 * 0.75 * I[:, 2]                      # :206-210
+    s["va_entropy_density_diff"] = four_pi_3 * I[:, 3]                                    # :156-166
+    s["wbar"] = I[:, 4]                                                                   # :139-149
+    s["ebar"] = (1 - 1 / mu_s) * wn + b.pp[:, 4]                                          # :89-91 e(wn, symmetric)
+    s["kinetic_energy_density"] = 3 / (4 * np.pi * vw3) * s["va_kinetic_energy_density"]  # :42-46
+    s["kinetic_energy_fraction"] = s["kinetic_energy_density"] / s["ebar"]               # :49-53
+    s["va_thermal_energy_density"] = np.pi * wn * s["v_sh"] ** 3 - s["va_kinetic_energy_density"] \
+        - s["va_trace_anomaly_diff"]                                                     # :191-195
+    s["thermal_energy_density"] = 3 / (4 * np.pi * vw3) * s["va_thermal_energy_density"]  # :56-60
+    s["va_enthalpy_density"] = 4 / 3 * s["thermal_energy_density"]                        # :153-155
+    s["kappa"] = s["va_kinetic_energy_density"] / torch.abs(s["va_trace_anomaly_diff"])   # :94-106
+    s["omega"] = s["va_thermal_energy_density_diff"] / torch.abs(s["va_trace_anomaly_diff"])   # :122-133
+    s["ubarf2"] = s["kinetic_energy_density"] / I[:, 7]                                   # :136 (w[-1])
+    s["mean_adiabatic_index"] = s["wbar"] / s["ebar"]
+    # nu of Giombi et al. at the volume-averaged enthalpy, broken phase (models/model.py:688-698)
+    wq = s["va_enthalpy_density"]
+    om = (wq / mu_b - b.pp[:, 5]) / ((1 - 1 / mu_b) * wq + b.pp[:, 5])
+    s["nu_gdh2024"] = (1 - 3 * om) / (1 + 3 * om)
+    return b
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bubble object (one point)
+# ---------------------------------------------------------------------------------------------------------------
+
+class Bubble:
+    """A solution of the hydrodynamic equations (bubble.py:34-632); a view of a one-point device batch."""
+
+    _THERMO = ("kappa", "omega", "kinetic_energy_density", "kinetic_energy_fraction", "thermal_energy_density",
+               "va_enthalpy_density", "va_kinetic_energy_density", "va_thermal_energy_density",
+               "va_thermal_energy_density_diff", "va_trace_anomaly_diff", "va_entropy_density_diff", "ubarf2", "wbar",
+               "ebar", "mean_adiabatic_index")
+
+    def __init__(self, model: Model, v_wall: float, alpha_n: float, solve: bool = True, sol_type: SolutionType = None,
+                 label_latex: str = None, label_unicode: str = None, wn_guess: float = None, wm_guess: float = None,
+                 theta_bar: bool = False, t_end: float = T_END_DEFAULT, n_xi: int = N_XI_DEFAULT,
+                 thin_shell_t_points_min: int = THIN_SHELL_T_POINTS_MIN, use_bag_solver: bool = False,
+                 use_giese_solver: bool = False, log_success: bool = False, allow_invalid: bool = False,
+                 log_invalid: bool = True):
+        if use_bag_solver or use_giese_solver or theta_bar:
+            raise NotImplementedError("use_bag_solver / use_giese_solver / theta_bar are outside the hot path")
+        if v_wall < 0 or v_wall > 1:
+            raise ValueError(f"Invalid v_wall={v_wall}")
+        model.validate_alpha_n(alpha_n, allow_invalid=allow_invalid, log_invalid=log_invalid)
+        self.model, self.v_wall, self.alpha_n = model, v_wall, alpha_n
+        self.wn = float(model.wn(alpha_n))
+        self.alpha_theta_bar_n = float(model.alpha_theta_bar_n_from_alpha_n(alpha_n, wn=self.wn))
+        if sol_type is None or sol_type is SolutionType.UNKNOWN:
+            sol_type = model.solution_type(v_wall, alpha_n, wn=self.wn)
+        if sol_type in (SolutionType.UNKNOWN, SolutionType.ERROR):
+            raise ValueError(
+                f"Could not determine solution type automatically for model={model.name}, v_wall={v_wall}, "
+                f"alpha_n={alpha_n}. Got sol_type={sol_type}. Please choose it manually.")      # transition.py:47-69
+        self.sol_type = sol_type
+        self.t_end, self.n_xi, self.thin_shell_t_points_min = t_end, n_xi, thin_shell_t_points_min
+        self.Tn = float(model.temp(self.wn, Phase.SYMMETRIC))
+        if self.Tn > model.T_crit and not allow_invalid:
+            raise ValueError(f"Bubbles form only when T_nuc < T_crit. Got: T_nuc={self.Tn}, T_crit={model.T_crit}")
+        self.Psi_n = float(model.Psi_n(self.wn))
+        self.solved = False
+        self.solver_failed = self.no_solution_found = False
+        self.negative_entropy_flux = self.negative_net_entropy_change = False
+        self.numerical_error = self.unphysical_alpha_plus = False
+        self.label_latex = label_latex or rf"{model.label_latex}, $v_w={v_wall}, \alpha_n={alpha_n}$"
+        self.label_unicode = label_unicode or f"{model.label_unicode}, v_w={v_wall}, alpha_n={alpha_n}"
+        self.notes: tp.List[str] = []
+        self.v = self.w = self.xi = self.phase = None
+        self._batch: tp.Optional[BubbleBatch] = None
+        if solve:
+            self.solve()
+
+    def solve(self, sum_rtol_warning: float = 1.5e-2, sum_rtol_error: float = 5e-2, **_):
+        batch = sweep_bubbles(self.model, [self.v_wall], [self.alpha_n], [SOL_CODE[self.sol_type]], self.n_xi,
+                              self.t_end, self.thin_shell_t_points_min)
+        self._batch = batch
+        st = int(batch.status[0])
+        if st not in (0, 5):
+            self.no_solution_found = True              # bubble.py:290-295 (IndexError / RuntimeError in the solver)
+            return
+        self.solver_failed = st == 5
+        self.v, self.w, self.xi = batch.shells.profile(0)
+        sc = {k: float(v[0]) for k, v in batch.scal.items()}
+        for k in ("vp", "vm", "vp_tilde", "vm_tilde", "v_sh", "vm_sh", "vm_tilde_sh", "wp", "wm", "wm_sh", "v_cj"):
+            setattr(self, k, sc[k])
+        self._sc = sc
+        m = self.model
+        self.sn = float(m.s(self.wn, Phase.SYMMETRIC))
+        self.sm = float(m.s(self.wm, Phase.BROKEN))
+        if self.sol_type == SolutionType.DETON:
+            self.sp, self.sm_sh = self.sn, self.sm
+        else:
+            self.sp = float(m.s(self.wp, Phase.SYMMETRIC))
+            self.sm_sh = float(m.s(self.wm_sh, Phase.SYMMETRIC))
+        self.w_center = self.w[0]
+        self.solved = True
+        self.phase = find_phase(self.xi, self.v_wall)
+        self.alpha_plus = m.alpha_plus(self.wp, self.wm, vp_tilde=self.vp_tilde, sol_type=self.sol_type)
+        self.alpha_theta_bar_plus = m.alpha_theta_bar_plus(self.wp)
+        if np.isnan(self.alpha_plus):
+            self.alpha_plus = m.alpha_plus(self.wp, self.wm, nan_on_invalid=False)
+            self.unphysical_alpha_plus = True
+        g = lambda v: 1 / np.sqrt(1 - v ** 2)
+        self.entropy_flux_p = g(self.vp_tilde) * self.vp_tilde * self.sp
+        self.entropy_flux_m = g(self.vm_tilde) * self.vm_tilde * self.sm
+        self.entropy_flux_diff = self.entropy_flux_m - self.entropy_flux_p
+        if self.entropy_flux_p < 0 or self.entropy_flux_m < 0 or self.entropy_flux_diff < 0:
+            self.negative_entropy_flux = True
+        if sc["va_entropy_density_diff"] < 0:
+            self.negative_net_entropy_change = True
+        if not np.isclose(sc["kappa"] + sc["omega"], 1, rtol=sum_rtol_warning):
+            if not np.isclose(sc["kappa"] + sc["omega"], 1, rtol=sum_rtol_error):
+                self.numerical_error = True
+
+    def __getattr__(self, name):
+        if name in Bubble._THERMO:
+            if not self.__dict__.get("solved", False):
+                raise NotYetSolvedError
+            return self.__dict__["_sc"][name]
+        raise AttributeError(name)
+
+    @property
+    def vp_tilde_sh(self):
+        return self.v_sh
+
+    def export(self, path: str = None):
+        data = {"model": self.model.export(), "v_wall": self.v_wall, "alpha_n": self.alpha_n, "sol_type": self.sol_type,
+                "t_end": self.t_end, "n_xi": self.n_xi, "thin_shell_limit": self.thin_shell_t_points_min, "v": self.v,
+                "w": self.w, "xi": self.xi, "notes": self.notes}
+        for k in ("alpha_plus", "sp", "sm", "sm_sh", "sn", "Tn", "v_cj", "vp", "vm", "vp_tilde", "vm_tilde", "v_sh",
+                  "vm_sh", "vm_tilde_sh", "wn", "wp", "wm", "wm_sh"):
+            data[k] = getattr(self, k, None)
+        if path is not None:
+            import json
+            with open(path, "w") as f:
+                json.dump(data, f, default=lambda o: o.tolist() if hasattr(o, "tolist") else str(o))
+        return data
+
+
+def find_phase(xi: np.ndarray, v_wall: float) -> np.ndarray:
+    """props.py:22-32."""
+    i_wall = int(np.argmax(xi >= v_wall))
+    phase = np.zeros_like(xi)
+    if i_wall == 0:
+        return phase
+    phase[:i_wall - 1] = Phase.BROKEN.value
+    if np.isclose(xi[i_wall], v_wall):
+        phase[i_wall - 1] = Phase.BROKEN.value
+    return phase
+
+
+def sound_shell_generic(model: Model, v_wall: float, alpha_n: float, sol_type: SolutionType = None, wn: float = None,
+                        t_end: float = T_END_DEFAULT, n_xi: int = N_XI_DEFAULT,
+                        thin_shell_limit: int = THIN_SHELL_T_POINTS_MIN, wn_rtol: float = 1e-4, **_):
+    """fluid.py:848-1052: the 17-tuple (v, w, xi, sol_type, vp, vm, vp_tilde, vm_tilde, v_sh, vm_sh, vm_tilde_sh, wp,
+    wm, wm_sh, v_cj, solver_failed, elapsed)."""
+    import time
+    t0 = time.perf_counter()
+    codes = None if sol_type is None else [SOL_CODE[sol_type]]
+    b = sweep_bubbles(model, [v_wall], [alpha_n], codes, n_xi, t_end, thin_shell_limit, wn_rtol, thermo=False)
+    st = int(b.status[0])
+    if st not in (0, 5):
+        raise RuntimeError(f"The fluid shell solver failed with status {st}")
+    v, w, xi = b.shells.profile(0)
+    sc = {k: float(x[0]) for k, x in b.scal.items()}
+    return (v, w, xi, CODE_SOL[int(b.sol_type[0])], sc["vp"], sc["vm"], sc["vp_tilde"], sc["vm_tilde"], sc["v_sh"],
+            sc["vm_sh"], sc["vm_tilde_sh"], sc["wp"], sc["wm"], sc["wm_sh"], sc["v_cj"], st == 5,
+            time.perf_counter() - t0)
+
+
+fluid_shell_generic = sound_shell_generic

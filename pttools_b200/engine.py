@@ -17,6 +17,7 @@ from . import _lib
 from ._lib import A2Plan, Eos, GwPlan, SdvPlan
 
 N_XI_DEFAULT = 5000
+Y_DEFAULT = np.logspace(-1, 3, 1000)
 Z_ST_THRESH = 50.0
 DZ_ST_BLEND = np.pi
 T_TILDE_MIN, T_TILDE_MAX = 0.01, 20.0
@@ -230,6 +231,46 @@ def bag_profiles(v_wall, alpha_plus, sol_type, n_xi=N_XI_DEFAULT, w_n=None) -> S
     return ShellBatch(v_wall, None, alpha_plus, sol_type, status, rows[0], rows[1], rows[2], off, npts, scalars, n_xi)
 
 
+GEN_SCALARS = ("vp", "vm", "vp_tilde", "vm_tilde", "v_sh", "vm_sh", "vm_tilde_sh", "wp", "wm", "wm_sh", "v_cj", "wn",
+               "wn_estimate", "solver_failed")
+
+
+def sweep_shells_generic(pg, n_xi=N_XI_DEFAULT, t_end=50.0, thin_shell_limit=100, wn_rtol=1e-4) -> ShellBatch:
+    """sound_shell_generic for a batch of points (pttools/bubble/fluid.py:848-1052); pg[n,16] as in the C header."""
+    torch = _torch()
+    lib = _lib.load()
+    pg = dev_f64(pg)
+    n = pg.shape[0]
+    cap = lib.ptt_generic_row_capacity(n_xi)
+    dev = pg.device
+    rows = [torch.empty((n, cap), dtype=torch.float64, device=dev) for _ in range(3)]
+    off = torch.empty(n, dtype=torch.int32, device=dev)
+    npts = torch.empty(n, dtype=torch.int32, device=dev)
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    scalars = torch.empty((n, 16), dtype=torch.float64, device=dev)
+    with STAGES.stage("shells_generic", 1):
+        _lib.check(lib.ptt_sweep_shells_generic(n, _ptr(pg), n_xi, float(t_end), int(thin_shell_limit), float(wn_rtol),
+                                                _ptr(rows[0]), _ptr(rows[1]), _ptr(rows[2]), cap, _ptr(off), _ptr(npts),
+                                                _ptr(scalars), _ptr(status), _lib.MEM_DEVICE, _stream_ptr(torch)),
+                   "ptt_sweep_shells_generic")
+    return ShellBatch(pg[:, 0].contiguous(), pg[:, 1].contiguous(), None, pg[:, 2].to(torch.int32), status, rows[0],
+                      rows[1], rows[2], off, npts, scalars, n_xi)
+
+
+def shell_wall_values(shells: ShellBatch):
+    """props.v_and_w_from_solution for a batch of bag shells -> [n,8] = vp, vm, vp_tilde, vm_tilde, wp, wm, wn, 0."""
+    torch = _torch()
+    lib = _lib.load()
+    n = len(shells)
+    out = torch.empty((n, 8), dtype=torch.float64, device=shells.rows_v.device)
+    with STAGES.stage("wall_values", 1):
+        _lib.check(lib.ptt_shell_wall_values(n, _ptr(shells.rows_v), _ptr(shells.rows_w), _ptr(shells.rows_xi),
+                                             shells.rows_v.shape[1], _ptr(shells.off), _ptr(shells.npts),
+                                             _ptr(shells.v_wall), _ptr(shells.sol_type), _ptr(out), _stream_ptr(torch)),
+                   "ptt_shell_wall_values")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Spectrum plans (host: numpy, identical expressions to the reference; device: uploaded once)
 # ---------------------------------------------------------------------------------------------------------------
@@ -325,7 +366,7 @@ class SsmPlan:
 
     def __init__(self, y, cs=CS0, nt=NT_DEFAULT, n_z_lookup=NZ_LOOKUP_DEFAULT, nxi=NXI_DEFAULT,
                  z_st_thresh=Z_ST_THRESH, nuc_type="exponential", a=1.0, gamma=GAMMA_DEFAULT, mode="ssm",
-                 phase_rule=None, nz_int=None):
+                 phase_rule=None, nz_int=None, only_first_pass=False, only_lookup_pass=False):
         torch = _torch()
         y = np.asarray(y, dtype=np.float64)
         if np.any(y <= 0.0):
@@ -337,14 +378,17 @@ class SsmPlan:
         hi = y.max() * 0.5 * (1.0 + cs) / cs + eps
         self.z_lookup = 10.0 ** np.linspace(np.log10(lo), np.log10(hi), n_z_lookup)
         self.passes: tp.List[SdvPass] = []
+        self.has_y_pass = (mode == "ssm") and not only_lookup_pass
         if mode == "ssm":
-            self.passes.append(SdvPass(y, nt, self.nuc_type, self.a))
+            if self.has_y_pass:
+                self.passes.append(SdvPass(y, nt, self.nuc_type, self.a))
             self.phase_rule = 1 if phase_rule is None else phase_rule
         elif mode == "bag":
             self.phase_rule = 0 if phase_rule is None else phase_rule
         else:
             raise ValueError(mode)
-        self.passes.append(SdvPass(self.z_lookup, nt, self.nuc_type, self.a))
+        if not only_first_pass:
+            self.passes.append(SdvPass(self.z_lookup, nt, self.nuc_type, self.a))
         self.lookup_pass = self.passes[-1]
 
         # A^2 wavenumbers: all lookup grids concatenated
@@ -353,28 +397,7 @@ class SsmPlan:
         self.frac_all = np.concatenate([blend_fraction(p.qT, z_st_thresh) for p in self.passes])
         self.xi_re = np.linspace(0, 1 - 1 / nxi, nxi)     # calculators.py:100
 
-        # GW integral (spectrum.py:327-368), z = y * zeta
-        n_int = self.z_lookup.size if nz_int is None else int(nz_int)
-        zpf, zmf = (1 + cs) / (2 * cs), (1 - cs) / (2 * cs)
-        lz = np.linspace(np.log10(zmf), np.log10(zpf), n_int)
-        zeta = 10.0 ** lz
-        zeta2 = zpf + zmf - zeta
-        lz0 = np.log10(lo)
-        dlz = (np.log10(hi) - np.log10(lo)) / (n_z_lookup - 1)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            kern = ((zeta - zpf) ** 2 * (zeta - zmf) ** 2) / (zeta * zeta2)
-        self.gw = dict(
-            n_int=n_int, L1=lz / dlz, L2=np.log10(zeta2) / dlz, Z1=zeta, Z2=zeta2, G=_trapz_weights(zeta) * kern,
-            yterm=(np.log10(y) - lz0) / dlz,
-            prefactor=0.75 * gamma ** 2 * ((1 - cs ** 2) / cs ** 2) ** 2 / (4 * np.pi * cs))
-        y_tile = 128
-        span = (self.gw["yterm"][np.minimum(np.arange(0, y.size, y_tile) + y_tile - 1, y.size - 1)]
-                - self.gw["yterm"][::y_tile]).max()
-        lrange = max(self.gw["L1"].max(), self.gw["L2"].max()) - min(self.gw["L1"].min(), self.gw["L2"].min())
-        self.gw["y_tile"] = y_tile
-        self.gw["win_entries"] = int(np.ceil(span + lrange)) + 6
-        if self.gw["win_entries"] * 16 > SMEM_WINDOW_BYTES:
-            raise ValueError("spec_den_gw lookup window does not fit in shared memory")
+        self.gw = None if only_first_pass else build_gw_tables(self.z_lookup, y, cs, gamma, nz_int)
 
         # upload
         self._t = {}
@@ -385,8 +408,9 @@ class SsmPlan:
         for i, p in enumerate(self.passes):
             for k in ("qT", "z", "zterm", "T", "LT", "W"):
                 self._t[f"p{i}_{k}"] = up(getattr(p, k))
-        for k in ("L1", "L2", "Z1", "Z2", "G", "yterm"):
-            self._t["gw_" + k] = up(self.gw[k])
+        if self.gw is not None:
+            for k in ("L1", "L2", "Z1", "Z2", "G", "yterm"):
+                self._t["gw_" + k] = up(self.gw[k])
 
         self.a2_plan = A2Plan(n_z=self.z_all.size, n_seg=len(self.passes), seg=self._t["seg"].data_ptr(),
                               z=self._t["z_all"].data_ptr(), frac=self._t["frac_all"].data_ptr(), nxi=self.nxi,
@@ -398,17 +422,64 @@ class SsmPlan:
                 z=self._t[f"p{i}_z"].data_ptr(), zterm=self._t[f"p{i}_zterm"].data_ptr(),
                 T=self._t[f"p{i}_T"].data_ptr(), LT=self._t[f"p{i}_LT"].data_ptr(), W=self._t[f"p{i}_W"].data_ptr(),
                 inv_dlog=1.0 / p.dl, smem_bytes=p.smem_bytes))
-        g = self.gw
-        self.gw_plan = GwPlan(n_zl=self.z_lookup.size, n_y=y.size, n_int=g["n_int"], y_tile=g["y_tile"],
-                              z_lookup=self._t["z_lookup"].data_ptr(), y=self._t["y"].data_ptr(),
-                              yterm=self._t["gw_yterm"].data_ptr(), L1=self._t["gw_L1"].data_ptr(),
-                              L2=self._t["gw_L2"].data_ptr(), Z1=self._t["gw_Z1"].data_ptr(),
-                              Z2=self._t["gw_Z2"].data_ptr(), G=self._t["gw_G"].data_ptr(),
-                              prefactor=g["prefactor"], smem_bytes=g["win_entries"] * 16)
+        self.gw_plan = None if self.gw is None else make_gw_plan(self.gw, self._t, self.z_lookup.size, y.size)
 
     @property
     def n_a2(self):
         return int(self.z_all.size)
+
+
+def build_gw_tables(z_lookup, y, cs, gamma=GAMMA_DEFAULT, nz_int=None):
+    """Tables of the GW integral (spectrum.py:327-368) with the substitution z = y * zeta; z_lookup is log-uniform."""
+    n_zl = z_lookup.size
+    n_int = n_zl if nz_int is None else int(nz_int)
+    zpf, zmf = (1 + cs) / (2 * cs), (1 - cs) / (2 * cs)
+    lz = np.linspace(np.log10(zmf), np.log10(zpf), n_int)
+    zeta = 10.0 ** lz
+    zeta2 = zpf + zmf - zeta
+    lz0 = np.log10(z_lookup[0])
+    dlz = (np.log10(z_lookup[-1]) - lz0) / (n_zl - 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        kern = ((zeta - zpf) ** 2 * (zeta - zmf) ** 2) / (zeta * zeta2)
+    gw = dict(n_int=n_int, L1=lz / dlz, L2=np.log10(zeta2) / dlz, Z1=zeta, Z2=zeta2, G=_trapz_weights(zeta) * kern,
+              yterm=(np.log10(y) - lz0) / dlz,
+              prefactor=0.75 * gamma ** 2 * ((1 - cs ** 2) / cs ** 2) ** 2 / (4 * np.pi * cs))
+    y_tile = 128
+    span = (gw["yterm"][np.minimum(np.arange(0, y.size, y_tile) + y_tile - 1, y.size - 1)] - gw["yterm"][::y_tile]).max()
+    lrange = max(gw["L1"].max(), gw["L2"].max()) - min(gw["L1"].min(), gw["L2"].min())
+    gw["y_tile"] = y_tile
+    gw["win_entries"] = int(np.ceil(abs(span) + lrange)) + 6
+    if gw["win_entries"] * 16 > SMEM_WINDOW_BYTES:
+        raise ValueError("spec_den_gw lookup window does not fit in shared memory")
+    return gw
+
+
+def make_gw_plan(g, t, n_zl, n_y):
+    return GwPlan(n_zl=n_zl, n_y=n_y, n_int=g["n_int"], y_tile=g["y_tile"], z_lookup=t["z_lookup"].data_ptr(),
+                  y=t["y"].data_ptr(), yterm=t["gw_yterm"].data_ptr(), L1=t["gw_L1"].data_ptr(), L2=t["gw_L2"].data_ptr(),
+                  Z1=t["gw_Z1"].data_ptr(), Z2=t["gw_Z2"].data_ptr(), G=t["gw_G"].data_ptr(), prefactor=g["prefactor"],
+                  smem_bytes=g["win_entries"] * 16)
+
+
+class GwOnlyPlan:
+    """Plan for spec_den_gw_scaled on a user-supplied log-uniform z_lookup (spectrum.py:402-430)."""
+
+    def __init__(self, z_lookup, y, cs=CS0, gamma=GAMMA_DEFAULT, nz_int=None):
+        torch = _torch()
+        z_lookup = np.asarray(z_lookup, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        lz = np.log10(z_lookup)
+        if z_lookup.size < 2 or not np.allclose(lz, np.linspace(lz[0], lz[-1], z_lookup.size), rtol=0, atol=1e-9):
+            raise NotImplementedError("spec_den_gw_scaled: z_lookup must be log-uniform (gen_lookup / np.logspace)")
+        if np.any(np.diff(y) < 0):
+            raise NotImplementedError("spec_den_gw_scaled: y must be ascending")
+        self.y, self.z_lookup = y, z_lookup
+        self.gw = build_gw_tables(z_lookup, y, cs, gamma, nz_int)
+        up = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+        self._t = {"z_lookup": up(z_lookup), "y": up(y)}
+        for k in ("L1", "L2", "Z1", "Z2", "G", "yterm"):
+            self._t["gw_" + k] = up(self.gw[k])
+        self.gw_plan = make_gw_plan(self.gw, self._t, z_lookup.size, y.size)
 
 
 class A2OnlyPlan:
@@ -524,7 +595,7 @@ def spectra_from_shells(plan: SsmPlan, shells: ShellBatch, pp, slf=None, scale=N
     a2 = a2_batch(plan, shells, pp)
     res = SpectrumBatch(y=plan.y, pow_gw=None, sd_gw=None)
     v_wall = pp[:, 0].contiguous()
-    if plan.mode == "ssm":
+    if plan.mode == "ssm" and plan.has_y_pass:
         sdv_y = spec_den_v_batch(plan, 0, a2, v_wall)
         res.sd_v = sdv_y
         res.pow_v = pow_spec_batch(plan._t["y"], sdv_y)

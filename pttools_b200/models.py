@@ -1,0 +1,343 @@
+"""Host-side equations of state with the reference's Model interface (pttools/models/{model,analytic,bag,const_cs}.py).
+
+Only the two models named by the hot path are provided.  Both are "mu-nu" models,
+    p = a (T/T0)^(mu-4) T^4 - V,   w = mu a (T/T0)^(mu-4) T^4,   e = w - p,   mu = 1 + 1/cs2  (per phase),
+the bag model being mu_s = mu_b = 4.  Everything here is closed-form scalar/array algebra that the reference
+also evaluates on the host once per model or per parameter point; the device receives the few numbers it needs
+(cs2, mu, V per phase) as a POD (ptt_eos_t).
+"""
+from __future__ import annotations
+
+import enum
+import logging
+
+import numpy as np
+
+logger = logging.getLogger(__name__)
+
+
+@enum.unique
+class Phase(float, enum.Enum):
+    """pttools/bubble/boundary.py:27-33."""
+    SYMMETRIC = 0.
+    BROKEN = 1.
+
+
+@enum.unique
+class SolutionType(str, enum.Enum):
+    """pttools/bubble/boundary.py:37-62."""
+    DETON = "Detonation"
+    ERROR = "Error"
+    HYBRID = "Hybrid"
+    SUB_DEF = "Subsonic deflagration"
+    UNKNOWN = "Unknown"
+
+
+SOL_CODE = {SolutionType.SUB_DEF: 0, SolutionType.HYBRID: 1, SolutionType.DETON: 2, SolutionType.ERROR: -1,
+            SolutionType.UNKNOWN: -1}
+CODE_SOL = {0: SolutionType.SUB_DEF, 1: SolutionType.HYBRID, 2: SolutionType.DETON, -1: SolutionType.ERROR}
+
+
+class Model:
+    """Common implementation; see BagModel / ConstCSModel for the constructors of the reference."""
+    DEFAULT_NAME = None
+    TEMPERATURE_IS_PHYSICAL = False
+    DEFAULT_T_MIN = 1e-3            # models/base.py:22
+
+    def __init__(self, css2, csb2, V_s=1.0, V_b=0.0, a_s=None, a_b=None, T_ref=1.0, T_min=None, name=None,
+                 label_latex=None, label_unicode=None, allow_invalid=False):
+        if a_b is None:
+            a_b = 1.0                                   # analytic.py:184-189
+        if a_s is None:
+            a_s = 1.1 * a_b
+        if V_s < V_b and not allow_invalid:
+            raise ValueError(f"The bubble will not expand, when V_s < V_b. Got: V_s={V_s}, V_b={V_b}.")
+        self.css2, self.csb2 = float(css2), float(csb2)
+        self.css, self.csb = np.sqrt(self.css2), np.sqrt(self.csb2)
+        self.mu_s, self.mu_b = 1 + 1 / self.css2, 1 + 1 / self.csb2
+        self.V_s, self.V_b, self.a_s, self.a_b = float(V_s), float(V_b), float(a_s), float(a_b)
+        self.T_ref = float(T_ref)
+        self.T_min = self.DEFAULT_T_MIN if T_min is None else T_min
+        self.T_max = np.inf
+        self.name = self.DEFAULT_NAME if name is None else name
+        self.temperature_is_physical = self.TEMPERATURE_IS_PHYSICAL
+        self.bag_wn_const = 4 / 3 * (self.V_s - self.V_b)            # analytic.py:80
+        self.label_latex = label_latex or self.name
+        self.label_unicode = label_unicode or self.name
+        self.w_min = max(self.w(self.T_min, Phase.SYMMETRIC), self.w(self.T_min, Phase.BROKEN))   # model.py:95-100
+        self.w_max = np.inf
+        self.T_crit = self.critical_temp()
+        self.w_crit = float(self.w(self.T_crit, Phase.SYMMETRIC))    # model.py:460-474
+        self.w_at_alpha_n_min, self.alpha_n_min = self.w_crit, float(self.alpha_n(self.w_crit))
+
+    # --- thermodynamic functions of temperature
+    def _powfac(self, temp, mu):
+        return (temp / self.T_ref) ** (mu - 4) * temp ** 4
+
+    def p_temp(self, temp, phase):
+        ps = self.a_s * self._powfac(temp, self.mu_s) - self.V_s
+        pb = self.a_b * self._powfac(temp, self.mu_b) - self.V_b
+        return pb * phase + ps * (1 - phase)
+
+    def e_temp(self, temp, phase):
+        es = (self.mu_s - 1) * self.a_s * self._powfac(temp, self.mu_s) + self.V_s
+        eb = (self.mu_b - 1) * self.a_b * self._powfac(temp, self.mu_b) + self.V_b
+        return eb * phase + es * (1 - phase)
+
+    def s_temp(self, temp, phase):
+        ss = self.mu_s * self.a_s * (temp / self.T_ref) ** (self.mu_s - 4) * temp ** 3
+        sb = self.mu_b * self.a_b * (temp / self.T_ref) ** (self.mu_b - 4) * temp ** 3
+        return sb * phase + ss * (1 - phase)
+
+    def w(self, temp, phase):
+        ws = self.mu_s * self.a_s * self._powfac(temp, self.mu_s)
+        wb = self.mu_b * self.a_b * self._powfac(temp, self.mu_b)
+        return wb * phase + ws * (1 - phase)
+
+    def temp(self, w, phase):
+        w = np.where(np.asarray(w, dtype=float) < 0, np.nan, w)
+        ts = self.T_ref * (w / (self.mu_s * self.a_s * self.T_ref ** 4)) ** (1 / self.mu_s)
+        tb = self.T_ref * (w / (self.mu_b * self.a_b * self.T_ref ** 4)) ** (1 / self.mu_b)
+        out = tb * phase + ts * (1 - phase)
+        return out if np.ndim(out) else float(out)
+
+    # --- functions of enthalpy (model.py:641-766)
+    def cs2(self, w, phase):
+        return (phase * self.csb2 + (1 - phase) * self.css2) * np.ones_like(w)
+
+    def cs2_max(self, w_max=None, phase=Phase.BROKEN, **kw):
+        return (self.csb2 if phase == Phase.BROKEN else self.css2), np.nan
+
+    cs2_min = cs2_max
+
+    def p(self, w, phase):
+        return self.p_temp(self.temp(w, phase), phase)
+
+    def e(self, w, phase):
+        return self.e_temp(self.temp(w, phase), phase)
+
+    def s(self, w, phase):
+        return self.s_temp(self.temp(w, phase), phase)
+
+    def theta(self, w, phase):
+        return 0.25 * (self.e(w, phase) - 3 * self.p(w, phase))
+
+    def omega(self, w, phase):
+        t = self.temp(w, phase)
+        return self.p_temp(t, phase) / self.e_temp(t, phase)
+
+    def nu_gdh2024(self, w, phase=Phase.BROKEN):
+        om = self.omega(w, phase)
+        return (1 - 3 * om) / (1 + 3 * om)
+
+    def gp(self, w, phase):
+        t = self.temp(w, phase)
+        return 30 / np.pi ** 2 * self.e_temp(t, phase) / t ** 4       # model.py:683-686 (calls ge_temp)
+
+    gs = gp
+
+    def Psi_n(self, wn):
+        tn = self.temp(wn, Phase.SYMMETRIC)
+        return self.w(tn, Phase.BROKEN) / self.w(tn, Phase.SYMMETRIC)
+
+    # --- transition strength
+    def delta_theta(self, wp, wm):
+        return self.theta(wp, Phase.SYMMETRIC) - self.theta(wm, Phase.BROKEN)
+
+    def alpha_n(self, wn, **kw):
+        tn = self.temp(wn, Phase.SYMMETRIC)                             # const_cs.py:161-199
+        return (1 - 4 / self.mu_s) / 3 - (1 - 4 / self.mu_b) / 3 * self.w(tn, Phase.BROKEN) / wn + self.bag_wn_const / wn
+
+    def alpha_plus(self, wp, wm, vp_tilde=None, sol_type=None, error_on_invalid=False, nan_on_invalid=True, **kw):
+        ap = (1 - 4 / self.mu_s) / 3 - (1 - 4 / self.mu_b) * wm / (3 * wp) + self.bag_wn_const / wp   # const_cs.py:454
+        if nan_on_invalid:                                               # model.py:368-405
+            if sol_type in (SolutionType.SUB_DEF, SolutionType.HYBRID):
+                bad = (ap < 0) | (ap >= 1 / 3)
+            elif vp_tilde is not None:
+                bad = (ap < 0) | (((1 + ap) * vp_tilde + (1 - 3 * ap) / (3 * vp_tilde)) ** 2 - 4 / 3 < 0)
+            else:
+                bad = ap < 0
+            ap = np.where(bad, np.nan, ap)
+            ap = ap if np.ndim(ap) else float(ap)
+        return ap
+
+    def alpha_theta_bar_n_from_alpha_n(self, alpha_n, wn=None, **kw):
+        if wn is None:
+            wn = self.wn(alpha_n)
+        tn = self.temp(wn, Phase.SYMMETRIC)                              # model.py:347-354
+        diff = (1 - 1 / (3 * self.csb2)) * (self.p_temp(tn, Phase.SYMMETRIC) - self.p_temp(tn, Phase.BROKEN)) / wn
+        return alpha_n + diff
+
+    def alpha_theta_bar_plus(self, wp, **kw):
+        return (1 - self.mu_b / self.mu_s) / 3 + self.mu_b / 4 * self.bag_wn_const / wp   # const_cs.py:507-519
+
+    def validate_alpha_n(self, alpha_n, allow_invalid=False, log_invalid=True):
+        if alpha_n < 0 or alpha_n < self.alpha_n_min:                    # model.py:813-823
+            msg = f"Invalid alpha_n={alpha_n}. Minimum for the model: {self.alpha_n_min}"
+            if log_invalid:
+                logger.error(msg)
+            if not allow_invalid:
+                raise ValueError(msg)
+
+    def wn(self, alpha_n, wn_guess=None, **kw):
+        """Enthalpy at the nucleation temperature for given alpha_n (vectorised)."""
+        alpha_n = np.asarray(alpha_n, dtype=float)
+        if np.isclose(self.mu_b, 4):                                     # bag.py:316-339, const_cs.py:715-728
+            out = self.bag_wn_const / (alpha_n + (4 / self.mu_s - 1) / 3)
+            out = np.where(out < 0, np.nan, out)
+        else:
+            # alpha_n(wn) is monotonic below w_crit: safeguarded Newton on log(wn) (the reference: fsolve, model.py:856-922)
+            lo = np.full(alpha_n.shape, np.log(self.w_min))
+            hi = np.full(alpha_n.shape, np.log(self.w_crit))
+            x = np.full(alpha_n.shape, np.log(0.9 * self.w_crit))
+            f_lo = self.alpha_n(np.exp(lo)) - alpha_n
+            sign = np.sign(f_lo)
+            for _ in range(200):
+                f = self.alpha_n(np.exp(x)) - alpha_n
+                same = np.sign(f) == sign
+                lo = np.where(same, x, lo)
+                hi = np.where(same, hi, x)
+                h = 1e-6
+                df = (self.alpha_n(np.exp(x + h)) - alpha_n - f) / h
+                with np.errstate(all="ignore"):
+                    xn = x - f / df
+                bad = ~np.isfinite(xn) | (xn <= lo) | (xn >= hi)
+                xn = np.where(bad, 0.5 * (lo + hi), xn)
+                if np.all(np.abs(xn - x) <= 1e-15 * np.abs(x) + 1e-300):
+                    x = xn
+                    break
+                x = xn
+            out = np.exp(x)
+            out = np.where(np.abs(self.alpha_n(out) - alpha_n) > 1e-9 * np.maximum(1.0, np.abs(alpha_n)), np.nan, out)
+        return out if out.ndim else float(out)
+
+    def critical_temp(self):
+        if np.isclose(self.mu_s, 4) and np.isclose(self.mu_b, 4):
+            return ((self.V_s - self.V_b) / (self.a_s - self.a_b)) ** 0.25      # bag.py:186-192
+        # a_s (T/T0)^mu_s - a_b (T/T0)^mu_b = (V_s - V_b) T0^4 ... solved by bisection in log T (const_cs.py:521-523)
+        f = lambda t: self.a_s * (t / self.T_ref) ** self.mu_s - self.a_b * (t / self.T_ref) ** self.mu_b \
+            + (self.V_b - self.V_s) * self.T_ref ** 4
+        lo, hi = self.T_min, max(1e4, 10 * self.T_ref)
+        ts = np.logspace(np.log10(lo), np.log10(hi), 2000)
+        fs = f(ts)
+        idx = np.nonzero(np.sign(fs[:-1]) != np.sign(fs[1:]))[0]
+        if idx.size == 0:
+            raise ValueError("All models should have p_s(T>T_crit) > p_b(T>T_crit) for T_crit to exist.")
+        # the reference's fsolve starts at T_ref: take the sign change closest to it
+        k = idx[np.argmin(np.abs(np.log(ts[idx]) - np.log(self.T_ref)))]
+        a, b = ts[k], ts[k + 1]
+        for _ in range(200):
+            mid = 0.5 * (a + b)
+            if np.sign(f(mid)) == np.sign(f(a)):
+                a = mid
+            else:
+                b = mid
+        return 0.5 * (a + b)
+
+    # --- wall-speed classification
+    def v_chapman_jouguet(self, alpha_n, wn=None):
+        """chapman_jouguet.py:151-264 (analytical branches)."""
+        if self.DEFAULT_NAME == "bag":
+            return 1 / np.sqrt(3) * (1 + np.sqrt(2 * alpha_n + 3 * alpha_n ** 2)) / (1 + alpha_n)
+        atbp = self.alpha_theta_bar_n_from_alpha_n(alpha_n, wn=wn)
+        disc = 3 * atbp * (1 - self.csb2 + 3 * self.csb2 * atbp)
+        return (1 + np.sqrt(disc)) / (1 / self.csb + 3 * self.csb * atbp)
+
+    def solution_type_codes(self, v_wall, alpha_n, wn=None, an_max_bag=None):
+        """Vectorised solution_type -> integer codes (0 sub-def, 1 hybrid, 2 detonation, -1 error)."""
+        raise NotImplementedError
+
+    def solution_type(self, v_wall, alpha_n, wn=None, **kw):
+        return CODE_SOL[int(self.solution_type_codes(np.asarray([v_wall]), np.asarray([alpha_n]),
+                                                     None if wn is None else np.asarray([wn]))[0])]
+
+    def eos_params(self):
+        """(css2, csb2, V_s, V_b, name_is_bag) for the device."""
+        return self.css2, self.csb2, self.V_s, self.V_b, 1.0 if self.name == "bag" else 0.0
+
+    def export(self):
+        return {"name": self.name, "label_latex": self.label_latex, "label_unicode": self.label_unicode,
+                "T_min": self.T_min, "T_max": self.T_max, "t_ref": self.T_ref, "V_s": self.V_s, "V_b": self.V_b,
+                "a_s": self.a_s, "a_b": self.a_b, "css2": self.css2, "csb2": self.csb2, "mu_s": self.mu_s,
+                "mu_b": self.mu_b}
+
+
+class BagModel(Model):
+    """pttools/models/bag.py:32-346."""
+    DEFAULT_NAME = "bag"
+
+    def __init__(self, V_s=1.0, V_b=0.0, a_s=None, a_b=None, alpha_n_min=None, name=None, **kw):
+        if alpha_n_min is not None:
+            # bag.py:120-137: a_s = a_b / (1 - 3 alpha_n_min * 0.999), capped by the default
+            a_b_ = 1.0 if a_b is None else a_b
+            a_s_def = 1.1 * a_b_ if a_s is None else a_s
+            a_s = min(a_s_def, a_b_ / (1 - 3 * alpha_n_min * 0.999))
+            a_b = a_b_
+        super().__init__(1 / 3, 1 / 3, V_s=V_s, V_b=V_b, a_s=a_s, a_b=a_b, name=name, **kw)
+        if self.a_s <= self.a_b:
+            raise ValueError("The bag model must have a_s > a_b for the critical temperature to be non-negative.")
+
+    def theta(self, w, phase):
+        return (self.V_b * phase + self.V_s * (1 - phase)) * np.ones_like(w)     # bag.py:311-316
+
+    def alpha_n(self, wn, **kw):
+        return self.bag_wn_const / wn                                            # analytic.py:97-119
+
+    def alpha_plus(self, wp, wm=None, vp_tilde=None, sol_type=None, nan_on_invalid=True, **kw):
+        ap = self.bag_wn_const / wp
+        if nan_on_invalid:
+            if sol_type in (SolutionType.SUB_DEF, SolutionType.HYBRID):
+                bad = (ap < 0) | (ap >= 1 / 3)
+            elif vp_tilde is not None:
+                bad = (ap < 0) | (((1 + ap) * vp_tilde + (1 - 3 * ap) / (3 * vp_tilde)) ** 2 - 4 / 3 < 0)
+            else:
+                bad = ap < 0
+            ap = np.where(bad, np.nan, ap)
+            ap = ap if np.ndim(ap) else float(ap)
+        return ap
+
+    def solution_type_codes(self, v_wall, alpha_n, wn=None, an_max_bag=None):
+        """identify_solution_type_bag (transition.py:19-44); an_max_bag = alpha_n_max_deflagration_bag(v_wall)."""
+        from . import engine
+        v_wall = np.asarray(v_wall, dtype=float)
+        if an_max_bag is None:
+            an_max_bag = engine.bag_alpha_n_max_unique(v_wall)[0].cpu().numpy()
+        cs0 = 1 / np.sqrt(3)
+        ap_max_det = np.where(v_wall < cs0, 0.0, (1 - np.sqrt(3) * v_wall) ** 2 / (3 * (1 - v_wall ** 2)))
+        out = np.full(v_wall.shape, -1, dtype=np.int32)
+        defl = alpha_n < an_max_bag
+        out[defl & (v_wall <= cs0)] = 0
+        out[defl & (v_wall > cs0)] = 1
+        out[alpha_n < ap_max_det] = 2
+        return out
+
+
+class ConstCSModel(Model):
+    """pttools/models/const_cs.py:43-737."""
+    DEFAULT_NAME = "const_cs"
+
+    def __init__(self, css2, csb2, V_s=1.0, V_b=0.0, a_s=None, a_b=None, T_ref=1.0, name=None, **kw):
+        css2, csb2 = float(css2), float(csb2)
+        for nm, c in (("css2", css2), ("csb2", csb2)):
+            if not 0 < c <= 1:
+                raise ValueError(f"{nm} has to be 0 < c_s^2 <= 1")
+        if css2 > 1 / 3 and np.isclose(css2, 1 / 3):
+            css2 = 1 / 3
+        if csb2 > 1 / 3 and np.isclose(csb2, 1 / 3):
+            csb2 = 1 / 3
+        super().__init__(css2, csb2, V_s=V_s, V_b=V_b, a_s=a_s, a_b=a_b, T_ref=T_ref, name=name, **kw)
+
+    def solution_type_codes(self, v_wall, alpha_n, wn=None, an_max_bag=None):
+        """const_cs.py:633-655."""
+        v_wall = np.asarray(v_wall, dtype=float)
+        alpha_n = np.asarray(alpha_n, dtype=float)
+        if wn is None:
+            wn = self.wn(alpha_n)
+        atbp = self.alpha_theta_bar_n_from_alpha_n(alpha_n, wn=wn)
+        b = 3 * atbp - 1 - v_wall ** 2 * (1 / self.csb2 + 3 * atbp)
+        a = v_wall / self.csb2
+        disc = b ** 2 - 4 * a * v_wall
+        out = np.full(v_wall.shape, 2, dtype=np.int32)
+        out[(b > 0) | (disc < 0)] = 1
+        out[v_wall ** 2 < self.csb2] = 0
+        return out

@@ -102,3 +102,75 @@ def shell_chunk_points(n_xi: int, budget_bytes: float = 24e9) -> int:
     """How many shells to solve per launch: bounded by the profile rows (3 arrays of row_capacity doubles each)."""
     cap = 5002 + n_xi + 2
     return int(max(1024, min(65536, budget_bytes // (3 * 8 * cap))))
+
+
+def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multiplier=1.0, nuc_type="exponential",
+                  nt=engine.NT_DEFAULT, n_z_lookup=engine.NZ_LOOKUP_DEFAULT, z_st_thresh=engine.Z_ST_THRESH,
+                  n_xi=engine.N_XI_DEFAULT, Tn=None, g_star=None, gs_star=None, suppression="default",
+                  chunk=2048, shell_chunk=None, want_pow_v=True, keep_bubbles=False) -> SweepResult:
+    """Spectrum(Bubble(model, v_wall, alpha_n), y, r_star=...) for every point of a sweep: the model-independent shell
+    solve, the thermodynamic scalars, the SSM chain and Omega_gw,0 (pttools/analysis/parallel.py:157-187 ->
+    bubble.py:232-352 -> ssmtools/spectrum.py:96-115 -> omgw0/omgw0_ssm.py:123-131), one model for all points."""
+    from . import bubble as bub
+    from . import omgw0 as om
+    torch = engine._torch()
+    vw = np.asarray(v_wall, dtype=float).reshape(-1)
+    an = np.asarray(alpha_n, dtype=float).reshape(-1)
+    n = vw.size
+    y = engine.Y_DEFAULT if y is None else np.asarray(y, dtype=float)
+    cs = float(np.sqrt(model.csb2))                                   # spectrum.py:99 (cs2 is constant per phase)
+    plan = engine.SsmPlan(y, cs=cs, nt=nt, n_z_lookup=n_z_lookup, z_st_thresh=z_st_thresh, nuc_type=nuc_type, a=1.0,
+                          mode="ssm", only_lookup_pass=not want_pow_v)
+    scale = None
+    if r_star is not None:
+        # omgw0_ssm.py:62-131: model temperatures are not physical for both in-scope models -> the overrides apply
+        g_eff = om.G_STAR_DEFAULT if g_star is None else gs_star
+        gs_eff = g_eff if gs_star is None else gs_star
+        fgw0 = om.F_gw0(g_star=g_eff, gs_star=gs_eff)
+        if suppression == "default":
+            sup = om.DEFAULT_SUPPRESSION.points(vw, an)
+        elif suppression is None:
+            sup = np.ones_like(vw)
+        else:
+            sup = suppression.points(vw, an)
+        scale = engine.dev_f64(r_star * fgw0 * sup)
+    dev = "cuda"
+    pow_gw = torch.empty((n, y.size), dtype=torch.float64, device=dev)
+    pow_v = torch.empty((n, y.size), dtype=torch.float64, device=dev) if want_pow_v else None
+    omgw0 = torch.empty((n, y.size), dtype=torch.float64, device=dev) if scale is not None else None
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    scal: tp.Dict[str, tp.Any] = {}
+    if shell_chunk is None:
+        shell_chunk = max(chunk, min(n, int(24e9 // (3 * 8 * (2 * n_xi + 4)))))
+    bubbles = []
+    for s0 in range(0, n, shell_chunk):
+        e0 = min(n, s0 + shell_chunk)
+        bb = bub.sweep_bubbles(model, vw[s0:e0], an[s0:e0], n_xi=n_xi)
+        status[s0:e0], st[s0:e0] = bb.status, bb.sol_type
+        for k, v in bb.scal.items():
+            scal.setdefault(k, torch.empty(n, dtype=torch.float64, device=dev))[s0:e0] = v
+        # source lifetime factor, spectrum.py:123-136
+        nu_ = bb.scal["nu_gdh2024"]
+        slf = 1 / (1 + 2 * nu_)
+        if r_star is not None and not np.isinf(lifetime_multiplier):
+            slf = slf * (1 - (1 + lifetime_multiplier * 2 * r_star / torch.sqrt(bb.scal["kinetic_energy_fraction"]))
+                         ** (-1 - 2 * nu_))
+        for s in range(s0, e0, chunk):
+            e = min(e0, s + chunk)
+            sub = bb.shells.slice(s - s0, e - s0)
+            res = engine.spectra_from_shells(plan, sub, bb.pp[s - s0:e - s0].contiguous(),
+                                             slf=slf[s - s0:e - s0].contiguous(),
+                                             scale=None if scale is None else scale[s:e].contiguous())
+            pow_gw[s:e] = res.pow_gw
+            if want_pow_v:
+                pow_v[s:e] = res.pow_v
+            if omgw0 is not None:
+                omgw0[s:e] = res.omgw0
+        if keep_bubbles:
+            bubbles.append(bb)
+    out = SweepResult(engine.dev_f64(vw), engine.dev_f64(an), st, status, None, y, pow_gw=pow_gw, pow_v=pow_v,
+                      omgw0=omgw0, scalars=scal)
+    if keep_bubbles:
+        out.bubbles = bubbles
+    return out

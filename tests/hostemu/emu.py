@@ -33,6 +33,7 @@ def lib():
         _lib.emu_bag_forward.argtypes = [d, d, i, i, pd]
         _lib.emu_bag_find_alpha_plus.argtypes = [d, d, i, d, pd, pi, pi]
         _lib.emu_bag_profile.argtypes = [d, d, i, i, d, pd, pd, pd, pi, pi, pi]
+        _lib.emu_generic_solve.argtypes = [pd, d, d, i, d, d, pd, i, d, i, d, pd, pd, pd, pi, pi, pd]
     return _lib
 
 
@@ -70,3 +71,22 @@ def bag_profile(v_wall, ap, sol_type, n_xi, w_n=1.0):
     rc = lib().emu_bag_profile(v_wall, ap, sol_type, n_xi, w_n, _p(v), _p(w), _p(xi), C.byref(off), C.byref(npts), C.byref(nw))
     s = slice(off.value, off.value + npts.value)
     return rc, v[s].copy(), w[s].copy(), xi[s].copy(), nw.value
+
+
+GEN_SCALARS = ["vp", "vm", "vp_tilde", "vm_tilde", "v_sh", "vm_sh", "vm_tilde_sh", "wp", "wm", "wm_sh", "v_cj", "wn",
+               "wn_estimate", "solver_failed"]
+
+
+def generic_solve(eos, v_wall, alpha_n, sol_type, wn, v_cj, guess, n_xi=5000, t_end=50.0, thin=100, wn_rtol=1e-4):
+    """eos: (css2, csb2, V_s, V_b, bag_name); guess: (vp, vp_tilde, wp, wm)."""
+    css2, csb2, V_s, V_b, bag_name = eos
+    e = np.array([css2, csb2, 1 + 1 / css2, 1 + 1 / csb2, V_s, V_b, float(bag_name)])
+    g = np.array(guess, dtype=float)
+    cap = lib().emu_gen_row_capacity(n_xi)
+    v, w, xi = np.full(cap, np.nan), np.full(cap, np.nan), np.full(cap, np.nan)
+    off, npts = C.c_int(0), C.c_int(0)
+    scal = np.empty(16)
+    rc = lib().emu_generic_solve(_p(e), v_wall, alpha_n, sol_type, wn, v_cj, _p(g), n_xi, t_end, thin, wn_rtol,
+                                 _p(v), _p(w), _p(xi), C.byref(off), C.byref(npts), _p(scal))
+    s = slice(off.value, off.value + npts.value)
+    return rc, v[s].copy(), w[s].copy(), xi[s].copy(), dict(zip(GEN_SCALARS, scal))

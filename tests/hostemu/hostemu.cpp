@@ -1,7 +1,7 @@
 // TEST-ONLY host emulation of the device algorithm headers (pttools_b200/csrc/*.cuh compiled with g++).
 // It exists so that the per-thread device logic can be unit-tested in a container without a GPU.
 // The product package never loads this library; it only ever runs the nvcc-built CUDA kernels.
-#include "../../pttools_b200/csrc/ptt_bag.cuh"
+#include "../../pttools_b200/csrc/ptt_generic.cuh"
 
 using namespace ptt;
 
@@ -47,5 +47,21 @@ int emu_bag_profile(double v_wall, double ap, int sol_type, int n_xi, double w_n
 }
 
 int emu_row_capacity(int n_xi) { return profile_row_capacity(n_xi); }
+int emu_gen_row_capacity(int n_xi) { return gen_row_capacity(n_xi); }
+
+// eos[7] = {css2, csb2, mu_s, mu_b, V_s, V_b, bag_name}; guess[4] = {vp, vp_tilde, wp, wm}; scal[16] out
+int emu_generic_solve(const double* eos, double v_wall, double alpha_n, int sol_type, double wn, double v_cj,
+                      const double* guess, int n_xi, double t_end, int thin, double wn_rtol,
+                      double* v, double* w, double* xi, int* off, int* npts, double* scal) {
+    EosDev m{eos[0], eos[1], eos[2], eos[3], eos[4], eos[5], (int)eos[6]};
+    GenericGuess g{guess[0], guess[1], guess[2], guess[3]};
+    RowOut row{v, w, xi};
+    GenericOut o = generic_solve_point(m, v_wall, alpha_n, sol_type, wn, v_cj, g, n_xi, t_end, thin, wn_rtol, row);
+    *off = o.off; *npts = o.npts;
+    double vals[16] = {o.vp, o.vm, o.vp_tilde, o.vm_tilde, o.v_sh, o.vm_sh, o.vm_tilde_sh, o.wp, o.wm, o.wm_sh, o.v_cj,
+                       o.wn, o.wn_estimate, (double)o.solver_failed, 0, 0};
+    for (int i = 0; i < 16; ++i) scal[i] = vals[i];
+    return o.status;
+}
 
 }

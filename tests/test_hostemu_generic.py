@@ -1,0 +1,73 @@
+"""CPU: the device-side model-independent solver (csrc/ptt_generic.cuh through the TEST-ONLY host emulation) against
+fixtures produced by the reference itself (tests/golden/ref_generic_bubbles.npz) and against the oracle."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu"))
+import emu  # noqa: E402
+from oracle import models, shell_generic as sg  # noqa: E402
+from util_compare import curve_errors  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODELS = {"bag": models.bag_model(1.1, 1, 1), "cs_quarter_third": models.const_cs_model(1 / 4, 1 / 3, 1.5, 1, 1),
+          "cs_third_quarter": models.const_cs_model(1 / 3, 1 / 4, 5, 1, 1),
+          "cs_032_third": models.const_cs_model(1 / 3 - 0.01, 1 / 3, 1.5, 1, 1)}
+
+
+@pytest.fixture(scope="module")
+def fixtures():
+    d = np.load(os.path.join(GOLDEN, "ref_generic_bubbles.npz"))
+    ref = sg.FluidReference(dict(np.load(os.path.join(GOLDEN, "ref_fluid_reference.npz"))))
+    return d, ref
+
+
+def test_oracle_reproduces_reference_runs(fixtures):
+    """The oracle's generic solver is pinned by outputs of the reference itself (bit-level agreement)."""
+    d, ref = fixtures
+    names = list(d["scalar_names"])
+    warnings.filterwarnings("ignore")
+    for mname in ("bag", "cs_third_quarter"):
+        m = MODELS[mname]
+        for i, (vw, an) in enumerate(d[f"{mname}__points"][:6]):
+            if f"{mname}__v_{i}" not in d:
+                continue
+            sol = sg.sound_shell_generic(m, vw, an, ref)
+            assert sol["v"].size == d[f"{mname}__v_{i}"].size
+            np.testing.assert_allclose(sol["v"], d[f"{mname}__v_{i}"], rtol=1e-8, atol=1e-12)
+            np.testing.assert_allclose(sol["w"], d[f"{mname}__w_{i}"], rtol=1e-8)
+            np.testing.assert_allclose(sol["xi"], d[f"{mname}__xi_{i}"], rtol=1e-8, atol=1e-12)
+            sc = dict(zip(names, d[f"{mname}__scal_{i}"]))
+            bs = sg.bubble_scalars(m, sol, vw)
+            for k in ("kappa", "omega", "kinetic_energy_fraction", "va_enthalpy_density", "ubarf2", "wbar"):
+                np.testing.assert_allclose(bs[k], sc[k], rtol=1e-8)
+            np.testing.assert_allclose(sol["wm"], sc["wm"], rtol=1e-8)
+
+
+@pytest.mark.parametrize("mname", list(MODELS))
+def test_device_algorithm_matches_reference_runs(fixtures, mname):
+    d, ref = fixtures
+    names = list(d["scalar_names"])
+    m = MODELS[mname]
+    for i, (vw, an) in enumerate(d[f"{mname}__points"]):
+        if f"{mname}__v_{i}" not in d:
+            continue
+        v, w, xi = d[f"{mname}__v_{i}"], d[f"{mname}__w_{i}"], d[f"{mname}__xi_{i}"]
+        sc = dict(zip(names, d[f"{mname}__scal_{i}"]))
+        st = int(d[f"{mname}__flags_{i}"][0])
+        wn = m.wn(an)
+        g = ref.get(vw, an, st)
+        rc, gv, gw, gx, gs = emu.generic_solve((m.css2, m.csb2, m.V_s, m.V_b, m.kind == "bag"), vw, an, st, wn,
+                                               sg.v_chapman_jouguet(m, an, wn), (g[0], g[2], g[4] * wn, g[5] * wn))
+        assert rc == 0 and gs["solver_failed"] == 0
+        ev, ew = curve_errors(gx, gv, gw, xi, v, w, vw)
+        assert ev < 1e-6 and ew < 1e-6                      # north_star: profiles within 1e-6 relative
+        for k in ("wm", "wp", "v_sh", "vp", "vm", "vp_tilde", "vm_tilde", "wm_sh"):
+            if sc[k] != 0:
+                np.testing.assert_allclose(gs[k], sc[k], rtol=1e-6)
+        np.testing.assert_allclose(gw[0], w[0], rtol=1e-6)
+        if st != 2:
+            assert gv.size == v.size or abs(v[-4]) < 1e-8     # same tau-grid unless the shock is located in numerical noise
