@@ -155,7 +155,7 @@ class ShellBatch:
     n_xi: int
 
     def __len__(self):
-        return self.v_wall.numel()
+        return self.rows_v.shape[0]
 
     def slice(self, a, b):
         """Row-block view [a, b) of the batch (no copies)."""
