@@ -30,8 +30,18 @@ GRID_N = 1000
 STRIDE = 999983                      # prime, coprime with 10^6
 Y = np.logspace(-1, 3, 1000)         # ssmtools/const.py:20
 NPT = (2000, 10000, 10000)           # NPTDEFAULT (ssmtools/const.py:10-19): n_xi, nt, n_z_lookup
-WORKLOAD = ("config2: BagModel grid v_wall=linspace(0.05,0.95,1000) x alpha_n=linspace(0.005,0.5,1000); per point "
-            "sound_shell_bag(n_xi=2000) + power_gw_scaled_bag(z=logspace(-1,3,1000), npt=(2000,10000,10000))")
+N_XI = 5000                          # bubble/const.py:12
+R_STAR = 0.1
+WORKLOADS = {
+    # the reference's new API: what create_spectra(model, v_walls, alpha_ns, spectrum_kwargs={"r_star": 0.1}) computes
+    "generic": ("config2/5: BagModel(alpha_n_min=0.005) grid v_wall=linspace(0.05,0.95,1000) x alpha_n=linspace(0.005,0.5,"
+                "1000); per point Bubble(model, v_wall, alpha_n) [model-independent solver, n_xi=5000, t_end=50] + "
+                "Spectrum(bubble, r_star=0.1) [y=logspace(-1,3,1000), nt=10^4, n_z_lookup=10^4, nxi=2000] -> pow_v, pow_gw, "
+                "omgw0"),
+    # the reference's old bag API
+    "bag": ("config2: BagModel grid v_wall=linspace(0.05,0.95,1000) x alpha_n=linspace(0.005,0.5,1000); per point "
+            "sound_shell_bag(n_xi=2000) + power_gw_scaled_bag(z=logspace(-1,3,1000), npt=(2000,10000,10000))"),
+}
 
 
 def batch_points(step: int, rank: int, world: int, batch: int):
@@ -45,17 +55,41 @@ def batch_points(step: int, rank: int, world: int, batch: int):
 # CPU arm (oracle port of the reference algorithm) -- also the cpu_baseline leg of the GPU arm
 # ---------------------------------------------------------------------------------------------------------------
 
+_CPU = {}
+
+
+def _cpu_setup(path):
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import models, shell_generic as sg
+    _CPU["path"] = path
+    if path == "generic":
+        _CPU["model"] = models.bag_model(a_s=1.0 / (1 - 3 * 0.005 * 0.999), a_b=1.0, V_s=1.0)
+        _CPU["ref"] = sg.FluidReference(dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_fluid_reference.npz"))))
+
+
 def _cpu_point(args):
     vw, an = args
-    from oracle import shell_bag as sb, ssm
+    from oracle import shell_bag as sb, shell_generic as sg, ssm
     if sb.identify_solution_type(vw, an) == sb.ERROR:
         return 0
-    ssm.power_gw_scaled_bag(Y, (vw, an), NPT)
+    if _CPU["path"] == "bag":
+        ssm.power_gw_scaled_bag(Y, (vw, an), NPT)
+        return 1
+    m = _CPU["model"]
+    try:
+        sol = sg.sound_shell_generic(m, vw, an, _CPU["ref"])
+        sc = sg.bubble_scalars(m, sol, vw)
+        sp = ssm.ssm_spectrum(m, sol, sc, vw, y=Y, r_star=R_STAR)
+        ssm.omgw0_scale(R_STAR, 1.0) * sp["pow_gw"]
+    except (ValueError, RuntimeError, IndexError):
+        return 0
     return 1
 
 
-def cpu_run(points, cores):
+def cpu_run(points, cores, path):
     import multiprocessing as mp
+    _cpu_setup(path)          # before the fork: workers inherit the model and the starting-guess table
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
         pool.map(_cpu_point, points, chunksize=1)
@@ -71,7 +105,7 @@ def reference_arm(args):
     times = []
     for s in range(args.warmup + args.steps):
         vw, an = batch_points(s, 0, 1, per_step)
-        dt = cpu_run(list(zip(vw, an)), cores)
+        dt = cpu_run(list(zip(vw, an)), cores, args.path)
         if s >= args.warmup:
             times.append(dt)
     total = float(np.sum(times))
@@ -81,7 +115,7 @@ def reference_arm(args):
         "impl": "reference", "metric": "bubble+GW spectra/sec", "value": value, "unit": "spectra/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": per_step},
+        "config": {"workload": WORKLOADS[args.path], "batch_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "spectra/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -149,14 +183,27 @@ def gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
-    plan = engine.SsmPlan(Y, cs=engine.CS0, nt=NPT[1], n_z_lookup=NPT[2], nxi=NPT[0], mode="bag")
+    from pttools_b200.models import BagModel
+    from pttools_b200 import fluid_reference
+    if args.path == "bag":
+        plan = engine.SsmPlan(Y, cs=engine.CS0, nt=NPT[1], n_z_lookup=NPT[2], nxi=NPT[0], mode="bag")
+    else:
+        model = BagModel(alpha_n_min=0.005)
+        plan = engine.SsmPlan(Y, cs=float(np.sqrt(model.csb2)), nt=NPT[1], n_z_lookup=NPT[2], nxi=NPT[0], mode="ssm")
+        fluid_reference.ref()         # starting-guess table: once per process, like the reference's pre-fork warm-up
     gather_buf = [torch.empty((B, Y.size), dtype=torch.float64, device="cuda") for _ in range(world)] \
         if (world > 1 and rank == 0) else None
 
     def device_step(s, vw_d, an_d):
-        res = sweep.power_gw_scaled_bag_sweep(vw_d, an_d, Y, NPT, chunk=args.chunk, plan=plan)
+        if args.path == "bag":
+            res = sweep.power_gw_scaled_bag_sweep(vw_d, an_d, Y, NPT, chunk=args.chunk, plan=plan)
+            table = res.pow_gw
+        else:
+            res = sweep.sweep_spectra(model, vw_d, an_d, y=Y, r_star=R_STAR, n_xi=N_XI, chunk=args.chunk, plan=plan)
+            table = res.omgw0
         if world > 1:
-            dist.gather(res.pow_gw, gather_buf, dst=0)
+            dist.gather(table, gather_buf, dst=0)
+        res.table = table
         return res
 
     def barrier():
@@ -207,7 +254,7 @@ def gpu_arm(args):
         vw_d = pin_in[0].to("cuda", non_blocking=True)
         an_d = pin_in[1].to("cuda", non_blocking=True)
         res = device_step(s, vw_d, an_d)
-        pin_out.copy_(res.pow_gw, non_blocking=True)
+        pin_out.copy_(res.table, non_blocking=True)
         torch.cuda.synchronize()
         return float(np.nanmax(pin_out.numpy()[:, 0]))
 
@@ -230,7 +277,7 @@ def gpu_arm(args):
         n_sdv = plan.lookup_pass.z.size
         n_launch_pts = min(args.chunk, B)
         alg = {
-            # 10 flop per (z_i, T_j) lookup-and-accumulate
+            # 10 flop per (z_i, T_j) lookup-and-accumulate (SURVEY.md 8d, K6)
             "spec_den_v": 10.0 * n_sdv * NPT[1] * n_launch_pts,
             # 25 flop per (y_i, z_k) integrand with two lookups
             "spec_den_gw": 25.0 * Y.size * plan.gw["n_int"] * n_launch_pts,
@@ -249,14 +296,14 @@ def gpu_arm(args):
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = max(cores, 8)
             vw, an = batch_points(0, 0, 1, n_cpu)
-            dt = cpu_run(list(zip(vw, an)), cores)
+            dt = cpu_run(list(zip(vw, an)), cores, args.path)
             cpu = {"value": n_cpu / dt, "unit": "spectra/s", "cores": cores, "kind": "port",
                    "sample": f"first {n_cpu} points of step 0 (same grid, same sizes), fork pool of {cores} processes, {dt:.1f} s"}
         out = {
             "metric": "bubble+GW spectra/sec", "value": value, "unit": "spectra/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu_per_step": B, "chunk": args.chunk,
+            "config": {"workload": WORKLOADS[args.path], "batch_per_gpu_per_step": B, "chunk": args.chunk,
                        "l2": "per-step working set (profiles + A2 + lookup tables, ~1 MB per point) exceeds the 126 MB L2; "
                              "every step uses fresh points",
                        "valid_points_in_timed_region": n_ok, "wall_ms_per_step": wall_ms / args.steps},
@@ -278,9 +325,10 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1024)
-    ap.add_argument("--chunk", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--chunk", type=int, default=2048)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--path", default="generic", choices=["generic", "bag"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

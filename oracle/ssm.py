@@ -242,3 +242,43 @@ def power_gw_scaled_bag(z, params, npt=(NXI, NT, NZ_LOOKUP), z_st_thresh=Z_ST_TH
 def power_v_bag(z, params, npt=(NXI, NT, NZ_LOOKUP), z_st_thresh=Z_ST_THRESH, profile=None):
     """spectrum.py:297-324."""
     return pow_spec(z, spec_den_v_bag(z, params, npt, z_st_thresh, profile=profile))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a16-a20 for Bubble objects: SSMSpectrum.compute and Spectrum.omgw0
+# ---------------------------------------------------------------------------------------------------------------
+
+def a2_e_conserving(model, sol, scal, z, cs, z_st_thresh=Z_ST_THRESH, nxi=NXI):
+    """ssm.py:35-81 for a solved bubble (sol: profile dict of shell_generic.sound_shell_generic, scal: bubble_scalars)."""
+    v, w, xi = sol["v"], sol["w"], sol["xi"]
+    e = model.e(w, scal["phase"])
+    lam_orig = (e - e[-1]) / w[-1]
+    return a2_from_profile(z, v, w, xi, lam_orig, cs, z_st_thresh, nxi)
+
+
+def ssm_spectrum(model, sol, scal, v_wall, y=None, z_st_thresh=Z_ST_THRESH, nuc_type="exponential", nt=NT,
+                 n_z_lookup=NZ_LOOKUP, r_star=None, lifetime_multiplier=1.0):
+    """SSMSpectrum.compute (spectrum.py:96-136). Returns dict(a2, cs, spec_den_v, pow_v, z_lookup, spec_den_gw, pow_gw)."""
+    y = Y_DEFAULT if y is None else y
+    cs = float(np.sqrt(model.cs2(scal["va_enthalpy_density"], 1.0)))
+    qt = qt_lookup_grid(y)
+    a2 = a2_e_conserving(model, sol, scal, qt, cs, z_st_thresh)[0]
+    sdv = spec_den_v_core(y, a2, qt, v_wall, nuc_type, 1.0, nt)
+    pow_v = pow_spec(y, sdv)
+    z_lookup = gen_lookup(y, cs, n_z_lookup, eps=1e-8)
+    qt2 = qt_lookup_grid(z_lookup)
+    a2_2 = a2_e_conserving(model, sol, scal, qt2, cs, z_st_thresh)[0]
+    sdv2 = spec_den_v_core(z_lookup, a2_2, qt2, v_wall, nuc_type, 1.0, nt)
+    nu_ = float(model.nu_gdh2024(scal["va_enthalpy_density"]))
+    slf = 1 / (1 + 2 * nu_)
+    if r_star is not None and not np.isinf(lifetime_multiplier):
+        slf *= 1 - (1 + lifetime_multiplier * 2 * r_star / np.sqrt(scal["kinetic_energy_fraction"])) ** (-1 - 2 * nu_)
+    sd_gw, _ = spec_den_gw_scaled(z_lookup, sdv2, y, cs, source_lifetime_factor=slf)
+    return dict(a2=a2, cs=cs, spec_den_v=sdv, pow_v=pow_v, z_lookup=z_lookup, spec_den_gw=sd_gw,
+                pow_gw=pow_spec(y, sd_gw), source_lifetime_factor=slf)
+
+
+def omgw0_scale(r_star, suppression_factor, g_star=100.0, gs_star=100.0, g0=2.0, gs0=3.91):
+    """r_* F_gw0 Sigma of Spectrum.omgw0 (omgw0_ssm.py:123-131, 191-204; const.py:10-40)."""
+    om_gamma0 = 3.57e-5 * gs0 ** (4 / 3) / g0
+    return r_star * om_gamma0 * (gs0 / gs_star) ** (4 / 3) * g_star / g0 * suppression_factor

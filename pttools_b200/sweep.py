@@ -107,20 +107,23 @@ def shell_chunk_points(n_xi: int, budget_bytes: float = 24e9) -> int:
 def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multiplier=1.0, nuc_type="exponential",
                   nt=engine.NT_DEFAULT, n_z_lookup=engine.NZ_LOOKUP_DEFAULT, z_st_thresh=engine.Z_ST_THRESH,
                   n_xi=engine.N_XI_DEFAULT, Tn=None, g_star=None, gs_star=None, suppression="default",
-                  chunk=2048, shell_chunk=None, want_pow_v=True, keep_bubbles=False) -> SweepResult:
+                  chunk=2048, shell_chunk=None, want_pow_v=True, keep_bubbles=False, plan=None) -> SweepResult:
     """Spectrum(Bubble(model, v_wall, alpha_n), y, r_star=...) for every point of a sweep: the model-independent shell
     solve, the thermodynamic scalars, the SSM chain and Omega_gw,0 (pttools/analysis/parallel.py:157-187 ->
     bubble.py:232-352 -> ssmtools/spectrum.py:96-115 -> omgw0/omgw0_ssm.py:123-131), one model for all points."""
     from . import bubble as bub
     from . import omgw0 as om
     torch = engine._torch()
-    vw = np.asarray(v_wall, dtype=float).reshape(-1)
-    an = np.asarray(alpha_n, dtype=float).reshape(-1)
+    to_np = lambda a: a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a, dtype=float)
+    vw = to_np(v_wall).astype(float).reshape(-1)
+    an = to_np(alpha_n).astype(float).reshape(-1)
     n = vw.size
     y = engine.Y_DEFAULT if y is None else np.asarray(y, dtype=float)
     cs = float(np.sqrt(model.csb2))                                   # spectrum.py:99 (cs2 is constant per phase)
-    plan = engine.SsmPlan(y, cs=cs, nt=nt, n_z_lookup=n_z_lookup, z_st_thresh=z_st_thresh, nuc_type=nuc_type, a=1.0,
-                          mode="ssm", only_lookup_pass=not want_pow_v)
+    if plan is None:
+        plan = engine.SsmPlan(y, cs=cs, nt=nt, n_z_lookup=n_z_lookup, z_st_thresh=z_st_thresh, nuc_type=nuc_type,
+                              a=1.0, mode="ssm", only_lookup_pass=not want_pow_v)
+    want_pow_v = want_pow_v and plan.has_y_pass
     scale = None
     if r_star is not None:
         # omgw0_ssm.py:62-131: model temperatures are not physical for both in-scope models -> the overrides apply
