@@ -138,6 +138,9 @@ typedef struct ptt_a2_plan {
     int32_t nxi;          /* resampling size for lambda (ssm.py:40, default 2000) */
     int32_t phase_rule;   /* 0: xi < v_wall (boundary.get_phase, old bag path); 1: props.find_phase (Bubble path) */
     const double* xi_re;  /* [nxi] = linspace(0, 1-1/nxi, nxi) */
+    double z_exact_max;   /* largest z that takes the exact (trapezoid) branch, i.e. with frac < 1 */
+    int32_t force_direct; /* 1: one sine per (z, xi) pair (validation); 0: block-moment evaluation of the same sum */
+    int32_t reserved;
 } ptt_a2_plan_t;
 
 /* a2_e_conserving / a2_e_conserving_bag                                       pttools/ssmtools/ssm.py:35-140

@@ -26,7 +26,8 @@ class Eos(C.Structure):
 
 class A2Plan(C.Structure):
     _fields_ = [("n_z", C.c_int32), ("n_seg", C.c_int32), ("seg", C.c_void_p), ("z", C.c_void_p),
-                ("frac", C.c_void_p), ("nxi", C.c_int32), ("phase_rule", C.c_int32), ("xi_re", C.c_void_p)]
+                ("frac", C.c_void_p), ("nxi", C.c_int32), ("phase_rule", C.c_int32), ("xi_re", C.c_void_p),
+                ("z_exact_max", C.c_double), ("force_direct", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SdvPlan(C.Structure):

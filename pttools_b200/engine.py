@@ -294,6 +294,14 @@ def blend_fraction(z: np.ndarray, z_st_thresh: float = Z_ST_THRESH) -> np.ndarra
     return frac
 
 
+FORCE_DIRECT_ST = False     # validation switch: evaluate the exact sine transform with one sine per (z, xi) pair
+
+
+def z_exact_max(z: np.ndarray, frac: np.ndarray) -> float:
+    sel = frac < 1.0
+    return float(np.max(z[sel])) if np.any(sel) else 0.0
+
+
 def qt_lookup_grid(z: np.ndarray):
     """qT_lookup of spec_den_v (spectrum.py:503-515) and its log-grid parameters (l0, dlog10)."""
     lmin, lmax = np.log10(np.min(z)), np.log10(np.max(z))
@@ -414,7 +422,8 @@ class SsmPlan:
 
         self.a2_plan = A2Plan(n_z=self.z_all.size, n_seg=len(self.passes), seg=self._t["seg"].data_ptr(),
                               z=self._t["z_all"].data_ptr(), frac=self._t["frac_all"].data_ptr(), nxi=self.nxi,
-                              phase_rule=self.phase_rule, xi_re=self._t["xi_re"].data_ptr())
+                              phase_rule=self.phase_rule, xi_re=self._t["xi_re"].data_ptr(),
+                              z_exact_max=z_exact_max(self.z_all, self.frac_all), force_direct=int(FORCE_DIRECT_ST))
         self.sdv_plans = []
         for i, p in enumerate(self.passes):
             self.sdv_plans.append(SdvPlan(
@@ -485,7 +494,7 @@ class GwOnlyPlan:
 class A2OnlyPlan:
     """Plan for a2_e_conserving on one arbitrary ascending z grid (ssm.py:35-140)."""
 
-    def __init__(self, z, nxi=NXI_DEFAULT, z_st_thresh=Z_ST_THRESH, phase_rule=1):
+    def __init__(self, z, nxi=NXI_DEFAULT, z_st_thresh=Z_ST_THRESH, phase_rule=1, force_direct=False):
         torch = _torch()
         z = np.asarray(z, dtype=np.float64)
         self.nxi = int(nxi)
@@ -495,9 +504,11 @@ class A2OnlyPlan:
         up = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device="cuda")
         self._t = {"seg": up(self.seg, torch.int32), "z": up(z), "frac": up(blend_fraction(z, z_st_thresh)),
                    "xi_re": up(self.xi_re)}
+        frac = blend_fraction(z, z_st_thresh)
         self.a2_plan = A2Plan(n_z=z.size, n_seg=1, seg=self._t["seg"].data_ptr(), z=self._t["z"].data_ptr(),
                               frac=self._t["frac"].data_ptr(), nxi=self.nxi, phase_rule=phase_rule,
-                              xi_re=self._t["xi_re"].data_ptr())
+                              xi_re=self._t["xi_re"].data_ptr(), z_exact_max=z_exact_max(z, frac),
+                              force_direct=int(force_direct or FORCE_DIRECT_ST))
 
     @property
     def n_a2(self):
