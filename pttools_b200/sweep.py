@@ -177,3 +177,55 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
     if keep_bubbles:
         out.bubbles = bubbles
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Multi-GPU: static sharding, no collective in the solve, one gather of the result table at the end
+# ---------------------------------------------------------------------------------------------------------------
+
+def distributed_table(compute: tp.Callable[[np.ndarray], "np.ndarray | tp.Any"], n_points: int, n_cols: int,
+                      sol_type: tp.Optional[np.ndarray] = None, device: str = "cuda", dst: int = 0):
+    """Runs `compute(indices) -> [len(indices), n_cols] float64 tensor` on this rank's shard of range(n_points) and
+    gathers the full [n_points, n_cols] table on rank `dst` (None elsewhere).
+
+    Every (v_wall, alpha_n, model) point is independent (the reference maps one future per point,
+    speedup/parallel.py:134-137), so the ranks never talk during the solve; the only exchange step is the final
+    gather (NCCL over NVLink on a GPU box, gloo in the CPU tests).  Works without torch.distributed initialised
+    (single process)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    mine = shard_indices(n_points, rank, world, sol_type)
+    block = compute(mine)
+    block = torch.as_tensor(block, dtype=torch.float64, device=device).reshape(len(mine), n_cols)
+    if world == 1:
+        out = torch.empty((n_points, n_cols), dtype=torch.float64, device=device)
+        out[torch.as_tensor(mine, device=device)] = block
+        return out
+    # shards differ by at most one row: pad to a common size so that a plain gather can be used
+    rows = (n_points + world - 1) // world
+    padded = torch.zeros((rows, n_cols), dtype=torch.float64, device=device)
+    padded[: len(mine)] = block
+    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bufs, dst=dst)
+    if rank != dst:
+        return None
+    out = torch.empty((n_points, n_cols), dtype=torch.float64, device=device)
+    for r in range(world):
+        idx = shard_indices(n_points, r, world, sol_type)
+        out[torch.as_tensor(idx, device=device)] = bufs[r][: len(idx)]
+    return out
+
+
+def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, **kw):
+    """10^6-point style sweep sharded over the ranks of torch.distributed: Omega_gw,0(f) table [n, n_y] on rank 0."""
+    vw = np.asarray(v_wall, dtype=float).reshape(-1)
+    an = np.asarray(alpha_n, dtype=float).reshape(-1)
+    y = engine.Y_DEFAULT if y is None else np.asarray(y, dtype=float)
+    codes = model.solution_type_codes(vw, an, np.asarray(model.wn(an), dtype=float))
+
+    def compute(idx):
+        return sweep_spectra(model, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False, **kw).omgw0
+
+    return distributed_table(compute, vw.size, y.size, sol_type=codes)
