@@ -68,6 +68,8 @@ SIGNATURES = {
     "ptt_a2_work_stride": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "ptt_spec_den_v_batch": (C.c_int, [C.POINTER(SdvPlan), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_int64, C.c_void_p]),
+    "ptt_spec_den_v_group": (C.c_int, [C.POINTER(SdvPlan), C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ptt_spec_den_gw_batch": (C.c_int, [C.POINTER(GwPlan), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_pow_spec_batch": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -97,25 +97,32 @@ def create_spectra(model: Model, v_walls: np.ndarray, alpha_ns: np.ndarray, func
                    spectrum_kwargs: tp.Dict[str, tp.Any] = None):
     """parallel.py:157-187."""
     v_walls, alpha_ns = np.asarray(v_walls, dtype=float), np.asarray(alpha_ns, dtype=float)
-    vw, an = np.meshgrid(v_walls, alpha_ns)
+    # device order: v_wall-major and ascending (points that share v_wall are contiguous); objects go back into the
+    # reference's [i_alpha, i_vw] layout (parallel.py:126-130)
+    order_vw = np.argsort(v_walls, kind="stable")
+    vw = np.repeat(v_walls[order_vw], alpha_ns.size)
+    an = np.tile(alpha_ns, v_walls.size)
     sk = dict(spectrum_kwargs or {})
     bk = bubble_kwargs or {}
-    res = sweep.sweep_spectra(model, vw.ravel(), an.ravel(), y=sk.get("y"), r_star=sk.get("r_star"),
+    nuc = sk.get("nuc_type", "exponential")
+    res = sweep.sweep_spectra(model, vw, an, y=sk.get("y"), r_star=sk.get("r_star"),
                               lifetime_multiplier=sk.get("lifetime_multiplier", 1.0),
-                              nuc_type=str(getattr(sk.get("nuc_type", "exponential"), "value", sk.get("nuc_type", "exponential"))),
+                              nuc_type=str(getattr(nuc, "value", nuc)),
                               nt=sk.get("nt", 10000), n_z_lookup=sk.get("n_z_lookup", 10000),
                               z_st_thresh=sk.get("z_st_thresh", 50.0), n_xi=bk.get("n_xi", bub.N_XI_DEFAULT),
                               Tn=sk.get("Tn"), g_star=sk.get("g_star"), gs_star=sk.get("gs_star"), keep_bubbles=True)
-    objs = np.empty(vw.shape, dtype=object)
-    flat = objs.reshape(-1)
+    objs = np.empty((alpha_ns.size, v_walls.size), dtype=object)
     k = 0
     for bb in res.bubbles:
         for j in range(len(bb)):
             bview = BubbleView(bb, j, model)
             if not bview.solved and not allow_bubble_failure:
                 raise RuntimeError(f"Solver crashed with v_wall={bview.v_wall}, alpha_n={bview.alpha_n}.")
-            flat[k] = SpectrumView(res, k, bview, sk.get("r_star")) if bview.solved else None
+            i_vw, i_alpha = order_vw[k // alpha_ns.size], k % alpha_ns.size
+            objs[i_alpha, i_vw] = SpectrumView(res, k, bview, sk.get("r_star")) if bview.solved else None
             k += 1
+    flat = objs.reshape(-1)
+    vw = objs          # only .shape is used below
     if func is None:
         return objs
     return objs, _apply(func, flat, vw.shape, kwargs)

@@ -1,0 +1,200 @@
+// K6': spec_den_v for a group of profiles that share v_wall, as a banded FP64 matrix product.
+//
+// _spec_den_v_core (pttools/ssmtools/spectrum.py:451-486) evaluates, for every wavenumber z_i,
+//     P(z_i) = factor * sum_j W_j * interp(A2)(s_i T_j),   s_i = z_i / (b_R v_w),
+// and np.interp is linear in the table values:  interp(A2)(x) = (1-t) A2[e] + t A2[e+1].  The weights depend on
+// (z_i, T_j, v_w) only -- not on the profile -- so for the n_p profiles of a sweep that share v_w
+//     P[i, p] = factor * sum_k Omega[i, k] * A2[p, k],      Omega[i, k] = sum_j W_j * (weight of knot k at s_i T_j).
+// Omega is banded (each z_i sees the 3.3 decades of T-tilde): it is built once per group (sdv_weights_kernel, the
+// same index arithmetic as the gather kernel) and multiplied with the A2 table by an FP64 tensor-core GEMM
+// (mma.sync m8n8k4 f64 -- there is no tcgen05 kind for FP64).  Identical linear-interpolation weights, different
+// summation order; the gather kernel (ptt_ssm.cu) remains for profiles that do not share v_w.
+#include "ptt_host.cuh"
+
+namespace ptt {
+
+constexpr int GM_BM = 128;      // rows (wavenumbers) per CTA
+constexpr int GM_BN = 128;      // columns (profiles) per CTA
+constexpr int GM_BK = 16;
+constexpr int GM_PITCH = GM_BK + 4;   // doubles; conflict-free fragment loads (half-warp covers all 32 banks)
+constexpr int GM_THREADS = 256;
+
+// Omega, tile-banded: tile t (GM_BM rows) stores [GM_BM][kw] weights for knots e_base[t] + kk, kk in [0, kw).
+// One thread per row: T-tilde samples are visited in ascending order, the knot index is non-decreasing, so the two
+// running knot accumulators are flushed in order and every entry of the row is written exactly once.
+__global__ void __launch_bounds__(128) sdv_weights_kernel(
+    const int n_q, const int n_z, const int nt, const double* __restrict__ qT, const double* __restrict__ z,
+    const double* __restrict__ zterm, const double* __restrict__ T, const double* __restrict__ LT,
+    const double* __restrict__ W, const double v_wall, const double inv_dlog, const int kw,
+    const int* __restrict__ e_base, double* __restrict__ omega) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_rows = ((n_z + GM_BM - 1) / GM_BM) * GM_BM;
+    if (i >= n_rows) return;
+    double* row = omega + (size_t)i * kw;
+    if (i >= n_z) {
+        for (int kk = 0; kk < kw; ++kk) row[kk] = 0.0;
+        return;
+    }
+    const double b_R = cbrt(8.0 * M_PI);
+    const double bv = b_R * v_wall;
+    const double shift = -log10(bv) * inv_dlog;
+    const double s = z[i] / bv;
+    const double ub = zterm[i] + shift;
+    const int eb = e_base[i / GM_BM];
+    int cur = eb;               // knot whose weight is being accumulated in acc0 (acc1: knot cur + 1)
+    double acc0 = 0.0, acc1 = 0.0;
+    int kk_written = 0;
+    for (int j = 0; j < nt; ++j) {
+        const double x = s * T[j];
+        int e = __double2int_rd(ub + LT[j]);
+        double w0, w1;
+        const double wj = W[j];
+        if (e < 0 || x < qT[0]) { e = 0; w0 = wj; w1 = 0.0; }                       // np.interp left clamp
+        else if (e >= n_q - 1 || x >= qT[n_q - 1]) { e = n_q - 2; w0 = 0.0; w1 = wj; }   // right clamp: all on the last knot
+        else {
+            // arithmetic index may be off by one on a razor edge: the weights then extrapolate the neighbouring
+            // segment by ~1e-12 of its length, i.e. the same value (continuous interpolant)
+            const double x0 = qT[e], x1 = qT[e + 1];
+            const double t = (x - x0) / (x1 - x0);
+            w0 = wj * (1.0 - t);
+            w1 = wj * t;
+        }
+        while (cur < e) {       // flush knots that can no longer receive weight
+            if (kk_written < kw) row[kk_written] = acc0;
+            ++kk_written;
+            acc0 = acc1;
+            acc1 = 0.0;
+            ++cur;
+        }
+        // e == cur here (e is non-decreasing in j because u is)
+        acc0 += w0;
+        acc1 += w1;
+    }
+    if (kk_written < kw) row[kk_written] = acc0;
+    ++kk_written;
+    if (kk_written < kw) row[kk_written] = acc1;
+    ++kk_written;
+    for (int kk = kk_written; kk < kw; ++kk) row[kk] = 0.0;
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// out[p, i] = factor * sum_kk omega[i, kk] * a2[p, e_base[tile(i)] + kk]
+__global__ void __launch_bounds__(GM_THREADS) sdv_gemm_kernel(
+    const int n_z, const int n_p, const int n_q, const int kw, const int* __restrict__ e_base,
+    const double* __restrict__ omega, const double* __restrict__ a2, const long long a2_stride, const double factor,
+    double* __restrict__ out, const long long out_stride) {
+    extern __shared__ double gm_smem[];
+    double (*As)[GM_BM * GM_PITCH] = reinterpret_cast<double (*)[GM_BM * GM_PITCH]>(gm_smem);
+    double (*Bs)[GM_BN * GM_PITCH] = reinterpret_cast<double (*)[GM_BN * GM_PITCH]>(gm_smem + 2 * GM_BM * GM_PITCH);
+    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;          // 4 x 2 warps; warp tile 32 (m) x 64 (n)
+    const int eb = e_base[tile_m];
+    const double* Ag = omega + (size_t)tile_m * GM_BM * kw;
+    // global -> shared: thread loads 8 consecutive k of one row (A) and of one column/profile (B)
+    const int lr = tid >> 1, lk = (tid & 1) * 8;
+    const int p_load = tile_n * GM_BN + lr;
+    const bool p_ok = p_load < n_p;
+    const double* Bg = a2 + (long long)(p_ok ? p_load : 0) * a2_stride;
+    double ra[8], rb[8];
+    auto load_regs = [&](const int k0) {
+        const double* ap = Ag + (size_t)lr * kw + k0 + lk;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ra[q] = (k0 + lk + q < kw) ? ap[q] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = eb + k0 + lk + q;
+            rb[q] = (p_ok && k < n_q && k0 + lk + q < kw) ? Bg[k] : 0.0;
+        }
+    };
+    auto store_smem = [&](const int buf) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            As[buf][lr * GM_PITCH + lk + q] = ra[q];
+            Bs[buf][lr * GM_PITCH + lk + q] = rb[q];
+        }
+    };
+    double acc[4][8][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+
+    const int n_k = (kw + GM_BK - 1) / GM_BK;
+    load_regs(0);
+    store_smem(0);
+    __syncthreads();
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int kt = 0; kt < n_k; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < n_k) load_regs((kt + 1) * GM_BK);
+        const double* Asb = As[buf] + (wm * 32 + fr) * GM_PITCH + fk;
+        const double* Bsb = Bs[buf] + (wn * 64 + fr) * GM_PITCH + fk;
+#pragma unroll
+        for (int k4 = 0; k4 < GM_BK; k4 += 4) {
+            double af[4], bf[8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = Asb[a * 8 * GM_PITCH + k4];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) bf[b] = Bsb[b * 8 * GM_PITCH + k4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        if (kt + 1 < n_k) {
+            store_smem(buf ^ 1);
+        }
+        __syncthreads();
+    }
+    // C fragment: row = lane / 4, cols = 2 * (lane % 4) + {0, 1}
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = tile_m * GM_BM + wm * 32 + a * 8 + fr;
+        if (i >= n_z) continue;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int p0 = tile_n * GM_BN + wn * 64 + b * 8 + 2 * fk;
+            if (p0 < n_p) out[(long long)p0 * out_stride + i] = factor * acc[a][b][0];
+            if (p0 + 1 < n_p) out[(long long)(p0 + 1) * out_stride + i] = factor * acc[a][b][1];
+        }
+    }
+}
+
+}  // namespace ptt
+
+using namespace ptt;
+
+// a2: [n_p, a2_stride] tables of the group's profiles (device); omega: scratch of n_tiles*128*kw doubles;
+// e_base: [n_tiles] int32 (device) first knot of every row tile for this v_wall (host-computed from the plan).
+extern "C" int ptt_spec_den_v_group(const ptt_sdv_plan_t* plan, int n_p, const double* a2, int64_t a2_stride,
+                                    double v_wall, int kw, const int32_t* e_base, double* omega, double* out,
+                                    int64_t out_stride, void* stream_) {
+    if (!plan || n_p < 0 || !a2 || !e_base || !omega || !out || kw < 2)
+        return set_error(PTT_E_ARG, "ptt_spec_den_v_group: null pointer or bad size");
+    if (n_p == 0) return PTT_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int n_tiles = (plan->n_z + GM_BM - 1) / GM_BM;
+    sdv_weights_kernel<<<(n_tiles * GM_BM + 127) / 128, 128, 0, stream>>>(plan->n_q, plan->n_z, plan->nt, plan->qT, plan->z,
+                                                                         plan->zterm, plan->T, plan->LT, plan->W, v_wall,
+                                                                         plan->inv_dlog, kw, e_base, omega);
+    const double b_R = cbrt(8.0 * M_PI);
+    const double bv = b_R * v_wall;
+    const double factor = 2.0 / (bv * bv * bv * bv * bv * bv);
+    dim3 grid(n_tiles, (n_p + GM_BN - 1) / GM_BN);
+    const int smem = 2 * (GM_BM + GM_BN) * GM_PITCH * (int)sizeof(double);
+    {
+        const cudaError_t e = cudaFuncSetAttribute(sdv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return set_cuda_error("sdv_gemm_kernel smem", e);
+    }
+    sdv_gemm_kernel<<<grid, GM_THREADS, smem, stream>>>(plan->n_z, n_p, plan->n_q, kw, e_base, omega, a2, a2_stride, factor,
+                                                     out, out_stride);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("ptt_spec_den_v_group", e);
+    return PTT_OK;
+}

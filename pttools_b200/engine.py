@@ -569,8 +569,79 @@ def spec_den_v_batch(plan: SsmPlan, ipass: int, a2, v_wall):
     out = torch.empty((P, sp.n_z), dtype=torch.float64, device=a2.device)
     a2_view_ptr = C.c_void_p(a2.data_ptr() + 8 * int(plan.seg[ipass]))
     with STAGES.stage("spec_den_v" if ipass == len(plan.passes) - 1 else "spec_den_v_y", 1):
-        _lib.check(lib.ptt_spec_den_v_batch(C.byref(sp), P, a2_view_ptr, a2.shape[1], _ptr(v_wall), _ptr(out), sp.n_z,
+        _lib.check(lib.ptt_spec_den_v_batch(C.byref(sp), P, a2_view_ptr, a2.stride(0), _ptr(v_wall), _ptr(out), sp.n_z,
                                             _stream_ptr(torch)), "ptt_spec_den_v_batch")
+    return out
+
+
+GROUP_MIN = 96          # smallest run of equal v_wall worth the banded matrix product
+USE_GROUPED_SDV = True
+
+
+def _group_band(p: SdvPass, v_wall: float):
+    """First knot of every 128-row tile and the common band width for one wall speed (host side of K6')."""
+    b_r = (8.0 * np.pi) ** (1.0 / 3.0)
+    shift = -np.log10(b_r * v_wall) / p.dl
+    n_z, n_q = p.z.size, p.qT.size
+    i0 = np.arange(0, n_z, 128)
+    i1 = np.minimum(i0 + 128, n_z) - 1
+    e_first = np.floor(p.zterm[i0] + p.LT[0] + shift).astype(np.int64) - 1
+    e_base = np.clip(e_first, 0, max(n_q - 2, 0))
+    e_last = np.clip(np.floor(p.zterm[i1] + p.LT[-1] + shift).astype(np.int64) + 1, 0, n_q - 2) + 1
+    kw = int((e_last - e_base).max()) + 3
+    kw = ((kw + 15) // 16) * 16
+    return e_base.astype(np.int32), kw
+
+
+def spec_den_v_group(plan: SsmPlan, ipass: int, a2, v_wall: float, out):
+    """_spec_den_v_core for profiles that share v_wall, as a banded FP64 GEMM (ptt_spec_den_v_group).
+    a2: [n_p, n_a2] rows of the group; out: [n_p, n_z] destination view."""
+    torch = _torch()
+    lib = _lib.load()
+    sp, p = plan.sdv_plans[ipass], plan.passes[ipass]
+    e_base, kw = _group_band(p, v_wall)
+    n_tiles = e_base.size
+    key = ("omega", ipass)
+    need = n_tiles * 128 * kw
+    buf = plan._t.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(int(need * 1.02) + 1024, dtype=torch.float64, device=a2.device)
+        plan._t[key] = buf
+    eb = torch.as_tensor(e_base, device=a2.device)
+    a2_ptr = C.c_void_p(a2.data_ptr() + 8 * int(plan.seg[ipass]))
+    with STAGES.stage("spec_den_v_group" if ipass == len(plan.passes) - 1 else "spec_den_v_group_y", 2):
+        _lib.check(lib.ptt_spec_den_v_group(C.byref(sp), a2.shape[0], a2_ptr, a2.stride(0), float(v_wall), kw, _ptr(eb),
+                                            _ptr(buf), _ptr(out), out.stride(0), _stream_ptr(torch)),
+                   "ptt_spec_den_v_group")
+    return out
+
+
+def spec_den_v_auto(plan: SsmPlan, ipass: int, a2, v_wall):
+    """spec_den_v for a batch: runs of >= GROUP_MIN consecutive profiles with the same v_wall go through the banded
+    matrix product, everything else through the gather kernel."""
+    torch = _torch()
+    P = a2.shape[0]
+    n_z = plan.sdv_plans[ipass].n_z
+    if not USE_GROUPED_SDV or P < GROUP_MIN:
+        return spec_den_v_batch(plan, ipass, a2, v_wall)
+    vw = v_wall.detach().cpu().numpy()
+    cuts = np.concatenate(([0], np.nonzero(np.diff(vw) != 0)[0] + 1, [P]))
+    runs = [(int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:])]
+    if not any(b - a >= GROUP_MIN for a, b in runs):
+        return spec_den_v_batch(plan, ipass, a2, v_wall)
+    out = torch.empty((P, n_z), dtype=torch.float64, device=a2.device)
+    small_start = None
+    for a, b in runs + [(P, P)]:
+        big = (b - a) >= GROUP_MIN
+        if (big or a == P) and small_start is not None:          # flush the pending run of small groups
+            out[small_start:a] = spec_den_v_batch(plan, ipass, a2[small_start:a], v_wall[small_start:a].contiguous())
+            small_start = None
+        if a == P:
+            break
+        if big:
+            spec_den_v_group(plan, ipass, a2[a:b], float(vw[a]), out[a:b])
+        elif small_start is None:
+            small_start = a
     return out
 
 
@@ -607,12 +678,12 @@ def spectra_from_shells(plan: SsmPlan, shells: ShellBatch, pp, slf=None, scale=N
     res = SpectrumBatch(y=plan.y, pow_gw=None, sd_gw=None)
     v_wall = pp[:, 0].contiguous()
     if plan.mode == "ssm" and plan.has_y_pass:
-        sdv_y = spec_den_v_batch(plan, 0, a2, v_wall)
+        sdv_y = spec_den_v_auto(plan, 0, a2, v_wall)
         res.sd_v = sdv_y
         res.pow_v = pow_spec_batch(plan._t["y"], sdv_y)
         if keep:
             res.a2 = a2[:, : int(plan.seg[1])]
-    sdv_l = spec_den_v_batch(plan, len(plan.passes) - 1, a2, v_wall)
+    sdv_l = spec_den_v_auto(plan, len(plan.passes) - 1, a2, v_wall)
     if keep:
         res.sd_v_lookup = sdv_l
     res.sd_gw, res.pow_gw, res.omgw0 = spec_den_gw_batch(plan, sdv_l, slf, scale)

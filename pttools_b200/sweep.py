@@ -118,6 +118,12 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
     vw = to_np(v_wall).astype(float).reshape(-1)
     an = to_np(alpha_n).astype(float).reshape(-1)
     n = vw.size
+    # Points that share v_wall share the lifetime-convolution weights (K6'): process the sweep sorted by v_wall and
+    # undo the permutation on the way out.
+    perm = np.argsort(vw, kind="stable")
+    sorted_already = bool(np.all(perm == np.arange(n)))
+    if not sorted_already:
+        vw, an = vw[perm], an[perm]
     y = engine.Y_DEFAULT if y is None else np.asarray(y, dtype=float)
     cs = float(np.sqrt(model.csb2))                                   # spectrum.py:99 (cs2 is constant per phase)
     if plan is None:
@@ -172,6 +178,14 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
                 omgw0[s:e] = res.omgw0
         if keep_bubbles:
             bubbles.append(bb)
+    if not sorted_already:
+        if keep_bubbles:
+            raise NotImplementedError("keep_bubbles needs points ordered by v_wall (grid sweeps are)")
+        inv = torch.as_tensor(np.argsort(perm), device=dev)
+        unperm = lambda t: None if t is None else t[inv]
+        pow_gw, pow_v, omgw0, status, st = (unperm(t) for t in (pow_gw, pow_v, omgw0, status, st))
+        scal = {k: v[inv] for k, v in scal.items()}
+        vw, an = vw[np.argsort(perm)], an[np.argsort(perm)]
     out = SweepResult(engine.dev_f64(vw), engine.dev_f64(an), st, status, None, y, pow_gw=pow_gw, pow_v=pow_v,
                       omgw0=omgw0, scalars=scal)
     if keep_bubbles:

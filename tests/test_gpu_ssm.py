@@ -161,3 +161,26 @@ def test_moment_and_direct_sine_transforms_agree():
         # row maximum as well
         for r in range(x.shape[0]):
             np.testing.assert_allclose(x[r], y[r], rtol=1e-7, atol=1e-10 * np.abs(y[r]).max())
+
+
+def test_grouped_gemm_spec_den_v_matches_gather_kernel():
+    """K6' (banded FP64 matrix product for profiles that share v_wall) against the gather kernel K6."""
+    import torch
+    from pttools_b200 import engine
+    rng = np.random.default_rng(5)
+    n_p = 200
+    y = np.logspace(-1, 3, 300)
+    plan = engine.SsmPlan(y, nt=1500, n_z_lookup=1800, mode="ssm")
+    a2 = torch.as_tensor(np.abs(rng.normal(size=(n_p, plan.n_a2))) * np.logspace(0, -12, plan.n_a2)[None, :], device="cuda")
+    for v_wall in (0.05, 0.5, 0.95):
+        vw = torch.full((n_p,), v_wall, dtype=torch.float64, device="cuda")
+        for ipass in (0, 1):
+            ref = engine.spec_den_v_batch(plan, ipass, a2, vw).cpu().numpy()
+            out = torch.empty((n_p, plan.sdv_plans[ipass].n_z), dtype=torch.float64, device="cuda")
+            engine.spec_den_v_group(plan, ipass, a2, v_wall, out)
+            np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-11)
+    # mixed batch: two big groups and some singletons through the dispatcher
+    vw = np.concatenate([np.full(120, 0.3), [0.31, 0.32, 0.33], np.full(77, 0.6)])
+    got = engine.spec_den_v_auto(plan, 1, a2, engine.dev_f64(vw)).cpu().numpy()
+    ref = engine.spec_den_v_batch(plan, 1, a2, engine.dev_f64(vw)).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-11)
