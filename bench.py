@@ -3,9 +3,10 @@
 
 A "step" is one pass of the hot path (fluid shell solve -> A^2 -> spec_den_v -> spec_den_gw -> pow_gw) over one
 batch of points of the 1000 x 1000 BagModel grid v_wall = linspace(0.05, 0.95, 1000) x alpha_n = linspace(0.005, 0.5,
-1000) at the reference's default resolutions.  Batches are disjoint pseudo-random subsets of the grid (index stride
-999983 mod 10^6), so every step sees the grid's mix of deflagrations / hybrids / detonations / no-solution points
-and no step re-uses another step's data.  With N GPUs every rank works on its own batch (weak scaling) and the
+1000) at the reference's default resolutions.  A batch is a set of complete v_wall rows of the grid (8 rows x 1000
+alpha_n by default, rows spread over the v_wall range with stride 619 mod 1000), i.e. the order in which a grid sweep
+is processed; every step sees deflagrations, hybrids, detonations and no-solution points and no step re-uses another
+step's data.  With N GPUs every rank works on its own batch (weak scaling) and the
 result block is gathered on rank 0 over NCCL, as a sharded sweep would do.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
@@ -44,10 +45,21 @@ WORKLOADS = {
 }
 
 
+ROW_STRIDE = 619                     # coprime with 1000: consecutive batches take v_wall rows spread over the range
+
+
 def batch_points(step: int, rank: int, world: int, batch: int):
-    j = (np.arange(batch, dtype=np.int64) + (step * world + rank) * batch) * STRIDE % (GRID_N * GRID_N)
+    """Points of one batch.  A batch of a multiple of 1000 points is a set of complete v_wall rows of the grid (all
+    1000 alpha_n each), rows spread over [0.05, 0.95] -- the order in which a grid sweep is processed; other batch
+    sizes take a pseudo-random scatter of the grid (stride 999983 mod 10^6)."""
     v_walls = np.linspace(0.05, 0.95, GRID_N)
     alpha_ns = np.linspace(0.005, 0.5, GRID_N)
+    if batch % GRID_N == 0:
+        rows_per = batch // GRID_N
+        rows = ((np.arange(rows_per, dtype=np.int64) + (step * world + rank) * rows_per) * ROW_STRIDE) % GRID_N
+        rows = np.sort(rows)
+        return np.repeat(v_walls[rows], GRID_N), np.tile(alpha_ns, rows_per)
+    j = (np.arange(batch, dtype=np.int64) + (step * world + rank) * batch) * STRIDE % (GRID_N * GRID_N)
     return v_walls[j % GRID_N].copy(), alpha_ns[j // GRID_N].copy()
 
 
@@ -282,6 +294,12 @@ def gpu_arm(args):
             # 25 flop per (y_i, z_k) integrand with two lookups
             "spec_den_gw": 25.0 * Y.size * plan.gw["n_int"] * n_launch_pts,
         }
+        if "spec_den_v_group" in stage_ms:
+            # banded matrix product: 2 flop per (z_i, knot, profile) MAC over the band + the weight build; per launch =
+            # one v_wall row of the grid (1000 profiles)
+            from pttools_b200.engine import _group_band
+            _, kw = _group_band(plan.lookup_pass, 0.5)
+            alg["spec_den_v_group"] = 2.0 * n_sdv * kw * GRID_N + 10.0 * n_sdv * NPT[1]
         dom = max((k for k in stage_ms if k in alg), key=lambda k: stage_ms[k]["ms"], default=None)
         roofline = None
         if dom:
@@ -325,8 +343,8 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8192)
-    ap.add_argument("--chunk", type=int, default=2048)
+    ap.add_argument("--batch", type=int, default=8000)
+    ap.add_argument("--chunk", type=int, default=2000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="generic", choices=["generic", "bag"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

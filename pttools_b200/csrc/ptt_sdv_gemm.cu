@@ -20,61 +20,66 @@ constexpr int GM_PITCH = GM_BK + 4;   // doubles; conflict-free fragment loads (
 constexpr int GM_THREADS = 256;
 
 // Omega, tile-banded: tile t (GM_BM rows) stores [GM_BM][kw] weights for knots e_base[t] + kk, kk in [0, kw).
-// One thread per row: T-tilde samples are visited in ascending order, the knot index is non-decreasing, so the two
-// running knot accumulators are flushed in order and every entry of the row is written exactly once.
+// One warp per row (omega is zero-filled beforehand): lane l visits the T-tilde samples [l*nt/32, (l+1)*nt/32) in
+// ascending order; the knot index is non-decreasing, so two running knot accumulators are flushed in order.  Knots
+// that only this lane's samples can touch are stored; the two first and two last knots of the lane's range may also
+// receive weight from the neighbouring lanes and are accumulated atomically.
+constexpr int WT_LANES = 32;
+
 __global__ void __launch_bounds__(128) sdv_weights_kernel(
     const int n_q, const int n_z, const int nt, const double* __restrict__ qT, const double* __restrict__ z,
     const double* __restrict__ zterm, const double* __restrict__ T, const double* __restrict__ LT,
     const double* __restrict__ W, const double v_wall, const double inv_dlog, const int kw,
     const int* __restrict__ e_base, double* __restrict__ omega) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_rows = ((n_z + GM_BM - 1) / GM_BM) * GM_BM;
-    if (i >= n_rows) return;
+    const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gthread / WT_LANES;
+    const int lane = gthread % WT_LANES;
+    if (i >= n_z) return;
     double* row = omega + (size_t)i * kw;
-    if (i >= n_z) {
-        for (int kk = 0; kk < kw; ++kk) row[kk] = 0.0;
-        return;
-    }
     const double b_R = cbrt(8.0 * M_PI);
     const double bv = b_R * v_wall;
     const double shift = -log10(bv) * inv_dlog;
     const double s = z[i] / bv;
     const double ub = zterm[i] + shift;
     const int eb = e_base[i / GM_BM];
-    int cur = eb;               // knot whose weight is being accumulated in acc0 (acc1: knot cur + 1)
+    const int per = (nt + WT_LANES - 1) / WT_LANES;
+    const int j0 = lane * per, j1 = min(nt, j0 + per);
+    if (j0 >= j1) return;
+    const double q_first = qT[0], q_last = qT[n_q - 1];
+    int cur = -1, first = -1;
     double acc0 = 0.0, acc1 = 0.0;
-    int kk_written = 0;
-    for (int j = 0; j < nt; ++j) {
+    for (int j = j0; j < j1; ++j) {
         const double x = s * T[j];
         int e = __double2int_rd(ub + LT[j]);
         double w0, w1;
         const double wj = W[j];
-        if (e < 0 || x < qT[0]) { e = 0; w0 = wj; w1 = 0.0; }                       // np.interp left clamp
-        else if (e >= n_q - 1 || x >= qT[n_q - 1]) { e = n_q - 2; w0 = 0.0; w1 = wj; }   // right clamp: all on the last knot
+        if (e < 0 || x < q_first) { e = 0; w0 = wj; w1 = 0.0; }                      // np.interp left clamp
+        else if (e >= n_q - 1 || x >= q_last) { e = n_q - 2; w0 = 0.0; w1 = wj; }    // right clamp: all on the last knot
         else {
-            // arithmetic index may be off by one on a razor edge: the weights then extrapolate the neighbouring
+            // the arithmetic index may be off by one on a razor edge: the weights then extrapolate the neighbouring
             // segment by ~1e-12 of its length, i.e. the same value (continuous interpolant)
             const double x0 = qT[e], x1 = qT[e + 1];
             const double t = (x - x0) / (x1 - x0);
             w0 = wj * (1.0 - t);
             w1 = wj * t;
         }
-        while (cur < e) {       // flush knots that can no longer receive weight
-            if (kk_written < kw) row[kk_written] = acc0;
-            ++kk_written;
+        if (cur < 0) { cur = e; first = e; }
+        while (cur < e) {        // knot `cur` can no longer receive weight from this lane
+            const int kk = cur - eb;
+            if (kk >= 0 && kk < kw) {
+                if (cur <= first + 1) atomicAdd(&row[kk], acc0); else row[kk] = acc0;
+            }
             acc0 = acc1;
             acc1 = 0.0;
             ++cur;
         }
-        // e == cur here (e is non-decreasing in j because u is)
         acc0 += w0;
         acc1 += w1;
     }
-    if (kk_written < kw) row[kk_written] = acc0;
-    ++kk_written;
-    if (kk_written < kw) row[kk_written] = acc1;
-    ++kk_written;
-    for (int kk = kk_written; kk < kw; ++kk) row[kk] = 0.0;
+    int kk = cur - eb;
+    if (kk >= 0 && kk < kw) atomicAdd(&row[kk], acc0);
+    ++kk;
+    if (kk >= 0 && kk < kw) atomicAdd(&row[kk], acc1);
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
@@ -180,9 +185,14 @@ extern "C" int ptt_spec_den_v_group(const ptt_sdv_plan_t* plan, int n_p, const d
     if (n_p == 0) return PTT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int n_tiles = (plan->n_z + GM_BM - 1) / GM_BM;
-    sdv_weights_kernel<<<(n_tiles * GM_BM + 127) / 128, 128, 0, stream>>>(plan->n_q, plan->n_z, plan->nt, plan->qT, plan->z,
-                                                                         plan->zterm, plan->T, plan->LT, plan->W, v_wall,
-                                                                         plan->inv_dlog, kw, e_base, omega);
+    {
+        const cudaError_t e = cudaMemsetAsync(omega, 0, sizeof(double) * (size_t)n_tiles * GM_BM * (size_t)kw, stream);
+        if (e != cudaSuccess) return set_cuda_error("ptt_spec_den_v_group memset", e);
+    }
+    const long long wt_threads = (long long)plan->n_z * WT_LANES;
+    sdv_weights_kernel<<<(unsigned)((wt_threads + 127) / 128), 128, 0, stream>>>(
+        plan->n_q, plan->n_z, plan->nt, plan->qT, plan->z, plan->zterm, plan->T, plan->LT, plan->W, v_wall,
+        plan->inv_dlog, kw, e_base, omega);
     const double b_R = cbrt(8.0 * M_PI);
     const double bv = b_R * v_wall;
     const double factor = 2.0 / (bv * bv * bv * bv * bv * bv);

@@ -597,8 +597,13 @@ __global__ void __launch_bounds__(SDV_THREADS) spec_den_v_kernel(
 }
 
 // --- K7: spec_den_gw_scaled -----------------------------------------------------------------------------------
-constexpr int GW_THREADS = 128;
-constexpr int GW_TT = 256;
+// CTA = (tile of GW_YT wavenumbers y, point): the window of the P_v lookup the tile can touch sits in shared memory as
+// (a_k, b_k).  A warp owns GW_R consecutive y_i; its lanes stride over the integration variable zeta_k, so the
+// per-k tables (zeta_k, log zeta'_k, G_k) are read coalesced once per GW_R evaluations and neighbouring lanes hit the
+// same or adjacent lookup entries (broadcast, no bank conflicts); a shuffle reduction closes the trapezoid sum.
+constexpr int GW_THREADS = 256;
+constexpr int GW_R = 4;
+constexpr int GW_YT = (GW_THREADS / 32) * GW_R;     // 32 wavenumbers per CTA
 
 __global__ void __launch_bounds__(GW_THREADS) spec_den_gw_kernel(
     const int n_zl, const int n_y, const int n_int, const int y_tile, const double* __restrict__ z_lookup,
@@ -608,12 +613,12 @@ __global__ void __launch_bounds__(GW_THREADS) spec_den_gw_kernel(
     const double* __restrict__ slf, const double* __restrict__ scale, double* __restrict__ sd_gw,
     double* __restrict__ pow_gw, double* __restrict__ omgw0, const int win_cap) {
     extern __shared__ double2 s_tab[];
-    __shared__ double s_L1[GW_TT], s_L2[GW_TT], s_Z1[GW_TT], s_Z2[GW_TT], s_G[GW_TT];
     __shared__ double s_red[GW_THREADS];
     const int p = blockIdx.y;
     const int i0 = blockIdx.x * y_tile;
     const int i1 = min(n_y, i0 + y_tile);
     const double* fp = pv + (long long)p * pv_stride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     double umin = INFINITY, umax = -INFINITY;
     for (int i = i0 + threadIdx.x; i < i1; i += GW_THREADS) {
@@ -630,7 +635,7 @@ __global__ void __launch_bounds__(GW_THREADS) spec_den_gw_kernel(
     e_lo = max(0, min(n_zl, e_lo));
     e_hi = max(0, min(n_zl, e_hi));
     const int n_win = e_hi - e_lo + 1;
-    if (n_win > win_cap) {
+    if (n_win > win_cap) {                       // host mis-sized the tile: fail loudly
         for (int i = i0 + threadIdx.x; i < i1; i += GW_THREADS) {
             const long long o = (long long)p * n_y + i;
             if (sd_gw) sd_gw[o] = NAN;
@@ -653,42 +658,45 @@ __global__ void __launch_bounds__(GW_THREADS) spec_den_gw_kernel(
     }
     __syncthreads();
 
-    for (int ib = i0; ib < i1; ib += GW_THREADS) {
-        const int i = ib + threadIdx.x;
-        const bool act = i < i1;
-        const double yi = act ? y[i] : 1.0;
-        const double ub = act ? yterm[i] + 1.0 - (double)e_lo : 0.0;
-        double acc = 0.0;
-        for (int k0 = 0; k0 < n_int; k0 += GW_TT) {
-            const int m = min(GW_TT, n_int - k0);
-            __syncthreads();
-            for (int k = threadIdx.x; k < m; k += GW_THREADS) {
-                s_L1[k] = L1[k0 + k]; s_L2[k] = L2[k0 + k]; s_Z1[k] = Z1[k0 + k]; s_Z2[k] = Z2[k0 + k]; s_G[k] = G[k0 + k];
-            }
-            __syncthreads();
-            if (act) {
+    for (int ib = i0 + warp * GW_R; ib < i1; ib += (GW_THREADS / 32) * GW_R) {
+        double yi[GW_R], ub[GW_R], acc[GW_R];
+#pragma unroll
+        for (int r = 0; r < GW_R; ++r) {
+            const int i = min(ib + r, n_y - 1);
+            yi[r] = y[i];
+            ub[r] = yterm[i] + 1.0 - (double)e_lo;
+            acc[r] = 0.0;
+        }
 #pragma unroll 2
-                for (int k = 0; k < m; ++k) {
-                    int e1 = __double2int_rd(ub + s_L1[k]);
-                    int e2 = __double2int_rd(ub + s_L2[k]);
-                    e1 = max(0, min(n_win - 1, e1));
-                    e2 = max(0, min(n_win - 1, e2));
-                    const double2 t1 = s_tab[e1];
-                    const double2 t2 = s_tab[e2];
-                    const double p1 = fma(t1.y, yi * s_Z1[k], t1.x);
-                    const double p2 = fma(t2.y, yi * s_Z2[k], t2.x);
-                    acc = fma(s_G[k] * p1, p2, acc);
-                }
+        for (int k = lane; k < n_int; k += 32) {
+            const double l1 = L1[k], l2 = L2[k], z1 = Z1[k], z2 = Z2[k], g = G[k];
+#pragma unroll
+            for (int r = 0; r < GW_R; ++r) {
+                int e1 = __double2int_rd(ub[r] + l1);
+                int e2 = __double2int_rd(ub[r] + l2);
+                e1 = max(0, min(n_win - 1, e1));
+                e2 = max(0, min(n_win - 1, e2));
+                const double2 t1 = s_tab[e1];
+                const double2 t2 = s_tab[e2];
+                const double p1 = fma(t1.y, yi[r] * z1, t1.x);
+                const double p2 = fma(t2.y, yi[r] * z2, t2.x);
+                acc[r] = fma(g * p1, p2, acc[r]);
             }
         }
-        if (act) {
-            // p_gw = pref/y * trapz(...) with z = y zeta  =>  pref * y^2 * sum_k G_k P(y zeta_k) P(y zeta'_k)
-            const double sd = prefactor * yi * yi * acc * slf[p];
-            const long long o = (long long)p * n_y + i;
-            if (sd_gw) sd_gw[o] = sd;
-            const double pw = yi * yi * yi / (2.0 * M_PI * M_PI) * sd;
-            if (pow_gw) pow_gw[o] = pw;
-            if (omgw0 && scale) omgw0[o] = scale[p] * pw;
+#pragma unroll
+        for (int r = 0; r < GW_R; ++r) {
+            double a = acc[r];
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+            const int i = ib + r;
+            if (lane == 0 && i < i1) {
+                // p_gw = pref/y * trapz(...) with z = y zeta  =>  pref * y^2 * sum_k G_k P(y zeta_k) P(y zeta'_k)
+                const double sd = prefactor * yi[r] * yi[r] * a * slf[p];
+                const long long o = (long long)p * n_y + i;
+                if (sd_gw) sd_gw[o] = sd;
+                const double pw = yi[r] * yi[r] * yi[r] / (2.0 * M_PI * M_PI) * sd;
+                if (pow_gw) pow_gw[o] = pw;
+                if (omgw0 && scale) omgw0[o] = scale[p] * pw;
+            }
         }
     }
 }
@@ -812,8 +820,8 @@ extern "C" int ptt_spec_den_v_batch(const ptt_sdv_plan_t* plan, int P, const dou
 extern "C" int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const double* pv, int64_t pv_stride,
                                      const double* slf, const double* scale, double* sd_gw, double* pow_gw,
                                      double* omgw0, void* stream_) {
-    if (!plan || P < 0 || !pv || !slf || plan->y_tile < 1)
-        return set_error(PTT_E_ARG, "ptt_spec_den_gw_batch: null pointer or bad size");
+    if (!plan || P < 0 || !pv || !slf || plan->y_tile < 1 || plan->y_tile % GW_R != 0)
+        return set_error(PTT_E_ARG, "ptt_spec_den_gw_batch: null pointer or bad size (y_tile must be a multiple of 4)");
     if (P == 0) return PTT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int smem = plan->smem_bytes;

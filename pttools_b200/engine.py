@@ -453,7 +453,7 @@ def build_gw_tables(z_lookup, y, cs, gamma=GAMMA_DEFAULT, nz_int=None):
     gw = dict(n_int=n_int, L1=lz / dlz, L2=np.log10(zeta2) / dlz, Z1=zeta, Z2=zeta2, G=_trapz_weights(zeta) * kern,
               yterm=(np.log10(y) - lz0) / dlz,
               prefactor=0.75 * gamma ** 2 * ((1 - cs ** 2) / cs ** 2) ** 2 / (4 * np.pi * cs))
-    y_tile = 128
+    y_tile = 32
     span = (gw["yterm"][np.minimum(np.arange(0, y.size, y_tile) + y_tile - 1, y.size - 1)] - gw["yterm"][::y_tile]).max()
     lrange = max(gw["L1"].max(), gw["L2"].max()) - min(gw["L1"].min(), gw["L2"].min())
     gw["y_tile"] = y_tile
