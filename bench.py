@@ -3,7 +3,7 @@
 
 A "step" is one pass of the hot path (fluid shell solve -> A^2 -> spec_den_v -> spec_den_gw -> pow_gw) over one
 batch of points of the 1000 x 1000 BagModel grid v_wall = linspace(0.05, 0.95, 1000) x alpha_n = linspace(0.005, 0.5,
-1000) at the reference's default resolutions.  A batch is a set of complete v_wall rows of the grid (8 rows x 1000
+1000) at the reference's default resolutions.  A batch is a set of complete v_wall rows of the grid (32 rows x 1000
 alpha_n by default, rows spread over the v_wall range with stride 619 mod 1000), i.e. the order in which a grid sweep
 is processed; every step sees deflagrations, hybrids, detonations and no-solution points and no step re-uses another
 step's data.  With N GPUs every rank works on its own batch (weak scaling) and the
@@ -113,16 +113,19 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    per_step = max(cores, 8)
+    per_step = 2 * max(cores, 8)
     times = []
     for s in range(args.warmup + args.steps):
-        vw, an = batch_points(s, 0, 1, per_step)
+        vw, an = batch_points(s, 0, 1, 32000)
+        pick = np.linspace(0, vw.size - 1, per_step).astype(int)      # spread over the rows and strengths of the batch
+        vw, an = vw[pick], an[pick]
         dt = cpu_run(list(zip(vw, an)), cores, args.path)
         if s >= args.warmup:
             times.append(dt)
     total = float(np.sum(times))
     value = per_step * args.steps / total
-    sample = f"{per_step} grid points per step (stride {STRIDE}), {args.steps} steps, fork pool of {cores} processes"
+    sample = (f"{per_step} grid points per step spread evenly over the GPU arm's batch of the same step, "
+              f"{args.steps} steps, fork pool of {cores} processes")
     print(json.dumps({
         "impl": "reference", "metric": "bubble+GW spectra/sec", "value": value, "unit": "spectra/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -312,11 +315,13 @@ def gpu_arm(args):
         cores = len(os.sched_getaffinity(0))
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            n_cpu = max(cores, 8)
-            vw, an = batch_points(0, 0, 1, n_cpu)
-            dt = cpu_run(list(zip(vw, an)), cores, args.path)
+            n_cpu = 4 * max(cores, 8)
+            vw, an = batch_points(0, 0, 1, B)
+            pick = np.linspace(0, B - 1, n_cpu).astype(int)
+            dt = cpu_run(list(zip(vw[pick], an[pick])), cores, args.path)
             cpu = {"value": n_cpu / dt, "unit": "spectra/s", "cores": cores, "kind": "port",
-                   "sample": f"first {n_cpu} points of step 0 (same grid, same sizes), fork pool of {cores} processes, {dt:.1f} s"}
+                   "sample": f"{n_cpu} points spread evenly over the batch of step 0 (same grid, same sizes), "
+                             f"fork pool of {cores} processes, {dt:.1f} s"}
         out = {
             "metric": "bubble+GW spectra/sec", "value": value, "unit": "spectra/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -343,7 +348,7 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8000)
+    ap.add_argument("--batch", type=int, default=32000)
     ap.add_argument("--chunk", type=int, default=2000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="generic", choices=["generic", "bag"])

@@ -12,7 +12,7 @@ constexpr int GEN_SCALARS = 16;
 //             css2, csb2, V_s, V_b, bag_name, 0, 0}
 // scalars[n,16] = {vp, vm, vp_tilde, vm_tilde, v_sh, vm_sh, vm_tilde_sh, wp, wm, wm_sh, v_cj, wn, wn_estimate,
 //                  solver_failed, 0, 0}   (the reference's 17-tuple, fluid.py:1052)
-__global__ void __launch_bounds__(128) generic_solve_kernel(
+__global__ void __launch_bounds__(64) generic_solve_kernel(
     const int n, const double* __restrict__ pg, const int n_xi, const double t_end, const int thin,
     const double wn_rtol, double* __restrict__ rows_v, double* __restrict__ rows_w, double* __restrict__ rows_xi,
     const long long row_stride, int* __restrict__ off, int* __restrict__ npts, double* __restrict__ scalars,
@@ -107,7 +107,7 @@ extern "C" int ptt_sweep_shells_generic(int n, const double* pg, int n_xi, doubl
     double* d_sc = sg.out(scalars, nn * GEN_SCALARS);
     int* d_st = sg.out(status, nn);
     if (!sg.ok()) return sg.fail();
-    generic_solve_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, d_pg, n_xi, t_end, thin_shell_limit, wn_rtol, d_rv, d_rw,
+    generic_solve_kernel<<<(n + 63) / 64, 64, 0, stream>>>(n, d_pg, n_xi, t_end, thin_shell_limit, wn_rtol, d_rv, d_rw,
                                                               d_rx, (long long)row_stride, d_off, d_np, d_sc, d_st);
     return sg.finish("generic_solve_kernel");
 }

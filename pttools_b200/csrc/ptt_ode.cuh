@@ -37,7 +37,9 @@ PTT_HD void rhs(const double cs2, const State& y, State& d) {
     const double v2 = y.v * y.v;
     const double one_xiv = 1.0 - xiv;
     d.v = 2.0 * y.v * cs2 * (1.0 - v2) * one_xiv;
-    d.w = (y.w / (1.0 - v2)) * (xi_v / one_xiv) * (1.0 / cs2 + 1.0) * d.v;
+    // dw = w/(1-v^2) * (xi-v)/(1-xi v) * (1/cs2 + 1) * dv; with dv = 2 v cs2 (1-v^2)(1-xi v) the two quotients cancel
+    // exactly: dw = 2 v w (xi - v) (1 + cs2)  -- no division on the hot path (same value up to rounding)
+    d.w = 2.0 * y.v * y.w * xi_v * (1.0 + cs2);
     d.xi = y.xi * (xi_v * xi_v - cs2 * one_xiv * one_xiv);
 }
 
@@ -147,7 +149,8 @@ struct Dopri5 {
                 failed = true;
                 return false;
             }
-            double fac = (err > 0.0) ? 0.9 * pow(err, -0.2) : 5.0;
+            // step-size factor 0.9 err^(-1/5): single precision is plenty for a step-size heuristic
+            double fac = (err > 0.0) ? 0.9 * (double)powf((float)fmin(fmax(err, 1e-30), 1e30), -0.2f) : 5.0;
             if (fac < 0.2) fac = 0.2;
             if (fac > 5.0) fac = 5.0;
             if (err <= 1.0) {

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) integrate_kernel(
     }
 }
 
-__global__ void __launch_bounds__(128) bag_anmax_kernel(const int n, const double* __restrict__ v_wall,
+__global__ void __launch_bounds__(64) bag_anmax_kernel(const int n, const double* __restrict__ v_wall,
                                                         double* __restrict__ out, int* __restrict__ status) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) bag_anmax_kernel(const int n, const doubl
     if (status) status[i] = st;
 }
 
-__global__ void __launch_bounds__(128) bag_root_kernel(
+__global__ void __launch_bounds__(64) bag_root_kernel(
     const int n, const double* __restrict__ v_wall, const double* __restrict__ alpha_n, const int n_xi,
     const double* __restrict__ an_max, double* __restrict__ alpha_plus, int* __restrict__ sol_type,
     int* __restrict__ status) {
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128) bag_root_kernel(
     status[i] = r.status;
 }
 
-__global__ void __launch_bounds__(128) bag_profile_kernel(
+__global__ void __launch_bounds__(64) bag_profile_kernel(
     const int n, const double* __restrict__ v_wall, const double* __restrict__ alpha_plus,
     const int* __restrict__ sol_type, const int n_xi, const double* __restrict__ w_n, double* __restrict__ rows_v,
     double* __restrict__ rows_w, double* __restrict__ rows_xi, const long long row_stride, int* __restrict__ off,
@@ -163,7 +163,7 @@ extern "C" int ptt_bag_alpha_n_max(int n, const double* v_wall, double* out, int
     double* d_out = sg.out(out, (size_t)n);
     int* d_st = status ? sg.out(status, (size_t)n) : nullptr;
     if (!sg.ok()) return sg.fail();
-    bag_anmax_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, d_vw, d_out, d_st);
+    bag_anmax_kernel<<<(n + 63) / 64, 64, 0, stream>>>(n, d_vw, d_out, d_st);
     return sg.finish("bag_anmax_kernel");
 }
 
@@ -182,7 +182,7 @@ extern "C" int ptt_bag_find_alpha_plus(int n, const double* v_wall, const double
     int* d_ty = sg.out(sol_type, (size_t)n);
     int* d_st = sg.out(status, (size_t)n);
     if (!sg.ok()) return sg.fail();
-    bag_root_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, d_vw, d_an, n_xi, d_am, d_ap, d_ty, d_st);
+    bag_root_kernel<<<(n + 63) / 64, 64, 0, stream>>>(n, d_vw, d_an, n_xi, d_am, d_ap, d_ty, d_st);
     return sg.finish("bag_root_kernel");
 }
 
@@ -206,7 +206,7 @@ extern "C" int ptt_bag_profiles(int n, const double* v_wall, const double* alpha
     double* d_sc = scalars ? sg.out(scalars, 4 * nn) : nullptr;
     int* d_st = sg.inout(status, nn);
     if (!sg.ok()) return sg.fail();
-    bag_profile_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, d_vw, d_ap, d_ty, n_xi, d_wn, d_rv, d_rw, d_rx,
+    bag_profile_kernel<<<(n + 63) / 64, 64, 0, stream>>>(n, d_vw, d_ap, d_ty, n_xi, d_wn, d_rv, d_rw, d_rx,
                                                             (long long)row_stride, d_off, d_np, d_sc, d_st);
     return sg.finish("bag_profile_kernel");
 }
@@ -232,9 +232,9 @@ extern "C" int ptt_sweep_shells_bag(int n, const double* v_wall, const double* a
     double* d_sc = scalars ? sg.out(scalars, 4 * nn) : nullptr;
     int* d_st = sg.out(status, nn);
     if (!sg.ok()) return sg.fail();
-    const int grid = (n + 127) / 128;
-    bag_root_kernel<<<grid, 128, 0, stream>>>(n, d_vw, d_an, n_xi, d_am, d_ap, d_ty, d_st);
-    bag_profile_kernel<<<grid, 128, 0, stream>>>(n, d_vw, d_ap, d_ty, n_xi, nullptr, d_rv, d_rw, d_rx,
+    const int grid = (n + 63) / 64;
+    bag_root_kernel<<<grid, 64, 0, stream>>>(n, d_vw, d_an, n_xi, d_am, d_ap, d_ty, d_st);
+    bag_profile_kernel<<<grid, 64, 0, stream>>>(n, d_vw, d_ap, d_ty, n_xi, nullptr, d_rv, d_rw, d_rx,
                                                  (long long)row_stride, d_off, d_np, d_sc, d_st);
     return sg.finish("ptt_sweep_shells_bag");
 }

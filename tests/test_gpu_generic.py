@@ -123,3 +123,35 @@ def test_create_spectra_grid_api():
     assert objs.shape == (2, 2)
     assert objs[0, 0].bubble.v_wall == 0.5 and objs[1, 1].bubble.alpha_n == 0.15
     assert np.all(np.isfinite(objs[0, 1].pow_gw)) and objs[0, 1].omgw0().shape == (100,)
+
+
+def test_spectrum_chain_through_grouped_matrix_product():
+    """Same fixtures as above with the banded-GEMM spec_den_v forced on (runs of equal v_wall of any length)."""
+    from pttools_b200 import engine, sweep
+    d = np.load(os.path.join(GOLDEN, "ref_generic_spectra.npz"))
+    model = _models()["bag"]
+    pts = d["bag__points"]
+    old = engine.GROUP_MIN
+    engine.GROUP_MIN = 1
+    try:
+        res = sweep.sweep_spectra(model, pts[:, 0], pts[:, 1], y=d["y"], r_star=0.1).numpy()
+    finally:
+        engine.GROUP_MIN = old
+    for i in range(len(pts)):
+        np.testing.assert_allclose(res.pow_v[i], d[f"bag__pow_v_{i}"], rtol=1e-5)
+        np.testing.assert_allclose(res.omgw0[i], d[f"bag__omgw0_{i}"], rtol=1e-5)
+
+
+def test_unsorted_input_order_is_restored():
+    from pttools_b200 import sweep
+    model = _models()["bag"]
+    vw = np.array([0.7, 0.5, 0.9, 0.5])
+    an = np.array([0.1, 0.1, 0.1, 0.2])
+    y = np.logspace(-1, 3, 60)
+    kw = dict(y=y, r_star=0.1, nt=300, n_z_lookup=400, n_xi=1000)
+    res = sweep.sweep_spectra(model, vw, an, **kw).numpy()
+    np.testing.assert_array_equal(res.v_wall, vw)
+    for i in range(4):
+        one = sweep.sweep_spectra(model, vw[i:i + 1], an[i:i + 1], **kw).numpy()
+        np.testing.assert_allclose(res.pow_gw[i], one.pow_gw[0], rtol=1e-12)
+        np.testing.assert_allclose(res.scalars["kappa"][i], one.scalars["kappa"][0], rtol=1e-12)
