@@ -667,9 +667,16 @@ __global__ void __launch_bounds__(GW_THREADS) spec_den_gw_kernel(
             ub[r] = yterm[i] + 1.0 - (double)e_lo;
             acc[r] = 0.0;
         }
+        // L1 is linspace(log zeta_-, log zeta_+)/dlog: regenerate it (same formula as numpy's linspace), and
+        // zeta'_k = (zeta_+ + zeta_-) - zeta_k: two of the five per-k tables need no load
+        const double l1_0 = L1[0];
+        const double dl1 = (n_int > 1) ? (L1[n_int - 1] - l1_0) / (double)(n_int - 1) : 0.0;
+        const double zsum = Z1[0] + Z2[0];
 #pragma unroll 2
         for (int k = lane; k < n_int; k += 32) {
-            const double l1 = L1[k], l2 = L2[k], z1 = Z1[k], z2 = Z2[k], g = G[k];
+            const double l2 = L2[k], z1 = Z1[k], g = G[k];
+            const double l1 = fma((double)k, dl1, l1_0);
+            const double z2 = zsum - z1;
 #pragma unroll
             for (int r = 0; r < GW_R; ++r) {
                 int e1 = __double2int_rd(ub[r] + l1);
