@@ -273,9 +273,12 @@ class BagModel(Model):
             a_s_def = 1.1 * a_b_ if a_s is None else a_s
             a_s = min(a_s_def, a_b_ / (1 - 3 * alpha_n_min * 0.999))
             a_b = a_b_
+        if (1.1 * (1.0 if a_b is None else a_b) if a_s is None else a_s) <= (1.0 if a_b is None else a_b):
+            raise ValueError("The bag model must have a_s > a_b for the critical temperature to be non-negative. "
+                             f"Got: a_s={a_s}, a_b={a_b}")                       # bag.py:76-80
+        if V_s <= V_b and not kw.get("allow_invalid", False):
+            raise ValueError(f"The bubble will not expand in the Bag model, when V_s <= V_b. Got: V_s = V_b = {V_s}")
         super().__init__(1 / 3, 1 / 3, V_s=V_s, V_b=V_b, a_s=a_s, a_b=a_b, name=name, **kw)
-        if self.a_s <= self.a_b:
-            raise ValueError("The bag model must have a_s > a_b for the critical temperature to be non-negative.")
 
     def theta(self, w, phase):
         return (self.V_b * phase + self.V_s * (1 - phase)) * np.ones_like(w)     # bag.py:311-316

@@ -1,0 +1,113 @@
+"""GPU: the reference-facing call surface (names, argument meaning, error behaviour) on top of the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import shell_bag as sb
+from oracle import ssm as ossm
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_xi_v_plane_golden_through_fluid_integrate_param():
+    """tests/paper/test_plane.py of the reference: 9 deflagration curves, tau = -+100, 1000 samples, summed.  The
+    reference accepts other integrators at 8e-4 ... 2e-2 against its odeint golden; here 1e-5."""
+    from pttools_b200.bubble import fluid_integrate_param
+    golden = np.load(os.path.join(GOLDEN, "ref_goldens.npz"))["xi_v_plane"]
+    n_xi = 1000
+    data = np.zeros((6, 9, n_xi))
+    for i, xi0 in enumerate(np.linspace(1 / 10, 1 - 1 / 10, 9)):
+        vb, wb, xb, t = fluid_integrate_param(xi0, 1, xi0, phase=0., t_end=-100., n_xi=n_xi)
+        vf, wf, xf, _ = fluid_integrate_param(xi0, 1, xi0, phase=0., t_end=100., n_xi=n_xi)
+        assert t[0] == 0.0 and t[-1] == -100.0
+        vb = vb.copy()
+        with np.errstate(invalid="ignore"):
+            vb[vb < sb.v_shock_bag(xb)] = np.nan
+        data[:, i, :] = [vb, wb, xb, vf, wf, xf]
+    got = np.nansum(data, axis=2)
+    np.testing.assert_allclose(got[1:], golden[1:], rtol=1e-5)
+    np.testing.assert_allclose(got[0, :2], golden[0, :2], rtol=1e-5)
+
+
+def test_old_bag_api_functions():
+    from pttools_b200 import bubble
+    from pttools_b200.models import SolutionType
+    assert bubble.identify_solution_type_bag(0.5, 0.1) == SolutionType.SUB_DEF
+    assert bubble.identify_solution_type_bag(0.7, 0.1) == SolutionType.HYBRID
+    assert bubble.identify_solution_type_bag(0.9, 0.1) == SolutionType.DETON
+    assert bubble.identify_solution_type_bag(0.2, 0.45) == SolutionType.ERROR
+    np.testing.assert_allclose(bubble.alpha_n_max_bag(0.5), sb.alpha_n_max_deflagration(0.5), rtol=5e-7)
+    np.testing.assert_allclose(bubble.find_alpha_plus_bag(0.5, 0.1), sb.find_alpha_plus(0.5, 0.1), rtol=5e-7)
+    assert np.isnan(bubble.find_alpha_plus_bag(0.2, 0.45))
+    ap = bubble.find_alpha_plus_bag(np.array([0.5, 0.7]), 0.1)
+    assert ap.shape == (2,)
+    v, w, xi = bubble.sound_shell_bag(0.2, 0.45)
+    assert v.size == 1 and np.isnan(v[0])                       # fluid_bag.py:61-73
+    with pytest.raises(ValueError):
+        bubble.sound_shell_bag(1.5, 0.1)
+    v, w, xi = bubble.sound_shell_alpha_plus(0.5, 0.0841, SolutionType.SUB_DEF, n_xi=1000)
+    vo, wo, xio = sb.shell_alpha_plus(0.5, 0.0841, sb.SUB_DEF, 1000)
+    assert v.size == vo.size
+    np.testing.assert_allclose(v, vo, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        bubble.fluid_integrate_param(float("nan"), 1.0, 0.5, phase=0., t_end=-50., n_xi=100)   # integrate.py:133
+
+
+def test_ssmtools_wrappers_and_errors():
+    from pttools_b200 import ssmtools as ssm
+    z = np.logspace(-1, 3, 80)
+    npt = (800, 300, 400)
+    got = ssm.power_gw_scaled_bag(z, (0.5, 0.1), npt=npt)
+    np.testing.assert_allclose(got, ossm.power_gw_scaled_bag(z, (0.5, 0.1), npt=npt), rtol=1e-5)
+    got = ssm.power_v_bag(z, (0.7, 0.1, ssm.NucType.SIMULTANEOUS, (1.,)), npt=npt)
+    np.testing.assert_allclose(got, ossm.power_v_bag(z, (0.7, 0.1, "simultaneous", (1.,)), npt=npt), rtol=1e-5)
+    with pytest.raises(ValueError):
+        ssm.power_gw_scaled_bag(np.array([0.0, 1.0]), (0.5, 0.1))            # spectrum.py:277-278
+    with pytest.raises(ValueError):
+        ssm.power_gw_scaled_bag(z, (0.2, 0.6))                               # check_physical_params
+    # spec_den_gw_scaled with and without y (spectrum.py:371-399)
+    x = ssm.gen_lookup(z, ssm.CS0, 400, eps=1e-8)
+    sdv = ossm.spec_den_v_bag(x, (0.5, 0.1), npt)
+    p1, y1 = ssm.spec_den_gw_scaled(x, sdv, z)
+    p2, y2 = ossm.spec_den_gw_scaled(x, sdv, z)
+    np.testing.assert_allclose(p1, p2, rtol=1e-10)
+    p1, y1 = ssm.spec_den_gw_scaled(x, sdv)
+    p2, y2 = ossm.spec_den_gw_scaled(x, sdv)
+    np.testing.assert_allclose(y1, y2, rtol=1e-14)
+    np.testing.assert_allclose(p1, p2, rtol=1e-10)
+    with pytest.raises(TypeError):
+        ssm.spec_den_gw_scaled(x, sdv[:-1], z)
+    with pytest.raises(ValueError):
+        ssm.spec_den_gw_scaled(x, sdv, z * 10)                               # "Range of z_lookup is not large enough."
+    # sin_transform: scalar and array z, oracle profile
+    v, w, xi = sb.sound_shell_bag(0.5, 0.1, 800)
+    np.testing.assert_allclose(ssm.sin_transform(z, xi, v), ossm.sin_transform(z, xi, v), rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(ssm.sin_transform(3.0, xi, v), np.trapezoid(v * np.sin(3.0 * xi), xi), rtol=1e-10)
+    np.testing.assert_allclose(ssm.pow_spec(z, np.ones_like(z)), z ** 3 / (2 * np.pi ** 2))
+    a2 = ssm.a2_e_conserving_bag(z, 0.5, 0.1, npt=npt)[0]
+    np.testing.assert_allclose(a2, ossm.a2_e_conserving_bag(z, 0.5, 0.1, npt)[0], rtol=1e-5, atol=1e-12 * a2.max())
+
+
+def test_bubble_constructor_errors():
+    from pttools_b200.bubble import Bubble
+    from pttools_b200.models import BagModel, ConstCSModel
+    m = BagModel(a_s=1.1, a_b=1, V_s=1)
+    with pytest.raises(ValueError):
+        Bubble(m, 1.2, 0.1)                                  # bubble.py:57-58
+    with pytest.raises(ValueError):
+        Bubble(m, 0.5, 0.01)                                 # alpha_n below alpha_n_min (model.py:813-820)
+    with pytest.raises(ValueError):
+        Bubble(m, 0.2, 0.45)                                 # no solution type (transition.py:47-69)
+    with pytest.raises(ValueError):
+        BagModel(a_s=0.9, a_b=1, V_s=1)                      # bag.py:76-80
+    b = Bubble(ConstCSModel(1 / 4, 1 / 3, a_s=1.5, a_b=1, V_s=1), 0.5, 0.2, solve=False)
+    assert not b.solved
+    from pttools_b200.bubble import NotYetSolvedError
+    with pytest.raises(NotYetSolvedError):
+        b.kappa
+    b.solve()
+    assert b.solved and 0 < b.kappa < 1 and b.phase.size == b.xi.size
+    data = b.export()
+    assert data["v_wall"] == 0.5 and data["model"]["css2"] == 0.25
