@@ -202,6 +202,25 @@ typedef struct ptt_gw_plan {
 int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const double* pv, int64_t pv_stride, const double* slf,
                           const double* scale, double* sd_gw, double* pow_gw, double* omgw0, void* stream);
 
+/* spec_den_gw_scaled, cell formulation for large batches (same trapezoid sum over the same samples, regrouped by runs of
+ * samples that share both np.interp segments; spectrum.py:327-368).  The cells depend on the plan only:
+ *   cap   = ptt_gw_cells_capacity(n_zl, n_int, lrange), lrange = max(L1, L2) - min(L1, L2) of the plan
+ *   ptt_gw_cells_build fills ncell[n_y] (-1: cap too small), meta[n_y, cap], coef[n_y, cap, 4]   (device memory)
+ * table: device scratch of ptt_gw_cells_table_size(n_zl, P) doubles.  Outputs as ptt_spec_den_gw_batch. */
+typedef struct ptt_gw_cells {
+    int32_t cap;
+    int32_t reserved;
+    const int32_t* ncell;
+    const int32_t* meta;
+    const double* coef;
+} ptt_gw_cells_t;
+int ptt_gw_cells_capacity(int n_zl, int n_int, double lrange);
+int ptt_gw_cells_build(const ptt_gw_plan_t* plan, int cap, int32_t* ncell, int32_t* meta, double* coef, void* stream);
+int64_t ptt_gw_cells_table_size(int n_zl, int P);
+int ptt_spec_den_gw_cells_batch(const ptt_gw_plan_t* plan, const ptt_gw_cells_t* cells, int P, const double* pv,
+                                int64_t pv_stride, const double* slf, const double* scale, double* table,
+                                double* sd_gw, double* pow_gw, double* omgw0, void* stream);
+
 /* pow_spec(z, spec_den) = z^3/(2 pi^2) spec_den, row-wise                         spectrum.py:230-240 */
 int ptt_pow_spec_batch(int P, int n_z, const double* z, const double* spec_den, int64_t stride, double* out,
                        void* stream);

@@ -44,6 +44,11 @@ class GwPlan(C.Structure):
                 ("prefactor", C.c_double), ("smem_bytes", C.c_int32), ("reserved", C.c_int32)]
 
 
+class GwCells(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("reserved", C.c_int32), ("ncell", C.c_void_p), ("meta", C.c_void_p),
+                ("coef", C.c_void_p)]
+
+
 # name -> (restype, argtypes); the test-suite checks that every symbol of include/pttools_b200.h is here and exported
 SIGNATURES = {
     "ptt_last_error": (C.c_char_p, []),
@@ -72,6 +77,12 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ptt_spec_den_gw_batch": (C.c_int, [C.POINTER(GwPlan), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ptt_gw_cells_capacity": (C.c_int, [C.c_int, C.c_int, C.c_double]),
+    "ptt_gw_cells_build": (C.c_int, [C.POINTER(GwPlan), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ptt_gw_cells_table_size": (C.c_int64, [C.c_int, C.c_int]),
+    "ptt_spec_den_gw_cells_batch": (C.c_int, [C.POINTER(GwPlan), C.POINTER(GwCells), C.c_int, C.c_void_p, C.c_int64,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]),
     "ptt_pow_spec_batch": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ptt_generic_row_capacity": (C.c_int, [C.c_int]),
     "ptt_sweep_shells_generic": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_void_p,

@@ -14,7 +14,7 @@ import typing as tp
 import numpy as np
 
 from . import _lib
-from ._lib import A2Plan, Eos, GwPlan, SdvPlan
+from ._lib import A2Plan, Eos, GwCells, GwPlan, SdvPlan
 
 N_XI_DEFAULT = 5000
 Y_DEFAULT = np.logspace(-1, 3, 1000)
@@ -645,7 +645,43 @@ def spec_den_v_auto(plan: SsmPlan, ipass: int, a2, v_wall):
     return out
 
 
-def spec_den_gw_batch(plan: SsmPlan, pv, slf=None, scale=None, want_sd=True):
+GW_CELLS_MIN = 128      # smallest batch for which building/using the per-plan cell tables pays
+USE_GW_CELLS = True
+
+
+def gw_cells(plan):
+    """Cell tables of the GW integral for this plan (csrc/ptt_gw_cells.cu), built on the device on first use."""
+    cached = getattr(plan, "_gw_cells", None)
+    if cached is not None:
+        return cached
+    torch = _torch()
+    lib = _lib.load()
+    g = plan.gw
+    lrange = max(g["L1"].max(), g["L2"].max()) - min(g["L1"].min(), g["L2"].min())
+    n_zl, n_y = int(plan.z_lookup.size), int(plan.y.size)
+    cap = lib.ptt_gw_cells_capacity(n_zl, int(g["n_int"]), float(lrange))
+    if cap <= 0:
+        raise _lib.PttError("ptt_gw_cells_capacity: sizes out of range")
+    ncell = torch.empty(n_y, dtype=torch.int32, device="cuda")
+    meta = torch.zeros((n_y, cap), dtype=torch.int32, device="cuda")
+    coef = torch.zeros((n_y, cap, 4), dtype=torch.float64, device="cuda")
+    with STAGES.stage("gw_cells_build", 1):
+        _lib.check(lib.ptt_gw_cells_build(C.byref(plan.gw_plan), cap, _ptr(ncell), _ptr(meta), _ptr(coef),
+                                          _stream_ptr(torch)), "ptt_gw_cells_build")
+    if int(ncell.min().item()) < 0:
+        raise _lib.PttError("ptt_gw_cells_build: cell capacity exceeded")
+    used = int(ncell.max().item())
+    if used < cap:                       # keep only what is used (the tables stay resident with the plan)
+        meta, coef = meta[:, :used].contiguous(), coef[:, :used].contiguous()
+        cap = used
+    cells = GwCells(cap=cap, reserved=0, ncell=ncell.data_ptr(), meta=meta.data_ptr(), coef=coef.data_ptr())
+    plan._gw_cells = (cells, ncell, meta, coef)
+    return plan._gw_cells
+
+
+def spec_den_gw_batch(plan: SsmPlan, pv, slf=None, scale=None, want_sd=True, cells=None):
+    """spec_den_gw_scaled + pow_spec (+ omgw0 scale) for a batch.  cells=None: the cell formulation for batches of
+    GW_CELLS_MIN profiles or more, the per-sample kernel below that; True / False force one of them."""
     torch = _torch()
     lib = _lib.load()
     P = pv.shape[0]
@@ -656,6 +692,16 @@ def spec_den_gw_batch(plan: SsmPlan, pv, slf=None, scale=None, want_sd=True):
     sd = torch.empty((P, n_y), dtype=torch.float64, device=dev) if want_sd else None
     pw = torch.empty((P, n_y), dtype=torch.float64, device=dev)
     om = torch.empty((P, n_y), dtype=torch.float64, device=dev) if scale_t is not None else None
+    if cells is None:
+        cells = USE_GW_CELLS and P >= GW_CELLS_MIN
+    if cells:
+        cs = gw_cells(plan)[0]
+        table = torch.empty(lib.ptt_gw_cells_table_size(int(plan.z_lookup.size), P), dtype=torch.float64, device=dev)
+        with STAGES.stage("spec_den_gw_cells", 2):
+            _lib.check(lib.ptt_spec_den_gw_cells_batch(C.byref(plan.gw_plan), C.byref(cs), P, _ptr(pv), pv.shape[1],
+                                                       _ptr(slf_t), _ptr(scale_t), _ptr(table), _ptr(sd), _ptr(pw),
+                                                       _ptr(om), _stream_ptr(torch)), "ptt_spec_den_gw_cells_batch")
+        return sd, pw, om
     with STAGES.stage("spec_den_gw", 1):
         _lib.check(lib.ptt_spec_den_gw_batch(C.byref(plan.gw_plan), P, _ptr(pv), pv.shape[1], _ptr(slf_t), _ptr(scale_t),
                                              _ptr(sd), _ptr(pw), _ptr(om), _stream_ptr(torch)), "ptt_spec_den_gw_batch")

@@ -184,3 +184,36 @@ def test_grouped_gemm_spec_den_v_matches_gather_kernel():
     got = engine.spec_den_v_auto(plan, 1, a2, engine.dev_f64(vw)).cpu().numpy()
     ref = engine.spec_den_v_batch(plan, 1, a2, engine.dev_f64(vw)).cpu().numpy()
     np.testing.assert_allclose(got, ref, rtol=1e-11)
+
+
+@pytest.mark.parametrize("sizes", [(300, 1800, None), (64, 700, 333), (1000, 10000, None)])
+def test_gw_cell_formulation_matches_per_sample_kernel(sizes):
+    """K7' (cells of constant np.interp segments, lanes over profiles) against K7 (one lookup pair per sample) and, at
+    the small sizes, against the oracle's spec_den_gw_scaled; includes a ragged batch and a NaN profile."""
+    import torch
+    from pttools_b200 import engine
+    n_y, n_zl, nz_int = sizes
+    rng = np.random.default_rng(11)
+    y = np.logspace(-1, 3, n_y)
+    z_lookup = ssm.gen_lookup(y, sb.CS0, n_zl)
+    plan = engine.GwOnlyPlan(z_lookup, y, cs=sb.CS0, nz_int=nz_int)
+    n_p = 150 if n_zl < 5000 else 70
+    shape = z_lookup[None, :] ** rng.uniform(1, 4, (n_p, 1)) / (1 + (z_lookup[None, :] / rng.uniform(1, 30, (n_p, 1))) ** 8)
+    pv_h = shape * (1 + 0.3 * np.sin(3 * np.log(z_lookup))[None, :] * rng.uniform(0, 1, (n_p, 1)))
+    pv_h[7] = np.nan
+    pv = torch.as_tensor(pv_h, device="cuda")
+    slf = torch.as_tensor(rng.uniform(0.5, 2, n_p), device="cuda")
+    scale = torch.as_tensor(rng.uniform(1e-6, 1e-5, n_p), device="cuda")
+    a = engine.spec_den_gw_batch(plan, pv, slf, scale, cells=False)
+    b = engine.spec_den_gw_batch(plan, pv, slf, scale, cells=True)
+    for x, c in zip(a, b):
+        x, c = x.cpu().numpy(), c.cpu().numpy()
+        assert np.all(np.isnan(c[7]))
+        ok = np.arange(n_p) != 7
+        np.testing.assert_allclose(c[ok], x[ok], rtol=1e-11)
+    if n_zl < 5000:
+        sd = b[0].cpu().numpy()
+        for i in (0, 3, 149):
+            ref = ssm.spec_den_gw_scaled(z_lookup, pv_h[i], y, sb.CS0, source_lifetime_factor=float(slf[i]),
+                                         nz_int=nz_int)[0]
+            np.testing.assert_allclose(sd[i], ref, rtol=1e-10)
