@@ -242,13 +242,17 @@ def gpu_arm(args):
     t_wall = time.perf_counter()
     ev0.record()
     n_ok = 0
+    step_ev = [ev0]
     for s in range(args.warmup, total_steps):
         res = device_step(s, *inputs[s])
         n_ok += int((res.status == 0).sum())
+        step_ev.append(torch.cuda.Event(enable_timing=True))
+        step_ev[-1].record()
     ev1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall
     dev_ms = ev0.elapsed_time(ev1)
+    per_step_ms = [a.elapsed_time(b) for a, b in zip(step_ev[:-1], step_ev[1:])]
     stage_ms = engine.STAGES.summary()
     launches = engine.STAGES.launches - launches0
     engine.STAGES.enable(False)
@@ -297,6 +301,9 @@ def gpu_arm(args):
             # 25 flop per (y_i, z_k) integrand with two lookups
             "spec_den_gw": 25.0 * Y.size * plan.gw["n_int"] * n_launch_pts,
         }
+        if "spec_den_gw_cells" in stage_ms:
+            # cell formulation: 2 mul + 4 fma per (wavenumber, cell, profile); cells counted from the plan's tables
+            alg["spec_den_gw_cells"] = 10.0 * float(engine.gw_cells(plan)[1].sum().item()) * n_launch_pts
         if "spec_den_v_group" in stage_ms:
             # banded matrix product: 2 flop per (z_i, knot, profile) MAC over the band + the weight build; per launch =
             # one v_wall row of the grid (1000 profiles)
@@ -329,7 +336,7 @@ def gpu_arm(args):
             "config": {"workload": WORKLOADS[args.path], "batch_per_gpu_per_step": B, "chunk": args.chunk,
                        "l2": "per-step working set (profiles + A2 + lookup tables, ~1 MB per point) exceeds the 126 MB L2; "
                              "every step uses fresh points",
-                       "valid_points_in_timed_region": n_ok, "wall_ms_per_step": wall_ms / args.steps},
+                       "valid_points_in_timed_region": n_ok, "per_step_ms": per_step_ms, "wall_ms_per_step": wall_ms / args.steps},
             "clocks": clocks,
             "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "spectra/s", "h2d_bytes_per_step": 2 * 8 * B,
                     "d2h_bytes_per_step": 8 * B * int(Y.size), "steps": e2e_steps},
