@@ -16,8 +16,11 @@ constexpr int ENV_SIZE = 16;   // xi1, xi_w, xi2, f1, f_m, f_p, f2, valid, ...
 constexpr int MOM_NB = 128;                    // blocks over xi in [0, 1]
 constexpr int MOM_J = 12;                      // moments per block: sum_k g_k delta_k^j / j!,  j = 0..11
 constexpr int MOM_HDR = 8;                     // {b_lo, b_hi, ...}
-constexpr int MOM_SIZE = MOM_HDR + MOM_NB * MOM_J;
+constexpr int MOM_LEVELS = 8;                  // level l: 2^l blocks of width 2^-l; level 7 is the finest (MOM_NB)
+constexpr int MOM_BLOCKS = 2 * MOM_NB - 1;     // pyramid, level l starts at block 2^l - 1
+constexpr int MOM_SIZE = MOM_HDR + MOM_BLOCKS * MOM_J;
 constexpr double MOM_W = 1.0 / MOM_NB;
+constexpr double MOM_ZW = 0.4;                 // a block of width W serves z W <= 0.4
 constexpr double MOM_ZMAX = 51.2;              // (z W / 2)^12 / 12! < 1e-17 for z <= 51.2
 constexpr double FOUR_PI = 12.566370614359172953850573533118;
 
@@ -342,9 +345,10 @@ __global__ void __launch_bounds__(ST_THREADS) sin_transform_kernel(
 // The moments do not depend on z, the series converges to 1e-17 for z W / 2 <= 0.2, and sin/cos(z c_b) advance by a
 // constant rotation.  Same sum, ~N_xi / 6 times fewer flops than one sine per (z, xi) pair.
 __device__ void block_moments(const double* __restrict__ xi, const double* __restrict__ g, const int n,
-                              double* __restrict__ mom /* MOM_SIZE, global */, double* s_m /* MOM_NB*MOM_J shared */,
+                              double* __restrict__ mom /* MOM_SIZE, global */, double* s_pyr /* MOM_BLOCKS*MOM_J shared */,
                               int* s_lohi /* 2 shared */) {
     const int tid = threadIdx.x, nt = blockDim.x;
+    double* s_m = s_pyr + (MOM_NB - 1) * MOM_J;       // finest level
     for (int i = tid; i < MOM_NB * MOM_J; i += nt) s_m[i] = 0.0;
     if (tid == 0) { s_lohi[0] = MOM_NB; s_lohi[1] = -1; }
     __syncthreads();
@@ -384,7 +388,29 @@ __device__ void block_moments(const double* __restrict__ xi, const double* __res
         atomicMax(&s_lohi[1], cur);
     }
     __syncthreads();
-    for (int i = tid; i < MOM_NB * MOM_J; i += nt) mom[MOM_HDR + i] = s_m[i];
+    // Coarser levels by merging pairs of blocks: with delta' = delta + s (s = -+ half a child width),
+    //   M'_j = sum_children sum_{i<=j} s^(j-i)/(j-i)! M_i   - exact algebra, no new truncation.
+    for (int l = MOM_LEVELS - 2; l >= 0; --l) {
+        const int nb = 1 << l;
+        const double sh = 0.25 / (double)nb;            // half the child width
+        const double* child = s_pyr + (2 * nb - 1) * MOM_J;
+        double* par = s_pyr + (nb - 1) * MOM_J;
+        for (int i = tid; i < nb * MOM_J; i += nt) {
+            const int b = i / MOM_J, j = i - b * MOM_J;
+            const double* cl = child + (2 * b) * MOM_J;
+            const double* cr = cl + MOM_J;
+            double accl = 0.0, accr = 0.0, pw = 1.0;     // pw = sh^(j-i)/(j-i)!
+            for (int q = j; q >= 0; --q) {
+                // left child: centre = parent centre - sh  =>  delta' = delta - sh;  right child: delta' = delta + sh
+                accl = fma(((j - q) & 1) ? -pw : pw, cl[q], accl);
+                accr = fma(pw, cr[q], accr);
+                pw *= sh / (double)(j - q + 1);
+            }
+            par[i] = accl + accr;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < MOM_BLOCKS * MOM_J; i += nt) mom[MOM_HDR + i] = s_pyr[i];
     if (tid == 0) {
         mom[0] = (double)s_lohi[0];
         mom[1] = (double)s_lohi[1];
@@ -397,7 +423,7 @@ __global__ void __launch_bounds__(256) a2_moments_kernel(const int nxi, const do
                                                          const int* __restrict__ off, const int* __restrict__ npts,
                                                          double* __restrict__ work, const long long work_stride,
                                                          const WorkLayout lay) {
-    __shared__ double s_m[MOM_NB * MOM_J];
+    __shared__ double s_m[MOM_BLOCKS * MOM_J];
     __shared__ int s_lohi[2];
     const int p = blockIdx.x;
     const int N = npts[p];
@@ -413,18 +439,25 @@ __global__ void __launch_bounds__(256) a2_moments_kernel(const int nxi, const do
 
 constexpr int STM_THREADS = 256;
 
-// exact transform of one function from its moments, for this thread's z
-__device__ __forceinline__ double moment_transform(const double* __restrict__ s_mom, const double z) {
-    const int b_lo = (int)s_mom[0], b_hi = (int)s_mom[1];
-    if (b_hi < b_lo) return 0.0;
+// exact transform of one function from its moment pyramid, for this thread's z: the coarsest level whose blocks
+// satisfy z W <= MOM_ZW
+__device__ __forceinline__ double moment_transform(const double* __restrict__ mom, const double z) {
+    const int b_lo7 = (int)mom[0], b_hi7 = (int)mom[1];
+    if (b_hi7 < b_lo7) return 0.0;
+    int l = 0;
+    while (l < MOM_LEVELS - 1 && z > MOM_ZW * (double)(1 << l)) ++l;
+    const int nb = 1 << l;
+    const double W = 1.0 / (double)nb;
+    const int b_lo = b_lo7 >> (MOM_LEVELS - 1 - l), b_hi = b_hi7 >> (MOM_LEVELS - 1 - l);
+    const double* lev = mom + MOM_HDR + (nb - 1) * MOM_J;
     const double z2 = -z * z;
     double sb, cb;
-    sincos(z * ((double)b_lo + 0.5) * MOM_W, &sb, &cb);
+    sincos(z * ((double)b_lo + 0.5) * W, &sb, &cb);
     double sw, cw;
-    sincos(z * MOM_W, &sw, &cw);
+    sincos(z * W, &sw, &cw);
     double acc = 0.0;
     for (int b = b_lo; b <= b_hi; ++b) {
-        const double* m = s_mom + MOM_HDR + b * MOM_J;
+        const double* m = lev + b * MOM_J;
         // Horner in -z^2: even and odd moments
         double C = m[10], S = m[11];
         C = fma(C, z2, m[8]);  S = fma(S, z2, m[9]);
@@ -446,8 +479,6 @@ __device__ __forceinline__ double moment_transform(const double* __restrict__ s_
 __global__ void __launch_bounds__(STM_THREADS) sin_transform_moments_kernel(
     const int n_z, const double* __restrict__ z_all, const double* __restrict__ frac_all,
     const int* __restrict__ npts, double* __restrict__ work, const long long work_stride, const WorkLayout lay) {
-    __shared__ double s_mv[MOM_SIZE];
-    __shared__ double s_ml[MOM_SIZE];
     const int p = blockIdx.y;
     double* wk = work + (long long)p * work_stride;
     const int iz = blockIdx.x * STM_THREADS + threadIdx.x;
@@ -457,16 +488,10 @@ __global__ void __launch_bounds__(STM_THREADS) sin_transform_moments_kernel(
     const int need_exact = __syncthreads_or((active && frac < 1.0) ? 1 : 0);
     const int N = npts[p];
     double accA = 0.0, accB = 0.0;
-    if (need_exact && N >= 3) {
-        for (int i = threadIdx.x; i < MOM_SIZE; i += STM_THREADS) {
-            s_mv[i] = wk[lay.mom_v() + i];
-            s_ml[i] = wk[lay.mom_l() + i];
-        }
-        __syncthreads();
-        if (frac < 1.0) {
-            accA = moment_transform(s_mv, z);
-            accB = moment_transform(s_ml, z);
-        }
+    if (need_exact && N >= 3 && frac < 1.0) {
+        // the lanes of a warp walk the same blocks of the same level (z is ascending): uniform, L1-resident loads
+        accA = moment_transform(wk + lay.mom_v(), z);
+        accB = moment_transform(wk + lay.mom_l(), z);
     }
     if (!active) return;
     const double pref = FOUR_PI / z;
