@@ -119,184 +119,24 @@ struct GenericShockLocator {
     }
 };
 
-struct DeflagResult {
-    int status;         // ST_OK or a failure code (the reference returns DEFLAGRATION_NAN)
-    double vp, vp_tilde, wp;
-    double t_end_final; // end time of the accepted integration (after the thin-shell loop)
-    int i_shock;        // samples [0, i_shock) are kept
-    State sh;           // sample i_shock - 1: (vm_sh, wm_sh, xi_sh)
-    double wn_estimate;
-};
+// ---------------------------------------------------------------------------------------------------------------
+// The solver as a resumable machine.
+//
+// sound_shell_generic is a nest of loops (root finder -> residual -> thin-shell attempts -> ODE integration ->
+// samples).  Written as nested calls, every lane of a warp sits in its own copy of the integration loop at its own
+// place in the nest and the warp serialises (measured: 4.7 of 32 lanes active).  Here the nest is turned inside out:
+// the ONLY integration call site is in the driver loop of generic_solve_point, and everything around it is a state
+// machine that consumes the result of one integration and prepares the next one.  All lanes of a warp are then in
+// the same integration loop, whatever phase of the algorithm each of them is in.  The arithmetic and its order are
+// those of the nested formulation (fluid.py:121-288, 606-669, 697-843, 848-1052).
 
-// sound_shell_deflagration_common (fluid.py:121-288) in locate mode: everything but the profile arrays.
-PTT_HD DeflagResult deflagration_common(const EosDev& m, const double v_wall, const double vm_tilde, const double wn,
-                                        const double wm, const double cs_n, const double v_cj,
-                                        const double vp_tilde_guess, const int sol_type, const int n_xi,
-                                        const double t_end, const int thin_shell_limit) {
-    DeflagResult r;
-    r.status = ST_SOLVER_FAILED;
-    r.vp = r.vp_tilde = r.wp = r.wn_estimate = NAN;
-    r.i_shock = 0; r.t_end_final = -t_end;
-    r.sh.v = r.sh.w = r.sh.xi = NAN;
-    if (!(v_wall >= 0.0 && v_wall <= 1.0) || !(vm_tilde >= 0.0 && vm_tilde <= 1.0) || !(wn >= 0.0) || !(wm >= 0.0) ||
-        !(vp_tilde_guess >= 0.0 && vp_tilde_guess <= 1.0) || v_wall > v_cj)
-        return r;
-    // wall junction, broken -> symmetric: a deflagration accelerates the flow through the wall, v+ < v-  (root below cs_s)
-    const Junction j = solve_junction(m, vm_tilde, wm, 1, 0, vp_tilde_guess, -1);
-    if (!j.ok) return r;
-    r.vp_tilde = j.v2;
-    r.wp = j.w2;
-    r.vp = lorentz(v_wall, j.v2);        // -lorentz(vp_tilde, v_wall)
-    if (!(r.vp >= 0.0) || !(r.wp >= 0.0)) return r;
-    State y0;
-    y0.v = r.vp; y0.w = r.wp; y0.xi = v_wall;
-    GenericShockLocator loc;
-    double te = -t_end;
-    int i_shock = 0;
-    State sh;
-    for (int attempt = 0; attempt < 6; ++attempt) {     // first pass + up to 5 thin-shell refinements (fluid.py:223-271)
-        loc.reset(m, v_wall, cs_n, false);
-        const int rc = integrate_grid(m.css2, y0, te, n_xi, loc);
-        if (rc < 0) { r.status = ST_INTEGRATION_FAILED; return r; }
-        const int i_new = loc.found;
-        if (attempt == 0) {
-            if (i_new == 0 || i_new + 1 >= n_xi) return r;
-        } else {
-            if (i_new == 0 || i_new + 20 >= n_xi) break;           // keep the previous solution
-        }
-        i_shock = i_new;
-        sh = loc.prev;
-        r.t_end_final = te;
-        if (i_shock >= thin_shell_limit) break;
-        if (attempt == 5) break;
-        te = grid_time(te, n_xi, i_shock + 20);
-    }
-    if (i_shock <= 1) return r;
-    r.i_shock = i_shock;
-    r.sh = sh;
-    const double vm_tilde_sh = lorentz(sh.xi, sh.v);
-    r.wn_estimate = sh.w * gamma2(vm_tilde_sh) * vm_tilde_sh / (gamma2(sh.xi) * sh.xi);   // w2_junction, boundary.py:638
-    r.status = ST_OK;
-    return r;
-}
-
-struct GenericGuess {
-    double vp, vp_tilde, wp, wm;    // starting guesses (fluid reference table scaled by wn, fluid.py:925-949)
-};
-
-struct GenericRoot {
-    int status;
-    int sol_type;
-    double wm;          // enthalpy just behind the wall (w_center for subsonic deflagrations)
-    double vm_tilde;
-    double vp_tilde_guess;
-    bool solver_failed;
-    int iters;
-    DeflagResult d;     // last evaluation at wm
-};
-
-PTT_HD double generic_residual(const EosDev& m, const int sol_type, const double v_wall, const double wn,
-                               const double wm, const double cs_n, const double v_cj, const double vp_tilde_guess,
-                               const int n_xi, const double t_end, const int thin, DeflagResult& d) {
-    if (!(wm >= 0.0)) { d.status = ST_SOLVER_FAILED; return NAN; }
-    const double vm_tilde = (sol_type == SOL_HYBRID) ? sqrt(m.csb2) : v_wall;
-    d = deflagration_common(m, v_wall, vm_tilde, wn, wm, cs_n, v_cj, vp_tilde_guess, sol_type, n_xi, t_end, thin);
-    return d.wn_estimate - wn;
-}
-
-// sound_shell_solver_deflagration / _hybrid (fluid.py:606-669, 697-843): root of wn_estimate(wm) - wn.
-// Subsonic deflagrations: scipy's secant (root_scalar, x0 = 0.99 wm_guess, x1 = 1.01 wm_guess, atol 1.48e-8),
-// mirrored step by step.  Hybrids: the reference calls hybrd, which in one dimension is a finite-difference Newton
-// step followed by secant (Broyden) updates; the same is done here.
-PTT_HD GenericRoot generic_find_wm(const EosDev& m, const int sol_type, const double v_wall, const double wn,
-                                   const double cs_n, const double v_cj, const GenericGuess& g, const int n_xi,
-                                   const double t_end, const int thin, const double wn_rtol) {
-    GenericRoot r;
-    r.status = ST_OK; r.sol_type = sol_type; r.solver_failed = true; r.iters = 0;
-    r.wm = NAN;
-    r.vm_tilde = (sol_type == SOL_HYBRID) ? sqrt(m.csb2) : v_wall;
-    double vp_guess = g.vp;
-    double vpt_guess = g.vp_tilde;
-    if (sol_type == SOL_SUB_DEF) {
-        if (vp_guess > v_wall) vp_guess = 0.95 * v_wall;           // fluid.py:613-617
-        vpt_guess = lorentz(v_wall, vp_guess);                     // -lorentz(vp_guess, v_wall), fluid.py:79
-    }
-    r.vp_tilde_guess = vpt_guess;
-    DeflagResult d0, d1, d2;
-    double p0, p1, q0, q1;
-    bool converged = false;
-    double p = NAN;
-    // pass 0: the reference's primary solver; pass 1: its fallback (fsolve from wm_guess, fluid.py:629-640)
-    for (int pass = 0; pass < 2 && !converged; ++pass) {
-    const bool newton_start = (sol_type != SOL_SUB_DEF) || (pass == 1);
-    if (!newton_start) {
-        p0 = 0.99 * g.wm;
-        p1 = 1.01 * g.wm;
-        q0 = generic_residual(m, sol_type, v_wall, wn, p0, cs_n, v_cj, vpt_guess, n_xi, t_end, thin, d0);
-        q1 = generic_residual(m, sol_type, v_wall, wn, p1, cs_n, v_cj, vpt_guess, n_xi, t_end, thin, d1);
-    } else {
-        p0 = g.wm;
-        q0 = generic_residual(m, sol_type, v_wall, wn, p0, cs_n, v_cj, vpt_guess, n_xi, t_end, thin, d0);
-        const double h = 1.4901161193847656e-08 * fabs(p0);
-        double qh = generic_residual(m, sol_type, v_wall, wn, p0 + h, cs_n, v_cj, vpt_guess, n_xi, t_end, thin, d1);
-        const double J = (qh - q0) / h;
-        p1 = p0 - q0 / J;
-        if (!(p1 > 0.0) || !(p1 == p1)) p1 = 1.01 * p0;
-        // hybrd's first trust region is factor * |x| = 100 |x|: no clipping in practice
-        q1 = generic_residual(m, sol_type, v_wall, wn, p1, cs_n, v_cj, vpt_guess, n_xi, t_end, thin, d1);
-    }
-    p = p1;
-    if (q0 == q0 && q1 == q1) {
-        if (fabs(q1) < fabs(q0)) {
-            double t = p0; p0 = p1; p1 = t;
-            t = q0; q0 = q1; q1 = t;
-            const DeflagResult td = d0; d0 = d1; d1 = td;
-        }
-        const double atol = 1.48e-8;
-        const double rtol_h = 1.4901161193847656e-08;     // hybrd xtol (relative) for the hybrid branch
-        for (int it = 0; it < 50; ++it) {
-            r.iters = it + 1;
-            if (q1 == q0) {
-                p = 0.5 * (p1 + p0);
-                converged = (p1 == p0);
-                break;
-            }
-            if (fabs(q1) > fabs(q0)) p = (-q0 / q1 * p1 + p0) / (1.0 - q0 / q1);
-            else p = (-q1 / q0 * p0 + p1) / (1.0 - q1 / q0);
-            const double tol = newton_start ? rtol_h * fabs(p) : atol;
-            if (fabs(p - p1) <= tol) { converged = true; break; }
-            p0 = p1; q0 = q1; d0 = d1;
-            p1 = p;
-            q1 = generic_residual(m, sol_type, v_wall, wn, p1, cs_n, v_cj, vpt_guess, n_xi, t_end, thin, d1);
-            if (!(q1 == q1)) break;
-        }
-    }
-    if (sol_type != SOL_SUB_DEF) break;
-    }
-    if (!(p == p) || !(p > 0.0)) { r.status = ST_ROOT_NOT_CONVERGED; return r; }
-    // final evaluation at the root (fluid.py:642-653, 797-811)
-    const double qf = generic_residual(m, sol_type, v_wall, wn, p, cs_n, v_cj, vpt_guess, n_xi, t_end, thin, d2);
-    r.wm = p;
-    r.d = d2;
-    if (d2.status != ST_OK) { r.status = d2.status; return r; }
-    const bool close = fabs(d2.wn_estimate - wn) <= 1e-8 + wn_rtol * fabs(wn);     // np.isclose(wn_estimate, wn, rtol)
-    r.solver_failed = !(converged && close);
-    (void)qf;
-    return r;
-}
-
-// --- profile materialisation ----------------------------------------------------------------------------------
-// Row layout for the generic solver: the part behind the wall (2 still-fluid samples + up to n_xi samples) ends at
-// column gen_back_cap(n_xi); the wall -> shock part starts there.
-PTT_HD int gen_back_cap(const int n_xi) { return n_xi + 2; }
-PTT_HD int gen_row_capacity(const int n_xi) { return 2 * n_xi + 4; }
+enum JobKind : int { JOB_LOCATE = 0, JOB_EMIT = 1, JOB_CSTRIM = 2 };
 
 struct OffsetEmitter {
     RowOut row;
     int base;       // column of sample 0
     int dir;        // +1 forward, -1 reversed
     int limit;      // stop after this many samples (forward part: i_shock)
-    PTT_HD bool skip(const State&) const { return false; }
     PTT_HD bool visit(const int i, const State& y) {
         row.set(base + dir * i, y.v, y.w, y.xi);
         return i + 1 < limit;
@@ -309,13 +149,39 @@ struct CsTrimEmitter {      // trim_fluid_wall_to_cs for detonations (trim.py:20
     double cs2b;
     int hit;
     int last_i;
-    PTT_HD bool skip(const State&) const { return false; }
     PTT_HD bool visit(const int i, const State& y) {
         last_i = i;
         row.set(base - i, y.v, y.w, y.xi);
         if ((y.v <= 0.0) || (y.xi * y.xi <= cs2b)) { hit = i; return false; }
         return true;
     }
+};
+
+// One visitor type for every kind of integration, so that integrate_grid is instantiated (and entered) once.
+struct JobVisitor {
+    int kind;
+    GenericShockLocator loc;
+    OffsetEmitter oe;
+    CsTrimEmitter ce;
+    PTT_HD bool skip(const State& y_end) const { return kind == JOB_LOCATE && loc.skip(y_end); }
+    PTT_HD bool visit(const int i, const State& y) {
+        if (kind == JOB_LOCATE) return loc.visit(i, y);
+        if (kind == JOB_EMIT) return oe.visit(i, y);
+        return ce.visit(i, y);
+    }
+};
+
+struct DeflagResult {
+    int status;         // ST_OK or a failure code (the reference returns DEFLAGRATION_NAN)
+    double vp, vp_tilde, wp;
+    double t_end_final; // end time of the accepted integration (after the thin-shell loop)
+    int i_shock;        // samples [0, i_shock) are kept
+    State sh;           // sample i_shock - 1: (vm_sh, wm_sh, xi_sh)
+    double wn_estimate;
+};
+
+struct GenericGuess {
+    double vp, vp_tilde, wp, wm;    // starting guesses (fluid reference table scaled by wn, fluid.py:925-949)
 };
 
 struct GenericOut {
@@ -326,83 +192,342 @@ struct GenericOut {
     double vp, vm, vp_tilde, vm_tilde, v_sh, vm_sh, vm_tilde_sh, wp, wm, wm_sh, v_cj, wn, wn_estimate;
 };
 
+// Row layout for the generic solver: the part behind the wall (2 still-fluid samples + up to n_xi samples) ends at
+// column gen_back_cap(n_xi); the wall -> shock part starts there.
+PTT_HD int gen_back_cap(const int n_xi) { return n_xi + 2; }
+PTT_HD int gen_row_capacity(const int n_xi) { return 2 * n_xi + 4; }
+
+struct GenericMachine {
+    // what comes back from "advance": an integration to run, or nothing more to do
+    enum Phase : int { PH_LOCATE = 0, PH_EMIT_FWD = 1, PH_EMIT_BACK = 2, PH_CSTRIM = 3, PH_DONE = 4 };
+    // where the root finder waits for a residual
+    enum Root : int { RF_A0 = 0, RF_AH = 1, RF_A1 = 2, RF_IT = 3, RF_FINAL = 4 };
+
+    // --- constants of the point
+    EosDev m;
+    double v_wall, wn, cs_n, v_cj, t_end, wn_rtol;
+    int sol_type, n_xi, thin;
+    GenericGuess g;
+    RowOut row;
+    // --- pending integration
+    int phase;
+    double job_cs2, job_te;
+    State job_y0;
+    JobVisitor vis;
+    // --- residual evaluation in flight (sound_shell_deflagration_common, fluid.py:121-288)
+    DeflagResult d;
+    double vm_tilde, vpt_guess;
+    int attempt, i_shock;
+    State sh;
+    double te;
+    // --- root finder (fluid.py:606-669, 697-843)
+    int rf, pass, it;
+    bool newton_start, converged, solver_failed;
+    double p0, p1, q0, q1, p, h_fd;
+    // --- result
+    GenericOut o;
+    int nb, nf;
+
+    PTT_HD void fail(const int status) { o.status = status; phase = PH_DONE; }
+
+    // ---- residual -------------------------------------------------------------------------------------------
+    // Starts wn_estimate(wm) - wn.  Returns true if an integration is pending, false if the residual is already
+    // known (NaN, d.status says why).
+    PTT_HD bool resid_begin(const double wm) {
+        d.status = ST_SOLVER_FAILED;
+        d.vp = d.vp_tilde = d.wp = d.wn_estimate = NAN;
+        d.i_shock = 0; d.t_end_final = -t_end;
+        d.sh.v = d.sh.w = d.sh.xi = NAN;
+        if (!(wm >= 0.0)) return false;
+        if (!(v_wall >= 0.0 && v_wall <= 1.0) || !(vm_tilde >= 0.0 && vm_tilde <= 1.0) || !(wn >= 0.0) ||
+            !(vpt_guess >= 0.0 && vpt_guess <= 1.0) || v_wall > v_cj)
+            return false;
+        // wall junction, broken -> symmetric: a deflagration accelerates the flow through the wall, v+ < v-
+        // (root below cs_s)
+        const Junction j = solve_junction(m, vm_tilde, wm, 1, 0, vpt_guess, -1);
+        if (!j.ok) return false;
+        d.vp_tilde = j.v2;
+        d.wp = j.w2;
+        d.vp = lorentz(v_wall, j.v2);        // -lorentz(vp_tilde, v_wall)
+        if (!(d.vp >= 0.0) || !(d.wp >= 0.0)) return false;
+        job_y0.v = d.vp; job_y0.w = d.wp; job_y0.xi = v_wall;
+        job_cs2 = m.css2;
+        te = -t_end;
+        attempt = 0;
+        i_shock = 0;
+        locate_job();
+        return true;
+    }
+    PTT_HD void locate_job() {
+        vis.kind = JOB_LOCATE;
+        vis.loc.reset(m, v_wall, cs_n, false);
+        job_te = te;
+        phase = PH_LOCATE;
+    }
+    // After a locate integration: first pass + up to 5 thin-shell refinements (fluid.py:223-271).
+    // Returns true if another integration is pending, false if the residual is complete.
+    PTT_HD bool resid_after(const int rc) {
+        if (rc < 0) { d.status = ST_INTEGRATION_FAILED; return false; }
+        const int i_new = vis.loc.found;
+        bool more = false;
+        if (attempt == 0) {
+            if (i_new == 0 || i_new + 1 >= n_xi) return false;
+        }
+        if (attempt > 0 && (i_new == 0 || i_new + 20 >= n_xi)) {
+            // keep the previous solution
+        } else {
+            i_shock = i_new;
+            sh = vis.loc.prev;
+            d.t_end_final = te;
+            if (i_shock < thin && attempt < 5) {
+                te = grid_time(te, n_xi, i_shock + 20);
+                more = true;
+            }
+        }
+        if (more) {
+            ++attempt;
+            locate_job();
+            return true;
+        }
+        if (i_shock <= 1) return false;
+        d.i_shock = i_shock;
+        d.sh = sh;
+        const double vm_tilde_sh = lorentz(sh.xi, sh.v);
+        d.wn_estimate = sh.w * gamma2(vm_tilde_sh) * vm_tilde_sh / (gamma2(sh.xi) * sh.xi);   // w2_junction, boundary.py:638
+        d.status = ST_OK;
+        return false;
+    }
+
+    // ---- root finder ----------------------------------------------------------------------------------------
+    // Subsonic deflagrations: scipy's secant (root_scalar, x0 = 0.99 wm_guess, x1 = 1.01 wm_guess, atol 1.48e-8),
+    // mirrored step by step; if it fails, the reference's fallback (fsolve from wm_guess, fluid.py:629-640).
+    // Hybrids: the reference calls hybrd, which in one dimension is a finite-difference Newton step followed by
+    // secant (Broyden) updates; the same is done here.
+    // Each function returns true if an integration is pending; otherwise the residual it asked for is already
+    // known and the caller feeds it back with root_on_q.
+    PTT_HD bool pass_begin() {
+        newton_start = (sol_type != SOL_SUB_DEF) || (pass == 1);
+        p0 = newton_start ? g.wm : 0.99 * g.wm;
+        rf = RF_A0;
+        return resid_begin(p0);
+    }
+    // secant iteration header; returns 1 = integration pending, 0 = residual known without one, -1 = pass over
+    PTT_HD int iter_head() {
+        const double atol = 1.48e-8;
+        const double rtol_h = 1.4901161193847656e-08;     // hybrd xtol (relative) for the Newton-started branch
+        if (it >= 50) return -1;
+        if (q1 == q0) {
+            p = 0.5 * (p1 + p0);
+            converged = (p1 == p0);
+            return -1;
+        }
+        if (fabs(q1) > fabs(q0)) p = (-q0 / q1 * p1 + p0) / (1.0 - q0 / q1);
+        else p = (-q1 / q0 * p0 + p1) / (1.0 - q1 / q0);
+        const double tol = newton_start ? rtol_h * fabs(p) : atol;
+        if (fabs(p - p1) <= tol) { converged = true; return -1; }
+        p0 = p1; q0 = q1;
+        p1 = p;
+        rf = RF_IT;
+        return resid_begin(p1) ? 1 : 0;
+    }
+    // end of a pass (and possibly of the root search); same return convention as iter_head, -1 never
+    PTT_HD int pass_end() {
+        if (sol_type == SOL_SUB_DEF && pass == 0 && !converged) {
+            pass = 1;
+            return pass_begin() ? 1 : 0;
+        }
+        if (!(p == p) || !(p > 0.0)) { fail(ST_ROOT_NOT_CONVERGED); return 1; }
+        // final evaluation at the root (fluid.py:642-653, 797-811)
+        rf = RF_FINAL;
+        return resid_begin(p) ? 1 : 0;
+    }
+    // Consumes a completed residual.  Returns true when the machine has a pending integration or is done.
+    PTT_HD bool root_on_q() {
+        const double q = d.wn_estimate - wn;      // NaN if the evaluation failed
+        int r;
+        switch (rf) {
+        case RF_A0:
+            q0 = q;
+            if (!newton_start) {
+                p1 = 1.01 * g.wm;
+                rf = RF_A1;
+                return resid_begin(p1);
+            }
+            h_fd = 1.4901161193847656e-08 * fabs(p0);
+            rf = RF_AH;
+            return resid_begin(p0 + h_fd);
+        case RF_AH: {
+            const double J = (q - q0) / h_fd;
+            p1 = p0 - q0 / J;
+            if (!(p1 > 0.0) || !(p1 == p1)) p1 = 1.01 * p0;
+            // hybrd's first trust region is factor * |x| = 100 |x|: no clipping in practice
+            rf = RF_A1;
+            return resid_begin(p1);
+        }
+        case RF_A1:
+            q1 = q;
+            p = p1;
+            if (q0 == q0 && q1 == q1) {
+                if (fabs(q1) < fabs(q0)) {
+                    double t = p0; p0 = p1; p1 = t;
+                    t = q0; q0 = q1; q1 = t;
+                }
+                it = 0;
+                r = iter_head();
+            } else {
+                r = -1;
+            }
+            if (r < 0) r = pass_end();
+            return r == 1;
+        case RF_IT:
+            q1 = q;
+            if (!(q1 == q1)) {
+                r = -1;
+            } else {
+                ++it;
+                r = iter_head();
+            }
+            if (r < 0) r = pass_end();
+            return r == 1;
+        default:    // RF_FINAL
+            o.wm = p;
+            if (d.status != ST_OK) { fail(d.status); return true; }
+            {
+                const bool close = fabs(d.wn_estimate - wn) <= 1e-8 + wn_rtol * fabs(wn);     // np.isclose(.., rtol)
+                solver_failed = !(converged && close);
+            }
+            emit_fwd_job();
+            return true;
+        }
+    }
+
+    // ---- profile materialisation ------------------------------------------------------------------------------
+    PTT_HD void emit_fwd_job() {
+        // wall -> shock samples [0, i_shock) of the accepted integration
+        job_y0.v = d.vp; job_y0.w = d.wp; job_y0.xi = v_wall;
+        job_cs2 = m.css2;
+        job_te = d.t_end_final;
+        vis.kind = JOB_EMIT;
+        vis.oe.row = row; vis.oe.base = gen_back_cap(n_xi); vis.oe.dir = 1; vis.oe.limit = d.i_shock;
+        phase = PH_EMIT_FWD;
+    }
+    PTT_HD void finish(const double w_first) {
+        const int bc = gen_back_cap(n_xi);
+        const double dxi = 1.0 / (double)n_xi;
+        const double xi_first = (nb > 0) ? row.xi[bc - nb] : row.xi[bc];
+        const double w_center = fmin(o.wm, w_first);                   // fluid.py:1039
+        row.set(bc - nb - 1, 0.0, w_center, xi_first - dxi);
+        row.set(bc - nb - 2, 0.0, w_center, 0.0);
+        o.off = bc - nb - 2;
+        o.npts = 2 + nb + nf + 2;
+        phase = PH_DONE;
+    }
+
+    PTT_HD void start(const EosDev& m_, const double v_wall_, const int sol_type_, const double wn_, const double v_cj_,
+                      const GenericGuess& g_, const int n_xi_, const double t_end_, const int thin_,
+                      const double wn_rtol_, const RowOut& row_) {
+        m = m_; v_wall = v_wall_; sol_type = sol_type_; wn = wn_; v_cj = v_cj_; g = g_; n_xi = n_xi_; t_end = t_end_;
+        thin = thin_; wn_rtol = wn_rtol_; row = row_;
+        cs_n = sqrt(m.css2);
+        o.status = ST_OK; o.off = 0; o.npts = 0; o.solver_failed = 1;
+        o.vp = o.vm = o.vp_tilde = o.vm_tilde = o.v_sh = o.vm_sh = o.vm_tilde_sh = o.wp = o.wm = o.wm_sh = NAN;
+        o.v_cj = v_cj; o.wn = wn; o.wn_estimate = NAN;
+        nb = nf = 0;
+        solver_failed = true; converged = false;
+        p = NAN;
+        if (sol_type == SOL_DETON) {
+            // fluid.py:351-478.  Weak detonation: exit speed above the sound speed of the broken phase (root >= cs_b).
+            const Junction j = solve_junction(m, v_wall, wn, 0, 1, 0.0, +1);
+            if (!j.ok) { fail(ST_SOLVER_FAILED); return; }
+            const double vmt = j.v2, wm = j.w2;
+            const double vm = lorentz(v_wall, vmt);
+            job_y0.v = vm; job_y0.w = wm; job_y0.xi = v_wall;
+            job_cs2 = m.csb2;
+            job_te = -t_end;
+            vis.kind = JOB_CSTRIM;
+            vis.ce.row = row; vis.ce.base = gen_back_cap(n_xi) - 1; vis.ce.cs2b = m.csb2; vis.ce.hit = -1;
+            vis.ce.last_i = -1;
+            o.vp = 0.0; o.vm = vm; o.vp_tilde = v_wall; o.vm_tilde = vmt; o.v_sh = v_wall; o.vm_sh = vm;
+            o.vm_tilde_sh = vmt; o.wp = wn; o.wm = wm; o.wm_sh = wm;
+            phase = PH_CSTRIM;
+            return;
+        }
+        vm_tilde = (sol_type == SOL_HYBRID) ? sqrt(m.csb2) : v_wall;
+        double vp_guess = g.vp;
+        vpt_guess = g.vp_tilde;
+        if (sol_type == SOL_SUB_DEF) {
+            if (vp_guess > v_wall) vp_guess = 0.95 * v_wall;           // fluid.py:613-617
+            vpt_guess = lorentz(v_wall, vp_guess);                     // -lorentz(vp_guess, v_wall), fluid.py:79
+        }
+        pass = 0;
+        bool pending = pass_begin();
+        while (!pending) pending = root_on_q();
+    }
+
+    // Consumes the integration that was pending; afterwards either another one is pending or phase == PH_DONE.
+    PTT_HD void advance(const int rc) {
+        const int bc = gen_back_cap(n_xi);
+        const double dxi = 1.0 / (double)n_xi;
+        if (phase == PH_LOCATE) {
+            bool pending = resid_after(rc);
+            while (!pending) pending = root_on_q();
+            return;
+        }
+        if (rc < 0) { fail(ST_INTEGRATION_FAILED); return; }
+        if (phase == PH_CSTRIM) {
+            const int hit = vis.ce.hit;
+            nb = (hit < 0) ? n_xi - 2 : ((hit == 0) ? 1 : hit);
+            if (nb < 1) { fail(ST_INTEGRATION_FAILED); return; }
+            o.solver_failed = 0;
+            nf = 0;
+            const double w_first = row.w[bc - nb];
+            row.set(bc, 0.0, wn, v_wall + dxi);
+            row.set(bc + 1, 0.0, wn, 1.0);
+            finish(w_first);
+            return;
+        }
+        if (phase == PH_EMIT_FWD) {
+            nf = d.i_shock;
+            const double xi_last = row.xi[bc + nf - 1];
+            row.set(bc + nf, 0.0, wn, xi_last + dxi);
+            row.set(bc + nf + 1, 0.0, wn, 1.0);
+            o.vp = d.vp; o.vp_tilde = d.vp_tilde; o.vm_tilde = vm_tilde; o.vm = lorentz(vm_tilde, v_wall);
+            o.v_sh = d.sh.xi; o.vm_sh = d.sh.v; o.vm_tilde_sh = lorentz(d.sh.xi, d.sh.v);
+            o.wp = d.wp; o.wm_sh = d.sh.w; o.wn_estimate = d.wn_estimate;
+            o.solver_failed = solver_failed ? 1 : 0;
+            if (sol_type == SOL_HYBRID) {
+                // rarefaction tail behind the wall, n_xi samples, NOT trimmed (fluid.py:831-841)
+                o.vm = lorentz(v_wall, sqrt(m.csb2));
+                job_y0.v = o.vm; job_y0.w = o.wm; job_y0.xi = v_wall;
+                job_cs2 = m.csb2;
+                job_te = -t_end;
+                vis.kind = JOB_EMIT;
+                vis.oe.row = row; vis.oe.base = bc - 1; vis.oe.dir = -1; vis.oe.limit = n_xi;
+                phase = PH_EMIT_BACK;
+                return;
+            }
+            nb = 0;
+            finish(row.w[bc]);
+            return;
+        }
+        // PH_EMIT_BACK
+        nb = n_xi;
+        finish(row.w[bc - nb]);
+    }
+};
+
 // sound_shell_generic (fluid.py:848-1052) for one point, default arguments (no user guesses, no bag/Giese solver).
-// vm_tilde_ref / wm_ref: reference-table guesses for detonations (unscaled, fluid.py:969-973).
 PTT_HD GenericOut generic_solve_point(const EosDev& m, const double v_wall, const double alpha_n, const int sol_type,
                                       const double wn, const double v_cj, const GenericGuess& g, const int n_xi,
                                       const double t_end, const int thin, const double wn_rtol, const RowOut& row) {
-    GenericOut o;
-    o.status = ST_OK; o.off = 0; o.npts = 0; o.solver_failed = 1;
-    o.vp = o.vm = o.vp_tilde = o.vm_tilde = o.v_sh = o.vm_sh = o.vm_tilde_sh = o.wp = o.wm = o.wm_sh = NAN;
-    o.v_cj = v_cj; o.wn = wn; o.wn_estimate = NAN;
-    const double cs_n = sqrt(m.css2);
-    const double dxi = 1.0 / (double)n_xi;
-    const int bc = gen_back_cap(n_xi);
-    int nb = 0, nf = 0;             // samples behind / ahead of the wall (without the still-fluid points)
-    double w_first;                 // w of the first (innermost) moving sample
-
-    if (sol_type == SOL_DETON) {
-        // fluid.py:351-478.  Weak detonation: exit speed above the sound speed of the broken phase (root >= cs_b).
-        const Junction j = solve_junction(m, v_wall, wn, 0, 1, 0.0, +1);
-        if (!j.ok) { o.status = ST_SOLVER_FAILED; return o; }
-        const double vm_tilde = j.v2, wm = j.w2;
-        const double vm = lorentz(v_wall, vm_tilde);
-        State y0;
-        y0.v = vm; y0.w = wm; y0.xi = v_wall;
-        CsTrimEmitter em;
-        em.row = row; em.base = bc - 1; em.cs2b = m.csb2; em.hit = -1; em.last_i = -1;
-        const int rc = integrate_grid(m.csb2, y0, -t_end, n_xi, em);
-        if (rc < 0) { o.status = ST_INTEGRATION_FAILED; return o; }
-        nb = (em.hit < 0) ? n_xi - 2 : ((em.hit == 0) ? 1 : em.hit);
-        if (nb < 1) { o.status = ST_INTEGRATION_FAILED; return o; }
-        o.vp = 0.0; o.vm = vm; o.vp_tilde = v_wall; o.vm_tilde = vm_tilde; o.v_sh = v_wall; o.vm_sh = vm;
-        o.vm_tilde_sh = vm_tilde; o.wp = wn; o.wm = wm; o.wm_sh = wm;
-        o.solver_failed = 0;
-        nf = 0;
-        w_first = row.w[bc - nb];
-        row.set(bc, 0.0, wn, v_wall + dxi);
-        row.set(bc + 1, 0.0, wn, 1.0);
-    } else {
-        const GenericRoot r = generic_find_wm(m, sol_type, v_wall, wn, cs_n, v_cj, g, n_xi, t_end, thin, wn_rtol);
-        if (r.status != ST_OK) { o.status = r.status; return o; }
-        const DeflagResult& d = r.d;
-        // wall -> shock samples [0, i_shock) of the accepted integration
-        State y0;
-        y0.v = d.vp; y0.w = d.wp; y0.xi = v_wall;
-        OffsetEmitter fe;
-        fe.row = row; fe.base = bc; fe.dir = 1; fe.limit = d.i_shock;
-        int rc = integrate_grid(m.css2, y0, d.t_end_final, n_xi, fe);
-        if (rc < 0) { o.status = ST_INTEGRATION_FAILED; return o; }
-        nf = d.i_shock;
-        const double xi_last = row.xi[bc + nf - 1];
-        row.set(bc + nf, 0.0, wn, xi_last + dxi);
-        row.set(bc + nf + 1, 0.0, wn, 1.0);
-        o.vp = d.vp; o.vp_tilde = d.vp_tilde; o.vm_tilde = r.vm_tilde; o.vm = lorentz(r.vm_tilde, v_wall);
-        o.v_sh = d.sh.xi; o.vm_sh = d.sh.v; o.vm_tilde_sh = lorentz(d.sh.xi, d.sh.v);
-        o.wp = d.wp; o.wm = r.wm; o.wm_sh = d.sh.w; o.wn_estimate = d.wn_estimate;
-        o.solver_failed = r.solver_failed ? 1 : 0;
-        if (sol_type == SOL_HYBRID) {
-            // rarefaction tail behind the wall, n_xi samples, NOT trimmed (fluid.py:831-841)
-            o.vm = lorentz(v_wall, sqrt(m.csb2));
-            State yb;
-            yb.v = o.vm; yb.w = r.wm; yb.xi = v_wall;
-            OffsetEmitter be;
-            be.row = row; be.base = bc - 1; be.dir = -1; be.limit = n_xi;
-            rc = integrate_grid(m.csb2, yb, -t_end, n_xi, be);
-            if (rc < 0) { o.status = ST_INTEGRATION_FAILED; return o; }
-            nb = n_xi;
-        } else {
-            nb = 0;
-        }
-        w_first = (nb > 0) ? row.w[bc - nb] : row.w[bc];
+    (void)alpha_n;
+    GenericMachine mach;
+    mach.start(m, v_wall, sol_type, wn, v_cj, g, n_xi, t_end, thin, wn_rtol, row);
+    while (mach.phase != GenericMachine::PH_DONE) {
+        const int rc = integrate_grid(mach.job_cs2, mach.job_y0, mach.job_te, n_xi, mach.vis);
+        mach.advance(rc);
     }
-    const double xi_first = (nb > 0) ? row.xi[bc - nb] : row.xi[bc];
-    const double w_center = fmin(o.wm, w_first);                   // fluid.py:1039
-    row.set(bc - nb - 1, 0.0, w_center, xi_first - dxi);
-    row.set(bc - nb - 2, 0.0, w_center, 0.0);
-    o.off = bc - nb - 2;
-    o.npts = 2 + nb + nf + 2;
-    return o;
+    return mach.o;
 }
 
 }  // namespace ptt
