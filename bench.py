@@ -309,7 +309,9 @@ def gpu_arm(args):
             # one v_wall row of the grid (1000 profiles)
             from pttools_b200.engine import _group_band
             _, kw = _group_band(plan.lookup_pass, 0.5)
-            alg["spec_den_v_group"] = 2.0 * n_sdv * kw * GRID_N + 10.0 * n_sdv * NPT[1]
+            # one stage entry = the groups of one chunk (they run concurrently on side streams, fork -> join)
+            groups = max(1, n_launch_pts // GRID_N)
+            alg["spec_den_v_group"] = groups * (2.0 * n_sdv * kw * GRID_N + 10.0 * n_sdv * NPT[1])
         dom = max((k for k in stage_ms if k in alg), key=lambda k: stage_ms[k]["ms"], default=None)
         roofline = None
         if dom:

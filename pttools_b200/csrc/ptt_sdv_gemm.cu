@@ -17,7 +17,7 @@ constexpr int GM_BM = 128;      // rows (wavenumbers) per CTA
 constexpr int GM_BN = 128;      // columns (profiles) per CTA
 constexpr int GM_BK = 16;
 constexpr int GM_PITCH = GM_BK + 4;   // doubles; conflict-free fragment loads (half-warp covers all 32 banks)
-constexpr int GM_THREADS = 256;
+constexpr int GM_THREADS = 512;      // 16 warps: 4 (m) x 4 (n), warp tile 32 x 32 -> 4 warps per scheduler, <= 128 registers
 
 // Omega, tile-banded: tile t (GM_BM rows) stores [GM_BM][kw] weights for knots e_base[t] + kk, kk in [0, kw).
 // One warp per row (omega is zero-filled beforehand): lane l visits the T-tilde samples [l*nt/32, (l+1)*nt/32) in
@@ -98,37 +98,37 @@ __global__ void __launch_bounds__(GM_THREADS) sdv_gemm_kernel(
     double (*Bs)[GM_BN * GM_PITCH] = reinterpret_cast<double (*)[GM_BN * GM_PITCH]>(gm_smem + 2 * GM_BM * GM_PITCH);
     const int tile_m = blockIdx.x, tile_n = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 3, wn = warp >> 2;          // 4 x 2 warps; warp tile 32 (m) x 64 (n)
+    const int wm = warp & 3, wn = warp >> 2;          // 4 x 4 warps; warp tile 32 (m) x 32 (n)
     const int eb = e_base[tile_m];
     const double* Ag = omega + (size_t)tile_m * GM_BM * kw;
-    // global -> shared: thread loads 8 consecutive k of one row (A) and of one column/profile (B)
-    const int lr = tid >> 1, lk = (tid & 1) * 8;
+    // global -> shared: thread loads 4 consecutive k of one row (A) and of one column/profile (B)
+    const int lr = tid >> 2, lk = (tid & 3) * 4;
     const int p_load = tile_n * GM_BN + lr;
     const bool p_ok = p_load < n_p;
     const double* Bg = a2 + (long long)(p_ok ? p_load : 0) * a2_stride;
-    double ra[8], rb[8];
+    double ra[4], rb[4];
     auto load_regs = [&](const int k0) {
         const double* ap = Ag + (size_t)lr * kw + k0 + lk;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) ra[q] = (k0 + lk + q < kw) ? ap[q] : 0.0;
+        for (int q = 0; q < 4; ++q) ra[q] = (k0 + lk + q < kw) ? ap[q] : 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
             const int k = eb + k0 + lk + q;
             rb[q] = (p_ok && k < n_q && k0 + lk + q < kw) ? Bg[k] : 0.0;
         }
     };
     auto store_smem = [&](const int buf) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
             As[buf][lr * GM_PITCH + lk + q] = ra[q];
             Bs[buf][lr * GM_PITCH + lk + q] = rb[q];
         }
     };
-    double acc[4][8][2];
+    double acc[4][4][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+        for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
 
     const int n_k = (kw + GM_BK - 1) / GM_BK;
     load_regs(0);
@@ -139,18 +139,18 @@ __global__ void __launch_bounds__(GM_THREADS) sdv_gemm_kernel(
         const int buf = kt & 1;
         if (kt + 1 < n_k) load_regs((kt + 1) * GM_BK);
         const double* Asb = As[buf] + (wm * 32 + fr) * GM_PITCH + fk;
-        const double* Bsb = Bs[buf] + (wn * 64 + fr) * GM_PITCH + fk;
+        const double* Bsb = Bs[buf] + (wn * 32 + fr) * GM_PITCH + fk;
 #pragma unroll
         for (int k4 = 0; k4 < GM_BK; k4 += 4) {
-            double af[4], bf[8];
+            double af[4], bf[4];
 #pragma unroll
             for (int a = 0; a < 4; ++a) af[a] = Asb[a * 8 * GM_PITCH + k4];
 #pragma unroll
-            for (int b = 0; b < 8; ++b) bf[b] = Bsb[b * 8 * GM_PITCH + k4];
+            for (int b = 0; b < 4; ++b) bf[b] = Bsb[b * 8 * GM_PITCH + k4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
         if (kt + 1 < n_k) {
             store_smem(buf ^ 1);
@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(GM_THREADS) sdv_gemm_kernel(
         const int i = tile_m * GM_BM + wm * 32 + a * 8 + fr;
         if (i >= n_z) continue;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int p0 = tile_n * GM_BN + wn * 64 + b * 8 + 2 * fk;
+        for (int b = 0; b < 4; ++b) {
+            const int p0 = tile_n * GM_BN + wn * 32 + b * 8 + 2 * fk;
             if (p0 < n_p) out[(long long)p0 * out_stride + i] = factor * acc[a][b][0];
             if (p0 + 1 < n_p) out[(long long)(p0 + 1) * out_stride + i] = factor * acc[a][b][1];
         }

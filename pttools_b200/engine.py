@@ -593,15 +593,16 @@ def _group_band(p: SdvPass, v_wall: float):
     return e_base.astype(np.int32), kw
 
 
-def spec_den_v_group(plan: SsmPlan, ipass: int, a2, v_wall: float, out):
+def spec_den_v_group(plan: SsmPlan, ipass: int, a2, v_wall: float, out, slot: int = 0, timed: bool = True):
     """_spec_den_v_core for profiles that share v_wall, as a banded FP64 GEMM (ptt_spec_den_v_group).
-    a2: [n_p, n_a2] rows of the group; out: [n_p, n_z] destination view."""
+    a2: [n_p, n_a2] rows of the group; out: [n_p, n_z] destination view; slot: which Omega scratch buffer to use
+    (one per concurrently running group)."""
     torch = _torch()
     lib = _lib.load()
     sp, p = plan.sdv_plans[ipass], plan.passes[ipass]
     e_base, kw = _group_band(p, v_wall)
     n_tiles = e_base.size
-    key = ("omega", ipass)
+    key = ("omega", ipass, slot)
     need = n_tiles * 128 * kw
     buf = plan._t.get(key)
     if buf is None or buf.numel() < need:
@@ -609,11 +610,29 @@ def spec_den_v_group(plan: SsmPlan, ipass: int, a2, v_wall: float, out):
         plan._t[key] = buf
     eb = torch.as_tensor(e_base, device=a2.device)
     a2_ptr = C.c_void_p(a2.data_ptr() + 8 * int(plan.seg[ipass]))
-    with STAGES.stage("spec_den_v_group" if ipass == len(plan.passes) - 1 else "spec_den_v_group_y", 2):
-        _lib.check(lib.ptt_spec_den_v_group(C.byref(sp), a2.shape[0], a2_ptr, a2.stride(0), float(v_wall), kw, _ptr(eb),
-                                            _ptr(buf), _ptr(out), out.stride(0), _stream_ptr(torch)),
-                   "ptt_spec_den_v_group")
+    call = lambda: _lib.check(lib.ptt_spec_den_v_group(C.byref(sp), a2.shape[0], a2_ptr, a2.stride(0), float(v_wall), kw,
+                                                       _ptr(eb), _ptr(buf), _ptr(out), out.stride(0), _stream_ptr(torch)),
+                              "ptt_spec_den_v_group")
+    if timed:
+        with STAGES.stage(_group_stage_name(plan, ipass), 2):
+            call()
+    else:
+        call()
     return out
+
+
+def _group_stage_name(plan, ipass):
+    return "spec_den_v_group" if ipass == len(plan.passes) - 1 else "spec_den_v_group_y"
+
+
+SDV_STREAMS = 2         # groups of one call run on this many side streams (fills the last partial wave of each GEMM)
+_side_streams = []
+
+
+def _streams(torch, n):
+    while len(_side_streams) < n:
+        _side_streams.append(torch.cuda.Stream())
+    return _side_streams[:n]
 
 
 def spec_den_v_auto(plan: SsmPlan, ipass: int, a2, v_wall):
@@ -631,6 +650,7 @@ def spec_den_v_auto(plan: SsmPlan, ipass: int, a2, v_wall):
         return spec_den_v_batch(plan, ipass, a2, v_wall)
     out = torch.empty((P, n_z), dtype=torch.float64, device=a2.device)
     small_start = None
+    big_runs = []
     for a, b in runs + [(P, P)]:
         big = (b - a) >= GROUP_MIN
         if (big or a == P) and small_start is not None:          # flush the pending run of small groups
@@ -639,9 +659,30 @@ def spec_den_v_auto(plan: SsmPlan, ipass: int, a2, v_wall):
         if a == P:
             break
         if big:
-            spec_den_v_group(plan, ipass, a2[a:b], float(vw[a]), out[a:b])
+            big_runs.append((a, b))
         elif small_start is None:
             small_start = a
+    if len(big_runs) < 2 or SDV_STREAMS < 2:
+        for a, b in big_runs:
+            spec_den_v_group(plan, ipass, a2[a:b], float(vw[a]), out[a:b])
+        return out
+    # Independent groups on side streams: the tail wave of one matrix product overlaps the next group's work.
+    # One stage entry spans fork -> join on the launching stream.
+    main = torch.cuda.current_stream()
+    side = _streams(torch, min(SDV_STREAMS, len(big_runs)))
+    with STAGES.stage(_group_stage_name(plan, ipass), 2 * len(big_runs)):
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for k, (a, b) in enumerate(big_runs):
+            st = side[k % len(side)]
+            if k < len(side):
+                st.wait_event(fork)
+            with torch.cuda.stream(st):
+                spec_den_v_group(plan, ipass, a2[a:b], float(vw[a]), out[a:b], slot=k % len(side), timed=False)
+        for st in side:
+            join = torch.cuda.Event()
+            join.record(st)
+            main.wait_event(join)
     return out
 
 
