@@ -20,66 +20,57 @@ constexpr int GM_PITCH = GM_BK + 4;   // doubles; conflict-free fragment loads (
 constexpr int GM_THREADS = 512;      // 16 warps: 4 (m) x 4 (n), warp tile 32 x 32 -> 4 warps per scheduler, <= 128 registers
 
 // Omega, tile-banded: tile t (GM_BM rows) stores [GM_BM][kw] weights for knots e_base[t] + kk, kk in [0, kw).
-// One warp per row (omega is zero-filled beforehand): lane l visits the T-tilde samples [l*nt/32, (l+1)*nt/32) in
-// ascending order; the knot index is non-decreasing, so two running knot accumulators are flushed in order.  Knots
-// that only this lane's samples can touch are stored; the two first and two last knots of the lane's range may also
-// receive weight from the neighbouring lanes and are accumulated atomically.
-constexpr int WT_LANES = 32;
+// One thread per (row, knot), pull form: the T-tilde samples whose lookup lands in the segment left or right of the
+// knot are found arithmetically (LT is a linspace: ~1.4 samples per knot) and confirmed with the same floor() test
+// as the gather kernel, so every sample is counted exactly once; no atomics, no zero-fill, coalesced stores.
+// np.interp's end clamps put the whole weight of a sample on knot 0 (left) or knot n_q - 1 (right).
+// 1 / (qT[k+1] - qT[k]) for the weights kernel (one division per segment instead of one per sample)
+__global__ void sdv_recip_kernel(const int n_q, const double* __restrict__ qT, double* __restrict__ inv_dq) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_q - 1) inv_dq[k] = 1.0 / (qT[k + 1] - qT[k]);
+}
 
-__global__ void __launch_bounds__(128) sdv_weights_kernel(
+__global__ void __launch_bounds__(256) sdv_weights_kernel(
     const int n_q, const int n_z, const int nt, const double* __restrict__ qT, const double* __restrict__ z,
     const double* __restrict__ zterm, const double* __restrict__ T, const double* __restrict__ LT,
-    const double* __restrict__ W, const double v_wall, const double inv_dlog, const int kw,
-    const int* __restrict__ e_base, double* __restrict__ omega) {
-    const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = gthread / WT_LANES;
-    const int lane = gthread % WT_LANES;
-    if (i >= n_z) return;
-    double* row = omega + (size_t)i * kw;
-    const double b_R = cbrt(8.0 * M_PI);
-    const double bv = b_R * v_wall;
-    const double shift = -log10(bv) * inv_dlog;
+    const double* __restrict__ W, const double bv, const double shift, const int kw,
+    const int* __restrict__ e_base, const double* __restrict__ inv_dq, double* __restrict__ omega) {
+    const int i = blockIdx.y;
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= kw) return;
     const double s = z[i] / bv;
     const double ub = zterm[i] + shift;
-    const int eb = e_base[i / GM_BM];
-    const int per = (nt + WT_LANES - 1) / WT_LANES;
-    const int j0 = lane * per, j1 = min(nt, j0 + per);
-    if (j0 >= j1) return;
-    const double q_first = qT[0], q_last = qT[n_q - 1];
-    int cur = -1, first = -1;
-    double acc0 = 0.0, acc1 = 0.0;
-    for (int j = j0; j < j1; ++j) {
-        const double x = s * T[j];
-        int e = __double2int_rd(ub + LT[j]);
-        double w0, w1;
-        const double wj = W[j];
-        if (e < 0 || x < q_first) { e = 0; w0 = wj; w1 = 0.0; }                      // np.interp left clamp
-        else if (e >= n_q - 1 || x >= q_last) { e = n_q - 2; w0 = 0.0; w1 = wj; }    // right clamp: all on the last knot
-        else {
-            // the arithmetic index may be off by one on a razor edge: the weights then extrapolate the neighbouring
-            // segment by ~1e-12 of its length, i.e. the same value (continuous interpolant)
-            const double x0 = qT[e], x1 = qT[e + 1];
-            const double t = (x - x0) / (x1 - x0);
-            w0 = wj * (1.0 - t);
-            w1 = wj * t;
+    const int e = e_base[i / GM_BM] + kk;
+    double acc = 0.0;
+    if (e < n_q) {
+        const double lt0 = LT[0];
+        const double inv_dlt = (nt > 1) ? (double)(nt - 1) / (LT[nt - 1] - lt0) : 0.0;     // LT is a linspace
+        int j = 0;
+        if (e > 0) {
+            const double jf = ((double)(e - 1) - ub - lt0) * inv_dlt;
+            j = (jf > 1.0) ? ((jf < (double)nt) ? (int)jf - 1 : nt) : 0;
         }
-        if (cur < 0) { cur = e; first = e; }
-        while (cur < e) {        // knot `cur` can no longer receive weight from this lane
-            const int kk = cur - eb;
-            if (kk >= 0 && kk < kw) {
-                if (cur <= first + 1) atomicAdd(&row[kk], acc0); else row[kk] = acc0;
+        for (; j < nt; ++j) {
+            const int er = __double2int_rd(ub + LT[j]);
+            const double wj = W[j];
+            int eff;
+            double w0, w1;
+            if (er < 0) { eff = 0; w0 = wj; w1 = 0.0; }                          // np.interp left clamp
+            else if (er >= n_q - 1) { eff = n_q - 2; w0 = 0.0; w1 = wj; }          // right clamp: all on the last knot
+            else {
+                // the arithmetic index may be off by one on a razor edge: the weights then extrapolate the
+                // neighbouring segment by ~1e-12 of its length, i.e. the same value (continuous interpolant)
+                eff = er;
+                const double t = (s * T[j] - qT[er]) * inv_dq[er];
+                w0 = wj * (1.0 - t);
+                w1 = wj * t;
             }
-            acc0 = acc1;
-            acc1 = 0.0;
-            ++cur;
+            if (eff > e) break;                 // eff is non-decreasing in j
+            if (eff == e) acc += w0;
+            else if (eff == e - 1) acc += w1;
         }
-        acc0 += w0;
-        acc1 += w1;
     }
-    int kk = cur - eb;
-    if (kk >= 0 && kk < kw) atomicAdd(&row[kk], acc0);
-    ++kk;
-    if (kk >= 0 && kk < kw) atomicAdd(&row[kk], acc1);
+    omega[(size_t)i * kw + kk] = acc;
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
@@ -185,16 +176,14 @@ extern "C" int ptt_spec_den_v_group(const ptt_sdv_plan_t* plan, int n_p, const d
     if (n_p == 0) return PTT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int n_tiles = (plan->n_z + GM_BM - 1) / GM_BM;
-    {
-        const cudaError_t e = cudaMemsetAsync(omega, 0, sizeof(double) * (size_t)n_tiles * GM_BM * (size_t)kw, stream);
-        if (e != cudaSuccess) return set_cuda_error("ptt_spec_den_v_group memset", e);
-    }
-    const long long wt_threads = (long long)plan->n_z * WT_LANES;
-    sdv_weights_kernel<<<(unsigned)((wt_threads + 127) / 128), 128, 0, stream>>>(
-        plan->n_q, plan->n_z, plan->nt, plan->qT, plan->z, plan->zterm, plan->T, plan->LT, plan->W, v_wall,
-        plan->inv_dlog, kw, e_base, omega);
     const double b_R = cbrt(8.0 * M_PI);
     const double bv = b_R * v_wall;
+    // rows of the last tile beyond n_z are never written: the GEMM multiplies them into outputs it does not store
+    double* inv_dq = omega + (size_t)n_tiles * GM_BM * (size_t)kw;
+    sdv_recip_kernel<<<(plan->n_q + 255) / 256, 256, 0, stream>>>(plan->n_q, plan->qT, inv_dq);
+    sdv_weights_kernel<<<dim3((kw + 255) / 256, plan->n_z), 256, 0, stream>>>(
+        plan->n_q, plan->n_z, plan->nt, plan->qT, plan->z, plan->zterm, plan->T, plan->LT, plan->W, bv,
+        -log10(bv) * plan->inv_dlog, kw, e_base, inv_dq, omega);
     const double factor = 2.0 / (bv * bv * bv * bv * bv * bv);
     dim3 grid(n_tiles, (n_p + GM_BN - 1) / GM_BN);
     const int smem = 2 * (GM_BM + GM_BN) * GM_PITCH * (int)sizeof(double);

@@ -603,7 +603,7 @@ def spec_den_v_group(plan: SsmPlan, ipass: int, a2, v_wall: float, out, slot: in
     e_base, kw = _group_band(p, v_wall)
     n_tiles = e_base.size
     key = ("omega", ipass, slot)
-    need = n_tiles * 128 * kw
+    need = n_tiles * 128 * kw + p.qT.size
     buf = plan._t.get(key)
     if buf is None or buf.numel() < need:
         buf = torch.empty(int(need * 1.02) + 1024, dtype=torch.float64, device=a2.device)
