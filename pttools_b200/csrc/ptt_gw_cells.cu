@@ -11,15 +11,27 @@
 // default sizes a wavenumber has ~2500 cells instead of 10^4 samples, and a cell costs 6 FMAs and one 16-byte load
 // per profile instead of ~11 FP64 instructions and two shared-memory lookups per sample.
 //
-// Mapping: lanes <-> profiles (two per lane), warp <-> one wavenumber, CTA = 8 adjacent wavenumbers of the same 64
-// profiles.  The (a, b) tables are stored entry-major, T[e][p], so that a warp reads one entry of 32 profiles as one
+// Mapping: lanes <-> profiles (GC_PPL per lane), warp <-> one wavenumber, CTA = GC_WARPS adjacent wavenumbers of the
+// same 32 * GC_PPL profiles.  The (a, b) tables are stored entry-major, T[e][p], so that a warp reads one entry of 32 profiles as one
 // coalesced 512-byte request; the 8 warps of a CTA walk nearly the same entries, which keeps them in L1.
 #include "ptt_host.cuh"
 
 namespace ptt {
 
-constexpr int GC_WARPS = 8;
-constexpr int GC_PPW = 64;        // profiles per warp (2 per lane)
+#ifndef PTT_GC_WARPS
+#define PTT_GC_WARPS 8
+#endif
+#ifndef PTT_GC_PPL
+#define PTT_GC_PPL 2
+#endif
+#ifndef PTT_GC_PF
+#define PTT_GC_PF 0
+#endif
+constexpr int GC_WARPS = PTT_GC_WARPS;    // adjacent wavenumbers per CTA
+constexpr int GC_PPL = PTT_GC_PPL;        // profiles per lane
+constexpr int GC_PPW = 32 * GC_PPL;       // profiles per warp
+constexpr int GC_PF = PTT_GC_PF;          // L1 prefetch distance in events; 0 = off (measured: 8..32 are 15-25 % slower,
+                                          // the kernel is bound by L1/L2 throughput, not by latency)
 
 // One thread per wavenumber: walk the samples in order and emit one event per change of either lookup segment.
 // meta = (entry << 1) | which  (which = 0: lookup of y*zeta, 1: lookup of y*zeta'), coef = S0..S3 of the samples from
@@ -113,29 +125,56 @@ __global__ void __launch_bounds__(GC_WARPS * 32) spec_den_gw_cells_kernel(
     const int* __restrict__ m = meta + (long long)i * cap;
     const double2* __restrict__ cf = reinterpret_cast<const double2*>(coef + (long long)i * cap * 4);
     const double2* __restrict__ Tp = T + p0;
-    double2 A0 = make_double2(0.0, 0.0), A1 = A0, B0 = A0, B1 = A0;
-    double acc0 = 0.0, acc1 = 0.0;
+    double2 A[GC_PPL], B[GC_PPL];
+    double acc[GC_PPL];
+#pragma unroll
+    for (int h = 0; h < GC_PPL; ++h) {
+        A[h] = make_double2(0.0, 0.0);
+        B[h] = A[h];
+        acc[h] = 0.0;
+    }
+    // tuning knob: request the rows of the events GC_PF ahead
+    if (GC_PF > 0) {
+        for (int c = 0; c < min(GC_PF, nc); ++c) {
+            const double2* row = Tp + (long long)(__ldg(m + c) >> 1) * Ppad;
+#pragma unroll
+            for (int h = 0; h < GC_PPL; ++h) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 32 * h));
+        }
+    }
 #pragma unroll 4
     for (int c = 0; c < nc; ++c) {
+        if (GC_PF > 0 && c + GC_PF < nc) {
+            const double2* prow = Tp + (long long)(__ldg(m + c + GC_PF) >> 1) * Ppad;
+#pragma unroll
+            for (int h = 0; h < GC_PPL; ++h) asm volatile("prefetch.global.L1 [%0];" ::"l"(prow + 32 * h));
+        }
         const int mm = __ldg(m + c);
         const double2 s01 = __ldg(cf + 2 * c), s23 = __ldg(cf + 2 * c + 1);
         const double2* row = Tp + (long long)(mm >> 1) * Ppad;
-        const double2 n0 = __ldg(row), n1 = __ldg(row + 32);
-        if (mm & 1) { B0 = n0; B1 = n1; } else { A0 = n0; A1 = n1; }     // warp-uniform
+        double2 nw[GC_PPL];
+#pragma unroll
+        for (int h = 0; h < GC_PPL; ++h) nw[h] = __ldg(row + 32 * h);
+        if (mm & 1) {                                     // warp-uniform
+#pragma unroll
+            for (int h = 0; h < GC_PPL; ++h) B[h] = nw[h];
+        } else {
+#pragma unroll
+            for (int h = 0; h < GC_PPL; ++h) A[h] = nw[h];
+        }
         // a1 (a2 S0 + b2 S2) + b1 (a2 S1 + b2 S3)
-        const double t0 = fma(B0.y, s23.x, B0.x * s01.x), u0 = fma(B0.y, s23.y, B0.x * s01.y);
-        const double t1 = fma(B1.y, s23.x, B1.x * s01.x), u1 = fma(B1.y, s23.y, B1.x * s01.y);
-        acc0 = fma(A0.x, t0, acc0);
-        acc1 = fma(A1.x, t1, acc1);
-        acc0 = fma(A0.y, u0, acc0);
-        acc1 = fma(A1.y, u1, acc1);
+#pragma unroll
+        for (int h = 0; h < GC_PPL; ++h) {
+            const double t = fma(B[h].y, s23.x, B[h].x * s01.x), u = fma(B[h].y, s23.y, B[h].x * s01.y);
+            acc[h] = fma(A[h].x, t, acc[h]);
+            acc[h] = fma(A[h].y, u, acc[h]);
+        }
     }
     const double yi = y[i];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < GC_PPL; ++h) {
         const int p = p0 + 32 * h;
         if (p >= P) continue;
-        const double a = (nc < 0) ? NAN : (h ? acc1 : acc0);
+        const double a = (nc < 0) ? NAN : acc[h];
         const double sd = prefactor * yi * yi * a * slf[p];
         const long long o = (long long)p * n_y + i;
         if (sd_gw) sd_gw[o] = sd;
