@@ -312,14 +312,29 @@ def gpu_arm(args):
             # one stage entry = the groups of one chunk (they run concurrently on side streams, fork -> join)
             groups = max(1, n_launch_pts // GRID_N)
             alg["spec_den_v_group"] = groups * (2.0 * n_sdv * kw * GRID_N + 10.0 * n_sdv * NPT[1])
+        # measured DRAM traffic per stage entry, from the committed ncu captures (profiles/r01_traffic.json)
+        traffic = {}
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+                tj = json.load(f)
+            per = lambda k: tj[k]["read"] + tj[k]["write"]
+            if args.path == "generic" and NPT == (2000, 10000, 10000):
+                traffic["spec_den_v_group"] = max(1, n_launch_pts // GRID_N) * (per("sdv_gemm_kernel") + per("sdv_weights_kernel"))
+                traffic["spec_den_gw_cells"] = (per("spec_den_gw_cells_kernel") + per("gw_table_kernel")) * n_launch_pts / 2000.0
+        except (OSError, KeyError, ValueError):
+            pass
         dom = max((k for k in stage_ms if k in alg), key=lambda k: stage_ms[k]["ms"], default=None)
         roofline = None
         if dom:
             dur = stage_ms[dom]["ms"] / max(1, stage_ms[dom]["n"]) * 1e-3
             ach = alg[dom] / dur / 1e12
-            roofline = {"kernel": dom, "bound": "fp64", "achieved": ach, "peak": peak / 1e12, "unit": "TFLOP/s",
-                        "frac": ach / (peak / 1e12), "traffic": None,
-                        "peak_source": "in-run FP64 FMA probe kernel (MEASURED_PEAKS.json has no FP64 entry)",
+            # spec_den_v_group = weights kernel + banded matrix product on the FP64 tensor pipe (DMMA): "tensor";
+            # everything else on this path is FP64 FMA-pipe work, reported against the same measured FP64 peak
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak / 1e12, "unit": "TFLOP/s",
+                        "frac": ach / (peak / 1e12), "traffic": traffic.get(dom),
+                        "precision": "fp64 (DMMA m8n8k4)" if dom.startswith("spec_den_v_group") else "fp64 (FMA pipe)",
+                        "peak_source": "in-run FP64 FMA probe kernel (MEASURED_PEAKS.json has no FP64 entry; the DMMA "
+                                       "pipe saturates at ~84 % of it, profiles/r01_ncu_sdv_group_v2.txt)",
                         "share_of_step": stage_ms[dom]["ms"] / dev_ms}
         cores = len(os.sched_getaffinity(0))
         cpu = None
