@@ -133,7 +133,7 @@ def reference_arm(args):
         "config": {"workload": WORKLOADS[args.path], "batch_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "spectra/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=RESULT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -362,9 +362,21 @@ def gpu_arm(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), file=RESULT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+RESULT = sys.stdout
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints its version banner to
+    fd 1): point fd 1 at stderr for the duration of the run and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 if __name__ == "__main__":
@@ -378,6 +390,7 @@ if __name__ == "__main__":
     ap.add_argument("--path", default="generic", choices=["generic", "bag"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    RESULT = _claim_stdout()
     if a.impl == "reference":
         reference_arm(a)
     else:
