@@ -103,6 +103,49 @@ fluid_shell_bag = sound_shell_bag
 fluid_shell_alpha_plus = sound_shell_alpha_plus
 
 
+def bag_quantities(v_wall, alpha_n, n_xi: int = N_XI_DEFAULT) -> tp.Dict[str, np.ndarray]:
+    """The bubble-averaged quantities of the old bag API for a batch of points, one shell kernel + one integral kernel:
+    ubarf2 = mean_kinetic_energy / w[-1] (quantities.py:442-456, 509-527), kappa = ubarf2 / (0.75 alpha_n) (:81-117),
+    ke_frac = ubarf2 / (0.75 (1 + alpha_n)) (:250-263), mean_enthalpy_change (:423-439).  NaN where the reference
+    has no solution (SolutionType.ERROR)."""
+    torch = engine._torch()
+    vw = np.atleast_1d(np.asarray(v_wall, dtype=np.float64))
+    an = np.broadcast_to(np.asarray(alpha_n, dtype=np.float64), vw.shape).copy()
+    shells = engine.sweep_shells_bag(vw, an, n_xi=n_xi)
+    pp2 = torch.zeros((vw.size, 12), dtype=torch.float64, device="cuda")
+    pp2[:, 0] = engine.dev_f64(vw)
+    pp2[:, 1], pp2[:, 2] = 4.0, 4.0                 # bag: mu = 4 in both phases
+    pp2[:, 5], pp2[:, 6], pp2[:, 7] = 1.0, 1.0, 1.0
+    I = engine.profile_integrals(shells, pp2).cpu().numpy()
+    ok = shells.status.cpu().numpy() == 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ubarf2 = np.where(ok, I[:, 0] / vw ** 3 / I[:, 7], np.nan)
+        out = {"ubarf2": ubarf2, "kappa": ubarf2 / (0.75 * an), "ke_frac": ubarf2 / (0.75 * (1 + an)),
+               "mean_enthalpy_change": np.where(ok, I[:, 2] / vw ** 3, np.nan)}
+    return out
+
+
+def _scalar_or_array(v_wall, arr):
+    return arr if isinstance(v_wall, np.ndarray) else type(v_wall)(arr[0])
+
+
+def get_ubarf2_bag(v_wall, alpha_n: float, n_xi: int = N_XI_DEFAULT, verbosity: int = 0):
+    """Mean square fluid velocity (quantities.py:328-346); v_wall may be a float or an array."""
+    if not isinstance(v_wall, (float, np.floating, np.ndarray)):
+        raise TypeError(f"Unknown type for v_wall: {type(v_wall)}")
+    return _scalar_or_array(v_wall, bag_quantities(v_wall, alpha_n, n_xi)["ubarf2"])
+
+
+def get_kappa_bag(v_wall, alpha_n: float, n_xi: int = N_XI_DEFAULT, verbosity: int = 0):
+    """Efficiency factor kappa (quantities.py:81-117)."""
+    return _scalar_or_array(v_wall, bag_quantities(v_wall, alpha_n, n_xi)["kappa"])
+
+
+def get_ke_frac_bag(v_wall, alpha_n: float, n_xi: int = N_XI_DEFAULT):
+    """Kinetic energy fraction of the total energy, bag equation of state (quantities.py:250-263)."""
+    return _scalar_or_array(v_wall, bag_quantities(v_wall, alpha_n, n_xi)["ke_frac"])
+
+
 def fluid_integrate_param(v0, w0, xi0, phase=-1., t_end=T_END_DEFAULT, n_xi=N_XI_DEFAULT, df_dtau_ptr=None,
                           method: str = "cuda", cs2_s: float = CS0_2, cs2_b: float = CS0_2):
     """integrate.py:81-135 as a one-lane batch.  `df_dtau_ptr` may be a Model (its sound speeds are used) or None

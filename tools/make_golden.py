@@ -184,8 +184,21 @@ def generic_spectra():
     np.savez_compressed(os.path.join(OUT, "ref_generic_spectra.npz"), **d)
 
 
+def suppression_ssm():
+    """The reference's stored results of calc_sup_ssm (tests/omgw0/test_suppression.py:32-59): integrals of
+    power_gw_scaled_bag over ln z and get_ubarf2_bag for the simulation points, npt = (2000, 200, 320)."""
+    import pttools.omgw0.suppression.suppression_ssm_data as pkg
+    src = os.path.dirname(os.path.abspath(pkg.__file__))
+    d = {}
+    for f in ("suppression_2_ssm", "suppression_no_hybrids_ssm"):
+        with np.load(os.path.join(src, f + ".npz")) as z:
+            for k in z:
+                d[f"{f}__{k}"] = z[k]
+    np.savez_compressed(os.path.join(OUT, "ref_suppression_ssm.npz"), **d)
+
+
 TASKS.update({"fluid_reference": fluid_reference_table, "generic_bubbles": generic_bubbles,
-              "generic_spectra": generic_spectra})
+              "generic_spectra": generic_spectra, "suppression_ssm": suppression_ssm})
 
 
 if __name__ == "__main__":
