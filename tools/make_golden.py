@@ -197,7 +197,15 @@ def suppression_ssm():
     np.savez_compressed(os.path.join(OUT, "ref_suppression_ssm.npz"), **d)
 
 
-TASKS.update({"fluid_reference": fluid_reference_table, "generic_bubbles": generic_bubbles,
+def model_tables():
+    """The reference's EOS known answers (tests/test_data/models/{bag,const_cs}.json, tests/models/base_model.py:41-100)."""
+    import json
+    root = os.path.join(REF_TEST_DATA, "models")
+    out = {n: json.load(open(os.path.join(root, n + ".json"))) for n in ("bag", "const_cs")}
+    json.dump(out, open(os.path.join(OUT, "ref_models.json"), "w"))
+
+
+TASKS.update({"model_tables": model_tables, "fluid_reference": fluid_reference_table, "generic_bubbles": generic_bubbles,
               "generic_spectra": generic_spectra, "suppression_ssm": suppression_ssm})
 
 
