@@ -87,6 +87,13 @@ def sound_shell_alpha_plus(v_wall: float, alpha_plus: float, sol_type=SolutionTy
     return sh.profile(0)
 
 
+def find_alpha_n_bag(v_wall: float, alpha_p: float, sol_type=SolutionType.UNKNOWN, n_xi: int = N_XI_DEFAULT, **_) -> float:
+    """alpha_n from alpha_+ for the bag model (alpha.py:229-255): alpha_+ w(wall) / w_n of the shell."""
+    _, w, xi = sound_shell_alpha_plus(v_wall, alpha_p, sol_type, n_xi)
+    n_wall = int(np.argmax(xi >= v_wall)) if np.any(xi >= v_wall) else 0        # props.find_v_index
+    return float(alpha_p * w[n_wall] / w[-1])
+
+
 def identify_solution_type_alpha_plus(v_wall: float, alpha_p: float) -> SolutionType:
     """transition.py:97-124."""
     if v_wall <= CS0:
