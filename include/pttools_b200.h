@@ -129,6 +129,14 @@ int ptt_sin_transform_batch(int P, const double* xi, const double* f, int64_t st
                             const int32_t* npts, int n_z, const double* z, const double* frac,
                             double* out, void* stream);
 
+/* Same operator for profiles that live on 0 <= xi <= 1 (fluid shells do) with the exact branch restricted to
+ * z <= 51.2 (z_st_thresh = 50 is): the trapezoid sum is evaluated from block moments of weight*f instead of one sine
+ * per (z, xi) pair - same sum, O(n_xi + 256 n_z) instead of O(n_xi n_z) per profile.  Rows that violate either
+ * precondition come back as NaN. */
+int ptt_sin_transform_unit_batch(int P, const double* xi, const double* f, int64_t stride, const int32_t* off,
+                            const int32_t* npts, int n_z, const double* z, const double* frac,
+                            double* out, void* stream);
+
 typedef struct ptt_a2_plan {
     int32_t n_z;          /* total number of wavenumbers (all lookup grids concatenated) */
     int32_t n_seg;        /* number of grids; gradients never cross a grid boundary */

@@ -510,6 +510,49 @@ __global__ void __launch_bounds__(STM_THREADS) sin_transform_moments_kernel(
     wk[lay.L() + iz] = pref * rB;
 }
 
+// Array-operator variant (sin_transform(z, xi, f) on profiles with 0 <= xi <= 1): moments of g = weight * f, then the
+// same per-wavenumber evaluation.  A profile with a sample outside [0, 1] is flagged and comes back as NaN.
+__global__ void __launch_bounds__(256) st_moments_kernel(const double* __restrict__ xi_all,
+                                                         const double* __restrict__ g_all, const long long stride,
+                                                         const int* __restrict__ off, const int* __restrict__ npts,
+                                                         double* __restrict__ mom_all) {
+    __shared__ double s_m[MOM_BLOCKS * MOM_J];
+    __shared__ int s_lohi[2];
+    const int p = blockIdx.x;
+    const int N = npts[p];
+    const long long base = (long long)p * stride + off[p];
+    const double* xi = xi_all + base;
+    double* mom = mom_all + (long long)p * MOM_SIZE;
+    int bad = 0;
+    for (int k = threadIdx.x; k < N; k += blockDim.x)
+        if (!(xi[k] >= 0.0 && xi[k] <= 1.0)) bad = 1;
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) mom[2] = bad ? 1.0 : 0.0;
+    if (bad) {
+        if (threadIdx.x == 0) { mom[0] = 1.0; mom[1] = 0.0; }
+        return;
+    }
+    block_moments(xi, g_all + base, N, mom, s_m, s_lohi);
+}
+
+__global__ void __launch_bounds__(STM_THREADS) st_transform_moments_kernel(
+    const int n_z, const double* __restrict__ z_all, const double* __restrict__ frac_all, const int* __restrict__ npts,
+    const double* __restrict__ mom_all, const double* __restrict__ env_all, double* __restrict__ out) {
+    const int p = blockIdx.y;
+    const int iz = blockIdx.x * STM_THREADS + threadIdx.x;
+    if (iz >= n_z) return;
+    const double z = z_all[iz], frac = frac_all[iz];
+    const double* mom = mom_all + (long long)p * MOM_SIZE;
+    const double* env = env_all + (long long)p * ENV_SIZE;
+    const int N = npts[p];
+    double r;
+    if (env[7] != 1.0 || N < 3 || mom[2] != 0.0 || (frac < 1.0 && z > MOM_ZMAX)) r = NAN;
+    else if (frac <= 0.0) r = moment_transform(mom, z);
+    else if (frac >= 1.0) r = envelope_transform(env, z);
+    else r = envelope_transform(env, z) * frac + moment_transform(mom, z) * (1.0 - frac);
+    out[(long long)p * n_z + iz] = r;
+}
+
 // --- K5c: |A|^2 from f and l (ssm.py:56, 74-81; speedup/functions.py:10-20) ----------------------------------
 __global__ void __launch_bounds__(256) a2_finish_kernel(
     const int n_z, const int n_seg, const int* __restrict__ seg, const double* __restrict__ z,
@@ -784,6 +827,35 @@ extern "C" int ptt_sin_transform_batch(int P, const double* xi, const double* f,
     const int rc = check_launch("sin_transform_kernel");
     cudaFreeAsync(g, stream);
     cudaFreeAsync(env, stream);
+    return rc;
+}
+
+extern "C" int ptt_sin_transform_unit_batch(int P, const double* xi, const double* f, int64_t stride, const int32_t* off,
+                                            const int32_t* npts, int n_z, const double* z, const double* frac,
+                                            double* out, void* stream_) {
+    if (P < 0 || n_z < 0 || !xi || !f || !off || !npts || !z || !frac || !out)
+        return set_error(PTT_E_ARG, "ptt_sin_transform_unit_batch: null pointer or bad size");
+    if (P == 0 || n_z == 0) return PTT_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    double* g = nullptr;
+    double* env = nullptr;
+    double* mom = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&g, sizeof(double) * (size_t)P * (size_t)stride, stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&env, sizeof(double) * (size_t)P * ENV_SIZE, stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&mom, sizeof(double) * (size_t)P * MOM_SIZE, stream);
+    if (e != cudaSuccess) {
+        if (g) cudaFreeAsync(g, stream);
+        if (env) cudaFreeAsync(env, stream);
+        return set_cuda_error("ptt_sin_transform_unit_batch alloc", e);
+    }
+    st_prep_kernel<<<P, 256, 0, stream>>>(xi, f, stride, off, npts, g, env);
+    st_moments_kernel<<<P, 256, 0, stream>>>(xi, g, stride, off, npts, mom);
+    dim3 grid((n_z + STM_THREADS - 1) / STM_THREADS, P);
+    st_transform_moments_kernel<<<grid, STM_THREADS, 0, stream>>>(n_z, z, frac, npts, mom, env, out);
+    const int rc = check_launch("st_transform_moments_kernel");
+    cudaFreeAsync(g, stream);
+    cudaFreeAsync(env, stream);
+    cudaFreeAsync(mom, stream);
     return rc;
 }
 

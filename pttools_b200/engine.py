@@ -777,8 +777,10 @@ def spectra_from_shells(plan: SsmPlan, shells: ShellBatch, pp, slf=None, scale=N
     return res
 
 
-def sin_transform_batch(z, xi, f, off, npts, z_st_thresh=Z_ST_THRESH):
-    """Batched sin_transform over ragged profiles stored as rows (calculators.py:161-190)."""
+def sin_transform_batch(z, xi, f, off, npts, z_st_thresh=Z_ST_THRESH, method="auto"):
+    """Batched sin_transform over ragged profiles stored as rows (calculators.py:161-190).
+    method: "direct" = one sine per (z, xi) pair; "moments" = block-moment evaluation of the same sum (needs
+    0 <= xi <= 1 and an exact branch that ends at z <= 51.2); "auto" picks moments when both hold."""
     torch = _torch()
     lib = _lib.load()
     zz = np.asarray(z, dtype=np.float64)
@@ -791,6 +793,17 @@ def sin_transform_batch(z, xi, f, off, npts, z_st_thresh=Z_ST_THRESH):
     off_t = torch.as_tensor(off, dtype=torch.int32, device=xi.device).reshape(-1).contiguous()
     npts_t = torch.as_tensor(npts, dtype=torch.int32, device=xi.device).reshape(-1).contiguous()
     out = torch.empty((P, zz.size), dtype=torch.float64, device=xi.device)
+    if method == "auto":
+        fr = blend_fraction(zz, z_st_thresh)
+        col = torch.arange(stride, device=xi.device)[None, :]
+        valid = (col >= off_t[:, None]) & (col < (off_t + npts_t)[:, None])
+        in_unit = bool(((xi >= 0.0) & (xi <= 1.0) | ~valid).all().item())
+        method = "moments" if (in_unit and z_exact_max(zz, fr) <= 51.2) else "direct"
+    if method == "moments":
+        _lib.check(lib.ptt_sin_transform_unit_batch(P, _ptr(xi), _ptr(f), stride, _ptr(off_t), _ptr(npts_t), zz.size,
+                                                    _ptr(z_d), _ptr(frac), _ptr(out), _stream_ptr(torch)),
+                   "ptt_sin_transform_unit_batch")
+        return out
     _lib.check(lib.ptt_sin_transform_batch(P, _ptr(xi), _ptr(f), stride, _ptr(off_t), _ptr(npts_t), zz.size, _ptr(z_d),
                                            _ptr(frac), _ptr(out), _stream_ptr(torch)), "ptt_sin_transform_batch")
     return out

@@ -217,3 +217,47 @@ def test_gw_cell_formulation_matches_per_sample_kernel(sizes):
             ref = ssm.spec_den_gw_scaled(z_lookup, pv_h[i], y, sb.CS0, source_lifetime_factor=float(slf[i]),
                                          nz_int=nz_int)[0]
             np.testing.assert_allclose(sd[i], ref, rtol=1e-10)
+
+
+def test_sin_transform_operator_moments_against_direct_and_oracle():
+    """Config-4 style inputs: f_p(xi) = max(0, cos(xi + phi_p)) on [xi_a, xi_b], shared uniform grid and a
+    ragged non-uniform variant; z all-exact and mixed exact/asymptotic.  The block-moment operator against the
+    one-sine-per-pair kernel (same sum: 1e-10 of the row maximum) and against the oracle's sin_transform."""
+    import torch
+    from pttools_b200 import engine
+    rng = np.random.default_rng(0)
+    P, n_xi = 48, 2048
+    phi, xa = rng.uniform(0, 1, P), rng.uniform(0.05, 0.5, P)
+    xb = xa + rng.uniform(0.05, 0.45, P)
+    xi_u = np.linspace(0, 1, n_xi)
+    rows_xi = np.zeros((P, n_xi + 7))
+    rows_f = np.zeros_like(rows_xi)
+    off = rng.integers(0, 7, P)
+    npts = np.full(P, n_xi)
+    for p in range(P):
+        if p % 2:       # ragged, non-uniform
+            npts[p] = rng.integers(300, n_xi)
+            x = np.sort(rng.uniform(0, 1, npts[p]))
+        else:
+            x = xi_u
+        rows_xi[p, off[p]:off[p] + npts[p]] = x
+        rows_f[p, off[p]:off[p] + npts[p]] = np.maximum(0, np.cos(x + phi[p])) * ((x > xa[p]) & (x < xb[p]))
+        rows_xi[p, :off[p]] = -5.0                     # padding must not matter
+    for z in (np.logspace(-1, np.log10(50), 512), np.logspace(-1, 3, 512)):
+        a = engine.sin_transform_batch(z, rows_xi, rows_f, off, npts, method="direct").cpu().numpy()
+        b = engine.sin_transform_batch(z, rows_xi, rows_f, off, npts, method="auto").cpu().numpy()
+        c = engine.sin_transform_batch(z, rows_xi, rows_f, off, npts, method="moments").cpu().numpy()
+        assert np.array_equal(b, c)                    # auto picked the moment path
+        for p in range(P):
+            np.testing.assert_allclose(c[p], a[p], rtol=1e-9, atol=1e-10 * np.abs(a[p]).max())
+        for p in (0, 1, 7):
+            x, f = rows_xi[p, off[p]:off[p] + npts[p]], rows_f[p, off[p]:off[p] + npts[p]]
+            np.testing.assert_allclose(c[p], ssm.sin_transform(z, x, f), rtol=1e-8, atol=1e-10 * np.abs(a[p]).max())
+    # a profile outside [0, 1] must not be silently wrong: auto falls back to the direct kernel, forced moments -> NaN
+    rows_xi[3, off[3] + npts[3] - 1] = 1.5
+    z = np.logspace(-1, 1, 64)
+    d = engine.sin_transform_batch(z, rows_xi, rows_f, off, npts, method="moments").cpu().numpy()
+    assert np.all(np.isnan(d[3])) and np.all(np.isfinite(d[2]))
+    e = engine.sin_transform_batch(z, rows_xi, rows_f, off, npts, method="auto").cpu().numpy()
+    x, f = rows_xi[3, off[3]:off[3] + npts[3]], rows_f[3, off[3]:off[3] + npts[3]]
+    np.testing.assert_allclose(e[3], ssm.sin_transform(z, x, f), rtol=1e-8, atol=1e-12)
