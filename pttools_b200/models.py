@@ -319,7 +319,10 @@ class ConstCSModel(Model):
     """pttools/models/const_cs.py:43-737."""
     DEFAULT_NAME = "const_cs"
 
-    def __init__(self, css2, csb2, V_s=1.0, V_b=0.0, a_s=None, a_b=None, T_ref=1.0, name=None, **kw):
+    def __init__(self, css2, csb2, V_s=1.0, V_b=0.0, a_s=None, a_b=None, T_ref=1.0, name=None, alpha_n_min=None, **kw):
+        if alpha_n_min is not None:
+            raise NotImplementedError("ConstCSModel(alpha_n_min=...): the parameter search of const_cs.py:225-397 is "
+                                      "not part of this package; give a_s, a_b, V_s, V_b explicitly")
         css2, csb2 = float(css2), float(csb2)
         for nm, c in (("css2", css2), ("csb2", csb2)):
             if not 0 < c <= 1:

@@ -193,6 +193,38 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
     return out
 
 
+def sweep_models(models, v_walls, alpha_ns, y=None, rank: int = 0, world: int = 1, **kw) -> tp.List[tp.Dict[str, tp.Any]]:
+    """Spectra for several models on one (v_wall, alpha_n) grid - the multi-model sweeps of the reference's
+    examples/const_cs/const_cs_gw.py:153-187 (create_spectra once per model).  Per model the grid is restricted to
+    alpha_n >= model.alpha_n_min (Bubble raises below it, model.py:813-823); points are ordered v_wall-major so that
+    the grouped spec_den_v path applies; plans are shared between models with the same broken-phase sound speed.
+    With world > 1 the MODELS are dealt over the ranks (each model's sweep stays on one GPU).
+    Returns one dict per model of this rank: {"model", "index", "mask" [n_alpha, n_vw], "result" SweepResult with rows
+    in v_wall-major order of the masked grid, "i_alpha", "i_vw" row -> grid indices}."""
+    v_walls = np.asarray(v_walls, dtype=float)
+    alpha_ns = np.asarray(alpha_ns, dtype=float)
+    y = engine.Y_DEFAULT if y is None else np.asarray(y, dtype=float)
+    plans: tp.Dict[tp.Tuple, engine.SsmPlan] = {}
+    out = []
+    for im, model in enumerate(models):
+        if im % world != rank:
+            continue
+        ok_alpha = alpha_ns >= model.alpha_n_min
+        i_vw, i_al = np.meshgrid(np.arange(v_walls.size), np.nonzero(ok_alpha)[0], indexing="ij")     # v_wall-major
+        i_vw, i_al = i_vw.ravel(), i_al.ravel()
+        key = (round(float(model.csb2), 15), kw.get("nt", engine.NT_DEFAULT), kw.get("n_z_lookup", engine.NZ_LOOKUP_DEFAULT),
+               kw.get("z_st_thresh", engine.Z_ST_THRESH), kw.get("nuc_type", "exponential"))
+        if key not in plans:
+            plans[key] = engine.SsmPlan(y, cs=float(np.sqrt(model.csb2)), nt=key[1], n_z_lookup=key[2], z_st_thresh=key[3],
+                                        nuc_type=key[4], a=1.0, mode="ssm",
+                                        only_lookup_pass=not kw.get("want_pow_v", True))
+        res = sweep_spectra(model, v_walls[i_vw], alpha_ns[i_al], y=y, plan=plans[key], **kw) if i_vw.size else None
+        mask = np.zeros((alpha_ns.size, v_walls.size), dtype=bool)
+        mask[i_al, i_vw] = True
+        out.append({"model": model, "index": im, "mask": mask, "result": res, "i_alpha": i_al, "i_vw": i_vw})
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Multi-GPU: static sharding, no collective in the solve, one gather of the result table at the end
 # ---------------------------------------------------------------------------------------------------------------

@@ -149,3 +149,35 @@ def test_suppression_ssm_tables_through_the_sweep_operator():
         np.testing.assert_allclose(bubble.get_ke_frac_bag(np.array([vw[0]]), float(al[0])),
                                    ub[:1] / (0.75 * (1 + al[0])), rtol=1e-12)
     print("worst relative deviation of ssm_tot:", worst)
+
+
+def test_multi_model_sweep_matches_per_point_objects():
+    """Config 3 in miniature (examples/const_cs/const_cs_gw.py:153-187): four ConstCS models on one grid through
+    sweep_models, against Bubble + Spectrum objects built point by point."""
+    from pttools_b200 import sweep
+    from pttools_b200.bubble import Bubble
+    from pttools_b200.models import ConstCSModel
+    from pttools_b200.omgw0 import Spectrum
+    v_walls = np.linspace(0.3, 0.9, 4)
+    alpha_ns = np.array([0.05, 0.2, 0.35])
+    models = [ConstCSModel(css2=a, csb2=b, a_s=5, a_b=1, V_s=1) for a in (1 / 3, 1 / 4) for b in (1 / 3, 1 / 4)]
+    y = np.logspace(-1, 3, 120)
+    res = sweep.sweep_models(models, v_walls, alpha_ns, y=y, r_star=0.1, Tn=200, nt=800, n_z_lookup=900)
+    assert len(res) == 4
+    n_checked = 0
+    for r in res:
+        m, out = r["model"], r["result"]
+        assert r["mask"].sum() == out.v_wall.numel() and np.all(alpha_ns[r["i_alpha"]] >= m.alpha_n_min)
+        st = out.status.cpu().numpy()
+        om = out.omgw0.cpu().numpy()
+        for row in range(0, st.size, 2):
+            if st[row] != 0:
+                continue
+            vw, an = v_walls[r["i_vw"][row]], alpha_ns[r["i_alpha"][row]]
+            b = Bubble(m, v_wall=vw, alpha_n=an)
+            s = Spectrum(b, y=y, r_star=0.1, Tn=200, nt=800, n_z_lookup=900)
+            np.testing.assert_allclose(om[row], s.omgw0(), rtol=1e-9)
+            n_checked += 1
+    assert n_checked >= 6
+    with pytest.raises(NotImplementedError):
+        ConstCSModel(css2=1 / 3, csb2=1 / 4, alpha_n_min=0.05)
