@@ -574,7 +574,7 @@ def spec_den_v_batch(plan: SsmPlan, ipass: int, a2, v_wall):
     return out
 
 
-GROUP_MIN = 96          # smallest run of equal v_wall worth the banded matrix product
+GROUP_MIN = 24          # smallest run of equal v_wall worth the banded matrix product (break-even ~15 profiles)
 USE_GROUPED_SDV = True
 
 
