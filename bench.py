@@ -15,6 +15,7 @@ prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the
 workload on the host cores (the reference itself is python and cannot travel to the GPU box).
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -141,7 +142,9 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    # Started BEFORE the warm-up steps: the first nvidia-smi query on a fresh box initialises NVML and was seen to
+    # stall a running step by ~250 ms; only samples whose timestamp falls inside the timed region are used.
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -155,7 +158,12 @@ class ClockSampler:
         except OSError:
             pass
 
+    def mark_start(self):
+        self.t0 = datetime.datetime.now()
+
     def stop(self):
+        t1 = datetime.datetime.now()
+        t0 = getattr(self, "t0", None)
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -172,6 +180,9 @@ class ClockSampler:
             if len(c) < 9:
                 continue
             try:
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                if t0 is not None and not (t0 <= ts <= t1):
+                    continue
                 sm.append(float(c[1])); mx.append(float(c[2]))
             except ValueError:
                 continue
@@ -232,10 +243,12 @@ def gpu_arm(args):
     for s in range(total_steps):
         vw, an = batch_points(s, rank, world, B)
         inputs.append((engine.dev_f64(vw), engine.dev_f64(an)))
+    sampler = ClockSampler(local) if rank == 0 else None
     for s in range(args.warmup):
         device_step(s, *inputs[s])
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
     engine.STAGES.enable(True)
     launches0 = engine.STAGES.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -136,8 +136,18 @@ __global__ void __launch_bounds__(GC_WARPS * 32) spec_den_gw_cells_kernel(
     double f0[GC_PPL], f1[GC_PPL], g0[GC_PPL], g1[GC_PPL], acc[GC_PPL];
 #pragma unroll
     for (int h = 0; h < GC_PPL; ++h) f0[h] = f1[h] = g0[h] = g1[h] = acc[h] = 0.0;
+    // points without a shell carry NaN spectra (sweeps put them at the end of every v_wall row): a warp whose
+    // profiles are all NaN at the first knot has nothing to integrate
+    bool live = false;
+#pragma unroll
+    for (int h = 0; h < GC_PPL; ++h) live = live || (p0 + 32 * h < P && Fp[32 * h] == Fp[32 * h]);
+    const int n_ev = __any_sync(0xffffffffu, live) ? nc : 0;
+    if (n_ev == 0 && nc > 0) {
+#pragma unroll
+        for (int h = 0; h < GC_PPL; ++h) acc[h] = NAN;
+    }
 #pragma unroll GC_UNROLL
-    for (int c = 0; c < nc; ++c) {
+    for (int c = 0; c < n_ev; ++c) {
         const int mm = __ldg(m + c);
         const double2 c0 = __ldg(cf + 2 * c), c1 = __ldg(cf + 2 * c + 1);     // {C00, C01}, {C10, C11}
         const double* row = Fp + (long long)(mm >> 1) * Ppad;

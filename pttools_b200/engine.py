@@ -635,15 +635,17 @@ def _streams(torch, n):
     return _side_streams[:n]
 
 
-def spec_den_v_auto(plan: SsmPlan, ipass: int, a2, v_wall):
+def spec_den_v_auto(plan: SsmPlan, ipass: int, a2, v_wall, v_wall_host=None, valid_host=None):
     """spec_den_v for a batch: runs of >= GROUP_MIN consecutive profiles with the same v_wall go through the banded
-    matrix product, everything else through the gather kernel."""
+    matrix product, everything else through the gather kernel.  v_wall_host: the same wall speeds on the host (saves
+    a device read-back); valid_host: bool per profile - trailing profiles of a run that have no shell (their A^2 is
+    NaN) are left out of the matrix product and get NaN directly."""
     torch = _torch()
     P = a2.shape[0]
     n_z = plan.sdv_plans[ipass].n_z
     if not USE_GROUPED_SDV or P < GROUP_MIN:
         return spec_den_v_batch(plan, ipass, a2, v_wall)
-    vw = v_wall.detach().cpu().numpy()
+    vw = v_wall.detach().cpu().numpy() if v_wall_host is None else np.asarray(v_wall_host, dtype=float)
     cuts = np.concatenate(([0], np.nonzero(np.diff(vw) != 0)[0] + 1, [P]))
     runs = [(int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:])]
     if not any(b - a >= GROUP_MIN for a, b in runs):
@@ -659,7 +661,14 @@ def spec_den_v_auto(plan: SsmPlan, ipass: int, a2, v_wall):
         if a == P:
             break
         if big:
-            big_runs.append((a, b))
+            b_eff = b
+            if valid_host is not None:
+                ok = np.nonzero(valid_host[a:b])[0]
+                b_eff = a + (int(ok[-1]) + 1 if ok.size else 0)
+                if b_eff < b:
+                    out[b_eff:b] = float("nan")
+            if b_eff > a:
+                big_runs.append((a, b_eff))
         elif small_start is None:
             small_start = a
     if len(big_runs) < 2 or SDV_STREAMS < 2:
@@ -759,18 +768,21 @@ def pow_spec_batch(z_dev, sd):
     return out
 
 
-def spectra_from_shells(plan: SsmPlan, shells: ShellBatch, pp, slf=None, scale=None, keep=False) -> SpectrumBatch:
-    """Shell profiles -> A^2 -> spec_den_v -> spec_den_gw -> pow_gw (-> omgw0), all on the device."""
+def spectra_from_shells(plan: SsmPlan, shells: ShellBatch, pp, slf=None, scale=None, keep=False,
+                        v_wall_host=None, valid_host=None) -> SpectrumBatch:
+    """Shell profiles -> A^2 -> spec_den_v -> spec_den_gw -> pow_gw (-> omgw0), all on the device.
+    v_wall_host / valid_host: optional host copies of the wall speeds and of "this point has a shell" (see
+    spec_den_v_auto); results are the same with or without them."""
     a2 = a2_batch(plan, shells, pp)
     res = SpectrumBatch(y=plan.y, pow_gw=None, sd_gw=None)
     v_wall = pp[:, 0].contiguous()
     if plan.mode == "ssm" and plan.has_y_pass:
-        sdv_y = spec_den_v_auto(plan, 0, a2, v_wall)
+        sdv_y = spec_den_v_auto(plan, 0, a2, v_wall, v_wall_host, valid_host)
         res.sd_v = sdv_y
         res.pow_v = pow_spec_batch(plan._t["y"], sdv_y)
         if keep:
             res.a2 = a2[:, : int(plan.seg[1])]
-    sdv_l = spec_den_v_auto(plan, len(plan.passes) - 1, a2, v_wall)
+    sdv_l = spec_den_v_auto(plan, len(plan.passes) - 1, a2, v_wall, v_wall_host, valid_host)
     if keep:
         res.sd_v_lookup = sdv_l
     res.sd_gw, res.pow_gw, res.omgw0 = spec_den_gw_batch(plan, sdv_l, slf, scale)

@@ -165,12 +165,14 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
         if r_star is not None and not np.isinf(lifetime_multiplier):
             slf = slf * (1 - (1 + lifetime_multiplier * 2 * r_star / torch.sqrt(bb.scal["kinetic_energy_fraction"]))
                          ** (-1 - 2 * nu_))
+        valid = bb.status.cpu().numpy() == 0
         for s in range(s0, e0, chunk):
             e = min(e0, s + chunk)
             sub = bb.shells.slice(s - s0, e - s0)
             res = engine.spectra_from_shells(plan, sub, bb.pp[s - s0:e - s0].contiguous(),
                                              slf=slf[s - s0:e - s0].contiguous(),
-                                             scale=None if scale is None else scale[s:e].contiguous())
+                                             scale=None if scale is None else scale[s:e].contiguous(),
+                                             v_wall_host=vw[s:e], valid_host=valid[s - s0:e - s0])
             pow_gw[s:e] = res.pow_gw
             if want_pow_v:
                 pow_v[s:e] = res.pow_v
