@@ -474,6 +474,56 @@ __device__ __forceinline__ double moment_transform(const double* __restrict__ mo
     return acc;
 }
 
+// Two wavenumbers per thread from one pass over the blocks (the level is chosen for the larger of the two): the
+// moment loads - uniform across the warp, but each still a full write-back into the register file - are shared.
+__device__ __forceinline__ void moment_transform2(const double* __restrict__ mom, const double za, const double zb,
+                                                  double& ra, double& rb) {
+    ra = 0.0; rb = 0.0;
+    const int b_lo7 = (int)mom[0], b_hi7 = (int)mom[1];
+    if (b_hi7 < b_lo7) return;
+    const double zmax = fmax(za, zb);
+    int l = 0;
+    while (l < MOM_LEVELS - 1 && zmax > MOM_ZW * (double)(1 << l)) ++l;
+    const int nb = 1 << l;
+    const double W = 1.0 / (double)nb;
+    const int b_lo = b_lo7 >> (MOM_LEVELS - 1 - l), b_hi = b_hi7 >> (MOM_LEVELS - 1 - l);
+    const double* lev = mom + MOM_HDR + (nb - 1) * MOM_J;
+    const double za2 = -za * za, zb2 = -zb * zb;
+    const double c0 = ((double)b_lo + 0.5) * W;
+    double sa, ca, sb, cb, swa, cwa, swb, cwb;
+    sincos(za * c0, &sa, &ca);
+    sincos(zb * c0, &sb, &cb);
+    sincos(za * W, &swa, &cwa);
+    sincos(zb * W, &swb, &cwb);
+    for (int b = b_lo; b <= b_hi; ++b) {
+        const double* m = lev + b * MOM_J;
+        const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5], m6 = m[6], m7 = m[7],
+                     m8 = m[8], m9 = m[9], m10 = m[10], m11 = m[11];
+        double C = m10, S = m11;
+        C = fma(C, za2, m8);  S = fma(S, za2, m9);
+        C = fma(C, za2, m6);  S = fma(S, za2, m7);
+        C = fma(C, za2, m4);  S = fma(S, za2, m5);
+        C = fma(C, za2, m2);  S = fma(S, za2, m3);
+        C = fma(C, za2, m0);  S = fma(S, za2, m1);
+        ra = fma(sa, C, ra);
+        ra = fma(ca * za, S, ra);
+        C = m10; S = m11;
+        C = fma(C, zb2, m8);  S = fma(S, zb2, m9);
+        C = fma(C, zb2, m6);  S = fma(S, zb2, m7);
+        C = fma(C, zb2, m4);  S = fma(S, zb2, m5);
+        C = fma(C, zb2, m2);  S = fma(S, zb2, m3);
+        C = fma(C, zb2, m0);  S = fma(S, zb2, m1);
+        rb = fma(sb, C, rb);
+        rb = fma(cb * zb, S, rb);
+        double sn = fma(sa, cwa, ca * swa);
+        ca = fma(ca, cwa, -sa * swa);
+        sa = sn;
+        sn = fma(sb, cwb, cb * swb);
+        cb = fma(cb, cwb, -sb * swb);
+        sb = sn;
+    }
+}
+
 // Same interface role as sin_transform_kernel for the A^2 path (functions A = v on the profile grid, B = xi*lambda
 // on the uniform grid), exact part from block moments.
 __global__ void __launch_bounds__(STM_THREADS) sin_transform_moments_kernel(
@@ -481,33 +531,44 @@ __global__ void __launch_bounds__(STM_THREADS) sin_transform_moments_kernel(
     const int* __restrict__ npts, double* __restrict__ work, const long long work_stride, const WorkLayout lay) {
     const int p = blockIdx.y;
     double* wk = work + (long long)p * work_stride;
-    const int iz = blockIdx.x * STM_THREADS + threadIdx.x;
-    const bool active = iz < n_z;
-    const double z = active ? z_all[iz] : 1.0;
-    const double frac = active ? frac_all[iz] : 1.0;
-    const int need_exact = __syncthreads_or((active && frac < 1.0) ? 1 : 0);
+    const int iz0 = 2 * (blockIdx.x * STM_THREADS + threadIdx.x);        // two adjacent wavenumbers per thread
+    if (iz0 >= n_z) return;
+    const int n_here = min(2, n_z - iz0);
     const int N = npts[p];
-    double accA = 0.0, accB = 0.0;
-    if (need_exact && N >= 3 && frac < 1.0) {
-        // the lanes of a warp walk the same blocks of the same level (z is ascending): uniform, L1-resident loads
-        accA = moment_transform(wk + lay.mom_v(), z);
-        accB = moment_transform(wk + lay.mom_l(), z);
-    }
-    if (!active) return;
-    const double pref = FOUR_PI / z;
     const double* envA = wk + lay.env_v();
     const double* envB = wk + lay.env_l();
-    double rA, rB;
-    if (envA[7] != 1.0 || N < 3) rA = NAN;
-    else if (frac <= 0.0) rA = accA;
-    else if (frac >= 1.0) rA = envelope_transform(envA, z);
-    else rA = envelope_transform(envA, z) * frac + accA * (1.0 - frac);
-    if (envB[7] != 1.0 || N < 3) rB = NAN;
-    else if (frac <= 0.0) rB = accB;
-    else if (frac >= 1.0) rB = envelope_transform(envB, z);
-    else rB = envelope_transform(envB, z) * frac + accB * (1.0 - frac);
-    wk[lay.F() + iz] = pref * rA;
-    wk[lay.L() + iz] = pref * rB;
+    double z[2], frac[2], accA[2] = {0.0, 0.0}, accB[2] = {0.0, 0.0};
+    for (int q = 0; q < 2; ++q) {
+        z[q] = (q < n_here) ? z_all[iz0 + q] : 1.0;
+        frac[q] = (q < n_here) ? frac_all[iz0 + q] : 1.0;
+    }
+    if (N >= 3) {
+        // the lanes of a warp walk the same blocks of the same level (z is ascending): uniform, L1-resident loads
+        if (frac[0] < 1.0 && frac[1] < 1.0) {
+            moment_transform2(wk + lay.mom_v(), z[0], z[1], accA[0], accA[1]);
+            moment_transform2(wk + lay.mom_l(), z[0], z[1], accB[0], accB[1]);
+        } else {
+            for (int q = 0; q < 2; ++q)
+                if (frac[q] < 1.0) {
+                    accA[q] = moment_transform(wk + lay.mom_v(), z[q]);
+                    accB[q] = moment_transform(wk + lay.mom_l(), z[q]);
+                }
+        }
+    }
+    for (int q = 0; q < n_here; ++q) {
+        const double pref = FOUR_PI / z[q];
+        double rA, rB;
+        if (envA[7] != 1.0 || N < 3) rA = NAN;
+        else if (frac[q] <= 0.0) rA = accA[q];
+        else if (frac[q] >= 1.0) rA = envelope_transform(envA, z[q]);
+        else rA = envelope_transform(envA, z[q]) * frac[q] + accA[q] * (1.0 - frac[q]);
+        if (envB[7] != 1.0 || N < 3) rB = NAN;
+        else if (frac[q] <= 0.0) rB = accB[q];
+        else if (frac[q] >= 1.0) rB = envelope_transform(envB, z[q]);
+        else rB = envelope_transform(envB, z[q]) * frac[q] + accB[q] * (1.0 - frac[q]);
+        wk[lay.F() + iz0 + q] = pref * rA;
+        wk[lay.L() + iz0 + q] = pref * rB;
+    }
 }
 
 // Array-operator variant (sin_transform(z, xi, f) on profiles with 0 <= xi <= 1): moments of g = weight * f, then the
@@ -878,7 +939,7 @@ extern "C" int ptt_a2_batch(const ptt_a2_plan_t* plan, int P, const double* rows
         // profiles live on xi in [0, 1]: exact part by block moments
         a2_moments_kernel<<<P, 256, 0, stream>>>(plan->nxi, plan->xi_re, rows_xi, row_stride, off, npts, work, work_stride,
                                                  lay);
-        dim3 grid((plan->n_z + STM_THREADS - 1) / STM_THREADS, P);
+        dim3 grid((plan->n_z + 2 * STM_THREADS - 1) / (2 * STM_THREADS), P);
         sin_transform_moments_kernel<<<grid, STM_THREADS, 0, stream>>>(plan->n_z, plan->z, plan->frac, npts, work,
                                                                        work_stride, lay);
     } else {
