@@ -719,7 +719,9 @@ def gw_cells(plan):
         _lib.check(lib.ptt_gw_cells_build(C.byref(plan.gw_plan), cap, _ptr(ncell), _ptr(meta), _ptr(coef),
                                           _stream_ptr(torch)), "ptt_gw_cells_build")
     if int(ncell.min().item()) < 0:
-        raise _lib.PttError("ptt_gw_cells_build: cell capacity exceeded")
+        # capacity exceeded or a lookup that does not move monotonically: this plan stays on the per-sample kernel
+        plan._gw_cells = False
+        return False
     used = int(ncell.max().item())
     if used < cap:                       # keep only what is used (the tables stay resident with the plan)
         meta, coef = meta[:, :used].contiguous(), coef[:, :used].contiguous()
@@ -744,8 +746,9 @@ def spec_den_gw_batch(plan: SsmPlan, pv, slf=None, scale=None, want_sd=True, cel
     om = torch.empty((P, n_y), dtype=torch.float64, device=dev) if scale_t is not None else None
     if cells is None:
         cells = USE_GW_CELLS and P >= GW_CELLS_MIN
-    if cells:
-        cs = gw_cells(plan)[0]
+    tabs = gw_cells(plan) if cells else False
+    if tabs:
+        cs = tabs[0]
         table = torch.empty(lib.ptt_gw_cells_table_size(int(plan.z_lookup.size), P), dtype=torch.float64, device=dev)
         with STAGES.stage("spec_den_gw_cells", 2):
             _lib.check(lib.ptt_spec_den_gw_cells_batch(C.byref(plan.gw_plan), C.byref(cs), P, _ptr(pv), pv.shape[1],
