@@ -398,7 +398,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32000)
-    ap.add_argument("--chunk", type=int, default=2000)
+    ap.add_argument("--chunk", type=int, default=8000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="generic", choices=["generic", "bag"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -625,7 +625,8 @@ def _group_stage_name(plan, ipass):
     return "spec_den_v_group" if ipass == len(plan.passes) - 1 else "spec_den_v_group_y"
 
 
-SDV_STREAMS = 2         # groups of one call run on this many side streams (fills the last partial wave of each GEMM)
+SDV_STREAMS = int(__import__("os").environ.get("PTT_SDV_STREAMS", "2"))     # groups of one call run on this many side
+                                                                      # streams (fills the last partial wave of each GEMM)
 _side_streams = []
 
 

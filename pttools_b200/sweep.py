@@ -107,7 +107,7 @@ def shell_chunk_points(n_xi: int, budget_bytes: float = 24e9) -> int:
 def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multiplier=1.0, nuc_type="exponential",
                   nt=engine.NT_DEFAULT, n_z_lookup=engine.NZ_LOOKUP_DEFAULT, z_st_thresh=engine.Z_ST_THRESH,
                   n_xi=engine.N_XI_DEFAULT, Tn=None, g_star=None, gs_star=None, suppression="default",
-                  chunk=2048, shell_chunk=None, want_pow_v=True, keep_bubbles=False, plan=None) -> SweepResult:
+                  chunk=4096, shell_chunk=None, want_pow_v=True, keep_bubbles=False, plan=None) -> SweepResult:
     """Spectrum(Bubble(model, v_wall, alpha_n), y, r_star=...) for every point of a sweep: the model-independent shell
     solve, the thermodynamic scalars, the SSM chain and Omega_gw,0 (pttools/analysis/parallel.py:157-187 ->
     bubble.py:232-352 -> ssmtools/spectrum.py:96-115 -> omgw0/omgw0_ssm.py:123-131), one model for all points."""
