@@ -94,6 +94,7 @@ extern "C" int ptt_sweep_shells_generic(int n, const double* pg, int n_xi, doubl
                                         double wn_rtol, double* rows_v, double* rows_w, double* rows_xi,
                                         int64_t row_stride, int32_t* off, int32_t* npts, double* scalars,
                                         int32_t* status, int mem, void* stream_) {
+    if (n == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (n < 0 || n_xi < 32 || !pg || !rows_v || !rows_w || !rows_xi || !off || !npts || !scalars || !status ||
         row_stride < gen_row_capacity(n_xi))
         return set_error(PTT_E_ARG, "ptt_sweep_shells_generic: null pointer, bad size or row_stride too small");
@@ -115,6 +116,7 @@ extern "C" int ptt_sweep_shells_generic(int n, const double* pg, int n_xi, doubl
 extern "C" int ptt_shell_wall_values(int n, const double* rows_v, const double* rows_w, const double* rows_xi,
                                      int64_t row_stride, const int32_t* off, const int32_t* npts, const double* v_wall,
                                      const int32_t* sol_type, double* out, void* stream_) {
+    if (n == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (n < 0 || !rows_v || !rows_w || !rows_xi || !off || !npts || !v_wall || !sol_type || !out)
         return set_error(PTT_E_ARG, "ptt_shell_wall_values: null pointer");
     if (n == 0) return PTT_OK;

@@ -220,6 +220,7 @@ extern "C" int64_t ptt_gw_cells_table_size(int n_zl, int P) {
 extern "C" int ptt_spec_den_gw_cells_batch(const ptt_gw_plan_t* plan, const ptt_gw_cells_t* cells, int P,
                                            const double* pv, int64_t pv_stride, const double* slf, const double* scale,
                                            double* table, double* sd_gw, double* pow_gw, double* omgw0, void* stream_) {
+    if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (!plan || !cells || P < 0 || !pv || !slf || !table || !pow_gw || !cells->ncell || !cells->meta || !cells->coef ||
         cells->cap <= 0 || pv_stride < plan->n_zl)
         return set_error(PTT_E_ARG, "ptt_spec_den_gw_cells_batch: null pointer or bad size");

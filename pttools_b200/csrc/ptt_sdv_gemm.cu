@@ -171,6 +171,7 @@ using namespace ptt;
 extern "C" int ptt_spec_den_v_group(const ptt_sdv_plan_t* plan, int n_p, const double* a2, int64_t a2_stride,
                                     double v_wall, int kw, const int32_t* e_base, double* omega, double* out,
                                     int64_t out_stride, void* stream_) {
+    if (n_p == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (!plan || n_p < 0 || !a2 || !e_base || !omega || !out || kw < 2)
         return set_error(PTT_E_ARG, "ptt_spec_den_v_group: null pointer or bad size");
     if (n_p == 0) return PTT_OK;

@@ -138,6 +138,7 @@ extern "C" int ptt_profile_row_capacity(int n_xi) { return profile_row_capacity(
 extern "C" int ptt_integrate_batch(int n, const double* v0, const double* w0, const double* xi0, const double* phase,
                                    const double* t_end, int n_xi, const ptt_eos_t* eos, double* out_v, double* out_w,
                                    double* out_xi, int32_t* status, int mem, void* stream_) {
+    if (n == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (n < 0 || n_xi < 1 || !v0 || !w0 || !xi0 || !phase || !t_end || !eos || !out_v || !out_w || !out_xi || !status)
         return set_error(PTT_E_ARG, "ptt_integrate_batch: null pointer or bad size");
     if (n == 0) return PTT_OK;
@@ -155,6 +156,7 @@ extern "C" int ptt_integrate_batch(int n, const double* v0, const double* w0, co
 }
 
 extern "C" int ptt_bag_alpha_n_max(int n, const double* v_wall, double* out, int32_t* status, int mem, void* stream_) {
+    if (n == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (n < 0 || !v_wall || !out) return set_error(PTT_E_ARG, "ptt_bag_alpha_n_max: null pointer or bad size");
     if (n == 0) return PTT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -170,6 +172,7 @@ extern "C" int ptt_bag_alpha_n_max(int n, const double* v_wall, double* out, int
 extern "C" int ptt_bag_find_alpha_plus(int n, const double* v_wall, const double* alpha_n, int n_xi,
                                        const double* an_max, double* alpha_plus, int32_t* sol_type, int32_t* status,
                                        int mem, void* stream_) {
+    if (n == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (n < 0 || n_xi < 3 || !v_wall || !alpha_n || !alpha_plus || !sol_type || !status)
         return set_error(PTT_E_ARG, "ptt_bag_find_alpha_plus: null pointer or bad size");
     if (n == 0) return PTT_OK;
@@ -190,6 +193,7 @@ extern "C" int ptt_bag_profiles(int n, const double* v_wall, const double* alpha
                                 int n_xi, const double* w_n, double* rows_v, double* rows_w, double* rows_xi,
                                 int64_t row_stride, int32_t* off, int32_t* npts, double* scalars, int32_t* status,
                                 int mem, void* stream_) {
+    if (n == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (n < 0 || n_xi < 3 || !v_wall || !alpha_plus || !sol_type || !rows_v || !rows_w || !rows_xi || !off || !npts ||
         !status || row_stride < profile_row_capacity(n_xi))
         return set_error(PTT_E_ARG, "ptt_bag_profiles: null pointer, bad size or row_stride too small");
@@ -215,6 +219,7 @@ extern "C" int ptt_sweep_shells_bag(int n, const double* v_wall, const double* a
                                     double* rows_v, double* rows_w, double* rows_xi, int64_t row_stride, int32_t* off,
                                     int32_t* npts, double* alpha_plus, int32_t* sol_type, double* scalars,
                                     int32_t* status, int mem, void* stream_) {
+    if (n == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (n < 0 || n_xi < 3 || !v_wall || !alpha_n || !rows_v || !rows_w || !rows_xi || !off || !npts || !alpha_plus ||
         !sol_type || !status || row_stride < profile_row_capacity(n_xi))
         return set_error(PTT_E_ARG, "ptt_sweep_shells_bag: null pointer, bad size or row_stride too small");

@@ -871,6 +871,7 @@ static int check_launch(const char* what) {
 extern "C" int ptt_sin_transform_batch(int P, const double* xi, const double* f, int64_t stride, const int32_t* off,
                                        const int32_t* npts, int n_z, const double* z, const double* frac,
                                        double* out, void* stream_) {
+    if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (P < 0 || n_z < 0 || !xi || !f || !off || !npts || !z || !frac || !out)
         return set_error(PTT_E_ARG, "ptt_sin_transform_batch: null pointer or bad size");
     if (P == 0 || n_z == 0) return PTT_OK;
@@ -894,6 +895,7 @@ extern "C" int ptt_sin_transform_batch(int P, const double* xi, const double* f,
 extern "C" int ptt_sin_transform_unit_batch(int P, const double* xi, const double* f, int64_t stride, const int32_t* off,
                                             const int32_t* npts, int n_z, const double* z, const double* frac,
                                             double* out, void* stream_) {
+    if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (P < 0 || n_z < 0 || !xi || !f || !off || !npts || !z || !frac || !out)
         return set_error(PTT_E_ARG, "ptt_sin_transform_unit_batch: null pointer or bad size");
     if (P == 0 || n_z == 0) return PTT_OK;
@@ -924,6 +926,7 @@ extern "C" int ptt_a2_batch(const ptt_a2_plan_t* plan, int P, const double* rows
                             const double* rows_xi, int64_t row_stride, const int32_t* off, const int32_t* npts,
                             const double* pp, double* work, int64_t work_stride, double* a2, double* fp2_2,
                             double* lam2, void* stream_) {
+    if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (!plan || P < 0 || !rows_v || !rows_w || !rows_xi || !off || !npts || !pp || !work || !a2)
         return set_error(PTT_E_ARG, "ptt_a2_batch: null pointer or bad size");
     if (P == 0) return PTT_OK;
@@ -966,6 +969,7 @@ extern "C" int ptt_a2_work_stride(int row_stride, int nxi, int n_z) {
 
 extern "C" int ptt_spec_den_v_batch(const ptt_sdv_plan_t* plan, int P, const double* a2, int64_t a2_stride,
                                     const double* v_wall, double* out, int64_t out_stride, void* stream_) {
+    if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (!plan || P < 0 || !a2 || !v_wall || !out || plan->z_tile < 1)
         return set_error(PTT_E_ARG, "ptt_spec_den_v_batch: null pointer or bad size");
     if (P == 0) return PTT_OK;
@@ -985,6 +989,7 @@ extern "C" int ptt_spec_den_v_batch(const ptt_sdv_plan_t* plan, int P, const dou
 extern "C" int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const double* pv, int64_t pv_stride,
                                      const double* slf, const double* scale, double* sd_gw, double* pow_gw,
                                      double* omgw0, void* stream_) {
+    if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (!plan || P < 0 || !pv || !slf || plan->y_tile < 1 || plan->y_tile % GW_R != 0)
         return set_error(PTT_E_ARG, "ptt_spec_den_gw_batch: null pointer or bad size (y_tile must be a multiple of 4)");
     if (P == 0) return PTT_OK;
@@ -1004,6 +1009,7 @@ extern "C" int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const dou
 
 extern "C" int ptt_pow_spec_batch(int P, int n_z, const double* z, const double* spec_den, int64_t stride, double* out,
                                   void* stream_) {
+    if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (P < 0 || n_z < 0 || !z || !spec_den || !out) return set_error(PTT_E_ARG, "ptt_pow_spec_batch: null pointer");
     if (P == 0 || n_z == 0) return PTT_OK;
     dim3 grid((n_z + 255) / 256, P);

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(256) profile_integrals_kernel(
 extern "C" int ptt_profile_integrals_batch(int P, const double* rows_v, const double* rows_w, const double* rows_xi,
                                            int64_t row_stride, const int32_t* off, const int32_t* npts,
                                            const double* pp2, double* out, void* stream_) {
+    if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (P < 0 || !rows_v || !rows_w || !rows_xi || !off || !npts || !pp2 || !out)
         return ptt::set_error(PTT_E_ARG, "ptt_profile_integrals_batch: null pointer or bad size");
     if (P == 0) return PTT_OK;
