@@ -40,3 +40,23 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert "hostemu" not in txt, f
+
+
+def test_argument_checks_need_no_gpu():
+    """Return codes and ptt_last_error work without a device: an empty batch is valid whatever the pointers, a negative
+    count or a null pointer with n > 0 is PTT_E_ARG with a message."""
+    import ctypes as C
+    from pttools_b200 import _lib
+    lib = _lib.load()
+    null = C.c_void_p(0)
+    assert lib.ptt_bag_alpha_n_max(0, null, null, null, _lib.MEM_DEVICE, null) == 0
+    assert lib.ptt_pow_spec_batch(0, 10, null, null, 10, null, null) == 0
+    assert lib.ptt_profile_integrals_batch(0, null, null, null, 16, null, null, null, null, null) == 0
+    rc = lib.ptt_bag_alpha_n_max(-1, null, null, null, _lib.MEM_DEVICE, null)
+    assert rc < 0 and b"ptt_bag_alpha_n_max" in lib.ptt_last_error()
+    rc = lib.ptt_bag_alpha_n_max(3, null, null, null, _lib.MEM_DEVICE, null)
+    assert rc < 0
+    with pytest.raises(_lib.PttError):
+        _lib.check(rc, "ptt_bag_alpha_n_max")
+    assert lib.ptt_profile_row_capacity(2000) > 2 * 2000 and lib.ptt_generic_row_capacity(5000) == 2 * 5000 + 4
+    assert lib.ptt_gw_cells_capacity(10000, 10000, 1251.3) >= 2 * 1252
