@@ -246,6 +246,9 @@ int ptt_profile_integrals_batch(int P, const double* rows_v, const double* rows_
 
 /* FP64 FMA throughput probe used by bench.py for the roofline denominator (not part of the reference). */
 int ptt_fp64_peak_probe(int iters, double* out_flops_per_s, void* stream);
+/* mode 0: DFMA only, 1: DMMA m8n8k4 only, 2: both interleaved - measures what the FP64 tensor pipe can deliver on this
+ * part next to the FMA pipe (roofline documentation). */
+int ptt_fp64_pipe_probe(int mode, int iters, double* out_flops_per_s, void* stream);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,7 @@ SIGNATURES = {
     "ptt_profile_integrals_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_fp64_peak_probe": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_void_p]),
+    "ptt_fp64_pipe_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
 }
 
 _lib = None

@@ -1017,6 +1017,62 @@ extern "C" int ptt_pow_spec_batch(int P, int n_z, const double* z, const double*
     return check_launch("pow_spec_kernel");
 }
 
+// mode 0: DFMA only, 1: DMMA (m8n8k4) only, 2: both interleaved (are the FP64 FMA pipe and the FP64 tensor pipe the
+// same units?).  Flops counted: 2 per FMA lane-op, 512 per warp-level DMMA.
+__global__ void fp64_pipe_probe_kernel(const int mode, const int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    double c[8][2];
+    for (int q = 0; q < 8; ++q) { c[q][0] = 0.0; c[q][1] = 0.0; }
+    const double b = 1.0000001, cc = 1e-9, fa = 1e-3 * (threadIdx.x & 7), fb = 1e-3;
+    for (int i = 0; i < iters; ++i) {
+        if (mode != 1) {
+            a0 = fma(a0, b, cc); a1 = fma(a1, b, cc); a2 = fma(a2, b, cc); a3 = fma(a3, b, cc);
+            a4 = fma(a4, b, cc); a5 = fma(a5, b, cc); a6 = fma(a6, b, cc); a7 = fma(a7, b, cc);
+        }
+        if (mode != 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[q][0]), "+d"(c[q][1]) : "d"(fa), "d"(fb));
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    for (int q = 0; q < 8; ++q) s += c[q][0] + c[q][1];
+    if (s == 123.456) sink[0] = s;
+}
+
+extern "C" int ptt_fp64_pipe_probe(int mode, int iters, double* out_flops_per_s, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (mode < 0 || mode > 2 || iters < 1 || !out_flops_per_s) return set_error(PTT_E_ARG, "ptt_fp64_pipe_probe: bad argument");
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* sink = nullptr;
+    cudaMalloc((void**)&sink, sizeof(double));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const int blocks = sms * 8, threads = 256;
+    fp64_pipe_probe_kernel<<<blocks, threads, 0, stream>>>(mode, iters / 10 + 1, sink);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(a, stream);
+        fp64_pipe_probe_kernel<<<blocks, threads, 0, stream>>>(mode, iters, sink);
+        cudaEventRecord(b, stream);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double per_thread = (mode != 1 ? 2.0 * 8.0 : 0.0) + (mode != 0 ? 8.0 * 512.0 / 32.0 : 0.0);
+        const double flops = per_thread * (double)iters * (double)blocks * (double)threads / (ms * 1e-3);
+        if (flops > best) best = flops;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    *out_flops_per_s = best;
+    return check_launch("fp64_pipe_probe_kernel");
+}
+
 extern "C" int ptt_fp64_peak_probe(int iters, double* out_flops_per_s, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int dev = 0, sms = 0;

@@ -838,6 +838,15 @@ def profile_integrals(shells: ShellBatch, pp2):
     return out
 
 
+def fp64_pipe_flops(mode, iters=20000):
+    """Measured FP64 throughput of the FMA pipe (mode 0), of DMMA m8n8k4 (1), and of both interleaved (2)."""
+    torch = _torch()
+    lib = _lib.load()
+    out = C.c_double(0.0)
+    _lib.check(lib.ptt_fp64_pipe_probe(int(mode), iters, C.byref(out), _stream_ptr(torch)), "ptt_fp64_pipe_probe")
+    return out.value
+
+
 def fp64_peak_flops(iters=20000):
     torch = _torch()
     lib = _lib.load()
