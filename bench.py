@@ -346,8 +346,8 @@ def gpu_arm(args):
             roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak / 1e12, "unit": "TFLOP/s",
                         "frac": ach / (peak / 1e12), "traffic": traffic.get(dom),
                         "precision": "fp64 (DMMA m8n8k4)" if dom.startswith("spec_den_v_group") else "fp64 (FMA pipe)",
-                        "peak_source": "in-run FP64 FMA probe kernel (MEASURED_PEAKS.json has no FP64 entry; the DMMA "
-                                       "pipe saturates at ~84 % of it, profiles/r01_ncu_sdv_group_v2.txt)",
+                        "peak_source": "in-run FP64 FMA probe kernel (MEASURED_PEAKS.json has no FP64 entry); a DMMA-only "
+                                       "probe measures the same peak (37.0 TFLOP/s, engine.fp64_pipe_flops)",
                         "share_of_step": stage_ms[dom]["ms"] / dev_ms}
         cores = len(os.sched_getaffinity(0))
         cpu = None
