@@ -78,7 +78,7 @@ struct GenericShockLocator {
     int last_i;
     int first_close;    // first sample close to (cs_n, 0)
     bool turned;
-    State cur, prev, prev2;
+    State cur, prev, prev2, close_prev;     // close_prev: the sample before first_close
 
     PTT_HD void reset(const EosDev& m_, const double v_wall_, const double cs_n_, const bool full_) {
         m = m_; v_wall = v_wall_; cs_n = cs_n_; full = full_;
@@ -99,9 +99,12 @@ struct GenericShockLocator {
     PTT_HD bool visit(const int i, const State& y) {
         if (i > 0) {
             if (behind(y)) { found = i; cur = y; return false; }
+            if (first_close < 0 && near_cs(y)) { first_close = i; close_prev = prev; }
             if (!m.bag_name) {
-                if (first_close < 0 && near_cs(y)) first_close = i;
-                if (y.xi > cs_n && first_close > 0) { found = first_close; cur = y; return false; }   // shock.py:114-121
+                if (y.xi > cs_n && first_close > 0) {                                                // shock.py:114-121
+                    found = first_close; cur = y; prev = close_prev;
+                    return false;
+                }
                 if (y.xi < prev.xi) {
                     // the curve turned back before reaching the shock curve: i_right = argmax(xi) (shock.py:134-141)
                     turned = true;
@@ -268,7 +271,16 @@ struct GenericMachine {
     // Returns true if another integration is pending, false if the residual is complete.
     PTT_HD bool resid_after(const int rc) {
         if (rc < 0) { d.status = ST_INTEGRATION_FAILED; return false; }
-        const int i_new = vis.loc.found;
+        int i_new = vis.loc.found;
+        State before = vis.loc.prev;
+        if (i_new == 0 && vis.loc.first_close > 0) {
+            // The curve ran into the fixed point (xi, v) = (cs, 0) without ever getting behind the shock curve: a shock
+            // of vanishing strength at xi = cs+.  With the reference's integrator the index is then decided by LSODA
+            // noise (xi scatters above cs, where v <= v_shock ~ 1e-9 is met at once); the first sample that
+            // np.isclose()s the fixed point - the criterion shock.py:114-121 uses for the other models - is taken.
+            i_new = vis.loc.first_close;
+            before = vis.loc.close_prev;
+        }
         bool more = false;
         if (attempt == 0) {
             if (i_new == 0 || i_new + 1 >= n_xi) return false;
@@ -277,7 +289,7 @@ struct GenericMachine {
             // keep the previous solution
         } else {
             i_shock = i_new;
-            sh = vis.loc.prev;
+            sh = before;
             d.t_end_final = te;
             if (i_shock < thin && attempt < 5) {
                 te = grid_time(te, n_xi, i_shock + 20);

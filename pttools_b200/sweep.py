@@ -165,7 +165,7 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
         if r_star is not None and not np.isinf(lifetime_multiplier):
             slf = slf * (1 - (1 + lifetime_multiplier * 2 * r_star / torch.sqrt(bb.scal["kinetic_energy_fraction"]))
                          ** (-1 - 2 * nu_))
-        valid = bb.status.cpu().numpy() == 0
+        valid = bb.shells.npts.cpu().numpy() >= 3        # has a profile (points flagged solver_failed do, like the reference)
         for s in range(s0, e0, chunk):
             e = min(e0, s + chunk)
             sub = bb.shells.slice(s - s0, e - s0)

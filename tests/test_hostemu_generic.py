@@ -71,3 +71,26 @@ def test_device_algorithm_matches_reference_runs(fixtures, mname):
         np.testing.assert_allclose(gw[0], w[0], rtol=1e-6)
         if st != 2:
             assert gv.size == v.size or abs(v[-4]) < 1e-8     # same tau-grid unless the shock is located in numerical noise
+
+
+def test_vanishing_shock_points_follow_the_reference():
+    """Slow walls with strong transitions (v_wall < 0.1, alpha_n ~ 0.3): the flow runs into the fixed point
+    (xi, v) = (cs, 0) and the shock has vanishing strength.  The reference finds its index through LSODA noise; the
+    device algorithm takes the first sample that np.isclose()s the fixed point (shock.py:114-121 criterion).  Same root
+    and same curve; before this rule these points ended as solver failures."""
+    from pttools_b200.models import BagModel
+    pm = BagModel(alpha_n_min=0.005)                       # the model of bench.py
+    mo = models.bag_model(pm.a_s, pm.a_b, pm.V_s, pm.V_b)
+    ref = sg.FluidReference(dict(np.load(os.path.join(GOLDEN, "ref_fluid_reference.npz"))))
+    warnings.filterwarnings("ignore")
+    for vw, an in ((0.08783783783783783, 0.26414414414414417), (0.08783783783783783, 0.33400900900900904),
+                   (0.051341075157952554, 0.29217078105609173)):
+        sol = sg.sound_shell_generic(mo, vw, an, ref)
+        wn = mo.wn(an)
+        g = ref.get(vw, an, 0)
+        rc, gv, gw, gx, gs = emu.generic_solve((mo.css2, mo.csb2, mo.V_s, mo.V_b, True), vw, an, 0, wn,
+                                               sg.v_chapman_jouguet(mo, an, wn), (g[0], g[2], g[4] * wn, g[5] * wn))
+        assert rc == 0 and gs["solver_failed"] == 0 and not sol["solver_failed"]
+        np.testing.assert_allclose(gs["wm"], sol["wm"], rtol=1e-6)
+        ev, ew = curve_errors(gx, gv, gw, sol["xi"], sol["v"], sol["w"], vw)
+        assert ev < 1e-6 and ew < 1e-6
