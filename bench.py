@@ -117,7 +117,7 @@ def reference_arm(args):
     per_step = 2 * max(cores, 8)
     times = []
     for s in range(args.warmup + args.steps):
-        vw, an = batch_points(s, 0, 1, 32000)
+        vw, an = batch_points(s, 0, 1, args.batch)
         pick = np.linspace(0, vw.size - 1, per_step).astype(int)      # spread over the rows and strengths of the batch
         vw, an = vw[pick], an[pick]
         dt = cpu_run(list(zip(vw, an)), cores, args.path)
@@ -397,7 +397,7 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32000)
+    ap.add_argument("--batch", type=int, default=64000)
     ap.add_argument("--chunk", type=int, default=8000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="generic", choices=["generic", "bag"])
