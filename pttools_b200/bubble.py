@@ -187,6 +187,35 @@ class BubbleBatch:
     def __len__(self):
         return self.v_wall.numel()
 
+    def validity(self, sum_rtol_error: float = 5e-2) -> tp.Dict[str, np.ndarray]:
+        """The validity flags of Bubble.solve (bubble.py:123-131, 290-352) for every point of the sweep, as host bool
+        arrays: solved, solver_failed, no_solution_found, unphysical_alpha_plus, negative_entropy_flux,
+        negative_net_entropy_change, numerical_error.  One model for all points."""
+        if not isinstance(self.model, Model):
+            raise NotImplementedError("validity(): one model per sweep")
+        m = self.model
+        st = self.status.cpu().numpy()
+        sc = {k: self.scal[k].cpu().numpy() for k in ("vp_tilde", "vm_tilde", "wp", "wm", "kappa", "omega",
+                                                      "va_entropy_density_diff")}
+        code = self.sol_type.cpu().numpy()
+        wn = self.wn.cpu().numpy()
+        solved = (st == 0) | (st == 5)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            sp = np.where(code == 2, m.s(wn, Phase.SYMMETRIC), m.s(sc["wp"], Phase.SYMMETRIC))
+            sm = m.s(sc["wm"], Phase.BROKEN)
+            g = lambda v: 1 / np.sqrt(1 - v ** 2)
+            fp, fm = g(sc["vp_tilde"]) * sc["vp_tilde"] * sp, g(sc["vm_tilde"]) * sc["vm_tilde"] * sm
+            ap = np.array([m.alpha_plus(a, b, vp_tilde=c, sol_type=CODE_SOL.get(int(t)))
+                           if ok else np.nan for a, b, c, t, ok in zip(sc["wp"], sc["wm"], sc["vp_tilde"], code, solved)])
+            ksum = sc["kappa"] + sc["omega"]
+        return {
+            "solved": solved, "solver_failed": st == 5, "no_solution_found": ~solved,
+            "unphysical_alpha_plus": solved & np.isnan(ap),
+            "negative_entropy_flux": solved & ((fp < 0) | (fm < 0) | (fm - fp < 0)),
+            "negative_net_entropy_change": solved & (sc["va_entropy_density_diff"] < 0),
+            "numerical_error": solved & ~np.isclose(ksum, 1, rtol=sum_rtol_error),
+        }
+
 
 def _per_point(models, n, attr):
     if isinstance(models, Model):

@@ -181,3 +181,25 @@ def test_multi_model_sweep_matches_per_point_objects():
     assert n_checked >= 6
     with pytest.raises(NotImplementedError):
         ConstCSModel(css2=1 / 3, csb2=1 / 4, alpha_n_min=0.05)
+
+
+def test_batched_validity_flags_match_bubble_objects():
+    """BubbleBatch.validity() (the flags of Bubble.solve for a whole sweep) against Bubble objects point by point."""
+    from pttools_b200 import bubble as bub
+    from pttools_b200.models import BagModel, ConstCSModel
+    for model in (BagModel(a_s=1.1, a_b=1, V_s=1), ConstCSModel(css2=1 / 3, csb2=1 / 4, a_s=5, a_b=1, V_s=1)):
+        vw = np.repeat([0.3, 0.62, 0.85], 4)
+        an = np.tile([max(0.06, 1.01 * model.alpha_n_min), 0.3, 0.4, 0.48], 3)
+        bb = bub.sweep_bubbles(model, vw, an)
+        flags = bb.validity()
+        assert flags["solved"].any()
+        for i in range(vw.size):
+            try:
+                b = bub.Bubble(model, v_wall=float(vw[i]), alpha_n=float(an[i]))
+            except (ValueError, RuntimeError):
+                assert not flags["solved"][i]
+                continue
+            assert bool(flags["solved"][i]) == bool(b.solved)
+            for name in ("solver_failed", "no_solution_found", "unphysical_alpha_plus", "negative_entropy_flux",
+                         "negative_net_entropy_change", "numerical_error"):
+                assert bool(flags[name][i]) == bool(getattr(b, name)), (model.name, vw[i], an[i], name)
