@@ -437,4 +437,333 @@ PTT_HD BagProfile bag_emit_profile(const double v_wall, const double alpha_plus,
     return p;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The bag solver as a resumable machine (same idea as GenericMachine in ptt_generic.cuh): find_alpha_plus_bag and
+// sound_shell_alpha_plus are nests of loops around the ODE integration; written as nested calls every lane of a warp
+// sits in its own inlined copy of the integration loop and the warp serialises.  Here the only integration call site
+// is the driver loop of bag_machine_run, and the logic around it consumes one integration and prepares the next.
+// Arithmetic and order are those of bag_find_alpha_plus / bag_forward / bag_emit_profile above (bit-identical
+// results, checked through the host emulation); the wall->shock passes of the root's last evaluation are reused for
+// the profile instead of being run again.
+
+enum BagJob : int { BJ_LOCATE = 0, BJ_EMIT_FWD = 1, BJ_EMIT_BACK = 2 };
+
+struct BagVisitor {
+    int kind;
+    ShockLocator loc;
+    ForwardEmitter fe;
+    BackwardEmitter be;
+    PTT_HD bool skip(const State& y_end) const { return kind == BJ_LOCATE && loc.skip(y_end); }
+    PTT_HD bool visit(const int i, const State& y) {
+        if (kind == BJ_LOCATE) return loc.visit(i, y);
+        if (kind == BJ_EMIT_FWD) return fe.visit(i, y);
+        return be.visit(i, y);
+    }
+};
+
+struct BagMachine {
+    enum Phase : int { PH_FWD1 = 0, PH_FWD2 = 1, PH_EMIT_FWD = 2, PH_EMIT_BACK = 3, PH_DONE = 4 };
+    enum RootState : int { R_NONE = 0, R_F0 = 1, R_F1 = 2, R_IT = 3 };
+
+    // --- point
+    double v_wall, alpha_n, w_n;
+    int n_xi;
+    bool want_profile;
+    RowOut row;
+    // --- pending integration
+    int phase;
+    State job_y0;
+    double job_te;
+    int job_n;
+    BagVisitor vis;
+    bool full_retry;            // the pending locate pass is the "never crossed" re-run in full mode
+    // --- wall->shock evaluation in flight (bag_forward)
+    double ap_eval;
+    WallSpeeds ws;
+    BagForward f;
+    // --- root finder (bag_find_alpha_plus)
+    int rstate, it;
+    double lo, hi, x0, f0, x1, f1, x2;
+    // --- results
+    BagRoot r;
+    BagProfile p;
+    int nf, nb;
+    double xif0, wf;
+
+    PTT_HD void finish_failed(const int status) { p.status = status; phase = PH_DONE; }
+
+    // ---- bag_forward, resumable ---------------------------------------------------------------------------------
+    PTT_HD void locate_job(const double te, const int n, const bool full) {
+        vis.kind = BJ_LOCATE;
+        vis.loc.reset(full);
+        job_te = te; job_n = n;
+        full_retry = full;
+    }
+    // returns true if an integration is pending, false if the evaluation is already over (f.status says why)
+    PTT_HD bool forward_begin(const double ap, const int sol_type) {
+        ap_eval = ap;
+        f.status = ST_OK;
+        f.i1 = 0; f.t_end2 = 0.0; f.n_fwd = 0; f.w1 = NAN; f.wn_raw = NAN;
+        f.last.v = f.last.w = f.last.xi = NAN;
+        ws = fluid_speeds_at_wall(v_wall, ap, sol_type);
+        if (!(ws.vfp_p == ws.vfp_p)) { f.status = ST_INVALID_INPUT; return false; }
+        job_y0.v = ws.vfp_p; job_y0.w = 1.0; job_y0.xi = v_wall;
+        locate_job(-T_END_DEFAULT, N_XI_DEFAULT, false);
+        phase = PH_FWD1;
+        return true;
+    }
+    // forward_pass's epilogue; returns false on failure
+    PTT_HD bool pass_result(const int n, int& n_keep, State& last, State& prev, State& y1) {
+        y1 = vis.loc.y1;
+        if (vis.loc.found >= 0) {
+            n_keep = vis.loc.found + 1;
+            last = vis.loc.cur;
+            prev = vis.loc.prev;
+        } else {
+            n_keep = n - 1;
+            last = vis.loc.prev2;
+            prev = vis.loc.prev2;
+            if (n_keep < 1) return false;
+        }
+        return true;
+    }
+    // After a locate integration of the evaluation in flight.  Returns true if another integration is pending,
+    // false when the evaluation is complete (f filled, f.status).
+    PTT_HD bool forward_after(const int rc) {
+        if (rc < 0) { f.status = ST_INTEGRATION_FAILED; return false; }
+        if (vis.loc.found < 0 && !full_retry) {
+            // never crossed: the reference's index stays -2 and the slice [: -1] silently drops the last sample
+            locate_job(job_te, job_n, true);
+            return true;
+        }
+        int nk;
+        State last, prev, y1;
+        if (!pass_result(job_n, nk, last, prev, y1)) { f.status = ST_INTEGRATION_FAILED; return false; }
+        if (phase == PH_FWD1) {
+            f.i1 = nk - 1;
+            f.t_end2 = grid_time(-T_END_DEFAULT, N_XI_DEFAULT, f.i1);
+            locate_job(f.t_end2, n_xi, false);
+            phase = PH_FWD2;
+            return true;
+        }
+        if (nk >= 2) shock_zoom(prev, last);
+        f.n_fwd = nk;
+        f.last = last;
+        f.w1 = (nk == 2) ? last.w : y1.w;
+        const double vfp_s = last.xi;
+        const double vfm_s = 1.0 / (3.0 * vfp_s);
+        f.wn_raw = last.w * enthalpy_ratio(vfm_s, vfp_s);
+        return false;
+    }
+
+    // ---- bag_find_alpha_plus, resumable ---------------------------------------------------------------------------
+    PTT_HD void root_fail(const int st) {
+        r.status = (st != ST_OK) ? st : ST_ROOT_NOT_CONVERGED;
+        rstate = R_NONE;
+    }
+    // Consumes a completed evaluation.  Returns true if an integration is pending, false if the root search is over.
+    PTT_HD bool root_on_eval() {
+        const double fv = ap_eval / f.wn_raw - alpha_n;          // bag_alpha_n_of_alpha_plus(...) - alpha_n
+        const int st = f.status;
+        for (;;) {
+            if (rstate == R_F0) {
+                f0 = fv;
+                if (st != ST_OK || !(f0 == f0)) { root_fail(st); return false; }
+                if (f0 < 0.0) lo = x0; else hi = x0;
+                x1 = x0 * ((f0 < 0.0) ? 1.001 : 0.999);
+                if (x1 <= lo || x1 >= hi) x1 = 0.5 * (lo + hi);
+                rstate = R_F1;
+                if (forward_begin(x1, r.sol_type)) return true;
+                root_fail(f.status);          // (an evaluation that cannot start has a NaN residual)
+                return false;
+            }
+            if (rstate == R_F1) {
+                f1 = fv;
+                if (st != ST_OK || !(f1 == f1)) { root_fail(st); return false; }
+                if (f1 < 0.0) { if (x1 > lo) lo = x1; } else { if (x1 < hi) hi = x1; }
+                r.status = ST_ROOT_NOT_CONVERGED;
+                it = 0;
+            } else {        // R_IT: fv belongs to x2
+                const double f2 = fv;
+                if (st != ST_OK || !(f2 == f2)) { root_fail(st); return false; }
+                if (f2 < 0.0) { if (x2 > lo) lo = x2; } else { if (x2 < hi) hi = x2; }
+                const double dx = fabs(x2 - x1);
+                x0 = x1; f0 = f1;
+                x1 = x2; f1 = f2;
+                if (dx <= 1e-13 * fabs(x2) || fabs(f2) <= 1e-14 * alpha_n || (hi - lo) <= 1e-14 * hi ||
+                    (dx <= 1e-10 * fabs(x2) && fabs(f2) <= 1e-11 * alpha_n)) {
+                    r.status = ST_OK;
+                    break;
+                }
+                ++it;
+            }
+            // loop header of the secant iteration
+            if (it >= 60) break;
+            r.iters = it + 1;
+            if (f1 == 0.0) { r.status = ST_OK; break; }
+            x2 = (f1 != f0) ? x1 - f1 * (x1 - x0) / (f1 - f0) : 0.5 * (lo + hi);
+            if (!(x2 > lo && x2 < hi)) x2 = 0.5 * (lo + hi);
+            rstate = R_IT;
+            if (forward_begin(x2, r.sol_type)) return true;
+            root_fail(f.status);
+            return false;
+        }
+        r.alpha_plus = x1;
+        rstate = R_NONE;
+        return false;
+    }
+
+    // ---- sound_shell_alpha_plus, resumable ------------------------------------------------------------------------
+    PTT_HD void profile_init() {
+        p.status = ST_OK; p.off = 0; p.npts = 0; p.n_wall = 0; p.xi_sh = v_wall; p.wn_raw = NAN;
+        nf = 0; nb = 0;
+        xif0 = v_wall + 1.0 / (double)n_xi;
+        wf = 1.0;
+    }
+    // the wall->shock evaluation `f` at r.alpha_plus is known: emit the forward part
+    PTT_HD void emit_forward_job() {
+        if (f.status != ST_OK) { finish_failed(f.status); return; }
+        job_y0.v = ws.vfp_p; job_y0.w = 1.0; job_y0.xi = v_wall;
+        job_te = f.t_end2; job_n = n_xi;
+        vis.kind = BJ_EMIT_FWD;
+        vis.fe.row = row; vis.fe.zero_hit = false; vis.fe.found = -1; vis.fe.last_i = -1;
+        phase = PH_EMIT_FWD;
+    }
+    PTT_HD void after_forward_part() {
+        row.set(ROW_BACK_CAP + nf, 0.0, wf, xif0);
+        row.set(ROW_BACK_CAP + nf + 1, 0.0, wf, 1.0);
+        if (r.sol_type != SOL_SUB_DEF) {
+            const double wm = 1.0 / enthalpy_ratio(ws.vfm_w, ws.vfp_w);
+            job_y0.v = ws.vfm_p; job_y0.w = wm; job_y0.xi = v_wall;
+            job_te = -T_END_DEFAULT; job_n = N_XI_DEFAULT;
+            vis.kind = BJ_EMIT_BACK;
+            vis.be.row = row; vis.be.cs2b = 1.0 / 3.0; vis.be.hit = -1; vis.be.last_i = -1;
+            vis.be.n_start = (r.sol_type == SOL_DETON) ? 0 : 1;
+            phase = PH_EMIT_BACK;
+            return;
+        }
+        const double dxi = 1.0 / (double)n_xi;
+        const double wm = 1.0 / enthalpy_ratio(ws.vfm_w, ws.vfp_w);
+        finalize(fmin(cs0_root(), v_wall) - dxi, wm);
+    }
+    PTT_HD void finalize(const double xib0, const double wb) {
+        row.set(ROW_BACK_CAP - nb - 1, 0.0, wb, xib0);
+        row.set(ROW_BACK_CAP - nb - 2, 0.0, wb, 0.0);
+        p.off = ROW_BACK_CAP - nb - 2;
+        p.npts = 2 + nb + nf + 2;
+        p.wn_raw = wf;
+        const double scale = w_n / wf;
+        for (int k = p.off; k < p.off + p.npts; ++k) row.w[k] = row.w[k] * scale;
+        int nw = 0;
+        for (int k = 0; k < p.npts; ++k) {
+            if (row.xi[p.off + k] >= v_wall) { nw = k; break; }
+        }
+        p.n_wall = nw;
+        phase = PH_DONE;
+    }
+    PTT_HD void profile_begin() {
+        profile_init();
+        if (r.sol_type == SOL_DETON) {
+            ws = fluid_speeds_at_wall(v_wall, r.alpha_plus, r.sol_type);
+            after_forward_part();
+            return;
+        }
+        emit_forward_job();
+    }
+
+    // ---- entry points ---------------------------------------------------------------------------------------------
+    // root (+ profile): find alpha_+ for (v_wall, alpha_n)
+    PTT_HD void start_root(const double v_wall_, const double alpha_n_, const int n_xi_, const double an_max_defl,
+                           const bool want_profile_, const double w_n_, const RowOut& row_) {
+        v_wall = v_wall_; alpha_n = alpha_n_; n_xi = n_xi_; want_profile = want_profile_; w_n = w_n_; row = row_;
+        phase = PH_DONE; rstate = R_NONE;
+        p.status = ST_OK; p.off = 0; p.npts = 0; p.n_wall = 0; p.xi_sh = v_wall; p.wn_raw = NAN;
+        r.iters = 0;
+        r.alpha_plus = NAN;
+        r.sol_type = identify_solution_type_bag(v_wall, alpha_n, an_max_defl);
+        if (r.sol_type == SOL_ERROR) { r.status = ST_NO_SOLUTION; return; }
+        if (r.sol_type == SOL_DETON) {
+            r.status = ST_OK; r.alpha_plus = alpha_n;
+            if (want_profile) profile_begin();
+            return;
+        }
+        double guess;
+        if (alpha_n < 0.05) {
+            guess = alpha_n;
+        } else {
+            const double ap_min = alpha_plus_min_hybrid(v_wall);
+            const double an_min = alpha_plus_max_detonation(v_wall);
+            const double slope = (1.0 / 3.0 - ap_min) / (an_max_defl - an_min);
+            guess = ap_min + slope * (alpha_n - an_min);
+        }
+        const double hi_lim = 1.0 / 3.0 - 1.0e-10;    // the reference's own upper probe (alpha.py:47)
+        lo = 0.0; hi = hi_lim;                         // residual < 0 at lo, > 0 at hi (alpha_n < an_max_defl)
+        if (guess <= lo) guess = 1e-3 * alpha_n;
+        if (guess >= hi) guess = 0.5 * (lo + hi);
+        x0 = guess;
+        rstate = R_F0;
+        if (!forward_begin(x0, r.sol_type)) { root_fail(f.status); phase = PH_DONE; }
+    }
+    // profile only: sound_shell_alpha_plus(v_wall, alpha_plus, sol_type)
+    PTT_HD void start_profile(const double v_wall_, const double alpha_plus, const int sol_type, const int n_xi_,
+                              const double w_n_, const RowOut& row_) {
+        v_wall = v_wall_; alpha_n = NAN; n_xi = n_xi_; want_profile = true; w_n = w_n_; row = row_;
+        phase = PH_DONE; rstate = R_NONE;
+        r.status = ST_OK; r.sol_type = sol_type; r.alpha_plus = alpha_plus; r.iters = 0;
+        if (sol_type == SOL_DETON) { profile_begin(); return; }
+        profile_init();
+        if (!forward_begin(alpha_plus, sol_type)) finish_failed(f.status);
+    }
+
+    // Consumes the integration that was pending; afterwards another one is pending or phase == PH_DONE.
+    PTT_HD void advance(const int rc) {
+        if (phase == PH_FWD1 || phase == PH_FWD2) {
+            if (forward_after(rc)) return;
+            // evaluation complete
+            if (rstate != R_NONE) {
+                if (root_on_eval()) return;
+                // root search over
+                if (r.status != ST_OK || !want_profile) { phase = PH_DONE; return; }
+                profile_init();          // f is the evaluation at r.alpha_plus (the last one made)
+            }
+            emit_forward_job();
+            return;
+        }
+        if (rc < 0) { finish_failed(ST_INTEGRATION_FAILED); return; }
+        if (phase == PH_EMIT_FWD) {
+            nf = (vis.fe.found >= 0) ? vis.fe.found + 1 : n_xi - 1;
+            if (nf >= 2) {
+                State l, q;
+                const int kl = ROW_BACK_CAP + nf - 1;
+                l.v = row.v[kl]; l.w = row.w[kl]; l.xi = row.xi[kl];
+                q.v = row.v[kl - 1]; q.w = row.w[kl - 1]; q.xi = row.xi[kl - 1];
+                shock_zoom(q, l);
+                row.set(kl, l.v, l.w, l.xi);
+            }
+            const int kl = ROW_BACK_CAP + nf - 1;
+            const double vfp_s = row.xi[kl];
+            const double vfm_s = 1.0 / (3.0 * vfp_s);
+            wf = row.w[kl] * enthalpy_ratio(vfm_s, vfp_s);
+            xif0 = vfp_s;
+            p.xi_sh = vfp_s;
+            after_forward_part();
+            return;
+        }
+        // PH_EMIT_BACK
+        int n_stop;
+        if (vis.be.hit < 0) n_stop = N_XI_DEFAULT - 2 + vis.be.n_start;       // slice [: -2] (+1 for hybrids)
+        else n_stop = ((vis.be.hit == 0) ? 1 : vis.be.hit) + vis.be.n_start;
+        nb = n_stop - vis.be.n_start;
+        if (nb < 1) { finish_failed(ST_INTEGRATION_FAILED); return; }
+        finalize(cs0_root(), row.w[ROW_BACK_CAP - nb]);
+    }
+
+    PTT_HD void run() {
+        while (phase != PH_DONE) {
+            const int rc = integrate_grid(1.0 / 3.0, job_y0, job_te, job_n, vis);
+            advance(rc);
+        }
+    }
+};
+
 }  // namespace ptt

@@ -78,7 +78,12 @@ __global__ void __launch_bounds__(64) bag_root_kernel(
         am = alpha_n_max_deflagration(vw, st);
         if (st != ST_OK) { alpha_plus[i] = NAN; sol_type[i] = SOL_ERROR; status[i] = st; return; }
     }
-    const BagRoot r = bag_find_alpha_plus(vw, an, n_xi, am);
+    BagMachine mach;
+    RowOut none;
+    none.v = none.w = none.xi = nullptr;
+    mach.start_root(vw, an, n_xi, am, false, 1.0, none);
+    mach.run();
+    const BagRoot& r = mach.r;
     alpha_plus[i] = (r.status == ST_OK) ? r.alpha_plus : NAN;
     sol_type[i] = r.sol_type;
     status[i] = r.status;
@@ -106,7 +111,10 @@ __global__ void __launch_bounds__(64) bag_profile_kernel(
         if (st_in == ST_OK) status[i] = ST_NO_SOLUTION;
         return;
     }
-    const BagProfile p = bag_emit_profile(v_wall[i], ap, type, n_xi, w_n ? w_n[i] : 1.0, row);
+    BagMachine mach;
+    mach.start_profile(v_wall[i], ap, type, n_xi, w_n ? w_n[i] : 1.0, row);
+    mach.run();
+    const BagProfile& p = mach.p;
     if (p.status != ST_OK) {
         row.set(0, NAN, NAN, NAN);
         off[i] = 0; npts[i] = 1;
@@ -238,6 +246,8 @@ extern "C" int ptt_sweep_shells_bag(int n, const double* v_wall, const double* a
     int* d_st = sg.out(status, nn);
     if (!sg.ok()) return sg.fail();
     const int grid = (n + 63) / 64;
+    // two launches on purpose: in the root search the lanes visit one sample per step, in the materialisation every
+    // tau-grid sample; fused into one kernel the lanes of a warp mix the two and the warp runs 11x slower (measured)
     bag_root_kernel<<<grid, 64, 0, stream>>>(n, d_vw, d_an, n_xi, d_am, d_ap, d_ty, d_st);
     bag_profile_kernel<<<grid, 64, 0, stream>>>(n, d_vw, d_ap, d_ty, n_xi, nullptr, d_rv, d_rw, d_rx,
                                                  (long long)row_stride, d_off, d_np, d_sc, d_st);

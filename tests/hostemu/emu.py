@@ -73,6 +73,24 @@ def bag_profile(v_wall, ap, sol_type, n_xi, w_n=1.0):
     return rc, v[s].copy(), w[s].copy(), xi[s].copy(), nw.value
 
 
+def bag_machine(v_wall, alpha_n, n_xi, an_max, mode=0, ap_in=0.0, sol_type_in=0, w_n=1.0):
+    """BagMachine through the host emulation: (root_status, profile_status, alpha_plus, sol_type, iters, v, w, xi,
+    n_wall, xi_sh, wn_raw)."""
+    cap = lib().emu_row_capacity(n_xi)
+    v, w, xi = np.full(cap, np.nan), np.full(cap, np.nan), np.full(cap, np.nan)
+    off, npts, nw, st, it, rs = (C.c_int(0) for _ in range(6))
+    ap, xs, wr = C.c_double(0), C.c_double(0), C.c_double(0)
+    f = lib().emu_bag_machine
+    f.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double] + \
+        [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_int)] * 3 + [C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                                                  C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                                                  C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    rc = f(mode, v_wall, alpha_n, n_xi, an_max, ap_in, sol_type_in, w_n, _p(v), _p(w), _p(xi), C.byref(off),
+           C.byref(npts), C.byref(nw), C.byref(ap), C.byref(st), C.byref(it), C.byref(xs), C.byref(wr), C.byref(rs))
+    s = slice(off.value, off.value + npts.value)
+    return rs.value, rc, ap.value, st.value, it.value, v[s].copy(), w[s].copy(), xi[s].copy(), nw.value, xs.value, wr.value
+
+
 GEN_SCALARS = ["vp", "vm", "vp_tilde", "vm_tilde", "v_sh", "vm_sh", "vm_tilde_sh", "wp", "wm", "wm_sh", "v_cj", "wn",
                "wn_estimate", "solver_failed"]
 

@@ -46,6 +46,20 @@ int emu_bag_profile(double v_wall, double ap, int sol_type, int n_xi, double w_n
     return p.status;
 }
 
+// BagMachine: root search + profile in one resumable machine (mode 0), or profile only (mode 1: ap_in, sol_type_in)
+int emu_bag_machine(int mode, double v_wall, double alpha_n, int n_xi, double anmax, double ap_in, int sol_type_in,
+                    double w_n, double* v, double* w, double* xi, int* off, int* npts, int* n_wall, double* ap,
+                    int* sol_type, int* iters, double* xi_sh, double* wn_raw, int* root_status) {
+    RowOut row{v, w, xi};
+    BagMachine m;
+    if (mode == 0) m.start_root(v_wall, alpha_n, n_xi, anmax, true, w_n, row);
+    else m.start_profile(v_wall, ap_in, sol_type_in, n_xi, w_n, row);
+    m.run();
+    *ap = m.r.alpha_plus; *sol_type = m.r.sol_type; *iters = m.r.iters; *root_status = m.r.status;
+    *off = m.p.off; *npts = m.p.npts; *n_wall = m.p.n_wall; *xi_sh = m.p.xi_sh; *wn_raw = m.p.wn_raw;
+    return m.p.status;
+}
+
 int emu_row_capacity(int n_xi) { return profile_row_capacity(n_xi); }
 int emu_gen_row_capacity(int n_xi) { return gen_row_capacity(n_xi); }
 

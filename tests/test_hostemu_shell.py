@@ -58,3 +58,24 @@ def test_profiles(v_wall, alpha_n):
     np.testing.assert_allclose(xi[-2], xio[-2], rtol=1e-6)
     np.testing.assert_allclose(w[0], wo[0], rtol=1e-6)
     assert nw == sb.find_v_index(xi, v_wall)
+
+
+def test_bag_machine_is_bit_identical_to_the_nested_formulation():
+    """BagMachine (the resumable form the kernels run: one integration call site) against bag_find_alpha_plus +
+    bag_emit_profile (the nested form) - same arithmetic in the same order, so identical bits."""
+    rng = np.random.default_rng(7)
+    pts = [(0.5, 0.1), (0.7, 0.1), (0.9, 0.1), (0.44, 0.0046), (0.62, 0.15), (0.92, 0.0046), (0.3, 0.4), (0.05, 0.3),
+           (0.2, 0.6)] + [(rng.uniform(0.05, 0.95), rng.uniform(0.005, 0.5)) for _ in range(16)]
+    for vw, an in pts:
+        am, _ = emu.anmax(vw)
+        rc_r, ap, typ, it = emu.find_alpha_plus(vw, an, 1500, am)
+        rs, rp, ap2, typ2, it2, v2, w2, x2, nw2, _, _ = emu.bag_machine(vw, an, 1500, am)
+        assert (rc_r, typ, it) == (rs, typ2, it2) and (ap == ap2 or (ap != ap and ap2 != ap2))
+        if rc_r == 0 and typ >= 0:
+            rc_p, v, w, x, nw = emu.bag_profile(vw, ap, typ, 1500)
+            assert rc_p == rp and nw == nw2
+            for a, b in ((v, v2), (w, w2), (x, x2)):
+                assert np.array_equal(a, b, equal_nan=True)
+            _, rp3, _, _, _, v3, w3, x3, nw3, _, _ = emu.bag_machine(vw, an, 1500, am, mode=1, ap_in=ap, sol_type_in=typ, w_n=1.7)
+            rc_p4, v4, w4, x4, nw4 = emu.bag_profile(vw, ap, typ, 1500, 1.7)
+            assert rp3 == rc_p4 and nw3 == nw4 and np.array_equal(w3, w4, equal_nan=True) and np.array_equal(v3, v4, equal_nan=True)
