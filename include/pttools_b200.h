@@ -103,7 +103,8 @@ int ptt_sweep_shells_bag(int n, const double* v_wall, const double* alpha_n, int
  * chapman_jouguet.py:151-264; the guesses come from the fluid-reference table, fluid.py:925-949).
  * Outputs: profile rows ([n,row_stride], row_stride >= ptt_generic_row_capacity(n_xi)), off/npts, and
  *   scalars[n,16] = {vp, vm, vp_tilde, vm_tilde, v_sh, vm_sh, vm_tilde_sh, wp, wm, wm_sh, v_cj, wn, wn_estimate,
- *                    solver_failed, 0, 0}  -- the reference's 17-tuple (fluid.py:1052).
+ *                    solver_failed, n_resid (residual evaluations of the root search, diagnostics), 0}  -- the
+ *                    reference's 17-tuple (fluid.py:1052).
  * status[i] = PTT_ST_SOLVER_FAILED where the reference sets solver_failed. */
 int ptt_generic_row_capacity(int n_xi);
 int ptt_sweep_shells_generic(int n, const double* pg, int n_xi, double t_end, int thin_shell_limit, double wn_rtol,

@@ -11,7 +11,18 @@ constexpr int GEN_SCALARS = 16;
 // pg[n,16] = {v_wall, alpha_n, sol_type, wn, v_cj, guess_vp, guess_vp_tilde, guess_wp, guess_wm,
 //             css2, csb2, V_s, V_b, bag_name, 0, 0}
 // scalars[n,16] = {vp, vm, vp_tilde, vm_tilde, v_sh, vm_sh, vm_tilde_sh, wp, wm, wm_sh, v_cj, wn, wn_estimate,
-//                  solver_failed, 0, 0}   (the reference's 17-tuple, fluid.py:1052)
+//                  solver_failed, n_resid, 0}   (the reference's 17-tuple, fluid.py:1052; n_resid: residual
+//                  evaluations of the root search, diagnostics)
+// The integration gets a register allocation of its own: the machine's state (root finder, residual in flight, results)
+// is live across every integration and, inlined, competes with the Runge-Kutta stages for the 255 registers.
+__device__ __noinline__ int generic_run_job(const double cs2, const State y0, const double te, const int n_xi,
+                                            JobVisitor* pv) {
+    JobVisitor vis = *pv;
+    const int rc = integrate_grid(cs2, y0, te, n_xi, vis);
+    *pv = vis;
+    return rc;
+}
+
 __global__ void __launch_bounds__(64) generic_solve_kernel(
     const int n, const double* __restrict__ pg, const int n_xi, const double t_end, const int thin,
     const double wn_rtol, double* __restrict__ rows_v, double* __restrict__ rows_w, double* __restrict__ rows_xi,
@@ -39,7 +50,13 @@ __global__ void __launch_bounds__(64) generic_solve_kernel(
         m.bag_name = (int)q[13];
         GenericGuess g;
         g.vp = q[5]; g.vp_tilde = q[6]; g.wp = q[7]; g.wm = q[8];
-        o = generic_solve_point(m, v_wall, alpha_n, sol_type, wn, v_cj, g, n_xi, t_end, thin, wn_rtol, row);
+        GenericMachine mach;
+        mach.start(m, v_wall, sol_type, wn, v_cj, g, n_xi, t_end, thin, wn_rtol, row);
+        while (mach.phase != GenericMachine::PH_DONE) {
+            const int rc = generic_run_job(mach.job_cs2, mach.job_y0, mach.job_te, n_xi, &mach.vis);
+            mach.advance(rc);
+        }
+        o = mach.o;
     } else {
         o.status = ST_INVALID_INPUT;
     }
@@ -55,7 +72,7 @@ __global__ void __launch_bounds__(64) generic_solve_kernel(
     npts[i] = o.npts;
     sc[0] = o.vp; sc[1] = o.vm; sc[2] = o.vp_tilde; sc[3] = o.vm_tilde; sc[4] = o.v_sh; sc[5] = o.vm_sh;
     sc[6] = o.vm_tilde_sh; sc[7] = o.wp; sc[8] = o.wm; sc[9] = o.wm_sh; sc[10] = o.v_cj; sc[11] = o.wn;
-    sc[12] = o.wn_estimate; sc[13] = (double)o.solver_failed; sc[14] = 0.0; sc[15] = 0.0;
+    sc[12] = o.wn_estimate; sc[13] = (double)o.solver_failed; sc[14] = (double)o.n_resid; sc[15] = 0.0;
     status[i] = o.solver_failed ? ST_SOLVER_FAILED : ST_OK;
 }
 

@@ -191,6 +191,7 @@ struct GenericOut {
     int status;
     int off, npts;
     int solver_failed;
+    int n_resid;        // residual evaluations of the root search (diagnostics)
     // the reference's 17-tuple scalars (fluid.py:1052)
     double vp, vm, vp_tilde, vm_tilde, v_sh, vm_sh, vm_tilde_sh, wp, wm, wm_sh, v_cj, wn, wn_estimate;
 };
@@ -204,7 +205,8 @@ struct GenericMachine {
     // what comes back from "advance": an integration to run, or nothing more to do
     enum Phase : int { PH_LOCATE = 0, PH_EMIT_FWD = 1, PH_EMIT_BACK = 2, PH_CSTRIM = 3, PH_DONE = 4 };
     // where the root finder waits for a residual
-    enum Root : int { RF_A0 = 0, RF_AH = 1, RF_A1 = 2, RF_IT = 3, RF_FINAL = 4 };
+    enum Root : int { RF_A0 = 0, RF_AH = 1, RF_A1 = 2, RF_IT = 3, RF_FINAL = 4, RF_H0 = 5, RF_HJ = 6, RF_HT = 7 };
+    enum PassKind : int { PK_SECANT = 0, PK_NEWTON = 1, PK_HYBRD = 2 };
 
     // --- constants of the point
     EosDev m;
@@ -227,16 +229,22 @@ struct GenericMachine {
     int rf, pass, it;
     bool newton_start, converged, solver_failed;
     double p0, p1, q0, q1, p, h_fd;
+    // MINPACK hybrd in one dimension (scipy fsolve: xtol 1.49012e-8, factor 100, maxfev 400, forward differences)
+    double hx, hf, hJ, hdiag, hdelta, hxnorm, hfnorm, hp, hpnorm;
+    int hiter, ncsuc, ncfail, nslow1, nslow2, nfev;
+    int n_resid;                // residual evaluations started (diagnostics: scalars[14])
+    bool jeval;
     // --- result
     GenericOut o;
     int nb, nf;
 
-    PTT_HD void fail(const int status) { o.status = status; phase = PH_DONE; }
+    PTT_HD void fail(const int status) { o.status = status; o.n_resid = n_resid; phase = PH_DONE; }
 
     // ---- residual -------------------------------------------------------------------------------------------
     // Starts wn_estimate(wm) - wn.  Returns true if an integration is pending, false if the residual is already
     // known (NaN, d.status says why).
     PTT_HD bool resid_begin(const double wm) {
+        ++n_resid;
         d.status = ST_SOLVER_FAILED;
         d.vp = d.vp_tilde = d.wp = d.wn_estimate = NAN;
         d.i_shock = 0; d.t_end_final = -t_end;
@@ -313,21 +321,95 @@ struct GenericMachine {
     // ---- root finder ----------------------------------------------------------------------------------------
     // Subsonic deflagrations: scipy's secant (root_scalar, x0 = 0.99 wm_guess, x1 = 1.01 wm_guess, atol 1.48e-8),
     // mirrored step by step; if it fails, the reference's fallback (fsolve from wm_guess, fluid.py:629-640).
-    // Hybrids: the reference calls hybrd, which in one dimension is a finite-difference Newton step followed by
-    // secant (Broyden) updates; the same is done here.
+    // Hybrids: fsolve from wm_guess (fluid.py:697-720).  fsolve is MINPACK's hybrd; in one dimension it is restated
+    // here in full (forward-difference Jacobian, trust region with the dogleg step clipped to it, Broyden updates,
+    // Jacobian recomputed after two failures, hybrd's five stopping tests): on the thin shells whose residual jumps
+    // with the tau-grid index of the shock, hybrd shrinks its trust region onto the jump and reports success, and so
+    // must this.
     // Each function returns true if an integration is pending; otherwise the residual it asked for is already
     // known and the caller feeds it back with root_on_q.
+    // Passes.  Subsonic deflagrations: secant, then the fsolve fallback.  Hybrids: fsolve.  fsolve is run in two
+    // stages: first its smooth-case behaviour (finite-difference Newton step, then secant updates - what hybrd does
+    // when every step succeeds; 6-8 evaluations), and only if that does not converge, hybrd proper (up to ~50).
+    PTT_HD int pass_kind() const {
+        const int k = (sol_type == SOL_SUB_DEF) ? pass : pass + 1;
+        return (k > 2) ? 2 : k;
+    }
     PTT_HD bool pass_begin() {
-        newton_start = (sol_type != SOL_SUB_DEF) || (pass == 1);
+        const int kind = pass_kind();
+        newton_start = kind != PK_SECANT;
+        if (kind == PK_HYBRD) {
+            hx = g.wm;
+            p = hx;
+            rf = RF_H0;
+            return resid_begin(hx);
+        }
         p0 = newton_start ? g.wm : 0.99 * g.wm;
         rf = RF_A0;
         return resid_begin(p0);
     }
+    // hybrd: forward-difference Jacobian at hx.  Returns 1 = integration pending, 0 = residual known without one.
+    PTT_HD int hybrd_jac() {
+        jeval = true;
+        h_fd = 1.4901161193847656e-08 * fabs(hx);
+        if (h_fd == 0.0) h_fd = 1.4901161193847656e-08;
+        rf = RF_HJ;
+        return resid_begin(hx + h_fd) ? 1 : 0;
+    }
+    // hybrd: dogleg step (in one dimension: the Newton step clipped to the trust region) and its trial evaluation
+    PTT_HD int hybrd_trial() {
+        const double pgn = (hJ != 0.0) ? -hf / hJ : ((hf >= 0.0) ? INFINITY : -INFINITY);
+        const double qnorm = hdiag * fabs(pgn);
+        hp = (qnorm <= hdelta) ? pgn : copysign(hdelta / hdiag, pgn);
+        hpnorm = hdiag * fabs(hp);
+        if (hiter == 1) hdelta = fmin(hdelta, hpnorm);
+        rf = RF_HT;
+        return resid_begin(hx + hp) ? 1 : 0;
+    }
+    // hybrd: consumes the trial residual q.  Returns 1 / 0 as above, -1 when the pass is over (converged set).
+    PTT_HD int hybrd_after_trial(const double q) {
+        const double xtol = 1.49012e-08, epsmch = 2.220446049250313e-16;
+        ++nfev;
+        const double fnorm1 = (q == q) ? fabs(q) : INFINITY;
+        double actred = -1.0;
+        if (fnorm1 < hfnorm) actred = 1.0 - (fnorm1 / hfnorm) * (fnorm1 / hfnorm);
+        const double temp = fabs(hf + hJ * hp);
+        double prered = 0.0;
+        if (temp < hfnorm) prered = 1.0 - (temp / hfnorm) * (temp / hfnorm);
+        const double ratio = (prered > 0.0) ? actred / prered : 0.0;
+        if (ratio < 0.1) {
+            ncsuc = 0; ++ncfail;
+            hdelta *= 0.5;
+        } else {
+            ncfail = 0; ++ncsuc;
+            if (ratio >= 0.5 || ncsuc > 1) hdelta = fmax(hdelta, hpnorm / 0.5);
+            if (fabs(ratio - 1.0) <= 0.1) hdelta = hpnorm / 0.5;
+        }
+        const double f_old = hf;
+        if (ratio >= 1e-4) {
+            hx += hp; hf = q;
+            hxnorm = hdiag * fabs(hx);
+            hfnorm = fnorm1;
+            ++hiter;
+        }
+        p = hx;
+        ++nslow1;
+        if (actred >= 0.001) nslow1 = 0;
+        if (jeval) ++nslow2;
+        if (actred >= 0.1) nslow2 = 0;
+        if (hdelta <= xtol * hxnorm || hfnorm == 0.0) { converged = true; return -1; }          // info = 1
+        if (nfev >= 400 || 0.1 * fmax(0.1 * hdelta, hpnorm) <= epsmch * hxnorm || nslow2 == 5 || nslow1 == 10)
+            return -1;                                                                           // info = 2 .. 5
+        if (ncfail == 2) return hybrd_jac();
+        if (q == q) hJ = (q - f_old) / hp;           // Broyden's rank-one update is the secant slope in one dimension
+        jeval = false;
+        return hybrd_trial();
+    }
     // secant iteration header; returns 1 = integration pending, 0 = residual known without one, -1 = pass over
     PTT_HD int iter_head() {
         const double atol = 1.48e-8;
-        const double rtol_h = 1.4901161193847656e-08;     // hybrd xtol (relative) for the Newton-started branch
-        if (it >= 50) return -1;
+        const double rtol_h = 1.4901161193847656e-08;     // hybrd xtol (relative) for the Newton-started pass
+        if (it >= (newton_start ? 12 : 50)) return -1;
         if (q1 == q0) {
             p = 0.5 * (p1 + p0);
             converged = (p1 == p0);
@@ -344,8 +426,8 @@ struct GenericMachine {
     }
     // end of a pass (and possibly of the root search); same return convention as iter_head, -1 never
     PTT_HD int pass_end() {
-        if (sol_type == SOL_SUB_DEF && pass == 0 && !converged) {
-            pass = 1;
+        if (!converged && pass_kind() != PK_HYBRD) {
+            ++pass;
             return pass_begin() ? 1 : 0;
         }
         if (!(p == p) || !(p > 0.0)) { fail(ST_ROOT_NOT_CONVERGED); return 1; }
@@ -376,6 +458,37 @@ struct GenericMachine {
             rf = RF_A1;
             return resid_begin(p1);
         }
+        case RF_H0:
+            hf = q;
+            nfev = 1;
+            hfnorm = fabs(hf);
+            hiter = 1; ncsuc = ncfail = nslow1 = nslow2 = 0;
+            if (!(hf == hf)) r = -1;
+            else r = hybrd_jac();
+            if (r < 0) r = pass_end();
+            return r == 1;
+        case RF_HJ:
+            ++nfev;
+            if (!(q == q)) {
+                r = -1;
+            } else {
+                hJ = (q - hf) / h_fd;
+                if (hiter == 1) {
+                    hdiag = fabs(hJ);
+                    if (hdiag == 0.0) hdiag = 1.0;
+                    hxnorm = hdiag * fabs(hx);
+                    hdelta = 100.0 * hxnorm;
+                    if (hdelta == 0.0) hdelta = 100.0;
+                }
+                hdiag = fmax(hdiag, fabs(hJ));
+                r = hybrd_trial();
+            }
+            if (r < 0) r = pass_end();
+            return r == 1;
+        case RF_HT:
+            r = hybrd_after_trial(q);
+            if (r < 0) r = pass_end();
+            return r == 1;
         case RF_A1:
             q1 = q;
             p = p1;
@@ -432,6 +545,7 @@ struct GenericMachine {
         row.set(bc - nb - 2, 0.0, w_center, 0.0);
         o.off = bc - nb - 2;
         o.npts = 2 + nb + nf + 2;
+        o.n_resid = n_resid;
         phase = PH_DONE;
     }
 
@@ -443,8 +557,9 @@ struct GenericMachine {
         cs_n = sqrt(m.css2);
         o.status = ST_OK; o.off = 0; o.npts = 0; o.solver_failed = 1;
         o.vp = o.vm = o.vp_tilde = o.vm_tilde = o.v_sh = o.vm_sh = o.vm_tilde_sh = o.wp = o.wm = o.wm_sh = NAN;
-        o.v_cj = v_cj; o.wn = wn; o.wn_estimate = NAN;
+        o.v_cj = v_cj; o.wn = wn; o.wn_estimate = NAN; o.n_resid = 0;
         nb = nf = 0;
+        n_resid = 0;
         solver_failed = true; converged = false;
         p = NAN;
         if (sol_type == SOL_DETON) {
