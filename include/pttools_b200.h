@@ -173,6 +173,8 @@ typedef struct ptt_sdv_plan {
     double inv_dlog;      /* 1 / dlog10z */
     int32_t smem_bytes;   /* dynamic shared memory per CTA */
     int32_t reserved;
+    const double* omega_ab; /* [3 nt + 1, 2] or NULL: (alpha, beta) of the knot weight omega(x) = alpha + beta X/qT[e] on
+                             * every piece between consecutive kinks of {LT_j - 1, LT_j, LT_j + 1} (ptt_spec_den_v_group) */
 } ptt_sdv_plan_t;
 
 /* spec_den_v core                                                        pttools/ssmtools/spectrum.py:451-486
@@ -183,7 +185,7 @@ int ptt_spec_den_v_batch(const ptt_sdv_plan_t* plan, int P, const double* a2, in
 /* spec_den_v for n_p profiles that SHARE v_wall, as a banded FP64 matrix product (same linear-interpolation weights as
  * np.interp in spectrum.py:451-459, summed per knot first).  kw: band width in knots per 128-row tile (multiple of 16),
  * e_base[n_tiles]: first knot of each tile for this v_wall (both computed by the host from the plan),
- * omega: device scratch of n_tiles*128*kw + n_q doubles.  out[p, i], like ptt_spec_den_v_batch. */
+ * omega: device scratch of n_tiles*128*kw + 2 n_q doubles.  out[p, i], like ptt_spec_den_v_batch. */
 int ptt_spec_den_v_group(const ptt_sdv_plan_t* plan, int n_p, const double* a2, int64_t a2_stride, double v_wall,
                          int kw, const int32_t* e_base, double* omega, double* out, int64_t out_stride, void* stream);
 

@@ -34,7 +34,7 @@ class SdvPlan(C.Structure):
     _fields_ = [("n_q", C.c_int32), ("n_z", C.c_int32), ("nt", C.c_int32), ("z_tile", C.c_int32),
                 ("qT", C.c_void_p), ("z", C.c_void_p), ("zterm", C.c_void_p), ("T", C.c_void_p),
                 ("LT", C.c_void_p), ("W", C.c_void_p), ("inv_dlog", C.c_double), ("smem_bytes", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("omega_ab", C.c_void_p)]
 
 
 class GwPlan(C.Structure):

@@ -24,17 +24,20 @@ constexpr int GM_THREADS = 512;      // 16 warps: 4 (m) x 4 (n), warp tile 32 x 
 // knot are found arithmetically (LT is a linspace: ~1.4 samples per knot) and confirmed with the same floor() test
 // as the gather kernel, so every sample is counted exactly once; no atomics, no zero-fill, coalesced stores.
 // np.interp's end clamps put the whole weight of a sample on knot 0 (left) or knot n_q - 1 (right).
-// 1 / (qT[k+1] - qT[k]) for the weights kernel (one division per segment instead of one per sample)
-__global__ void sdv_recip_kernel(const int n_q, const double* __restrict__ qT, double* __restrict__ inv_dq) {
+// 1 / (qT[k+1] - qT[k]) and 1 / qT[k] for the weights kernel (one division per knot instead of one per sample)
+__global__ void sdv_recip_kernel(const int n_q, const double* __restrict__ qT, double* __restrict__ inv_dq,
+                                 double* __restrict__ inv_q) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n_q - 1) inv_dq[k] = 1.0 / (qT[k + 1] - qT[k]);
+    if (k < n_q) inv_q[k] = 1.0 / qT[k];
 }
 
 __global__ void __launch_bounds__(256) sdv_weights_kernel(
     const int n_q, const int n_z, const int nt, const double* __restrict__ qT, const double* __restrict__ z,
     const double* __restrict__ zterm, const double* __restrict__ T, const double* __restrict__ LT,
     const double* __restrict__ W, const double bv, const double shift, const int kw,
-    const int* __restrict__ e_base, const double* __restrict__ inv_dq, double* __restrict__ omega) {
+    const int* __restrict__ e_base, const double* __restrict__ inv_dq, const double* __restrict__ inv_q,
+    const double2* __restrict__ omega_ab, double* __restrict__ omega) {
     const int i = blockIdx.y;
     const int kk = blockIdx.x * blockDim.x + threadIdx.x;
     if (kk >= kw) return;
@@ -42,9 +45,25 @@ __global__ void __launch_bounds__(256) sdv_weights_kernel(
     const double ub = zterm[i] + shift;
     const int e = e_base[i / GM_BM] + kk;
     double acc = 0.0;
-    if (e < n_q) {
-        const double lt0 = LT[0];
-        const double inv_dlt = (nt > 1) ? (double)(nt - 1) / (LT[nt - 1] - lt0) : 0.0;     // LT is a linspace
+    const double lt0 = LT[0];
+    const double inv_dlt = (nt > 1) ? (double)(nt - 1) / (LT[nt - 1] - lt0) : 0.0;     // LT is a linspace
+    if (omega_ab && e > 0 && e < n_q - 1) {
+        // Closed form.  As a function of x = e - (zterm_i + shift) the weight of an interior knot is
+        //     omega(x) = alpha_p + beta_p * (s_i / qT[e])
+        // on every piece p between two consecutive kinks LT_j - 1, LT_j, LT_j + 1 (the set of contributing samples is
+        // fixed there and np.interp's weight (X - x0)/(x1 - x0) on a log grid is linear in X / qT[e]); the plan
+        // carries (alpha, beta) per piece, and the piece index is the number of kinks below x.
+        const double x = (double)e - ub;
+        int piece = 0;
+#pragma unroll
+        for (int sgn = -1; sgn <= 1; ++sgn) {
+            const double yy = (x - (double)sgn - lt0) * inv_dlt;
+            int c = (yy > 0.0) ? __double2int_ru(yy) : 0;
+            piece += min(c, nt);
+        }
+        const double2 ab = omega_ab[piece];
+        acc = fma(ab.y, s * inv_q[e], ab.x);
+    } else if (e < n_q) {
         int j = 0;
         if (e > 0) {
             const double jf = ((double)(e - 1) - ub - lt0) * inv_dlt;
@@ -181,10 +200,12 @@ extern "C" int ptt_spec_den_v_group(const ptt_sdv_plan_t* plan, int n_p, const d
     const double bv = b_R * v_wall;
     // rows of the last tile beyond n_z are never written: the GEMM multiplies them into outputs it does not store
     double* inv_dq = omega + (size_t)n_tiles * GM_BM * (size_t)kw;
-    sdv_recip_kernel<<<(plan->n_q + 255) / 256, 256, 0, stream>>>(plan->n_q, plan->qT, inv_dq);
+    double* inv_q = inv_dq + plan->n_q;
+    sdv_recip_kernel<<<(plan->n_q + 255) / 256, 256, 0, stream>>>(plan->n_q, plan->qT, inv_dq, inv_q);
     sdv_weights_kernel<<<dim3((kw + 255) / 256, plan->n_z), 256, 0, stream>>>(
         plan->n_q, plan->n_z, plan->nt, plan->qT, plan->z, plan->zterm, plan->T, plan->LT, plan->W, bv,
-        -log10(bv) * plan->inv_dlog, kw, e_base, inv_dq, omega);
+        -log10(bv) * plan->inv_dlog, kw, e_base, inv_dq, inv_q,
+        reinterpret_cast<const double2*>(plan->omega_ab), omega);
     const double factor = 2.0 / (bv * bv * bv * bv * bv * bv);
     dim3 grid(n_tiles, (n_p + GM_BN - 1) / GM_BN);
     const int smem = 2 * (GM_BM + GM_BN) * GM_PITCH * (int)sizeof(double);

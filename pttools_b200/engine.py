@@ -361,6 +361,37 @@ class SdvPass:
             raise ValueError("spec_den_v lookup window does not fit in shared memory; reduce nt range or z density")
         self.z_tile, self.win_entries = best
         self.smem_bytes = self.win_entries * 16
+        self.omega_ab = _omega_pieces(self.LT, self.T, self.W, self.dl)
+
+
+def _omega_pieces(LT, T, W, dl):
+    """(alpha, beta) of the knot weight of K6' on every piece between consecutive kinks of {LT_j - 1, LT_j, LT_j + 1}.
+    With x = e - (zterm_i + shift) the samples whose lookup lands in the segment right of knot e are those with
+    x <= LT_j < x + 1 (weight 1 - t), left of it x - 1 <= LT_j < x (weight t), t = (X / x0 - 1) / D on the log grid
+    (D = 10^dl - 1), so that  omega = alpha + beta * X_i / qT[e]  with
+        alpha = (1 + 1/D) sum_A W_j - (1/D) sum_B W_j,   beta = -(1/D) sum_A W_j T_j + (10^dl / D) sum_B W_j T_j."""
+    nt = LT.size
+    D = 10.0 ** dl - 1.0
+    kinks = np.concatenate([LT - 1.0, LT, LT + 1.0])
+    label = np.repeat([0, 1, 2], nt)                       # 0: LT - 1, 1: LT, 2: LT + 1
+    order = np.argsort(kinks, kind="stable")
+    lab = label[order]
+    cnt = np.zeros((3, 3 * nt + 1), dtype=np.int64)        # kinks of each label among the first p sorted kinks
+    for k in range(3):
+        cnt[k, 1:] = np.cumsum(lab == k)
+    n_m1, n_0, n_p1 = cnt[0], cnt[1], cnt[2]               # A = [n_0, n_m1), B = [n_p1, n_0)
+    WT = W * T
+    sums = np.zeros((4, 3 * nt + 1))
+    for lo, hi, iw, iwt in ((n_0, n_m1, 0, 1), (n_p1, n_0, 2, 3)):
+        for k in range(int((hi - lo).max())):
+            idx = lo + k
+            ok = idx < hi
+            idx = np.minimum(idx, nt - 1)
+            sums[iw] += np.where(ok, W[idx], 0.0)
+            sums[iwt] += np.where(ok, WT[idx], 0.0)
+    alpha = (1.0 + 1.0 / D) * sums[0] - sums[2] / D
+    beta = -sums[1] / D + (10.0 ** dl / D) * sums[3]
+    return np.ascontiguousarray(np.stack([alpha, beta], axis=1))
 
 
 class SsmPlan:
@@ -416,6 +447,7 @@ class SsmPlan:
         for i, p in enumerate(self.passes):
             for k in ("qT", "z", "zterm", "T", "LT", "W"):
                 self._t[f"p{i}_{k}"] = up(getattr(p, k))
+            self._t[f"p{i}_omega_ab"] = up(p.omega_ab)
         if self.gw is not None:
             for k in ("L1", "L2", "Z1", "Z2", "G", "yterm"):
                 self._t["gw_" + k] = up(self.gw[k])
@@ -430,7 +462,8 @@ class SsmPlan:
                 n_q=p.qT.size, n_z=p.z.size, nt=p.nt, z_tile=p.z_tile, qT=self._t[f"p{i}_qT"].data_ptr(),
                 z=self._t[f"p{i}_z"].data_ptr(), zterm=self._t[f"p{i}_zterm"].data_ptr(),
                 T=self._t[f"p{i}_T"].data_ptr(), LT=self._t[f"p{i}_LT"].data_ptr(), W=self._t[f"p{i}_W"].data_ptr(),
-                inv_dlog=1.0 / p.dl, smem_bytes=p.smem_bytes))
+                inv_dlog=1.0 / p.dl, smem_bytes=p.smem_bytes,
+                omega_ab=self._t[f"p{i}_omega_ab"].data_ptr() if USE_OMEGA_PIECES else None))
         self.gw_plan = None if self.gw is None else make_gw_plan(self.gw, self._t, self.z_lookup.size, y.size)
 
     @property
@@ -574,6 +607,7 @@ def spec_den_v_batch(plan: SsmPlan, ipass: int, a2, v_wall):
     return out
 
 
+USE_OMEGA_PIECES = True      # K6' weights from the per-piece closed form (False: sample loop for every entry)
 GROUP_MIN = 24          # smallest run of equal v_wall worth the banded matrix product (break-even ~15 profiles)
 USE_GROUPED_SDV = True
 
@@ -603,7 +637,7 @@ def spec_den_v_group(plan: SsmPlan, ipass: int, a2, v_wall: float, out, slot: in
     e_base, kw = _group_band(p, v_wall)
     n_tiles = e_base.size
     key = ("omega", ipass, slot)
-    need = n_tiles * 128 * kw + p.qT.size
+    need = n_tiles * 128 * kw + 2 * p.qT.size
     buf = plan._t.get(key)
     if buf is None or buf.numel() < need:
         buf = torch.empty(int(need * 1.02) + 1024, dtype=torch.float64, device=a2.device)
