@@ -477,6 +477,7 @@ struct BagMachine {
     int job_n;
     BagVisitor vis;
     bool full_retry;            // the pending locate pass is the "never crossed" re-run in full mode
+    bool forward_only;          // stop after the wall->shock evaluation (alpha_n_max_deflagration)
     // --- wall->shock evaluation in flight (bag_forward)
     double ap_eval;
     WallSpeeds ws;
@@ -676,7 +677,7 @@ struct BagMachine {
     PTT_HD void start_root(const double v_wall_, const double alpha_n_, const int n_xi_, const double an_max_defl,
                            const bool want_profile_, const double w_n_, const RowOut& row_) {
         v_wall = v_wall_; alpha_n = alpha_n_; n_xi = n_xi_; want_profile = want_profile_; w_n = w_n_; row = row_;
-        phase = PH_DONE; rstate = R_NONE;
+        phase = PH_DONE; rstate = R_NONE; forward_only = false;
         p.status = ST_OK; p.off = 0; p.npts = 0; p.n_wall = 0; p.xi_sh = v_wall; p.wn_raw = NAN;
         r.iters = 0;
         r.alpha_plus = NAN;
@@ -708,11 +709,24 @@ struct BagMachine {
     PTT_HD void start_profile(const double v_wall_, const double alpha_plus, const int sol_type, const int n_xi_,
                               const double w_n_, const RowOut& row_) {
         v_wall = v_wall_; alpha_n = NAN; n_xi = n_xi_; want_profile = true; w_n = w_n_; row = row_;
-        phase = PH_DONE; rstate = R_NONE;
+        phase = PH_DONE; rstate = R_NONE; forward_only = false;
         r.status = ST_OK; r.sol_type = sol_type; r.alpha_plus = alpha_plus; r.iters = 0;
         if (sol_type == SOL_DETON) { profile_begin(); return; }
         profile_init();
         if (!forward_begin(alpha_plus, sol_type)) finish_failed(f.status);
+    }
+
+    // alpha_n_max_deflagration_bag(v_wall) (alpha.py:44-50): the wall->shock passes of the alpha_+ = 1/3 - 1e-10 shell on
+    // the default grid; the result is anmax() once phase == PH_DONE.
+    PTT_HD void start_anmax(const double v_wall_) {
+        v_wall = v_wall_; alpha_n = NAN; n_xi = N_XI_DEFAULT; want_profile = false; w_n = 1.0;
+        phase = PH_DONE; rstate = R_NONE; forward_only = true;
+        r.sol_type = (v_wall > cs0()) ? SOL_HYBRID : SOL_SUB_DEF;
+        forward_begin(1.0 / 3.0 - 1.0e-10, r.sol_type);
+    }
+    PTT_HD double anmax(int& status) const {
+        status = f.status;
+        return (f.status == ST_OK) ? (f.w1 / f.wn_raw) * (1.0 / 3.0) : NAN;
     }
 
     // Consumes the integration that was pending; afterwards another one is pending or phase == PH_DONE.
@@ -720,6 +734,7 @@ struct BagMachine {
         if (phase == PH_FWD1 || phase == PH_FWD2) {
             if (forward_after(rc)) return;
             // evaluation complete
+            if (forward_only) { phase = PH_DONE; return; }
             if (rstate != R_NONE) {
                 if (root_on_eval()) return;
                 // root search over

@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(64) bag_anmax_kernel(const int n, const double
         return;
     }
     int st;
-    out[i] = alpha_n_max_deflagration(vw, st);
+    BagMachine mach;
+    mach.start_anmax(vw);
+    mach.run();
+    out[i] = mach.anmax(st);
     if (status) status[i] = st;
 }
 

@@ -24,6 +24,13 @@ int emu_integrate(double v0, double w0, double xi0, double cs2, double t_end, in
 
 double emu_anmax(double v_wall, int* status) { return alpha_n_max_deflagration(v_wall, *status); }
 
+double emu_anmax_machine(double v_wall, int* status) {
+    BagMachine m;
+    m.start_anmax(v_wall);
+    m.run();
+    return m.anmax(*status);
+}
+
 int emu_bag_forward(double v_wall, double ap, int sol_type, int n_xi, double* out) {
     BagForward f = bag_forward(v_wall, ap, sol_type, n_xi);
     out[0] = f.i1; out[1] = f.t_end2; out[2] = f.n_fwd; out[3] = f.last.v; out[4] = f.last.w; out[5] = f.last.xi;
