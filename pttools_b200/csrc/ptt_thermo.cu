@@ -70,28 +70,39 @@ __global__ void __launch_bounds__(256) profile_integrals_kernel(
 
     const double theta_n = 0.25 * (1.0 - 4.0 / mu_s) * w_last + V_s;        // theta(w_n, symmetric)
     // entropy s(w, phase) = mu a (T/T0)^(mu-4) T^3,  T = T0 (w / (mu a T0^4))^(1/mu)   (const_cs.py:623-672; mu=4: bag.py)
+    // (mu = 4 in both phases - the bag equation of state - needs no pow: T = T_ref (w / (4 a T_ref^4))^(1/4), s = 4 a T^3)
+    const bool bag_like = (mu_s == 4.0) && (mu_b == 4.0);
     auto entropy = [&](const double ww, const bool broken) {
         const double mu = broken ? mu_b : mu_s, a = broken ? a_b : a_s;
-        const double T = T_ref * pow(ww / (mu * a * T_ref * T_ref * T_ref * T_ref), 1.0 / mu);
+        const double arg = ww / (mu * a * T_ref * T_ref * T_ref * T_ref);
+        if (bag_like) {
+            const double T = T_ref * sqrt(sqrt(arg));
+            return 4.0 * a * T * T * T;
+        }
+        const double T = T_ref * pow(arg, 1.0 / mu);
         return mu * a * pow(T / T_ref, mu - 4.0) * T * T * T;
     };
     const double s_n = entropy(w_last, false);
 
+    // np.trapezoid(f, xi^3) as a weighted sum over samples, weight_k = (xi_{k+1}^3 - xi_{k-1}^3) / 2 (one-sided at the
+    // ends): every integrand is evaluated once per sample
     double a_kin = 0.0, a_th = 0.0, a_dw = 0.0, a_ds = 0.0, a_wb = 0.0;
-    for (int k = tid; k < N - 1; k += blockDim.x) {
-        const double x0 = xi[k], x1 = xi[k + 1];
-        const double d3 = x1 * x1 * x1 - x0 * x0 * x0;
-        const double v0 = v[k], v1 = v[k + 1], w0 = w[k], w1 = w[k + 1];
-        const bool b0 = (phase_rule == 1) ? (k < n_broken) : (x0 < v_wall);
-        const bool b1 = (phase_rule == 1) ? (k + 1 < n_broken) : (x1 < v_wall);
-        const double f0 = w0 * v0 * v0 / (1.0 - v0 * v0), f1 = w1 * v1 * v1 / (1.0 - v1 * v1);
-        a_kin += 0.5 * d3 * (f0 + f1);
-        const double t0 = (b0 ? 0.25 * (1.0 - 4.0 / mu_b) * w0 + V_b : 0.25 * (1.0 - 4.0 / mu_s) * w0 + V_s) - theta_n;
-        const double t1 = (b1 ? 0.25 * (1.0 - 4.0 / mu_b) * w1 + V_b : 0.25 * (1.0 - 4.0 / mu_s) * w1 + V_s) - theta_n;
-        a_th += 0.5 * d3 * (t0 + t1);
-        a_dw += 0.5 * d3 * ((w0 - w_last) + (w1 - w_last));
-        a_ds += 0.5 * d3 * ((entropy(w0, b0) - s_n) + (entropy(w1, b1) - s_n));
-        if (k + 1 <= i_max) a_wb += 0.5 * d3 * (w0 + w1);
+    for (int k = tid; k < N; k += blockDim.x) {
+        const double xk = xi[k];
+        const double xm = (k > 0) ? xi[k - 1] : xk, xp = (k < N - 1) ? xi[k + 1] : xk;
+        const double x3m = xm * xm * xm, x3p = xp * xp * xp;
+        const double wgt = 0.5 * (x3p - x3m);
+        const double vk = v[k], wk = w[k];
+        const bool bk = (phase_rule == 1) ? (k < n_broken) : (xk < v_wall);
+        a_kin += wgt * (wk * vk * vk / (1.0 - vk * vk));
+        const double th = (bk ? 0.25 * (1.0 - 4.0 / mu_b) * wk + V_b : 0.25 * (1.0 - 4.0 / mu_s) * wk + V_s) - theta_n;
+        a_th += wgt * th;
+        a_dw += wgt * (wk - w_last);
+        a_ds += wgt * (entropy(wk, bk) - s_n);
+        if (k <= i_max) {
+            const double x3p_wb = (k < i_max) ? x3p : xk * xk * xk;      // the wbar integral stops at sample i_max
+            a_wb += 0.5 * (x3p_wb - x3m) * wk;
+        }
     }
     double vals[5] = {a_kin, a_th, a_dw, a_ds, a_wb};
     const int lane = tid & 31, wid = tid >> 5;
