@@ -315,8 +315,11 @@ def gpu_arm(args):
             "spec_den_gw": 25.0 * Y.size * plan.gw["n_int"] * n_launch_pts,
         }
         if "spec_den_gw_cells" in stage_ms:
-            # cell formulation: 2 mul + 4 fma per (wavenumber, cell, profile); cells counted from the plan's tables
-            alg["spec_den_gw_cells"] = 10.0 * float(engine.gw_cells(plan)[1].sum().item()) * n_launch_pts
+            # cell formulation: 2 mul + 4 fma per (wavenumber, cell, profile); the cells of a wavenumber are its
+            # segments of the first lookup plus the steps of the second one, counted from the plan's tables
+            _, nseg, meta, _ = engine.gw_cells(plan)
+            steps = sum(int(meta[i, 2:2 + int(n)].sum().item()) for i, n in enumerate(nseg.tolist()))
+            alg["spec_den_gw_cells"] = 10.0 * float(int(nseg.sum().item()) + steps) * n_launch_pts
         if "spec_den_v_group" in stage_ms:
             # banded matrix product: 2 flop per (z_i, knot, profile) MAC over the band + the weight build; per launch =
             # one v_wall row of the grid (1000 profiles)

@@ -214,9 +214,11 @@ int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const double* pv, in
                           const double* scale, double* sd_gw, double* pow_gw, double* omgw0, void* stream);
 
 /* spec_den_gw_scaled, cell formulation for large batches (same trapezoid sum over the same samples, regrouped by runs of
- * samples that share both np.interp segments; spectrum.py:327-368).  The cells depend on the plan only:
+ * samples that share both np.interp segments and collected per segment of the first lookup; spectrum.py:327-368).
+ * The tables depend on the plan only:
  *   cap   = ptt_gw_cells_capacity(n_zl, n_int, lrange), lrange = max(L1, L2) - min(L1, L2) of the plan
- *   ptt_gw_cells_build fills ncell[n_y] (-1: cap too small), meta[n_y, cap], coef[n_y, cap, 4]   (device memory)
+ *   ptt_gw_cells_build fills ncell[n_y] (< 0: not usable, fall back to ptt_spec_den_gw_batch), meta[n_y, cap + 2],
+ *   coef[n_y, ptt_gw_cells_coef_capacity(cap), 2]                                                   (device memory)
  * table: device scratch of ptt_gw_cells_table_size(n_zl, P) doubles.  Outputs as ptt_spec_den_gw_batch. */
 typedef struct ptt_gw_cells {
     int32_t cap;
@@ -226,6 +228,7 @@ typedef struct ptt_gw_cells {
     const double* coef;
 } ptt_gw_cells_t;
 int ptt_gw_cells_capacity(int n_zl, int n_int, double lrange);
+int ptt_gw_cells_coef_capacity(int cap);
 int ptt_gw_cells_build(const ptt_gw_plan_t* plan, int cap, int32_t* ncell, int32_t* meta, double* coef, void* stream);
 int64_t ptt_gw_cells_table_size(int n_zl, int P);
 int ptt_spec_den_gw_cells_batch(const ptt_gw_plan_t* plan, const ptt_gw_cells_t* cells, int P, const double* pv,

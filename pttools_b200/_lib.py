@@ -80,6 +80,7 @@ SIGNATURES = {
     "ptt_spec_den_gw_batch": (C.c_int, [C.POINTER(GwPlan), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_gw_cells_capacity": (C.c_int, [C.c_int, C.c_int, C.c_double]),
+    "ptt_gw_cells_coef_capacity": (C.c_int, [C.c_int]),
     "ptt_gw_cells_build": (C.c_int, [C.POINTER(GwPlan), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_gw_cells_table_size": (C.c_int64, [C.c_int, C.c_int]),
     "ptt_spec_den_gw_cells_batch": (C.c_int, [C.POINTER(GwPlan), C.POINTER(GwCells), C.c_int, C.c_void_p, C.c_int64,

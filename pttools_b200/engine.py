@@ -747,9 +747,10 @@ def gw_cells(plan):
     cap = lib.ptt_gw_cells_capacity(n_zl, int(g["n_int"]), float(lrange))
     if cap <= 0:
         raise _lib.PttError("ptt_gw_cells_capacity: sizes out of range")
+    cap_c = lib.ptt_gw_cells_coef_capacity(cap)
     ncell = torch.empty(n_y, dtype=torch.int32, device="cuda")
-    meta = torch.zeros((n_y, cap), dtype=torch.int32, device="cuda")
-    coef = torch.zeros((n_y, cap, 4), dtype=torch.float64, device="cuda")
+    meta = torch.zeros((n_y, cap + 2), dtype=torch.int32, device="cuda")
+    coef = torch.zeros((n_y, cap_c, 2), dtype=torch.float64, device="cuda")
     with STAGES.stage("gw_cells_build", 1):
         _lib.check(lib.ptt_gw_cells_build(C.byref(plan.gw_plan), cap, _ptr(ncell), _ptr(meta), _ptr(coef),
                                           _stream_ptr(torch)), "ptt_gw_cells_build")
@@ -757,10 +758,6 @@ def gw_cells(plan):
         # capacity exceeded or a lookup that does not move monotonically: this plan stays on the per-sample kernel
         plan._gw_cells = False
         return False
-    used = int(ncell.max().item())
-    if used < cap:                       # keep only what is used (the tables stay resident with the plan)
-        meta, coef = meta[:, :used].contiguous(), coef[:, :used].contiguous()
-        cap = used
     cells = GwCells(cap=cap, reserved=0, ncell=ncell.data_ptr(), meta=meta.data_ptr(), coef=coef.data_ptr())
     plan._gw_cells = (cells, ncell, meta, coef)
     return plan._gw_cells
