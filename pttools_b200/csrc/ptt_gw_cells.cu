@@ -136,7 +136,10 @@ __global__ void __launch_bounds__(1024) gw_table_kernel(const int n_zl, const in
     F[(long long)j * Ppad + p] = s_f[tx][ty];
 }
 
-__global__ void __launch_bounds__(GC_WARPS * 32) spec_den_gw_cells_kernel(
+#ifndef PTT_GC_MINB
+#define PTT_GC_MINB 1
+#endif
+__global__ void __launch_bounds__(GC_WARPS * 32, PTT_GC_MINB) spec_den_gw_cells_kernel(
     const int n_y, const int P, const int Ppad, const double* __restrict__ y, const int cap, const int cap_c,
     const int* __restrict__ ncell, const int* __restrict__ meta, const double* __restrict__ coef,
     const double* __restrict__ F, const double prefactor, const double* __restrict__ slf,
