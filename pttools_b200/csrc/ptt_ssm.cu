@@ -378,7 +378,7 @@ __device__ void block_moments(const double* __restrict__ xi, const double* __res
 #pragma unroll
         for (int j = 0; j < MOM_J; ++j) {
             m[j] += t;
-            t *= d / (double)(j + 1);
+            t *= d * (1.0 / (double)(j + 1));          // compile-time reciprocals: no division in the loop
         }
     }
     if (cur >= 0) {
