@@ -9,7 +9,7 @@ pv = torch.as_tensor(zl[None, :] ** 3 / (1 + (zl[None, :] / rng.uniform(1, 30, (
 t0 = time.time(); engine.gw_cells(plan); torch.cuda.synchronize(); print("cells build s", time.time() - t0, "cap", engine.gw_cells(plan)[0].cap)
 nc = engine.gw_cells(plan)[1].cpu().numpy(); print("ncell min/mean/max", nc.min(), nc.mean(), nc.max())
 for cells in (False, True):
-    for rep in range(3):
+    for rep in range(6):
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
         a.record(); out = engine.spec_den_gw_batch(plan, pv, None, None, cells=cells); b.record(); torch.cuda.synchronize()
         print("cells", cells, "ms", a.elapsed_time(b))

@@ -1,9 +1,9 @@
 #!/bin/bash
 # tuning sweep of the K7' mapping (run on the GPU box): warps per CTA (adjacent wavenumbers), profiles per lane,
 # minimum resident CTAs per SM (register cap)
-for v in "4 8 1" "4 8 4" "4 8 5" "4 6 4" "2 8 8" "4 4 6"; do
+for v in "4 8 1" "4 6 4" "4 6 1" "4 4 1" "2 8 1" "8 4 1"; do
   set -- $v
   PTT_NVCC_EXTRA="-DPTT_GC_WARPS=$1 -DPTT_GC_PPL=$2 -DPTT_GC_MINB=$3" python -m pttools_b200.build --force > /dev/null || exit 1
-  echo "warps=$1 ppl=$2 minb=$3: $(PYTHONPATH=. python tools/gw_time.py 2>&1 | grep 'cells True\|max rel' | tail -2 | tr '\n' ' ')"
+  echo "warps=$1 ppl=$2 minb=$3: $(PYTHONPATH=. python tools/gw_time.py 2>&1 | grep 'cells True' | tail -4 | tr '\n' ' ')"
 done
 python -m pttools_b200.build --force > /dev/null
