@@ -261,3 +261,35 @@ def test_sin_transform_operator_moments_against_direct_and_oracle():
     e = engine.sin_transform_batch(z, rows_xi, rows_f, off, npts, method="auto").cpu().numpy()
     x, f = rows_xi[3, off[3]:off[3] + npts[3]], rows_f[3, off[3]:off[3] + npts[3]]
     np.testing.assert_allclose(e[3], ssm.sin_transform(z, x, f), rtol=1e-8, atol=1e-12)
+
+
+def test_pow_specs_reference_table_all_rows():
+    """data_compare_nuc-test_reference.txt, the table the reference pins in tests/paper/test_pow_specs.py:27-69 at
+    rtol 1.72e-6: the integrals of P_v and P_gw over ln z for 10 shells x 2 nucleation types (Np = (10000, 1000),
+    z = logspace(log10 0.2, 3, 5000), spec_den_gw_scaled on z itself).  The oracle reproduces two rows at 1e-9
+    (tests/test_oracle_golden.py); here all ten through the kernels, at the reference's own tolerance (measured
+    worst case 6.4e-7, printed)."""
+    from pttools_b200 import engine
+    ref = np.load(os.path.join(GOLDEN, "ref_goldens.npz"))["data_compare_nuc_test_reference"]
+    alpha, vw = ref[:, 0].copy(), ref[:, 1].copy()
+    z = np.logspace(np.log10(0.2), np.log10(1000), 5000)
+    cs = sb.CS0
+    y = ssm.logspace(np.log10(z.min() * 2 * cs / (1 - cs)), np.log10(z.max() * 2 * cs / (1 + cs)), z.size)
+    shells = engine.sweep_shells_bag(vw, alpha, n_xi=10000)
+    assert np.all(shells.status.cpu().numpy() == 0)
+    pp = engine.point_params(vw, cs, 0.75, 0.75, 0.75 * alpha, 0.0)
+    gplan = engine.GwOnlyPlan(z, y, cs=cs)
+    worst = 0.0
+    for col, nuc in ((0, "simultaneous"), (1, "exponential")):
+        plan = engine.SsmPlan(z, cs=cs, nt=1000, nxi=10000, mode="ssm", phase_rule=0, nuc_type=nuc, only_first_pass=True)
+        a2 = engine.a2_batch(plan, shells, pp)
+        sdv = engine.spec_den_v_auto(plan, 0, a2, engine.dev_f64(vw))
+        pv = (z ** 3 / (2 * np.pi ** 2))[None, :] * sdv.cpu().numpy()
+        sd_gw = engine.spec_den_gw_batch(gplan, sdv.contiguous())[0].cpu().numpy()
+        pgw = (y ** 3 / (2 * np.pi ** 2))[None, :] * sd_gw
+        v2 = np.trapezoid(pv / z, z, axis=1)
+        omgw = np.trapezoid(pgw / y, y, axis=1)
+        for got, want in ((v2, ref[:, 2 + col]), (omgw, ref[:, 4 + col])):
+            worst = max(worst, float(np.abs(got / want - 1).max()))
+            np.testing.assert_allclose(got, want, rtol=1.72e-6)
+    print("worst relative deviation from data_compare_nuc-test_reference.txt:", worst)
