@@ -293,3 +293,27 @@ def test_pow_specs_reference_table_all_rows():
             worst = max(worst, float(np.abs(got / want - 1).max()))
             np.testing.assert_allclose(got, want, rtol=1.72e-6)
     print("worst relative deviation from data_compare_nuc-test_reference.txt:", worst)
+
+
+def test_bubble_txt_through_the_kernels():
+    """bubble.txt (tests/paper/test_bubble.py:23-37 of the reference, rtol 1e-7 there): sums over z of A^2, f'^2/2 and
+    (cs l)^2/2 for three weak (alpha 0.0046) and three intermediate (0.05) shells, Np = (10000, 1000).  Intermediate
+    shells: 2e-6 against the table.  Weak shells carry the reference's own LSODA noise (tie policy; up to
+    1.5e-5 in these sums): 3e-5 against the table, and 2e-6 against the restatement run with tight LSODA tolerances."""
+    from pttools_b200 import engine
+    ref = np.load(os.path.join(GOLDEN, "ref_goldens.npz"))["bubble"]
+    vw = np.array([0.92, 0.56, 0.44, 0.92, 0.56, 0.44])
+    alpha = np.array([0.0046] * 3 + [0.05] * 3)
+    z = np.logspace(np.log10(0.2), np.log10(1000), 5000)
+    shells = engine.sweep_shells_bag(vw, alpha, n_xi=10000)
+    pp = engine.point_params(vw, sb.CS0, 0.75, 0.75, 0.75 * alpha, 0.0)
+    a2, fp2, lam2 = engine.a2_batch(engine.A2OnlyPlan(z, nxi=10000, phase_rule=0), shells, pp, want_parts=True)
+    got = np.stack([np.full(6, z.sum()), a2.sum(1).cpu().numpy(), fp2.sum(1).cpu().numpy(), lam2.sum(1).cpu().numpy()], axis=1)
+    print("relative deviations from bubble.txt:", np.abs(got / ref - 1).max(axis=1))
+    np.testing.assert_allclose(got[3:], ref[3:], rtol=2e-6)
+    np.testing.assert_allclose(got[:3], ref[:3], rtol=3e-5)
+    for i in range(3):
+        with sb.lsoda_tolerances(1e-12, 1e-13):
+            prof = sb.sound_shell_bag(vw[i], alpha[i], 10000)
+            t = ssm.a2_e_conserving_bag(z, vw[i], alpha[i], npt=(10000, 1000), profile=prof)
+        np.testing.assert_allclose(got[i, 1:], [x.sum() for x in t], rtol=2e-6)
