@@ -140,3 +140,24 @@ def test_fluid_shell_tables_of_the_reference():
                        0.75 * sb.mean_enthalpy_change(v, w, xi, vw) / (0.75 * an * w[-1])]
                 np.testing.assert_allclose(got, ref[5:, i], rtol=3e-6)
     assert n_summed >= 3         # the subsonic deflagrations: no rarefaction wave, cut at a genuine shock
+
+
+def test_shell_txt_scalars():
+    """shell.txt (tests/paper/test_shells_bag.py:28-56, rtol 1e-7 there): sound_shell_dict(0.7, 0.052), a hybrid.  Its
+    array sums and sample counts depend on the noise-decided cut at the inner end of the rarefaction wave (DESIGN.md,
+    tie policy; the oracle reproduces them at 1e-9); the physical entries - r, alpha_+, ubarf2, K, kappa, dw - are
+    compared with the table here, the profile with the oracle's as a curve."""
+    import os
+    from pttools_b200 import bubble
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_goldens.npz"))["shell"]
+    vw, an = 0.7, 0.052
+    v, w, xi = bubble.sound_shell_bag(vw, an)
+    n_wall = int(np.argmax(xi >= vw))
+    ub = sb.ubarf_squared(v, w, xi, vw)
+    got = [w[n_wall] / w[n_wall - 1], an * w[-1] / w[n_wall], ub, ub / (0.75 * (1 + an)), ub / (0.75 * an),
+           0.75 * sb.mean_enthalpy_change(v, w, xi, vw) / (0.75 * an * w[-1])]
+    np.testing.assert_allclose(got, ref[8:14], rtol=3e-6)
+    d = sb.sound_shell_dict(vw, an)
+    ev, ew = curve_errors(xi, v, w, d["xi"], d["v"], d["w"], vw)
+    assert ev < 1e-6 and ew < 1e-6
+    assert xi.size - 2 - n_wall == d["n_sh"] - d["n_wall"]          # same number of samples between wall and shock
