@@ -347,64 +347,106 @@ __global__ void __launch_bounds__(ST_THREADS) sin_transform_kernel(
 __device__ void block_moments(const double* __restrict__ xi, const double* __restrict__ g, const int n,
                               double* __restrict__ mom /* MOM_SIZE, global */, double* s_pyr /* MOM_BLOCKS*MOM_J shared */,
                               int* s_lohi /* 2 shared */) {
+    // Warps walk the samples in chunks of MOM_CHUNK coalesced tiles of 32.  Consecutive samples nearly always fall in
+    // the same block, so a warp keeps the moments of its current block in registers and adds them to shared memory
+    // (a folding shuffle reduction + one atomic per moment) only when the block changes or the chunk ends; a tile that
+    // straddles blocks is walked once per distinct block.
+    constexpr int MOM_CHUNK = 4;
+    __shared__ double s_pw[(MOM_LEVELS - 1) * MOM_J];   // s_pw[l][d] = (half child width at level l)^d / d!
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, n_warps = nt >> 5;
     double* s_m = s_pyr + (MOM_NB - 1) * MOM_J;       // finest level
     for (int i = tid; i < MOM_NB * MOM_J; i += nt) s_m[i] = 0.0;
     if (tid == 0) { s_lohi[0] = MOM_NB; s_lohi[1] = -1; }
-    __syncthreads();
-    const int L = (n + nt - 1) / nt;
-    const int k0 = tid * L, k1 = min(n, k0 + L);
-    double m[MOM_J];
-    int cur = -1;
-    for (int k = k0; k < k1; ++k) {
-        const double gk = g[k];
-        if (gk == 0.0) continue;
-        const double x = xi[k];
-        int b = (int)(x * MOM_NB);
-        b = max(0, min(MOM_NB - 1, b));
-        if (b != cur) {
-            if (cur >= 0) {
-#pragma unroll
-                for (int j = 0; j < MOM_J; ++j) atomicAdd(&s_m[cur * MOM_J + j], m[j]);
-                atomicMin(&s_lohi[0], cur);
-                atomicMax(&s_lohi[1], cur);
-            }
-#pragma unroll
-            for (int j = 0; j < MOM_J; ++j) m[j] = 0.0;
-            cur = b;
-        }
-        const double d = x - ((double)b + 0.5) * MOM_W;
-        double t = gk;
-#pragma unroll
-        for (int j = 0; j < MOM_J; ++j) {
-            m[j] += t;
-            t *= d * (1.0 / (double)(j + 1));          // compile-time reciprocals: no division in the loop
-        }
+    if (tid < (MOM_LEVELS - 1) * MOM_J) {
+        const int l = tid / MOM_J, d = tid - l * MOM_J;
+        const double sh = 0.25 / (double)(1 << l);
+        double pw = 1.0;
+        for (int i = 1; i <= d; ++i) pw *= sh / (double)i;
+        s_pw[tid] = pw;
     }
-    if (cur >= 0) {
+    __syncthreads();
+    double m[MOM_J];
 #pragma unroll
-        for (int j = 0; j < MOM_J; ++j) atomicAdd(&s_m[cur * MOM_J + j], m[j]);
-        atomicMin(&s_lohi[0], cur);
-        atomicMax(&s_lohi[1], cur);
+    for (int j = 0; j < MOM_J; ++j) m[j] = 0.0;
+    int cur = -1;                                      // warp-uniform: block whose moments sit in m
+    static_assert(MOM_J == 12, "the butterfly below folds 12 -> 6 -> 3 -> 2 -> 1 values per lane");
+    auto flush = [&]() {
+        if (cur < 0) return;
+        // Butterfly that halves the values per lane at every step (13 shuffles instead of 60): afterwards lane L holds
+        // the warp total of moment j(L) = bit1 + 2 bit2 + 3 bit3 + 6 bit4 (bit1 + 2 bit2 == 3 is padding).
+        const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+        double a6[6], a3[4], a2[2];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const double send = h4 ? m[i] : m[i + 6], keep = h4 ? m[i + 6] : m[i];
+            a6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double send = h3 ? a6[i] : a6[i + 3], keep = h3 ? a6[i + 3] : a6[i];
+            a3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        a3[3] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double send = h2 ? a3[i] : a3[i + 2], keep = h2 ? a3[i + 2] : a3[i];
+            a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        const double send = h1 ? a2[0] : a2[1], keep = h1 ? a2[1] : a2[0];
+        double tot = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        const int jl = (h1 ? 1 : 0) + (h2 ? 2 : 0);
+        if (!(lane & 1) && jl < 3) atomicAdd(&s_m[cur * MOM_J + jl + (h3 ? 3 : 0) + (h4 ? 6 : 0)], tot);
+#pragma unroll
+        for (int j = 0; j < MOM_J; ++j) m[j] = 0.0;
+        if (lane == 0) { atomicMin(&s_lohi[0], cur); atomicMax(&s_lohi[1], cur); }
+        cur = -1;
+    };
+    const int n_tiles = (n + 31) >> 5;
+    for (int t0 = warp * MOM_CHUNK; t0 < n_tiles; t0 += n_warps * MOM_CHUNK) {
+        const int t1 = min(n_tiles, t0 + MOM_CHUNK);
+        for (int t = t0; t < t1; ++t) {
+            const int k = (t << 5) + lane;
+            const double gk = (k < n) ? g[k] : 0.0;
+            const double x = (k < n) ? xi[k] : 0.0;
+            const int b = (gk != 0.0) ? max(0, min(MOM_NB - 1, (int)(x * MOM_NB))) : -1;
+            unsigned act = __ballot_sync(0xffffffffu, b >= 0);
+            while (act) {                              // one pass per distinct block in the tile (nearly always one)
+                const int b0 = __shfl_sync(0xffffffffu, b, __ffs(act) - 1);
+                if (b0 != cur) { flush(); cur = b0; }
+                if (b == b0) {
+                    const double d = x - ((double)b0 + 0.5) * MOM_W;
+                    double tt = gk;
+#pragma unroll
+                    for (int j = 0; j < MOM_J; ++j) {
+                        m[j] += tt;
+                        tt *= d * (1.0 / (double)(j + 1));      // compile-time reciprocals: no division in the loop
+                    }
+                }
+                act &= ~__ballot_sync(0xffffffffu, b == b0);
+            }
+        }
+        flush();
     }
     __syncthreads();
     // Coarser levels by merging pairs of blocks: with delta' = delta + s (s = -+ half a child width),
     //   M'_j = sum_children sum_{i<=j} s^(j-i)/(j-i)! M_i   - exact algebra, no new truncation.
     for (int l = MOM_LEVELS - 2; l >= 0; --l) {
         const int nb = 1 << l;
-        const double sh = 0.25 / (double)nb;            // half the child width
+        const double* pwt = s_pw + l * MOM_J;
         const double* child = s_pyr + (2 * nb - 1) * MOM_J;
         double* par = s_pyr + (nb - 1) * MOM_J;
         for (int i = tid; i < nb * MOM_J; i += nt) {
             const int b = i / MOM_J, j = i - b * MOM_J;
             const double* cl = child + (2 * b) * MOM_J;
             const double* cr = cl + MOM_J;
-            double accl = 0.0, accr = 0.0, pw = 1.0;     // pw = sh^(j-i)/(j-i)!
+            double accl = 0.0, accr = 0.0;
             for (int q = j; q >= 0; --q) {
                 // left child: centre = parent centre - sh  =>  delta' = delta - sh;  right child: delta' = delta + sh
+                const double pw = pwt[j - q];
                 accl = fma(((j - q) & 1) ? -pw : pw, cl[q], accl);
                 accr = fma(pw, cr[q], accr);
-                pw *= sh / (double)(j - q + 1);
             }
             par[i] = accl + accr;
         }
@@ -615,30 +657,38 @@ __global__ void __launch_bounds__(STM_THREADS) st_transform_moments_kernel(
 }
 
 // --- K5c: |A|^2 from f and l (ssm.py:56, 74-81; speedup/functions.py:10-20) ----------------------------------
+constexpr int A2F_PPT = 8;      // profiles per thread: the stencil and 1/dz of a wavenumber are shared by all profiles
+
 __global__ void __launch_bounds__(256) a2_finish_kernel(
-    const int n_z, const int n_seg, const int* __restrict__ seg, const double* __restrict__ z,
+    const int P, const int n_z, const int n_seg, const int* __restrict__ seg, const double* __restrict__ z,
     const double* __restrict__ work, const long long work_stride, const long long offF, const long long offL,
     const double* __restrict__ pp, double* __restrict__ a2, double* __restrict__ fp2_2, double* __restrict__ lam2) {
-    const int p = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_z) return;
     int s0 = 0, s1 = n_z;
     for (int s = 0; s < n_seg; ++s)
         if (i >= seg[s] && i < seg[s + 1]) { s0 = seg[s]; s1 = seg[s + 1]; }
-    const double* F = work + (long long)p * work_stride + offF;
-    const double* L = work + (long long)p * work_stride + offL;
-    double gf, gz;
-    if (s1 - s0 < 2) { gf = NAN; gz = NAN; }
-    else if (i == s0) { gf = F[i + 1] - F[i]; gz = z[i + 1] - z[i]; }
-    else if (i == s1 - 1) { gf = F[i] - F[i - 1]; gz = z[i] - z[i - 1]; }
-    else { gf = (F[i + 1] - F[i - 1]) / 2.0; gz = (z[i + 1] - z[i - 1]) / 2.0; }
-    const double v_ft = gf / gz;
-    const double cs = pp[8 * p + 1];
-    const double cl = cs * L[i];
-    const long long o = (long long)p * n_z + i;
-    a2[o] = 0.25 * (v_ft * v_ft + cl * cl);
-    if (fp2_2) fp2_2[o] = v_ft * v_ft / 2.0;
-    if (lam2) lam2[o] = cl * cl / 2.0;
+    // np.gradient stencil of this wavenumber: (F[ia] - F[ib]) * wgt / gz, the factor wgt / gz formed once (<= 1 ulp from
+    // dividing per profile)
+    int ia, ib;
+    double wgt, gz;
+    if (s1 - s0 < 2) { ia = ib = i; wgt = NAN; gz = 1.0; }
+    else if (i == s0) { ia = i + 1; ib = i; wgt = 1.0; gz = z[i + 1] - z[i]; }
+    else if (i == s1 - 1) { ia = i; ib = i - 1; wgt = 1.0; gz = z[i] - z[i - 1]; }
+    else { ia = i + 1; ib = i - 1; wgt = 0.5; gz = (z[i + 1] - z[i - 1]) / 2.0; }
+    const double scale = wgt / gz;
+    const int p0 = blockIdx.y * A2F_PPT, p1 = min(P, p0 + A2F_PPT);
+    for (int p = p0; p < p1; ++p) {
+        const double* F = work + (long long)p * work_stride + offF;
+        const double* L = work + (long long)p * work_stride + offL;
+        const double v_ft = (F[ia] - F[ib]) * scale;
+        const double cs = pp[8 * p + 1];
+        const double cl = cs * L[i];
+        const long long o = (long long)p * n_z + i;
+        a2[o] = 0.25 * (v_ft * v_ft + cl * cl);
+        if (fp2_2) fp2_2[o] = v_ft * v_ft / 2.0;
+        if (lam2) lam2[o] = cl * cl / 2.0;
+    }
 }
 
 // --- K6: spec_den_v -------------------------------------------------------------------------------------------
@@ -953,8 +1003,8 @@ extern "C" int ptt_a2_batch(const ptt_a2_plan_t* plan, int P, const double* rows
             work + lay.F(), work_stride, plan->nxi, plan->xi_re, work + lay.hl(), work_stride, work + lay.env_l(),
             work_stride, work + lay.L(), work_stride, 1);
     }
-    dim3 grid2((plan->n_z + 255) / 256, P);
-    a2_finish_kernel<<<grid2, 256, 0, stream>>>(plan->n_z, plan->n_seg, plan->seg, plan->z, work, work_stride, lay.F(),
+    dim3 grid2((plan->n_z + 255) / 256, (P + A2F_PPT - 1) / A2F_PPT);
+    a2_finish_kernel<<<grid2, 256, 0, stream>>>(P, plan->n_z, plan->n_seg, plan->seg, plan->z, work, work_stride, lay.F(),
                                                 lay.L(), pp, a2, fp2_2, lam2);
     return check_launch("ptt_a2_batch");
 }

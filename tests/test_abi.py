@@ -59,4 +59,5 @@ def test_argument_checks_need_no_gpu():
     with pytest.raises(_lib.PttError):
         _lib.check(rc, "ptt_bag_alpha_n_max")
     assert lib.ptt_profile_row_capacity(2000) > 2 * 2000 and lib.ptt_generic_row_capacity(5000) == 2 * 5000 + 4
-    assert lib.ptt_gw_cells_capacity(10000, 10000, 1251.3) >= 2 * 1252
+    cap = lib.ptt_gw_cells_capacity(10000, 10000, 1251.3)
+    assert cap >= 1252 + 3 and cap % 4 == 0 and lib.ptt_gw_cells_coef_capacity(cap) >= 3 * cap
