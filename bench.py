@@ -153,7 +153,8 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms",
+                                       os.environ.get("PTT_BENCH_SAMPLER_MS", "100")], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             pass

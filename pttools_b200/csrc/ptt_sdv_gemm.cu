@@ -40,27 +40,38 @@ __global__ void __launch_bounds__(256) sdv_weights_kernel(
     const double2* __restrict__ omega_ab, double* __restrict__ omega) {
     const int i = blockIdx.y;
     const int kk = blockIdx.x * blockDim.x + threadIdx.x;
-    if (kk >= kw) return;
-    const double s = z[i] / bv;
+    __shared__ double s_scale;
+    if (threadIdx.x == 64) s_scale = z[i] / bv;                      // one division per row, not per knot
     const double ub = zterm[i] + shift;
-    const int e = e_base[i / GM_BM] + kk;
+    const int e0 = e_base[i / GM_BM] + blockIdx.x * blockDim.x;      // knot of thread 0
+    const int e = e0 + threadIdx.x;
     double acc = 0.0;
     const double lt0 = LT[0];
     const double inv_dlt = (nt > 1) ? (double)(nt - 1) / (LT[nt - 1] - lt0) : 0.0;     // LT is a linspace
+    // number of kinks LT_j below x(knot) = knot - (zterm_i + shift): x moves by exactly one per knot, so the three counts
+    // a knot needs (at x - 1, x, x + 1) are the counts of its neighbours: one per thread + a halo of two, through shared
+    // memory
+    __shared__ int s_cnt[256 + 2];
+    auto count_below = [&](const int knot) {
+        const double yy = ((double)knot - ub - lt0) * inv_dlt;
+        const int c = (yy > 0.0) ? __double2int_ru(yy) : 0;
+        return min(c, nt);
+    };
+    if (omega_ab) {
+        s_cnt[threadIdx.x + 1] = count_below(e);
+        if (threadIdx.x == 0) s_cnt[0] = count_below(e0 - 1);
+        if (threadIdx.x == 32) s_cnt[blockDim.x + 1] = count_below(e0 + (int)blockDim.x);
+    }
+    __syncthreads();
+    const double s = s_scale;
+    if (kk >= kw) return;
     if (omega_ab && e > 0 && e < n_q - 1) {
         // Closed form.  As a function of x = e - (zterm_i + shift) the weight of an interior knot is
         //     omega(x) = alpha_p + beta_p * (s_i / qT[e])
         // on every piece p between two consecutive kinks LT_j - 1, LT_j, LT_j + 1 (the set of contributing samples is
         // fixed there and np.interp's weight (X - x0)/(x1 - x0) on a log grid is linear in X / qT[e]); the plan
         // carries (alpha, beta) per piece, and the piece index is the number of kinks below x.
-        const double x = (double)e - ub;
-        int piece = 0;
-#pragma unroll
-        for (int sgn = -1; sgn <= 1; ++sgn) {
-            const double yy = (x - (double)sgn - lt0) * inv_dlt;
-            int c = (yy > 0.0) ? __double2int_ru(yy) : 0;
-            piece += min(c, nt);
-        }
+        const int piece = s_cnt[threadIdx.x] + s_cnt[threadIdx.x + 1] + s_cnt[threadIdx.x + 2];
         const double2 ab = omega_ab[piece];
         acc = fma(ab.y, s * inv_q[e], ab.x);
     } else if (e < n_q) {
