@@ -11,6 +11,8 @@ from __future__ import annotations
 import enum
 import logging
 
+import warnings
+
 import numpy as np
 
 logger = logging.getLogger(__name__)
@@ -66,9 +68,10 @@ class Model:
         self.label_unicode = label_unicode or self.name
         self.w_min = max(self.w(self.T_min, Phase.SYMMETRIC), self.w(self.T_min, Phase.BROKEN))   # model.py:95-100
         self.w_max = np.inf
-        self.T_crit = self.critical_temp()
-        self.w_crit = float(self.w(self.T_crit, Phase.SYMMETRIC))    # model.py:460-474
-        self.w_at_alpha_n_min, self.alpha_n_min = self.w_crit, float(self.alpha_n(self.w_crit))
+        self.T_crit = self.critical_temp(allow_fail=allow_invalid)
+        with np.errstate(all="ignore"):
+            self.w_crit = float(self.w(self.T_crit, Phase.SYMMETRIC))    # model.py:460-474
+        self.w_at_alpha_n_min, self.alpha_n_min = self.w_crit, self._alpha_n_min_checked(allow_fail=allow_invalid)
 
     # --- thermodynamic functions of temperature
     def _powfac(self, temp, mu):
@@ -211,28 +214,63 @@ class Model:
             out = np.where(np.abs(self.alpha_n(out) - alpha_n) > 1e-9 * np.maximum(1.0, np.abs(alpha_n)), np.nan, out)
         return out if out.ndim else float(out)
 
-    def critical_temp(self):
+    def _critical_temp_opt(self, temp):
+        """Zero at T_crit, where p_s = p_b (const_cs.py:521-523)."""
+        const = (self.V_b - self.V_s) * self.T_ref ** 4
+        return self.a_s * (temp / self.T_ref) ** self.mu_s - self.a_b * (temp / self.T_ref) ** self.mu_b + const
+
+    def critical_temp(self, guess=None, allow_fail=False):
+        """T_crit with p_s(T_crit) = p_b(T_crit).  Bag: closed form (bag.py:186-192).  Otherwise the reference's procedure
+        (model.py:476-557): MINPACK hybrd (scipy.optimize.fsolve, the same library call) from the guess T_ref
+        (const_cs.py:116-117), with the same validity checks and the same exceptions - the parameter search of
+        ConstCSModel(alpha_n_min=...) depends on which trial models are rejected."""
         if np.isclose(self.mu_s, 4) and np.isclose(self.mu_b, 4):
-            return ((self.V_s - self.V_b) / (self.a_s - self.a_b)) ** 0.25      # bag.py:186-192
-        # a_s (T/T0)^mu_s - a_b (T/T0)^mu_b = (V_s - V_b) T0^4 ... solved by bisection in log T (const_cs.py:521-523)
-        f = lambda t: self.a_s * (t / self.T_ref) ** self.mu_s - self.a_b * (t / self.T_ref) ** self.mu_b \
-            + (self.V_b - self.V_s) * self.T_ref ** 4
-        lo, hi = self.T_min, max(1e4, 10 * self.T_ref)
-        ts = np.logspace(np.log10(lo), np.log10(hi), 2000)
-        fs = f(ts)
-        idx = np.nonzero(np.sign(fs[:-1]) != np.sign(fs[1:]))[0]
-        if idx.size == 0:
-            raise ValueError("All models should have p_s(T>T_crit) > p_b(T>T_crit) for T_crit to exist.")
-        # the reference's fsolve starts at T_ref: take the sign change closest to it
-        k = idx[np.argmin(np.abs(np.log(ts[idx]) - np.log(self.T_ref)))]
-        a, b = ts[k], ts[k + 1]
-        for _ in range(200):
-            mid = 0.5 * (a + b)
-            if np.sign(f(mid)) == np.sign(f(a)):
-                a = mid
-            else:
-                b = mid
-        return 0.5 * (a + b)
+            return ((self.V_s - self.V_b) / (self.a_s - self.a_b)) ** 0.25
+        from scipy.optimize import fsolve
+        if guess is None:
+            guess = self.T_ref
+
+        def fail(kind, msg):
+            if not allow_fail:
+                raise kind(msg)
+
+        p_s_min, p_b_min = self.p_temp(self.T_min, Phase.SYMMETRIC), self.p_temp(self.T_min, Phase.BROKEN)
+        if p_s_min >= p_b_min:
+            fail(ValueError, "All models should have p_s(T=T_min) < p_b(T=T_min) for T_crit to exist. "
+                             f"Got: T_min={self.T_min}, p_s={p_s_min}, p_b={p_b_min}.")
+        t_arr = np.logspace(np.log10(self.T_min), np.log10(1e4), 10)
+        if np.all(self.p_temp(t_arr, Phase.SYMMETRIC) <= self.p_temp(t_arr, Phase.BROKEN)):
+            fail(ValueError, "All models should have p_s(T>T_crit) > p_b(T>T_crit) for T_crit to exist.")
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sol = fsolve(self._critical_temp_opt, x0=np.array([guess], dtype=float), full_output=True)
+        t_crit = float(sol[0][0])
+        if sol[2] != 1:
+            fail(RuntimeError, f"Could not find Tc with guess={guess}. Using Tc={t_crit}. Reason: {sol[3]}")
+        if t_crit <= self.T_min:
+            fail(ValueError, f"T_crit should be higher than T_min. Got: T_crit={t_crit}, T_min={self.T_min}")
+        with np.errstate(all="ignore"):
+            p_crit_s, p_crit_b = self.p_temp(t_crit, Phase.SYMMETRIC), self.p_temp(t_crit, Phase.BROKEN)
+        if not np.isclose(p_crit_s, p_crit_b):
+            fail(ValueError, f"Pressures do not match at T_crit. Got: p_s={p_crit_s}, p_b={p_crit_b}")
+        if p_crit_s < 0 or p_crit_b < 0:
+            fail(ValueError, f"Pressure cannot be negative at T_crit. Got: p_s={p_crit_s}, p_b={p_crit_b}")
+        return t_crit
+
+    def _alpha_n_min_checked(self, allow_fail=False):
+        """alpha_n at w_crit with the range checks of the reference (model.py:141-199, const_cs.py:161-199)."""
+        w = self.w_crit
+        if not allow_fail:
+            if np.isnan(w):
+                pass                                                     # logged only by the reference
+            elif w < self.w_min:
+                raise ValueError(f"Got wn={w} < w_min={self.w_min} for alpha_n.")
+        with np.errstate(all="ignore"):
+            an = float(self.alpha_n(w))
+        if an < 0 and not allow_fail:
+            raise ValueError(f"Got negative alpha_n={an} with wn={w}, mu_s={self.mu_s}, mu_b={self.mu_b}, "
+                             f"t_crit={self.T_crit}.")
+        return an
 
     # --- wall-speed classification
     def v_chapman_jouguet(self, alpha_n, wn=None):
@@ -320,9 +358,6 @@ class ConstCSModel(Model):
     DEFAULT_NAME = "const_cs"
 
     def __init__(self, css2, csb2, V_s=1.0, V_b=0.0, a_s=None, a_b=None, T_ref=1.0, name=None, alpha_n_min=None, **kw):
-        if alpha_n_min is not None:
-            raise NotImplementedError("ConstCSModel(alpha_n_min=...): the parameter search of const_cs.py:225-397 is "
-                                      "not part of this package; give a_s, a_b, V_s, V_b explicitly")
         css2, csb2 = float(css2), float(csb2)
         for nm, c in (("css2", css2), ("csb2", csb2)):
             if not 0 < c <= 1:
@@ -331,7 +366,70 @@ class ConstCSModel(Model):
             css2 = 1 / 3
         if csb2 > 1 / 3 and np.isclose(csb2, 1 / 3):
             csb2 = 1 / 3
+        if alpha_n_min is not None:
+            a_b_ = 1.0 if a_b is None else a_b                            # analytic.py:163-188 (get_a_g)
+            a_s_ = 1.1 * a_b_ if a_s is None else a_s
+            a_s, a_b, V_s, V_b = self.alpha_n_min_find_params(css2, csb2, alpha_n_min, a_s_default=a_s_, a_b=a_b_,
+                                                              V_s_default=V_s, V_b=V_b)
         super().__init__(css2, csb2, V_s=V_s, V_b=V_b, a_s=a_s, a_b=a_b, T_ref=T_ref, name=name, **kw)
+
+    @classmethod
+    def alpha_n_min_find_params(cls, css2, csb2, alpha_n_min_target, a_s_default, a_b, V_s_default=1.0, V_b=0.0,
+                                safety_factor_alpha=0.999, safety_factor_a=1.001, safety_factor_V=0.001, a_max=1e4):
+        """(a_s, a_b, V_s, V_b) of a model whose alpha_n_min is just below the target: the search of const_cs.py:225-397
+        with the same optimiser calls (scipy's bounded Brent minimiser on a_s for V_s and V_s/100, then L-BFGS-B on
+        (a_s, V_s)), the same acceptance tests and the same fall-back to the defaults."""
+        from scipy.optimize import minimize, minimize_scalar
+        if safety_factor_a < 1 or safety_factor_V < 0:
+            raise ValueError(f"Got invalid safety factors: a={safety_factor_a}, V={safety_factor_V}")
+        defaults = (a_s_default, a_b, V_s_default, V_b)
+        if np.isclose(1 + 1 / css2, 4) and np.isclose(1 + 1 / csb2, 4):        # bag.py:119-135
+            if a_s_default < 0 or a_b < 0 or V_s_default < 0 or V_b < 0:
+                raise ValueError(f"Invalid parameters: a_s_default={a_s_default}, a_b={a_b}, V_s_default={V_s_default}, "
+                                 f"V_b={V_b}")
+            a_s = a_b / (1 - 3 * alpha_n_min_target * safety_factor_alpha)
+            return (a_s_default if a_s_default < a_s else a_s), a_b, V_s_default, V_b
+        target = safety_factor_alpha * alpha_n_min_target
+
+        def objective(a_s, V_s):
+            try:
+                trial = cls(css2, csb2, a_s=a_s, a_b=a_b, V_s=V_s, V_b=V_b)
+            except (ValueError, RuntimeError):
+                return np.nan
+            return (trial.alpha_n_min - target) ** 2
+
+        base = None
+        try:
+            base = cls(css2, csb2, a_s=a_s_default, a_b=a_b, V_s=V_s_default)      # V_b = 0 here (const_cs.py:331)
+            if base.alpha_n_min < alpha_n_min_target:                            # already below the target
+                return defaults
+        except ValueError:
+            pass
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for V_s in (V_s_default, V_s_default / 100):
+                sol = minimize_scalar(objective, bracket=((a_s_default + a_b) / 2, a_s_default, 2 * a_s_default),
+                                      bounds=(a_b * safety_factor_a, a_max), args=(V_s,))
+                if sol.success:
+                    found = cls(css2, csb2, a_s=sol.x, a_b=a_b, V_s=V_s, V_b=V_b)
+                    if found.alpha_n_min <= alpha_n_min_target:
+                        return sol.x, a_b, V_s, V_b
+            sol = minimize(lambda x: objective(x[0], x[1]), x0=np.array([a_s_default, V_s_default], dtype=float),
+                           bounds=((a_b * safety_factor_a, None), (V_b + safety_factor_V, None)))
+        if not sol.success:
+            logger.error("Failed to find alpha_n_min. Reason: %s. Using given defaults a_s=%s, a_b=%s, V_s=%s, V_b=%s "
+                         "for css2=%s, csb2=%s.", sol.message, a_s_default, a_b, V_s_default, V_b, css2, csb2)
+            return defaults
+        a_s, V_s = sol.x[0], sol.x[1]
+        found = cls(css2, csb2, a_s=a_s, a_b=a_b, V_s=V_s, V_b=V_b)
+        if base is None:
+            raise RuntimeError("alpha_n_min search: the default parameters do not give a valid model to compare with")
+        if found.alpha_n_min > base.alpha_n_min:
+            logger.error("alpha_n_min solver returned greater alpha_n_min than with default values. Using defaults "
+                         "a_s=%s, a_b=%s, V_s=%s, V_b=%s for css2=%s, csb2=%s.", a_s_default, a_b, V_s_default, V_b, css2,
+                         csb2)
+            return defaults
+        return a_s, a_b, V_s, V_b
 
     def solution_type_codes(self, v_wall, alpha_n, wn=None, an_max_bag=None):
         """const_cs.py:633-655."""

@@ -179,8 +179,9 @@ def test_multi_model_sweep_matches_per_point_objects():
             np.testing.assert_allclose(om[row], s.omgw0(), rtol=1e-9)
             n_checked += 1
     assert n_checked >= 6
-    with pytest.raises(NotImplementedError):
-        ConstCSModel(css2=1 / 3, csb2=1 / 4, alpha_n_min=0.05)
+    # the constructor of config 3 (examples/const_cs/const_cs_gw.py:153-157): parameters found by the reference's search
+    m = ConstCSModel(css2=1 / 3, csb2=1 / 4, a_s=5, a_b=1, V_s=1, alpha_n_min=0.05)
+    np.testing.assert_allclose([m.a_s, m.alpha_n_min], [1.709755300249833, 0.049949674598450844], rtol=1e-9)
 
 
 def test_batched_validity_flags_match_bubble_objects():

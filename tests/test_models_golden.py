@@ -50,3 +50,39 @@ def test_oracle_models_against_reference_tables(tables):
     from oracle import models
     _check(models.bag_model(1.2, 1.1, 1.3), tables["bag"])
     _check(models.const_cs_model(0.4 ** 2, 1 / 3, 1.2, 1.1, 1.3), tables["const_cs"])
+
+
+def test_constcs_alpha_n_min_parameter_search():
+    """ConstCSModel(..., alpha_n_min=x) runs the parameter search of const_cs.py:225-397.  Fixture: what the reference
+    itself ends with (tools/make_golden.py::constcs_alpha_n_min) for 14 models - direct hits, the V_s/100 retry, the
+    two-parameter L-BFGS-B stage and the fall-back to the defaults are all in there."""
+    import logging
+    from pttools_b200.models import ConstCSModel
+    cases = json.load(open(os.path.join(GOLDEN, "ref_constcs_alpha_n_min.json")))
+    assert len(cases) >= 14
+    logging.disable(logging.CRITICAL)
+    try:
+        for c in cases:
+            kw = {} if c["a_s"] is None else {"a_s": c["a_s"]}
+            make = lambda: ConstCSModel(c["css2"], c["csb2"], a_b=c["a_b"], V_s=c["V_s"], alpha_n_min=c["alpha_n_min"], **kw)
+            if "raises" in c:
+                with pytest.raises(Exception) as info:
+                    make()
+                assert type(info.value).__name__ == c["raises"]
+                continue
+            m = make()
+            got = [m.a_s, m.a_b, m.V_s, m.V_b, m.alpha_n_min, m.T_crit, m.w_crit]
+            np.testing.assert_allclose(got, c["result"], rtol=1e-9, atol=1e-12, err_msg=str(c))
+    finally:
+        logging.disable(logging.NOTSET)
+
+
+def test_constcs_critical_temp_rejects_what_the_reference_rejects():
+    """model.py:476-557: no T_crit when p_s(T_min) >= p_b(T_min) or when p_s never exceeds p_b."""
+    from pttools_b200.models import ConstCSModel
+    with pytest.raises(ValueError):
+        ConstCSModel(0.3, 0.28, a_s=0.5, a_b=1.0, V_s=1.0)       # a_s < a_b with mu_s < mu_b: p_s stays below p_b
+    with pytest.raises(ValueError):
+        ConstCSModel(0.3, 0.28, a_s=2.0, a_b=1.0, V_s=0.5, V_b=1.0)      # V_s < V_b
+    m = ConstCSModel(0.3, 0.28, a_s=0.5, a_b=1.0, V_s=1.0, allow_invalid=True)
+    assert m.T_crit > 0

@@ -205,7 +205,37 @@ def model_tables():
     json.dump(out, open(os.path.join(OUT, "ref_models.json"), "w"))
 
 
-TASKS.update({"model_tables": model_tables, "fluid_reference": fluid_reference_table, "generic_bubbles": generic_bubbles,
+CONSTCS_ALPHA_N_MIN = [  # (css2, csb2, a_s or None, a_b, V_s, alpha_n_min)
+    (1 / 3, 1 / 3, 5, 1, 1, 0.05), (1 / 3, 1 / 4, 5, 1, 1, 0.05), (1 / 4, 1 / 3, 5, 1, 1, 0.05), (1 / 4, 1 / 4, 5, 1, 1, 0.05),
+    (0.3, 0.28, 5, 1, 1, 0.01), (1 / 3 - 0.01, 1 / 3, 5, 1, 1, 0.1), (0.25, 0.3, None, 1, 1, 0.02), (1 / 3, 0.3, 5, 1, 1, 0.2),
+    (0.29, 0.31, 5, 1, 1, 0.05), (0.32, 0.26, 3, 1.1, 1.3, 0.03), (1 / 3, 0.27, None, 1, 1, 0.15), (0.28, 0.28, 5, 1, 1, 0.08),
+    (1 / 3, 1 / 3 - 0.01, 5, 1, 1, 0.005), (0.31, 1 / 3, 2, 1, 0.5, 0.12)]
+
+
+def constcs_alpha_n_min():
+    """ConstCSModel(css2, csb2, a_s, a_b, V_s, alpha_n_min=...): the parameters the reference's search
+    (models/const_cs.py:225-397) ends with, and the resulting alpha_n_min, T_crit, w_crit."""
+    import json
+    import logging
+    from pttools.models.const_cs import ConstCSModel
+    logging.disable(logging.CRITICAL)
+    out = []
+    for css2, csb2, a_s, a_b, V_s, an in CONSTCS_ALPHA_N_MIN:
+        kw = {} if a_s is None else {"a_s": a_s}
+        entry = {"css2": css2, "csb2": csb2, "a_s": a_s, "a_b": a_b, "V_s": V_s, "alpha_n_min": an}
+        try:
+            m = ConstCSModel(css2=css2, csb2=csb2, a_b=a_b, V_s=V_s, alpha_n_min=an, **kw)
+            entry["result"] = [float(m.a_s), float(m.a_b), float(m.V_s), float(m.V_b), float(m.alpha_n_min),
+                               float(m.T_crit), float(m.w_crit)]
+        except Exception as e:       # noqa: BLE001 - the kind of failure is part of the fixture
+            entry["raises"] = type(e).__name__
+        print(entry)
+        out.append(entry)
+    logging.disable(logging.NOTSET)
+    json.dump(out, open(os.path.join(OUT, "ref_constcs_alpha_n_min.json"), "w"), indent=1)
+
+
+TASKS.update({"constcs_alpha_n_min": constcs_alpha_n_min, "model_tables": model_tables, "fluid_reference": fluid_reference_table, "generic_bubbles": generic_bubbles,
               "generic_spectra": generic_spectra, "suppression_ssm": suppression_ssm})
 
 
