@@ -111,6 +111,16 @@ int ptt_sweep_shells_generic(int n, const double* pg, int n_xi, double t_end, in
                              double* rows_v, double* rows_w, double* rows_xi, int64_t row_stride, int32_t* off,
                              int32_t* npts, double* scalars, int32_t* status, int mem, void* stream);
 
+/* The retries of the reference for points whose first root search failed (status PTT_ST_SOLVER_FAILED after
+ * ptt_sweep_shells_generic):  fsolve_vary's two varied starts (pttools/speedup/solvers.py:12-55, called at
+ * fluid.py:632 and :720) and, for hybrids, the 20-point backup scan (fluid.py:731-795).  idx[n_f] = rows of pg to retry;
+ * outputs are COMPACT (entry f belongs to point idx[f]) with the layout of ptt_sweep_shells_generic; rescued[f] = 1
+ * where a candidate start converged and a new profile was written (scalars[f,15] = 1 + its index in the reference's
+ * order), 0 where the reference, too, keeps the result of its first search.  Device pointers. */
+int ptt_generic_rescue(int n_f, const int32_t* idx, const double* pg, int n_xi, double t_end, int thin_shell_limit,
+                       double wn_rtol, double* rows_v, double* rows_w, double* rows_xi, int64_t row_stride, int32_t* off,
+                       int32_t* npts, double* scalars, int32_t* status, int32_t* rescued, void* stream);
+
 /* props.v_and_w_from_solution for a batch of bag shells (pttools/bubble/props.py:52-87): the entries of the
  * fluid-reference starting-guess table (fluid_reference.py:166-196).  Device pointers.
  * out[n,8] = {vp, vm, vp_tilde, vm_tilde, wp, wm, wn, 0}. */

@@ -12,7 +12,7 @@ import typing as tp
 
 import numpy as np
 
-from . import engine
+from . import _lib, engine
 from . import fluid_reference
 from .models import CODE_SOL, SOL_CODE, Model, Phase, SolutionType
 
@@ -183,6 +183,7 @@ class BubbleBatch:
     scal: tp.Dict[str, tp.Any]
     pp: tp.Any                # [n,8] parameters of ptt_a2_batch
     n_xi: int
+    retry_job: tp.Any = None  # sweep_bubbles(retry="async"): RetryJob still to be finished (finish_retry)
 
     def __len__(self):
         return self.v_wall.numel()
@@ -223,10 +224,75 @@ def _per_point(models, n, attr):
     return np.array([getattr(m, attr) for m in models], dtype=float)
 
 
+@dataclasses.dataclass
+class RetryJob:
+    """The retry search (engine.generic_retry) of the points of a batch whose first root search failed, possibly still
+    running on a side stream."""
+    pos: np.ndarray           # positions in the batch
+    shells: engine.ShellBatch  # compact results
+    rescued: tp.Any
+    pg: tp.Any
+    stream: tp.Any
+    thermo: bool
+
+
+_RETRY_STREAM = None
+
+
+def _retry_stream():
+    global _RETRY_STREAM
+    if _RETRY_STREAM is None:
+        _RETRY_STREAM = engine._torch().cuda.Stream()
+    return _RETRY_STREAM
+
+
+def finish_retry(b: BubbleBatch):
+    """Waits for the retry search of `b`, writes the rescued points back into `b` (profiles, scalars, status,
+    thermodynamic quantities) and returns (sub, pos): the rescued points as a BubbleBatch of their own and their
+    positions in `b`; (None, empty) if there was nothing to do."""
+    torch = engine._torch()
+    job, b.retry_job = b.retry_job, None
+    none = (None, np.zeros(0, dtype=np.int64))
+    if job is None:
+        return none
+    if job.stream is not None:
+        torch.cuda.current_stream().wait_stream(job.stream)
+    ok = job.rescued.cpu().numpy() != 0
+    if not ok.any():
+        return none
+    pos = job.pos[ok]
+    sel = torch.as_tensor(np.nonzero(ok)[0], device="cuda")
+    at = torch.as_tensor(pos, device="cuda", dtype=torch.int64)
+    sh = job.shells
+    sub_sh = engine.ShellBatch(sh.v_wall[sel], sh.alpha_n[sel], None, sh.sol_type[sel], sh.status[sel].contiguous(),
+                               sh.rows_v[sel], sh.rows_w[sel], sh.rows_xi[sel], sh.off[sel].contiguous(),
+                               sh.npts[sel].contiguous(), sh.scalars[sel].contiguous(), sh.n_xi)
+    model = b.model if isinstance(b.model, Model) else [b.model[int(i)] for i in pos]
+    n = pos.size
+    scal = {name: sub_sh.scalars[:, k] for k, name in enumerate(engine.GEN_SCALARS)}
+    sub = BubbleBatch(model, sub_sh, b.v_wall[at].contiguous(), b.alpha_n[at].contiguous(), b.wn[at].contiguous(),
+                      sub_sh.sol_type, sub_sh.status, scal, b.pp[at].contiguous(), b.n_xi)
+    if job.thermo:
+        add_thermo(sub, engine.dev_f64(1 + 1 / _per_point(model, n, "css2")),
+                   engine.dev_f64(1 + 1 / _per_point(model, n, "csb2")))
+    # write back
+    for dst, src in ((b.shells.rows_v, sub_sh.rows_v), (b.shells.rows_w, sub_sh.rows_w), (b.shells.rows_xi, sub_sh.rows_xi),
+                     (b.shells.off, sub_sh.off), (b.shells.npts, sub_sh.npts), (b.shells.scalars, sub_sh.scalars),
+                     (b.shells.status, sub_sh.status)):
+        dst.index_copy_(0, at, src)
+    for k, v in sub.scal.items():
+        if k not in engine.GEN_SCALARS and k in b.scal:        # the solver's scalars are views of shells.scalars
+            b.scal[k].index_copy_(0, at, v)
+    return sub, pos
+
+
 def sweep_bubbles(model, v_wall, alpha_n, sol_type=None, n_xi=N_XI_DEFAULT, t_end=T_END_DEFAULT,
-                  thin_shell_limit=THIN_SHELL_T_POINTS_MIN, wn_rtol=1e-4, thermo=True) -> BubbleBatch:
+                  thin_shell_limit=THIN_SHELL_T_POINTS_MIN, wn_rtol=1e-4, thermo=True, retry="sync") -> BubbleBatch:
     """Bubble(model, v_wall, alpha_n).solve() for every point of a sweep (bubble.py:232-352, fluid.py:848-1052).
-    `model` is one Model or a sequence with one Model per point."""
+    `model` is one Model or a sequence with one Model per point.
+    retry: what to do with the points whose root search did not converge, for which the reference varies the start
+    (fsolve_vary) and scans (hybrids): "sync" = retry and patch before returning; "async" = queue the retries on a side
+    stream and leave `retry_job` set (the caller ends with finish_retry); "off" = report them as solver failures."""
     torch = engine._torch()
     vw = np.asarray(v_wall, dtype=float).reshape(-1)
     an = np.asarray(alpha_n, dtype=float).reshape(-1)
@@ -265,8 +331,20 @@ def sweep_bubbles(model, v_wall, alpha_n, sol_type=None, n_xi=N_XI_DEFAULT, t_en
     pp = engine.point_params(pg[:, 0], cs_b, 1 - 1 / mu_s, 1 - 1 / mu_b, V_s, V_b)
     batch = BubbleBatch(model, shells, pg[:, 0].contiguous(), pg[:, 1].contiguous(), wn_d, shells.sol_type,
                         shells.status, scal, pp, n_xi)
+    if retry not in ("sync", "async", "off"):
+        raise ValueError(f"retry={retry!r}")
+    if retry != "off":
+        st_host = shells.status.cpu().numpy()
+        pos = np.nonzero(((st_host == _lib.ST_SOLVER_FAILED) | (st_host == _lib.ST_ROOT_NOT_CONVERGED)) &
+                         ((codes == 0) | (codes == 1)))[0]
+        if pos.size:
+            stream = _retry_stream() if retry == "async" else None
+            sub_sh, rescued = engine.generic_retry(pg, pos, n_xi, t_end, thin_shell_limit, wn_rtol, stream=stream)
+            batch.retry_job = RetryJob(pos, sub_sh, rescued, pg, stream, thermo)
     if thermo:
         add_thermo(batch, mu_s, mu_b)
+    if retry == "sync":
+        finish_retry(batch)
     return batch
 
 

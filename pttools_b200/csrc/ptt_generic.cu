@@ -76,6 +76,79 @@ __global__ void __launch_bounds__(64) generic_solve_kernel(
     status[i] = o.solver_failed ? ST_SOLVER_FAILED : ST_OK;
 }
 
+// K3r: what the reference does when its first root search fails (fsolve_vary with two varied starts,
+// speedup/solvers.py:12-55; for hybrids then the 20-point backup scan, fluid.py:731-795).  One warp per failed point,
+// one candidate start per lane, all root searches at once; the first candidate IN THE REFERENCE'S ORDER whose fsolve
+// converges gives wm, and only that lane evaluates the final profile.  Outputs are compact (row f of the failed
+// list); rescued[f] = 1 when a candidate converged and its profile was written.
+__global__ void __launch_bounds__(32) generic_rescue_kernel(
+    const int n_f, const int* __restrict__ idx, const double* __restrict__ pg, const int n_xi, const double t_end,
+    const int thin, const double wn_rtol, double* __restrict__ rows_v, double* __restrict__ rows_w,
+    double* __restrict__ rows_xi, const long long row_stride, int* __restrict__ off, int* __restrict__ npts,
+    double* __restrict__ scalars, int* __restrict__ status, int* __restrict__ rescued) {
+    const int f = blockIdx.x;
+    const int lane = threadIdx.x;
+    if (f >= n_f) return;
+    const double* q = pg + (size_t)idx[f] * GEN_PARAMS;
+    RowOut row;
+    row.v = rows_v + (size_t)f * row_stride;
+    row.w = rows_w + (size_t)f * row_stride;
+    row.xi = rows_xi + (size_t)f * row_stride;
+    const double v_wall = q[0];
+    const int sol_type = (int)q[2];
+    const double wn = q[3], v_cj = q[4];
+    if (lane == 0) rescued[f] = 0;
+    if (!(sol_type == SOL_SUB_DEF || sol_type == SOL_HYBRID)) return;
+    EosDev m;
+    m.css2 = q[9]; m.csb2 = q[10];
+    m.mu_s = 1.0 + 1.0 / m.css2; m.mu_b = 1.0 + 1.0 / m.csb2;
+    m.V_s = q[11]; m.V_b = q[12];
+    m.bag_name = (int)q[13];
+    GenericGuess g;
+    g.vp = q[5]; g.vp_tilde = q[6]; g.wp = q[7]; g.wm = q[8];
+    double x0 = NAN;
+    const bool exists = generic_retry_start(m, v_wall, sol_type, sqrt(m.css2), g.wm, g.vp_tilde, lane, x0);
+    GenericMachine mach;
+    mach.phase = GenericMachine::PH_HOLD;
+    mach.converged = false;
+    if (exists) {
+        g.wm = x0;
+        mach.start(m, v_wall, sol_type, wn, v_cj, g, n_xi, t_end, thin, wn_rtol, row, true);
+    }
+    int winner = -1;
+    for (;;) {
+        const bool running = mach.phase != GenericMachine::PH_DONE && mach.phase != GenericMachine::PH_HOLD;
+        const unsigned run_mask = __ballot_sync(0xffffffffu, running);
+        const unsigned conv_mask = __ballot_sync(0xffffffffu, exists && mach.phase == GenericMachine::PH_HOLD &&
+                                                                   mach.converged);
+        if (conv_mask) {
+            const int c = __ffs(conv_mask) - 1;
+            if (!(run_mask & ((1u << c) - 1u))) { winner = c; break; }      // every earlier candidate has failed
+        }
+        if (!run_mask) break;
+        if (running) {
+            const int rc = generic_run_job(mach.job_cs2, mach.job_y0, mach.job_te, n_xi, &mach.vis);
+            mach.advance(rc);
+        }
+    }
+    if (lane != winner) return;
+    mach.resume_final();
+    while (mach.phase != GenericMachine::PH_DONE) {
+        const int rc = generic_run_job(mach.job_cs2, mach.job_y0, mach.job_te, n_xi, &mach.vis);
+        mach.advance(rc);
+    }
+    const GenericOut o = mach.o;
+    if (o.status != ST_OK) return;
+    double* sc = scalars + (size_t)f * GEN_SCALARS;
+    off[f] = o.off;
+    npts[f] = o.npts;
+    sc[0] = o.vp; sc[1] = o.vm; sc[2] = o.vp_tilde; sc[3] = o.vm_tilde; sc[4] = o.v_sh; sc[5] = o.vm_sh;
+    sc[6] = o.vm_tilde_sh; sc[7] = o.wp; sc[8] = o.wm; sc[9] = o.wm_sh; sc[10] = o.v_cj; sc[11] = o.wn;
+    sc[12] = o.wn_estimate; sc[13] = (double)o.solver_failed; sc[14] = (double)o.n_resid; sc[15] = (double)(winner + 1);
+    status[f] = o.solver_failed ? ST_SOLVER_FAILED : ST_OK;
+    rescued[f] = 1;
+}
+
 // Wall quantities of a bag shell as the reference reads them off the arrays (props.v_and_w_from_solution,
 // props.py:52-87) -- used to build the starting-guess table of fluid_reference.py:166-196.
 __global__ void wall_values_kernel(const int n, const double* __restrict__ rows_v, const double* __restrict__ rows_w,
@@ -128,6 +201,22 @@ extern "C" int ptt_sweep_shells_generic(int n, const double* pg, int n_xi, doubl
     generic_solve_kernel<<<(n + 63) / 64, 64, 0, stream>>>(n, d_pg, n_xi, t_end, thin_shell_limit, wn_rtol, d_rv, d_rw,
                                                               d_rx, (long long)row_stride, d_off, d_np, d_sc, d_st);
     return sg.finish("generic_solve_kernel");
+}
+
+extern "C" int ptt_generic_rescue(int n_f, const int32_t* idx, const double* pg, int n_xi, double t_end,
+                                  int thin_shell_limit, double wn_rtol, double* rows_v, double* rows_w, double* rows_xi,
+                                  int64_t row_stride, int32_t* off, int32_t* npts, double* scalars, int32_t* status,
+                                  int32_t* rescued, void* stream_) {
+    if (n_f == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
+    if (n_f < 0 || n_xi < 32 || !idx || !pg || !rows_v || !rows_w || !rows_xi || !off || !npts || !scalars || !status ||
+        !rescued || row_stride < gen_row_capacity(n_xi))
+        return set_error(PTT_E_ARG, "ptt_generic_rescue: null pointer, bad size or row_stride too small");
+    generic_rescue_kernel<<<n_f, 32, 0, (cudaStream_t)stream_>>>(n_f, idx, pg, n_xi, t_end, thin_shell_limit, wn_rtol,
+                                                                  rows_v, rows_w, rows_xi, (long long)row_stride, off,
+                                                                  npts, scalars, status, rescued);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("generic_rescue_kernel", e);
+    return PTT_OK;
 }
 
 extern "C" int ptt_shell_wall_values(int n, const double* rows_v, const double* rows_w, const double* rows_xi,

@@ -203,7 +203,7 @@ PTT_HD int gen_row_capacity(const int n_xi) { return 2 * n_xi + 4; }
 
 struct GenericMachine {
     // what comes back from "advance": an integration to run, or nothing more to do
-    enum Phase : int { PH_LOCATE = 0, PH_EMIT_FWD = 1, PH_EMIT_BACK = 2, PH_CSTRIM = 3, PH_DONE = 4 };
+    enum Phase : int { PH_LOCATE = 0, PH_EMIT_FWD = 1, PH_EMIT_BACK = 2, PH_CSTRIM = 3, PH_DONE = 4, PH_HOLD = 5 };
     // where the root finder waits for a residual
     enum Root : int { RF_A0 = 0, RF_AH = 1, RF_A1 = 2, RF_IT = 3, RF_FINAL = 4, RF_H0 = 5, RF_HJ = 6, RF_HT = 7 };
     enum PassKind : int { PK_SECANT = 0, PK_NEWTON = 1, PK_HYBRD = 2 };
@@ -228,6 +228,7 @@ struct GenericMachine {
     // --- root finder (fluid.py:606-669, 697-843)
     int rf, pass, it;
     bool newton_start, converged, solver_failed;
+    bool hold;                  // candidate of the retry search: park (PH_HOLD) when the root search ends, before the final evaluation
     double p0, p1, q0, q1, p, h_fd;
     // MINPACK hybrd in one dimension (scipy fsolve: xtol 1.49012e-8, factor 100, maxfev 400, forward differences)
     double hx, hf, hJ, hdiag, hdelta, hxnorm, hfnorm, hp, hpnorm;
@@ -430,6 +431,7 @@ struct GenericMachine {
             ++pass;
             return pass_begin() ? 1 : 0;
         }
+        if (hold) { phase = PH_HOLD; return 1; }
         if (!(p == p) || !(p > 0.0)) { fail(ST_ROOT_NOT_CONVERGED); return 1; }
         // final evaluation at the root (fluid.py:642-653, 797-811)
         rf = RF_FINAL;
@@ -551,9 +553,9 @@ struct GenericMachine {
 
     PTT_HD void start(const EosDev& m_, const double v_wall_, const int sol_type_, const double wn_, const double v_cj_,
                       const GenericGuess& g_, const int n_xi_, const double t_end_, const int thin_,
-                      const double wn_rtol_, const RowOut& row_) {
+                      const double wn_rtol_, const RowOut& row_, const bool hold_ = false) {
         m = m_; v_wall = v_wall_; sol_type = sol_type_; wn = wn_; v_cj = v_cj_; g = g_; n_xi = n_xi_; t_end = t_end_;
-        thin = thin_; wn_rtol = wn_rtol_; row = row_;
+        thin = thin_; wn_rtol = wn_rtol_; row = row_; hold = hold_;
         cs_n = sqrt(m.css2);
         o.status = ST_OK; o.off = 0; o.npts = 0; o.solver_failed = 1;
         o.vp = o.vm = o.vp_tilde = o.vm_tilde = o.v_sh = o.vm_sh = o.vm_tilde_sh = o.wp = o.wm = o.wm_sh = NAN;
@@ -586,8 +588,17 @@ struct GenericMachine {
             if (vp_guess > v_wall) vp_guess = 0.95 * v_wall;           // fluid.py:613-617
             vpt_guess = lorentz(v_wall, vp_guess);                     // -lorentz(vp_guess, v_wall), fluid.py:79
         }
-        pass = 0;
+        // a retry candidate is one fsolve call from g.wm: no secant pass for subsonic deflagrations
+        pass = (hold && sol_type == SOL_SUB_DEF) ? 1 : 0;
         bool pending = pass_begin();
+        while (!pending) pending = root_on_q();
+    }
+    // A parked candidate goes on to the final evaluation at its root and the profile (fluid.py:642-653, 797-811).
+    PTT_HD void resume_final() {
+        hold = false;
+        if (!(p == p) || !(p > 0.0)) { fail(ST_ROOT_NOT_CONVERGED); return; }
+        rf = RF_FINAL;
+        bool pending = resid_begin(p);
         while (!pending) pending = root_on_q();
     }
 
@@ -642,6 +653,28 @@ struct GenericMachine {
         finish(row.w[bc - nb]);
     }
 };
+
+// What the reference tries after its first root search has failed, in its order (fsolve_vary, speedup/solvers.py:12-55;
+// backup scan of the hybrid solver, fluid.py:731-795):
+//   candidates 0, 1:   fsolve from wm_guess (1 +- 0.01) +- 1e-3
+//   candidates 2..21:  hybrids only - fsolve from wm_i = linspace(0.3 wm_guess, 3 wm_guess, 20)[i - 2], for the wm_i whose
+//                      v_plus lies above the shock curve at the wall
+// The first candidate whose fsolve reports convergence gives wm.  Returns false if candidate c does not exist.
+constexpr int GEN_RETRY_CANDIDATES = 22;
+PTT_HD bool generic_retry_start(const EosDev& m, const double v_wall, const int sol_type, const double cs_n,
+                                const double wm_guess, const double vp_tilde_guess, const int c, double& x0) {
+    if (c == 0) { x0 = wm_guess * 1.01 + 1e-3; return true; }
+    if (c == 1) { x0 = wm_guess * 0.99 - 1e-3; return true; }
+    if (sol_type != SOL_HYBRID || c >= GEN_RETRY_CANDIDATES) return false;
+    const double lo = 0.3 * wm_guess, hi = 3.0 * wm_guess;
+    const int i = c - 2;
+    x0 = (i == 19) ? hi : lo + (double)i * ((hi - lo) / 19.0);            // np.linspace(lo, hi, 20)
+    // v_plus_hybrid (boundary.py:600-618) against v_shock at the wall (shock.py:389-408)
+    const Junction j = solve_junction(m, sqrt(m.csb2), x0, 1, 0, vp_tilde_guess, -1);
+    if (!j.ok) return false;
+    const double vp = lorentz(v_wall, j.v2);
+    return vp > v_shock_generic(m, v_wall, cs_n);
+}
 
 // sound_shell_generic (fluid.py:848-1052) for one point, default arguments (no user guesses, no bag/Giese solver).
 PTT_HD GenericOut generic_solve_point(const EosDev& m, const double v_wall, const double alpha_n, const int sol_type,

@@ -257,6 +257,45 @@ def sweep_shells_generic(pg, n_xi=N_XI_DEFAULT, t_end=50.0, thin_shell_limit=100
                       rows[1], rows[2], off, npts, scalars, n_xi)
 
 
+def generic_retry(pg, idx_host, n_xi=N_XI_DEFAULT, t_end=50.0, thin_shell_limit=100, wn_rtol=1e-4, stream=None):
+    """The retries the reference makes when its first root search fails (fsolve_vary, speedup/solvers.py:12-55; backup
+    scan of the hybrid solver, fluid.py:731-795) for rows idx_host of pg (ptt_generic_rescue).  Returns a compact
+    ShellBatch (entry f = point idx_host[f]) and the int32 tensor `rescued`.  With `stream` the kernel is queued there
+    (after everything already queued on the current stream) and the caller synchronises before reading."""
+    torch = _torch()
+    lib = _lib.load()
+    idx_host = np.asarray(idx_host, dtype=np.int32)
+    n_f = idx_host.size
+    cap = lib.ptt_generic_row_capacity(n_xi)
+    dev = pg.device
+    idx = torch.as_tensor(idx_host, device=dev)
+    rows = [torch.full((n_f, cap), float("nan"), dtype=torch.float64, device=dev) for _ in range(3)]
+    off = torch.zeros(n_f, dtype=torch.int32, device=dev)
+    npts = torch.ones(n_f, dtype=torch.int32, device=dev)
+    status = torch.full((n_f,), _lib.ST_SOLVER_FAILED, dtype=torch.int32, device=dev)
+    scalars = torch.full((n_f, 16), float("nan"), dtype=torch.float64, device=dev)
+    rescued = torch.zeros(n_f, dtype=torch.int32, device=dev)
+
+    def launch():
+        _lib.check(lib.ptt_generic_rescue(n_f, _ptr(idx), _ptr(pg), n_xi, float(t_end), int(thin_shell_limit),
+                                          float(wn_rtol), _ptr(rows[0]), _ptr(rows[1]), _ptr(rows[2]), cap, _ptr(off),
+                                          _ptr(npts), _ptr(scalars), _ptr(status), _ptr(rescued), _stream_ptr(torch)),
+                   "ptt_generic_rescue")
+
+    if stream is None:
+        with STAGES.stage("shells_retry", 1):
+            launch()
+    else:
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            launch()
+        STAGES.launches += 1
+    idx_l = idx.long()
+    sub = ShellBatch(pg[idx_l, 0].contiguous(), pg[idx_l, 1].contiguous(), None, pg[idx_l, 2].to(torch.int32), status,
+                     rows[0], rows[1], rows[2], off, npts, scalars, n_xi)
+    return sub, rescued
+
+
 def shell_wall_values(shells: ShellBatch):
     """props.v_and_w_from_solution for a batch of bag shells -> [n,8] = vp, vm, vp_tilde, vm_tilde, wp, wm, wn, 0."""
     torch = _torch()

@@ -155,16 +155,23 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
     bubbles = []
     for s0 in range(0, n, shell_chunk):
         e0 = min(n, s0 + shell_chunk)
-        bb = bub.sweep_bubbles(model, vw[s0:e0], an[s0:e0], n_xi=n_xi)
+        # Points whose root search fails are retried the way the reference does (varied starts, backup scan); the
+        # retries run on a side stream under the spectrum stages of the other points and are folded in below.
+        bb = bub.sweep_bubbles(model, vw[s0:e0], an[s0:e0], n_xi=n_xi, retry="async")
         status[s0:e0], st[s0:e0] = bb.status, bb.sol_type
         for k, v in bb.scal.items():
             scal.setdefault(k, torch.empty(n, dtype=torch.float64, device=dev))[s0:e0] = v
-        # source lifetime factor, spectrum.py:123-136
-        nu_ = bb.scal["nu_gdh2024"]
-        slf = 1 / (1 + 2 * nu_)
-        if r_star is not None and not np.isinf(lifetime_multiplier):
-            slf = slf * (1 - (1 + lifetime_multiplier * 2 * r_star / torch.sqrt(bb.scal["kinetic_energy_fraction"]))
+
+        def lifetime_factor(b):
+            # source lifetime factor, spectrum.py:123-136
+            nu_ = b.scal["nu_gdh2024"]
+            f = 1 / (1 + 2 * nu_)
+            if r_star is not None and not np.isinf(lifetime_multiplier):
+                f = f * (1 - (1 + lifetime_multiplier * 2 * r_star / torch.sqrt(b.scal["kinetic_energy_fraction"]))
                          ** (-1 - 2 * nu_))
+            return f
+
+        slf = lifetime_factor(bb)
         valid = bb.shells.npts.cpu().numpy() >= 3        # has a profile (points flagged solver_failed do, like the reference)
         for s in range(s0, e0, chunk):
             e = min(e0, s + chunk)
@@ -178,6 +185,20 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
                 pow_v[s:e] = res.pow_v
             if omgw0 is not None:
                 omgw0[s:e] = res.omgw0
+        sub, pos = bub.finish_retry(bb)
+        if pos.size:
+            at = torch.as_tensor(pos + s0, device=dev, dtype=torch.int64)
+            res = engine.spectra_from_shells(plan, sub.shells, sub.pp, slf=lifetime_factor(sub).contiguous(),
+                                             scale=None if scale is None else scale[at].contiguous(),
+                                             v_wall_host=vw[pos + s0], valid_host=np.ones(pos.size, dtype=bool))
+            pow_gw[at] = res.pow_gw
+            if want_pow_v:
+                pow_v[at] = res.pow_v
+            if omgw0 is not None:
+                omgw0[at] = res.omgw0
+            status[at] = sub.status
+            for k, v in sub.scal.items():
+                scal[k][at] = v
         if keep_bubbles:
             bubbles.append(bb)
     if not sorted_already:

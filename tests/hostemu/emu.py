@@ -34,6 +34,7 @@ def lib():
         _lib.emu_bag_find_alpha_plus.argtypes = [d, d, i, d, pd, pi, pi]
         _lib.emu_bag_profile.argtypes = [d, d, i, i, d, pd, pd, pd, pi, pi, pi]
         _lib.emu_generic_solve.argtypes = [pd, d, d, i, d, d, pd, i, d, i, d, pd, pd, pd, pi, pi, pd]
+        _lib.emu_generic_rescue.argtypes = [pd, d, d, i, d, d, pd, i, d, i, d, pd, pd, pd, pi, pi, pd, pi]
     return _lib
 
 
@@ -108,3 +109,19 @@ def generic_solve(eos, v_wall, alpha_n, sol_type, wn, v_cj, guess, n_xi=5000, t_
                                  _p(v), _p(w), _p(xi), C.byref(off), C.byref(npts), _p(scal))
     s = slice(off.value, off.value + npts.value)
     return rc, v[s].copy(), w[s].copy(), xi[s].copy(), dict(zip(GEN_SCALARS, scal))
+
+
+def generic_rescue(eos, v_wall, alpha_n, sol_type, wn, v_cj, guess, n_xi=5000, t_end=50.0, thin=100, wn_rtol=1e-4):
+    """The retry search for a point whose first root search failed.  Returns (winner, status, v, w, xi, scalars);
+    winner = -1 if no candidate start converged."""
+    css2, csb2, V_s, V_b, bag_name = eos
+    e = np.array([css2, csb2, 1 + 1 / css2, 1 + 1 / csb2, V_s, V_b, float(bag_name)])
+    g = np.array(guess, dtype=float)
+    cap = lib().emu_gen_row_capacity(n_xi)
+    v, w, xi = np.full(cap, np.nan), np.full(cap, np.nan), np.full(cap, np.nan)
+    off, npts, st = C.c_int(0), C.c_int(0), C.c_int(0)
+    scal = np.full(16, np.nan)
+    win = lib().emu_generic_rescue(_p(e), v_wall, alpha_n, sol_type, wn, v_cj, _p(g), n_xi, t_end, thin, wn_rtol,
+                                   _p(v), _p(w), _p(xi), C.byref(off), C.byref(npts), _p(scal), C.byref(st))
+    s = slice(off.value, off.value + npts.value)
+    return win, st.value, v[s].copy(), w[s].copy(), xi[s].copy(), dict(zip(GEN_SCALARS, scal))

@@ -85,4 +85,44 @@ int emu_generic_solve(const double* eos, double v_wall, double alpha_n, int sol_
     return o.status;
 }
 
+
+// The retry search of generic_rescue_kernel, candidate by candidate in the reference's order (the kernel runs the
+// candidates in the lanes of a warp and takes the first converged one whose predecessors have all failed: same choice).
+// Returns the winning candidate (0-based) or -1; outputs as emu_generic_solve when a candidate won.
+int emu_generic_rescue(const double* eos, double v_wall, double alpha_n, int sol_type, double wn, double v_cj,
+                       const double* guess, int n_xi, double t_end, int thin, double wn_rtol,
+                       double* v, double* w, double* xi, int* off, int* npts, double* scal, int* status) {
+    (void)alpha_n;
+    EosDev m{eos[0], eos[1], eos[2], eos[3], eos[4], eos[5], (int)eos[6]};
+    RowOut row{v, w, xi};
+    *status = -1;
+    if (!(sol_type == SOL_SUB_DEF || sol_type == SOL_HYBRID)) return -1;
+    for (int c = 0; c < GEN_RETRY_CANDIDATES; ++c) {
+        GenericGuess g{guess[0], guess[1], guess[2], guess[3]};
+        double x0;
+        if (!generic_retry_start(m, v_wall, sol_type, sqrt(m.css2), g.wm, g.vp_tilde, c, x0)) continue;
+        g.wm = x0;
+        GenericMachine mach;
+        mach.start(m, v_wall, sol_type, wn, v_cj, g, n_xi, t_end, thin, wn_rtol, row, true);
+        while (mach.phase != GenericMachine::PH_DONE && mach.phase != GenericMachine::PH_HOLD) {
+            const int rc = integrate_grid(mach.job_cs2, mach.job_y0, mach.job_te, n_xi, mach.vis);
+            mach.advance(rc);
+        }
+        if (!(mach.phase == GenericMachine::PH_HOLD && mach.converged)) continue;
+        mach.resume_final();
+        while (mach.phase != GenericMachine::PH_DONE) {
+            const int rc = integrate_grid(mach.job_cs2, mach.job_y0, mach.job_te, n_xi, mach.vis);
+            mach.advance(rc);
+        }
+        const GenericOut o = mach.o;
+        *status = o.status;
+        *off = o.off; *npts = o.npts;
+        double vals[16] = {o.vp, o.vm, o.vp_tilde, o.vm_tilde, o.v_sh, o.vm_sh, o.vm_tilde_sh, o.wp, o.wm, o.wm_sh, o.v_cj,
+                           o.wn, o.wn_estimate, (double)o.solver_failed, (double)o.n_resid, (double)(c + 1)};
+        for (int i = 0; i < 16; ++i) scal[i] = vals[i];
+        return c;
+    }
+    return -1;
+}
+
 }

@@ -155,3 +155,45 @@ def test_unsorted_input_order_is_restored():
         one = sweep.sweep_spectra(model, vw[i:i + 1], an[i:i + 1], **kw).numpy()
         np.testing.assert_allclose(res.pow_gw[i], one.pow_gw[0], rtol=1e-12)
         np.testing.assert_allclose(res.scalars["kappa"][i], one.scalars["kappa"][0], rtol=1e-12)
+
+
+def test_retry_search_matches_the_reference_on_points_whose_first_search_fails():
+    """Fixture: the reference's Bubble at points of the bench grid where the first root search of the device algorithm
+    fails (tools/make_golden.py::retry_points).  With the reference's retries (fsolve_vary's varied starts, the hybrid
+    backup scan; generic_rescue_kernel) validity flags, tau-grid sizes and curves agree; without them the points are
+    solver failures.  Also through sweep_spectra, where the retries run on a side stream."""
+    import torch
+    from pttools_b200 import bubble, sweep
+    from pttools_b200.models import BagModel
+    d = np.load(os.path.join(GOLDEN, "ref_retry_points.npz"))
+    model = BagModel(alpha_n_min=0.005)
+    vw, an = d["points"][:, 0].copy(), d["points"][:, 1].copy()
+    ref_failed = np.array([bool(d[f"flags_{i}"][1]) for i in range(vw.size)])
+    off = bubble.sweep_bubbles(model, vw, an, retry="off")
+    assert (off.status.cpu().numpy() != 0).sum() >= 7
+    bb = bubble.sweep_bubbles(model, vw, an)
+    st = bb.status.cpu().numpy()
+    np.testing.assert_array_equal(st == 5, ref_failed)
+    assert np.all((st == 0) | (st == 5))
+    for i in np.nonzero(~ref_failed)[0]:
+        v, w, xi = bb.shells.profile(i)
+        assert v.size == d[f"v_{i}"].size
+        wn_ref, wm_ref, wp_ref, vsh_ref = d[f"scal_{i}"][:4]
+        got = [float(bb.scal[k][i]) for k in ("wm", "wp", "v_sh")]
+        np.testing.assert_allclose(got, [wm_ref, wp_ref, vsh_ref], rtol=2e-6)
+        ev, ew = curve_errors(xi, v, w, d[f"xi_{i}"], d[f"v_{i}"], d[f"w_{i}"], vw[i])
+        assert ev < 1e-6 and ew < 1e-6, (vw[i], an[i], ev, ew)
+    # thermodynamic scalars of the rescued points are those of their new profiles
+    one = bubble.Bubble(model, float(vw[3]), float(an[3]))
+    assert one.solved and not one.solver_failed
+    np.testing.assert_allclose(float(bb.scal["kappa"][3]), one.kappa, rtol=1e-12)
+    # sweep_spectra: retries queued on a side stream, folded in after the chunks
+    y = np.logspace(-1, 3, 60)
+    res = sweep.sweep_spectra(model, vw, an, y=y, r_star=0.1, nt=600, n_z_lookup=700)
+    np.testing.assert_array_equal(res.status.cpu().numpy() == 5, ref_failed)
+    ok = torch.as_tensor(~ref_failed, device="cuda")
+    assert torch.isfinite(res.pow_gw[ok]).all() and (res.pow_gw[ok] > 0).all()
+    np.testing.assert_allclose(res.scalars["kappa"].cpu().numpy(), bb.scal["kappa"].cpu().numpy(), rtol=1e-12)
+    from pttools_b200.omgw0 import Spectrum
+    s = Spectrum(one, y=y, r_star=0.1, nt=600, n_z_lookup=700)
+    np.testing.assert_allclose(res.pow_gw[3].cpu().numpy(), s.pow_gw, rtol=1e-9)

@@ -94,3 +94,39 @@ def test_vanishing_shock_points_follow_the_reference():
         np.testing.assert_allclose(gs["wm"], sol["wm"], rtol=1e-6)
         ev, ew = curve_errors(gx, gv, gw, sol["xi"], sol["v"], sol["w"], vw)
         assert ev < 1e-6 and ew < 1e-6
+
+
+def test_retry_search_follows_the_reference():
+    """Points whose first root search fails in the device algorithm (1e-4 of the bench grid).  The reference then varies
+    the starting guess (fsolve_vary, speedup/solvers.py:12-55) and, for hybrids, scans 20 starts (fluid.py:731-795);
+    the device retry search (generic_rescue_kernel, here its lane-by-lane emulation) makes the same attempts in the same
+    order.  Fixture: the reference's own Bubble at these points (tools/make_golden.py::retry_points)."""
+    from pttools_b200.models import BagModel
+    d = np.load(os.path.join(GOLDEN, "ref_retry_points.npz"))
+    pm = BagModel(alpha_n_min=0.005)
+    np.testing.assert_allclose([pm.a_s, pm.a_b, pm.V_s, pm.V_b], d["model"], rtol=1e-14)
+    ref = sg.FluidReference(dict(np.load(os.path.join(GOLDEN, "ref_fluid_reference.npz"))))
+    eos = (pm.css2, pm.csb2, pm.V_s, pm.V_b, True)
+    n_first_failed = 0
+    for i, (vw, an) in enumerate(d["points"]):
+        code, ref_failed, _ = d[f"flags_{i}"]
+        code = int(code)
+        wn_ref, wm_ref, wp_ref, vsh_ref = d[f"scal_{i}"][:4]
+        wn = float(pm.wn(an))
+        np.testing.assert_allclose(wn, wn_ref, rtol=1e-13)
+        g = ref.get(vw, an, code)
+        guess = (g[0], g[2], g[4] * wn, (0.3 if np.isnan(g[5]) else g[5]) * wn)
+        v_cj = float(pm.v_chapman_jouguet(an, wn))
+        rc, _, _, _, gs = emu.generic_solve(eos, vw, an, code, wn, v_cj, guess)
+        n_first_failed += int(rc != 0 or gs["solver_failed"] == 1)
+        win, st, gv, gw, gx, sc = emu.generic_rescue(eos, vw, an, code, wn, v_cj, guess)
+        if ref_failed:
+            # the reference keeps the result of its first search and flags it; so does the device path
+            assert win < 0 or sc["solver_failed"] == 1
+            continue
+        assert win >= 0 and st == 0 and sc["solver_failed"] == 0, (vw, an, win, st)
+        assert gv.size == d[f"v_{i}"].size                     # same tau-grid index of the shock
+        np.testing.assert_allclose([sc["wm"], sc["wp"], sc["v_sh"]], [wm_ref, wp_ref, vsh_ref], rtol=2e-6)
+        ev, ew = curve_errors(gx, gv, gw, d[f"xi_{i}"], d[f"v_{i}"], d[f"w_{i}"], vw)
+        assert ev < 1e-6 and ew < 1e-6, (vw, an, ev, ew)
+    assert n_first_failed >= 7          # the fixture is about points that need the retries

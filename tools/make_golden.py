@@ -205,6 +205,34 @@ def model_tables():
     json.dump(out, open(os.path.join(OUT, "ref_models.json"), "w"))
 
 
+# Points of the bench grid (BagModel(alpha_n_min=0.005), generic solver) whose FIRST root search fails in the device
+# algorithm, so that its result depends on the retries (fsolve_vary / backup scan) being the reference's.
+RETRY_POINTS = [(0.4545045045045045, 0.46085585585585587), (0.5211711711711712, 0.10310810810810812),
+                (0.6707207207207208, 0.4578828828828829), (0.7472972972972972, 0.06545045045045046),
+                (0.7554054054054054, 0.07436936936936937), (0.7617117117117117, 0.46779279279279284),
+                (0.8382882882882883, 0.23144144144144146), (0.8851351351351351, 0.43905405405405407),
+                (0.4815315315315315, 0.39594594594594595)]
+
+
+def retry_points():
+    """Bubble(model, v_wall, alpha_n) of the reference at RETRY_POINTS: flags, scalars, profile."""
+    import logging
+    from pttools.models import BagModel
+    from pttools.bubble import Bubble
+    logging.disable(logging.CRITICAL)
+    model = BagModel(alpha_n_min=0.005)
+    d = {"points": np.array(RETRY_POINTS), "model": np.array([model.a_s, model.a_b, model.V_s, model.V_b])}
+    for i, (vw, an) in enumerate(RETRY_POINTS):
+        b = Bubble(model, vw, an)
+        d[f"flags_{i}"] = np.array([{"Subsonic deflagration": 0, "Hybrid": 1, "Detonation": 2}[b.sol_type.value],
+                                    b.solver_failed, b.solved], dtype=float)
+        d[f"scal_{i}"] = np.array([b.wn, b.wm, b.wp, b.v_sh, b.vp, b.vm], dtype=float)
+        d[f"v_{i}"], d[f"w_{i}"], d[f"xi_{i}"] = b.v, b.w, b.xi
+        print(vw, an, b.sol_type.value, "failed" if b.solver_failed else "ok", b.v.size)
+    logging.disable(logging.NOTSET)
+    np.savez_compressed(os.path.join(OUT, "ref_retry_points.npz"), **d)
+
+
 CONSTCS_ALPHA_N_MIN = [  # (css2, csb2, a_s or None, a_b, V_s, alpha_n_min)
     (1 / 3, 1 / 3, 5, 1, 1, 0.05), (1 / 3, 1 / 4, 5, 1, 1, 0.05), (1 / 4, 1 / 3, 5, 1, 1, 0.05), (1 / 4, 1 / 4, 5, 1, 1, 0.05),
     (0.3, 0.28, 5, 1, 1, 0.01), (1 / 3 - 0.01, 1 / 3, 5, 1, 1, 0.1), (0.25, 0.3, None, 1, 1, 0.02), (1 / 3, 0.3, 5, 1, 1, 0.2),
@@ -235,7 +263,7 @@ def constcs_alpha_n_min():
     json.dump(out, open(os.path.join(OUT, "ref_constcs_alpha_n_min.json"), "w"), indent=1)
 
 
-TASKS.update({"constcs_alpha_n_min": constcs_alpha_n_min, "model_tables": model_tables, "fluid_reference": fluid_reference_table, "generic_bubbles": generic_bubbles,
+TASKS.update({"retry_points": retry_points, "constcs_alpha_n_min": constcs_alpha_n_min, "model_tables": model_tables, "fluid_reference": fluid_reference_table, "generic_bubbles": generic_bubbles,
               "generic_spectra": generic_spectra, "suppression_ssm": suppression_ssm})
 
 
