@@ -81,13 +81,15 @@ __global__ void __launch_bounds__(64) generic_solve_kernel(
 // one candidate start per lane, all root searches at once; the first candidate IN THE REFERENCE'S ORDER whose fsolve
 // converges gives wm, and only that lane evaluates the final profile.  Outputs are compact (row f of the failed
 // list); rescued[f] = 1 when a candidate converged and its profile was written.
-__global__ void __launch_bounds__(32) generic_rescue_kernel(
+constexpr int RESCUE_WARPS = 8;      // failed points per CTA: the retries of a batch then sit on one or two SMs, not on
+                                     // one SM per point (a resident retry warp keeps a 512-thread GEMM CTA off its SM)
+__global__ void __launch_bounds__(32 * RESCUE_WARPS) generic_rescue_kernel(
     const int n_f, const int* __restrict__ idx, const double* __restrict__ pg, const int n_xi, const double t_end,
     const int thin, const double wn_rtol, double* __restrict__ rows_v, double* __restrict__ rows_w,
     double* __restrict__ rows_xi, const long long row_stride, int* __restrict__ off, int* __restrict__ npts,
     double* __restrict__ scalars, int* __restrict__ status, int* __restrict__ rescued) {
-    const int f = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int f = blockIdx.x * RESCUE_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (f >= n_f) return;
     const double* q = pg + (size_t)idx[f] * GEN_PARAMS;
     RowOut row;
@@ -211,7 +213,7 @@ extern "C" int ptt_generic_rescue(int n_f, const int32_t* idx, const double* pg,
     if (n_f < 0 || n_xi < 32 || !idx || !pg || !rows_v || !rows_w || !rows_xi || !off || !npts || !scalars || !status ||
         !rescued || row_stride < gen_row_capacity(n_xi))
         return set_error(PTT_E_ARG, "ptt_generic_rescue: null pointer, bad size or row_stride too small");
-    generic_rescue_kernel<<<n_f, 32, 0, (cudaStream_t)stream_>>>(n_f, idx, pg, n_xi, t_end, thin_shell_limit, wn_rtol,
+    generic_rescue_kernel<<<(n_f + RESCUE_WARPS - 1) / RESCUE_WARPS, 32 * RESCUE_WARPS, 0, (cudaStream_t)stream_>>>(n_f, idx, pg, n_xi, t_end, thin_shell_limit, wn_rtol,
                                                                   rows_v, rows_w, rows_xi, (long long)row_stride, off,
                                                                   npts, scalars, status, rescued);
     const cudaError_t e = cudaGetLastError();
