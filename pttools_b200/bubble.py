@@ -256,8 +256,13 @@ def finish_retry(b: BubbleBatch):
     if job is None:
         return none
     if job.stream is not None:
+        # read the flags on the side stream: the host then waits for the retries only, not for whatever the current
+        # stream still has queued
+        with torch.cuda.stream(job.stream):
+            ok = job.rescued.cpu().numpy() != 0
         torch.cuda.current_stream().wait_stream(job.stream)
-    ok = job.rescued.cpu().numpy() != 0
+    else:
+        ok = job.rescued.cpu().numpy() != 0
     if not ok.any():
         return none
     pos = job.pos[ok]

@@ -164,6 +164,13 @@ class ShellBatch:
                           self.rows_v[a:b], self.rows_w[a:b], self.rows_xi[a:b], self.off[a:b], self.npts[a:b],
                           f(self.scalars), self.n_xi)
 
+    def take(self, idx):
+        """The shells at positions idx (int64 tensor) as a batch of their own (copies)."""
+        f = lambda t: None if t is None else t[idx].contiguous()
+        return ShellBatch(f(self.v_wall), f(self.alpha_n), f(self.alpha_plus), f(self.sol_type), f(self.status),
+                          self.rows_v[idx], self.rows_w[idx], self.rows_xi[idx], f(self.off), f(self.npts),
+                          f(self.scalars), self.n_xi)
+
     def profile(self, i):
         o, n = int(self.off[i]), int(self.npts[i])
         return (self.rows_v[i, o:o + n].cpu().numpy(), self.rows_w[i, o:o + n].cpu().numpy(),

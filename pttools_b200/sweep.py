@@ -173,7 +173,8 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
 
         slf = lifetime_factor(bb)
         valid = bb.shells.npts.cpu().numpy() >= 3        # has a profile (points flagged solver_failed do, like the reference)
-        for s in range(s0, e0, chunk):
+
+        def run_chunk(s):
             e = min(e0, s + chunk)
             sub = bb.shells.slice(s - s0, e - s0)
             res = engine.spectra_from_shells(plan, sub, bb.pp[s - s0:e - s0].contiguous(),
@@ -185,20 +186,47 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
                 pow_v[s:e] = res.pow_v
             if omgw0 is not None:
                 omgw0[s:e] = res.omgw0
-        sub, pos = bub.finish_retry(bb)
+
+        starts = list(range(s0, e0, chunk))
+        n_free = 1
+        if bb.retry_job is not None and len(starts) > 1:
+            # Chunks without retried points go first (at least one chunk does): the retries finish under them and are
+            # written into the batch before the chunks that hold such points start, so only the rescued points of chunks
+            # that have already run need a pass of their own - normally none.
+            where = bb.retry_job.pos + s0
+            cnt = [np.count_nonzero((where >= s) & (where < s + chunk)) for s in starts]
+            order = np.argsort(cnt, kind="stable")
+            starts = [starts[i] for i in order]
+            n_free = max(1, int(np.count_nonzero(np.asarray(cnt) == 0)))
+        for s in starts[:n_free]:
+            run_chunk(s)
+        _, pos = bub.finish_retry(bb)                    # rescued profiles, scalars, status now sit in bb
         if pos.size:
             at = torch.as_tensor(pos + s0, device=dev, dtype=torch.int64)
-            res = engine.spectra_from_shells(plan, sub.shells, sub.pp, slf=lifetime_factor(sub).contiguous(),
+            here = torch.as_tensor(pos, device=dev, dtype=torch.int64)
+            status[at] = bb.status[here]
+            for k, v in bb.scal.items():
+                scal[k][at] = v[here]
+            slf = lifetime_factor(bb)
+            valid[pos] = True
+        for s in starts[n_free:]:
+            run_chunk(s)
+        done_early = np.zeros(pos.shape, dtype=bool)
+        for s in starts[:n_free]:
+            done_early |= (pos + s0 >= s) & (pos + s0 < s + chunk)
+        late = pos[done_early]
+        if late.size:
+            here = torch.as_tensor(late, device=dev, dtype=torch.int64)
+            at = here + s0
+            res = engine.spectra_from_shells(plan, bb.shells.take(here), bb.pp[here].contiguous(),
+                                             slf=slf[here].contiguous(),
                                              scale=None if scale is None else scale[at].contiguous(),
-                                             v_wall_host=vw[pos + s0], valid_host=np.ones(pos.size, dtype=bool))
+                                             v_wall_host=vw[late + s0], valid_host=np.ones(late.size, dtype=bool))
             pow_gw[at] = res.pow_gw
             if want_pow_v:
                 pow_v[at] = res.pow_v
             if omgw0 is not None:
                 omgw0[at] = res.omgw0
-            status[at] = sub.status
-            for k, v in sub.scal.items():
-                scal[k][at] = v
         if keep_bubbles:
             bubbles.append(bb)
     if not sorted_already:

@@ -197,3 +197,15 @@ def test_retry_search_matches_the_reference_on_points_whose_first_search_fails()
     from pttools_b200.omgw0 import Spectrum
     s = Spectrum(one, y=y, r_star=0.1, nt=600, n_z_lookup=700)
     np.testing.assert_allclose(res.pow_gw[3].cpu().numpy(), s.pow_gw, rtol=1e-9)
+    # several chunks: the chunk with the fewest retried points runs first, the others see the rescued profiles in place
+    big_vw = np.concatenate([vw, np.full(7, 0.5), vw[:4] + 1e-3])
+    big_an = np.concatenate([an, np.linspace(0.05, 0.2, 7), an[:4]])
+    whole = sweep.sweep_spectra(model, big_vw, big_an, y=y, r_star=0.1, nt=600, n_z_lookup=700)
+    parts = sweep.sweep_spectra(model, big_vw, big_an, y=y, r_star=0.1, nt=600, n_z_lookup=700, chunk=5)
+    np.testing.assert_array_equal(whole.status.cpu().numpy(), parts.status.cpu().numpy())
+    fin = torch.isfinite(whole.pow_gw)
+    assert torch.equal(fin, torch.isfinite(parts.pow_gw)) and fin[:vw.size][ok].all()
+    np.testing.assert_allclose(parts.pow_gw[fin].cpu().numpy(), whole.pow_gw[fin].cpu().numpy(), rtol=1e-9)
+    np.testing.assert_allclose(parts.omgw0[fin].cpu().numpy(), whole.omgw0[fin].cpu().numpy(), rtol=1e-9)
+    np.testing.assert_allclose(parts.scalars["kappa"].cpu().numpy(), whole.scalars["kappa"].cpu().numpy(), rtol=1e-12,
+                               equal_nan=True)
