@@ -98,7 +98,9 @@ int ptt_sweep_shells_bag(int n, const double* v_wall, const double* alpha_n, int
 /* sound_shell_generic(model, v_wall, alpha_n, sol_type, wn, ...) for a whole sweep      pttools/bubble/fluid.py:848-1052
  * One row of pg per point (models may differ from point to point):
  *   pg[n,16] = {v_wall, alpha_n, sol_type, wn, v_cj, guess_vp, guess_vp_tilde, guess_wp, guess_wm,
- *               css2, csb2, V_s, V_b, model_name_is_bag, 0, 0}
+ *               css2, csb2, V_s, V_b, model_name_is_bag, s_coef_s, s_coef_b}
+ *   s_coef: entropy density s(w) = s_coef * w^(1 - 1/mu) of the phase, s_coef = (mu a)^(1/mu) T_ref^(4/mu - 1); read by
+ *   ptt_generic_rescue only (entropy-flux test of the scan starts, boundary.py:65-85)
  * (wn, v_cj and the solution type are closed-form host quantities of the model: models/bag.py:316, const_cs.py:633-737,
  * chapman_jouguet.py:151-264; the guesses come from the fluid-reference table, fluid.py:925-949).
  * Outputs: profile rows ([n,row_stride], row_stride >= ptt_generic_row_capacity(n_xi)), off/npts, and

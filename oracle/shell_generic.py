@@ -422,7 +422,19 @@ def sound_shell_generic(model: Eos, v_wall, alpha_n, ref: FluidReference, sol_ty
 
         s2 = fsolve_vary(solvable, np.array([wm_guess]))
         wm, found = s2[0][0], s2[2] == 1
-        # (the 20-point backup scan of fluid.py:731-795 is not restated: points that need it are flagged failed)
+        if not found:
+            # backup scan, fluid.py:731-795: fsolve from every wm_i whose v_plus lies above the shock curve at the wall
+            v_sh_wall = v_shock(model, wn, v_wall, cs_n)
+            for wm_i in np.linspace(0.3 * wm_guess, 3 * wm_guess, 20):
+                vpt_i, _ = solve_junction(model, np.sqrt(model.cs2(wm_i, BROKEN)), wm_i, BROKEN, SYMMETRIC,
+                                          vp_tilde_guess, wp_guess)
+                vp_i = -lorentz(vpt_i, v_wall)                               # v_plus_hybrid, boundary.py:600-618
+                if not vp_i > v_sh_wall:
+                    continue
+                s3 = fsolve(solvable, x0=wm_i, full_output=True)
+                if s3[2] == 1:
+                    wm, found = s3[0][0], True
+                    break
         v, w, xi, vp, vm, vp_tilde, vm_tilde, v_sh, vm_sh, vm_tilde_sh, wp, wn_est, wm_sh = hybrid(
             model, v_wall, wn, wm, cs_n, v_cj, vp_tilde_guess, wp_guess, t_end, n_xi, thin_shell_limit, allow_neg=True)
         if found and not np.isclose(wn_est, wn, rtol=wn_rtol):

@@ -327,6 +327,12 @@ def sweep_bubbles(model, v_wall, alpha_n, sol_type=None, n_xi=N_XI_DEFAULT, t_en
     for col, attr in ((9, "css2"), (10, "csb2"), (11, "V_s"), (12, "V_b")):
         pg[:, col] = engine.dev_f64(_per_point(model, n, attr))
     pg[:, 13] = engine.dev_f64(np.array([1.0 if m.name == "bag" else 0.0 for m in ([model] * n if single else model)]))
+    # entropy density s(w) = coef * w^(1 - 1/mu) per phase (s = w / T): the retry search applies the reference's
+    # entropy-flux test to its scan starts
+    a_s_, a_b_, t0 = (_per_point(model, n, k) for k in ("a_s", "a_b", "T_ref"))
+    mus, mub = 1 + 1 / _per_point(model, n, "css2"), 1 + 1 / _per_point(model, n, "csb2")
+    pg[:, 14] = engine.dev_f64((mus * a_s_) ** (1 / mus) * t0 ** (4 / mus - 1))
+    pg[:, 15] = engine.dev_f64((mub * a_b_) ** (1 / mub) * t0 ** (4 / mub - 1))
     shells = engine.sweep_shells_generic(pg, n_xi, t_end, thin_shell_limit, wn_rtol)
     scal = {name: shells.scalars[:, k] for k, name in enumerate(engine.GEN_SCALARS)}
     mu_s = engine.dev_f64(1 + 1 / _per_point(model, n, "css2"))

@@ -9,7 +9,8 @@ constexpr int GEN_PARAMS = 16;
 constexpr int GEN_SCALARS = 16;
 
 // pg[n,16] = {v_wall, alpha_n, sol_type, wn, v_cj, guess_vp, guess_vp_tilde, guess_wp, guess_wm,
-//             css2, csb2, V_s, V_b, bag_name, 0, 0}
+//             css2, csb2, V_s, V_b, bag_name, s_coef_s, s_coef_b}   (s_coef: entropy s(w) = s_coef w^(1-1/mu), used by
+//             the retry search only)
 // scalars[n,16] = {vp, vm, vp_tilde, vm_tilde, v_sh, vm_sh, vm_tilde_sh, wp, wm, wm_sh, v_cj, wn, wn_estimate,
 //                  solver_failed, n_resid, 0}   (the reference's 17-tuple, fluid.py:1052; n_resid: residual
 //                  evaluations of the root search, diagnostics)
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(32 * RESCUE_WARPS) generic_rescue_kernel(
     GenericGuess g;
     g.vp = q[5]; g.vp_tilde = q[6]; g.wp = q[7]; g.wm = q[8];
     double x0 = NAN;
-    const bool exists = generic_retry_start(m, v_wall, sol_type, sqrt(m.css2), g.wm, g.vp_tilde, lane, x0);
+    const bool exists = generic_retry_start(m, v_wall, sol_type, sqrt(m.css2), g.wm, g.vp_tilde, q[14], q[15], lane, x0);
     GenericMachine mach;
     mach.phase = GenericMachine::PH_HOLD;
     mach.converged = false;

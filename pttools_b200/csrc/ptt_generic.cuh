@@ -661,8 +661,10 @@ struct GenericMachine {
 //                      v_plus lies above the shock curve at the wall
 // The first candidate whose fsolve reports convergence gives wm.  Returns false if candidate c does not exist.
 constexpr int GEN_RETRY_CANDIDATES = 22;
+// s_coef_s / s_coef_b: entropy density s(w) = s_coef * w^(1 - 1/mu) of the two phases (both models; s = w / T).
 PTT_HD bool generic_retry_start(const EosDev& m, const double v_wall, const int sol_type, const double cs_n,
-                                const double wm_guess, const double vp_tilde_guess, const int c, double& x0) {
+                                const double wm_guess, const double vp_tilde_guess, const double s_coef_s,
+                                const double s_coef_b, const int c, double& x0) {
     if (c == 0) { x0 = wm_guess * 1.01 + 1e-3; return true; }
     if (c == 1) { x0 = wm_guess * 0.99 - 1e-3; return true; }
     if (sol_type != SOL_HYBRID || c >= GEN_RETRY_CANDIDATES) return false;
@@ -670,8 +672,15 @@ PTT_HD bool generic_retry_start(const EosDev& m, const double v_wall, const int 
     const int i = c - 2;
     x0 = (i == 19) ? hi : lo + (double)i * ((hi - lo) / 19.0);            // np.linspace(lo, hi, 20)
     // v_plus_hybrid (boundary.py:600-618) against v_shock at the wall (shock.py:389-408)
-    const Junction j = solve_junction(m, sqrt(m.csb2), x0, 1, 0, vp_tilde_guess, -1);
+    const double v1 = sqrt(m.csb2);
+    const Junction j = solve_junction(m, v1, x0, 1, 0, vp_tilde_guess, -1);
     if (!j.ok) return false;
+    // In the scan the wall junction is solved with allow_negative_entropy_flux_change = False (fluid.py:745-750): a
+    // start whose entropy flux gamma v s drops from the broken to the symmetric side gives NaN there and is skipped
+    // (check_entropy_fluxes, boundary.py:65-85, 339-352).
+    const double f1 = sqrt(gamma2(v1)) * v1 * s_coef_b * pow(x0, 1.0 - 1.0 / m.mu_b);
+    const double f2 = sqrt(gamma2(j.v2)) * j.v2 * s_coef_s * pow(j.w2, 1.0 - 1.0 / m.mu_s);
+    if (!(f1 >= 0.0) || !(f2 >= 0.0) || f2 - f1 < 0.0) return false;
     const double vp = lorentz(v_wall, j.v2);
     return vp > v_shock_generic(m, v_wall, cs_n);
 }

@@ -111,11 +111,11 @@ def generic_solve(eos, v_wall, alpha_n, sol_type, wn, v_cj, guess, n_xi=5000, t_
     return rc, v[s].copy(), w[s].copy(), xi[s].copy(), dict(zip(GEN_SCALARS, scal))
 
 
-def generic_rescue(eos, v_wall, alpha_n, sol_type, wn, v_cj, guess, n_xi=5000, t_end=50.0, thin=100, wn_rtol=1e-4):
+def generic_rescue(eos, v_wall, alpha_n, sol_type, wn, v_cj, guess, s_coef, n_xi=5000, t_end=50.0, thin=100, wn_rtol=1e-4):
     """The retry search for a point whose first root search failed.  Returns (winner, status, v, w, xi, scalars);
-    winner = -1 if no candidate start converged."""
+    winner = -1 if no candidate start converged.  s_coef = (s_coef_s, s_coef_b): s(w) = s_coef w^(1 - 1/mu)."""
     css2, csb2, V_s, V_b, bag_name = eos
-    e = np.array([css2, csb2, 1 + 1 / css2, 1 + 1 / csb2, V_s, V_b, float(bag_name)])
+    e = np.array([css2, csb2, 1 + 1 / css2, 1 + 1 / csb2, V_s, V_b, float(bag_name), s_coef[0], s_coef[1]])
     g = np.array(guess, dtype=float)
     cap = lib().emu_gen_row_capacity(n_xi)
     v, w, xi = np.full(cap, np.nan), np.full(cap, np.nan), np.full(cap, np.nan)

@@ -100,7 +100,7 @@ int emu_generic_rescue(const double* eos, double v_wall, double alpha_n, int sol
     for (int c = 0; c < GEN_RETRY_CANDIDATES; ++c) {
         GenericGuess g{guess[0], guess[1], guess[2], guess[3]};
         double x0;
-        if (!generic_retry_start(m, v_wall, sol_type, sqrt(m.css2), g.wm, g.vp_tilde, c, x0)) continue;
+        if (!generic_retry_start(m, v_wall, sol_type, sqrt(m.css2), g.wm, g.vp_tilde, eos[7], eos[8], c, x0)) continue;
         g.wm = x0;
         GenericMachine mach;
         mach.start(m, v_wall, sol_type, wn, v_cj, g, n_xi, t_end, thin, wn_rtol, row, true);

@@ -104,9 +104,13 @@ def test_retry_search_follows_the_reference():
     from pttools_b200.models import BagModel
     d = np.load(os.path.join(GOLDEN, "ref_retry_points.npz"))
     pm = BagModel(alpha_n_min=0.005)
+    mo = models.bag_model(pm.a_s, pm.a_b, pm.V_s, pm.V_b)
+    warnings.filterwarnings("ignore")
     np.testing.assert_allclose([pm.a_s, pm.a_b, pm.V_s, pm.V_b], d["model"], rtol=1e-14)
     ref = sg.FluidReference(dict(np.load(os.path.join(GOLDEN, "ref_fluid_reference.npz"))))
     eos = (pm.css2, pm.csb2, pm.V_s, pm.V_b, True)
+    s_coef = ((pm.mu_s * pm.a_s) ** (1 / pm.mu_s), (pm.mu_b * pm.a_b) ** (1 / pm.mu_b))      # s = w / T, T_ref = 1
+    np.testing.assert_allclose(pm.s(7.0, 0.0), s_coef[0] * 7.0 ** (1 - 1 / pm.mu_s), rtol=1e-14)
     n_first_failed = 0
     for i, (vw, an) in enumerate(d["points"]):
         code, ref_failed, _ = d[f"flags_{i}"]
@@ -119,7 +123,7 @@ def test_retry_search_follows_the_reference():
         v_cj = float(pm.v_chapman_jouguet(an, wn))
         rc, _, _, _, gs = emu.generic_solve(eos, vw, an, code, wn, v_cj, guess)
         n_first_failed += int(rc != 0 or gs["solver_failed"] == 1)
-        win, st, gv, gw, gx, sc = emu.generic_rescue(eos, vw, an, code, wn, v_cj, guess)
+        win, st, gv, gw, gx, sc = emu.generic_rescue(eos, vw, an, code, wn, v_cj, guess, s_coef)
         if ref_failed:
             # the reference keeps the result of its first search and flags it; so does the device path
             assert win < 0 or sc["solver_failed"] == 1
@@ -130,3 +134,15 @@ def test_retry_search_follows_the_reference():
         ev, ew = curve_errors(gx, gv, gw, d[f"xi_{i}"], d[f"v_{i}"], d[f"w_{i}"], vw)
         assert ev < 1e-6 and ew < 1e-6, (vw, an, ev, ew)
     assert n_first_failed >= 7          # the fixture is about points that need the retries
+    # Hybrids near v_wall = v_CJ where every start of the reference's backup scan is rejected by its entropy-flux test
+    # (the wall junction is solved with allow_negative_entropy_flux_change = False there, fluid.py:745-750) and the
+    # reference ends with solver_failed (profiles/r01_retry_flag_agreement.json): no candidate may win here either.
+    for vw, an in ((0.7364864864864865, 0.05554054054054054), (0.6454954954954955, 0.007972972972972973),
+                   (0.7644144144144144, 0.08427927927927929)):
+        wn = float(pm.wn(an))
+        g = ref.get(vw, an, 1)
+        guess = (g[0], g[2], g[4] * wn, (0.3 if np.isnan(g[5]) else g[5]) * wn)
+        sol = sg.sound_shell_generic(mo, vw, an, ref)
+        assert sol["solver_failed"]
+        win, st, *_ = emu.generic_rescue(eos, vw, an, 1, wn, float(pm.v_chapman_jouguet(an, wn)), guess, s_coef)
+        assert win < 0, (vw, an, win)
