@@ -146,3 +146,24 @@ def test_retry_search_follows_the_reference():
         assert sol["solver_failed"]
         win, st, *_ = emu.generic_rescue(eos, vw, an, 1, wn, float(pm.v_chapman_jouguet(an, wn)), guess, s_coef)
         assert win < 0, (vw, an, win)
+
+
+def test_oracle_reproduces_reference_retries():
+    """The oracle's fsolve_vary and backup scan (oracle/shell_generic.py) against the reference's bubbles at the retry
+    points: same flags, same arrays; and the reference-failed hybrids of profiles/r01_retry_flag_agreement.json stay
+    failed with the same array length (their backup scan rejects every start)."""
+    from pttools_b200.models import BagModel
+    d = np.load(os.path.join(GOLDEN, "ref_retry_points.npz"))
+    pm = BagModel(alpha_n_min=0.005)
+    mo = models.bag_model(pm.a_s, pm.a_b, pm.V_s, pm.V_b)
+    ref = sg.FluidReference(dict(np.load(os.path.join(GOLDEN, "ref_fluid_reference.npz"))))
+    warnings.filterwarnings("ignore")
+    for i, (vw, an) in enumerate(d["points"]):
+        sol = sg.sound_shell_generic(mo, vw, an, ref)
+        assert bool(sol["solver_failed"]) == bool(d[f"flags_{i}"][1])
+        assert sol["v"].size == d[f"v_{i}"].size
+        np.testing.assert_allclose(sol["v"], d[f"v_{i}"], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(sol["w"], d[f"w_{i}"], rtol=1e-8)
+    for vw, an, n_ref in ((0.7364864864864865, 0.05554054054054054, 5005), (0.8806306306306306, 0.4167567567567568, 5166)):
+        sol = sg.sound_shell_generic(mo, vw, an, ref)
+        assert sol["solver_failed"] and sol["v"].size == n_ref
