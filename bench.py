@@ -198,6 +198,35 @@ class ClockSampler:
         return out
 
 
+def _alg_work(plan, stats, n_points_step, n_samples_step):
+    """Algorithmic work per step of every stage (DESIGN.md section 3 states the per-unit figures)."""
+    from pttools_b200 import engine
+    n_sdv = plan.lookup_pass.z.size
+    steps = max(1, stats["steps"])
+    w = {}
+    # K6': banded matrix product, 2 flop per (z_i, knot, profile) over the band ACTUALLY multiplied (trailing
+    # no-solution profiles are trimmed: counted from the driver's own group list), + 10 flop per (z_i, T_j) for the
+    # weights, once per wall speed
+    w["spec_den_v_group"] = {"flop": (2.0 * stats["group_macs"] + 10.0 * n_sdv * NPT[1] * stats["group_count"]) / steps,
+                             "bound": "tensor", "precision": "fp64 (DMMA m8n8k4)"}
+    # K7': 2 mul + 4 fma per (wavenumber, cell, profile); cells counted from the plan's tables
+    _, nseg, meta, _ = engine.gw_cells(plan)
+    cells = float(int(nseg.sum().item()) + sum(int(meta[i, 2:2 + int(n)].sum().item()) for i, n in enumerate(nseg.tolist())))
+    w["spec_den_gw_cells"] = {"flop": 10.0 * cells * stats["gw_profiles"] / steps, "bound": "fp64", "precision": "fp64 (FMA pipe)"}
+    # K5: block-moment sine transform: 2^l blocks x 22 flop x 2 functions per exact wavenumber (2^l >= z / 0.4, l <= 7),
+    # 12 moments x 2 flop x 2 functions per profile sample for the finest level, ~60 flop per asymptotic wavenumber
+    z, fr = plan.z_all, plan.frac_all
+    zl = z[fr < 1.0]
+    blocks = np.minimum(128.0, 2.0 ** np.ceil(np.log2(np.maximum(zl / 0.4, 1.0))))
+    per_profile = 44.0 * blocks.sum() + 60.0 * np.count_nonzero(fr > 0.0)
+    w["a2"] = {"flop": (per_profile * stats["a2_profiles"] + 48.0 * (n_samples_step + 2000.0 * stats["a2_profiles"])) / steps,
+               "bound": "fp64", "precision": "fp64 (FMA pipe)"}
+    # K3: one thread per point, latency bound; its roofline is the HBM write of the materialised profiles,
+    # 3 arrays x 8 B per sample
+    w["shells_generic"] = {"bytes": 24.0 * n_samples_step / steps, "bound": "hbm", "precision": "fp64"}
+    return w
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -212,26 +241,22 @@ def gpu_arm(args):
     B = args.batch
     from pttools_b200.models import BagModel
     from pttools_b200 import fluid_reference
-    if args.path == "bag":
-        plan = engine.SsmPlan(Y, cs=engine.CS0, nt=NPT[1], n_z_lookup=NPT[2], nxi=NPT[0], mode="bag")
-    else:
-        model = BagModel(alpha_n_min=0.005)
-        plan = engine.SsmPlan(Y, cs=float(np.sqrt(model.csb2)), nt=NPT[1], n_z_lookup=NPT[2], nxi=NPT[0], mode="ssm")
-        fluid_reference.ref()         # starting-guess table: once per process, like the reference's pre-fork warm-up
-    gather_buf = [torch.empty((B, Y.size), dtype=torch.float64, device="cuda") for _ in range(world)] \
-        if (world > 1 and rank == 0) else None
+    model = BagModel(alpha_n_min=0.005)
+    plan = engine.SsmPlan(Y, cs=float(np.sqrt(model.csb2)), nt=NPT[1], n_z_lookup=NPT[2], nxi=NPT[0], mode="ssm",
+                          only_lookup_pass=not args.pow_v)
+    fluid_reference.ref()         # starting-guess table: once per process, like the reference's pre-fork warm-up
 
-    def device_step(s, vw_d, an_d):
-        if args.path == "bag":
-            res = sweep.power_gw_scaled_bag_sweep(vw_d, an_d, Y, NPT, chunk=args.chunk, plan=plan)
-            table = res.pow_gw
-        else:
-            res = sweep.sweep_spectra(model, vw_d, an_d, y=Y, r_star=R_STAR, n_xi=N_XI, chunk=args.chunk, plan=plan)
-            table = res.omgw0
-        if world > 1:
-            dist.gather(table, gather_buf, dst=0)
-        res.table = table
-        return res
+    def step_points(s):
+        """The points of step s for ALL ranks (the product API shards them: whole v_wall rows per rank)."""
+        parts = [batch_points(s, r, world, B) for r in range(world)]
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+    def device_step(s):
+        """One pass of the hot path through the product's sweep API: rank 0 ends with the Omega_gw,0 table of all
+        world x B points in HBM, in the order of the input points (config 5 of BASELINE.json)."""
+        vw, an = step_points(s)
+        return sweep.sweep_omgw0_distributed(model, vw, an, y=Y, r_star=R_STAR, n_xi=N_XI, chunk=args.chunk, plan=plan,
+                                             timing=True)
 
     def barrier():
         if world > 1:
@@ -239,27 +264,27 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     total_steps = args.warmup + args.steps
-    # ---- device-resident timing: inputs are in HBM before the clock starts
-    inputs = []
-    for s in range(total_steps):
-        vw, an = batch_points(s, rank, world, B)
-        inputs.append((engine.dev_f64(vw), engine.dev_f64(an)))
     sampler = ClockSampler(local) if rank == 0 else None
     for s in range(args.warmup):
-        device_step(s, *inputs[s])
+        device_step(s)
     barrier()
     if sampler:
         sampler.mark_start()
     engine.STAGES.enable(True)
     launches0 = engine.STAGES.launches
+    agg = {k: 0 for k in ("group_macs", "group_count", "group_profiles", "gw_profiles", "a2_profiles", "retried", "rescued")}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     ev0.record()
-    n_ok = 0
+    n_ok, n_samples = 0, 0.0
     step_ev = [ev0]
     for s in range(args.warmup, total_steps):
-        res = device_step(s, *inputs[s])
-        n_ok += int((res.status == 0).sum())
+        table = device_step(s)
+        st = sweep.LAST_LOCAL["result"]
+        for k in agg:
+            agg[k] += int(getattr(st.stats, k))
+        n_samples += float(torch.nan_to_num(st.scalars["npts"]).sum())
+        n_ok += int((st.status == 0).sum())
         step_ev.append(torch.cuda.Event(enable_timing=True))
         step_ev[-1].record()
     ev1.record()
@@ -275,21 +300,18 @@ def gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms = float(t[0]), float(t[1])
+    del table
 
-    # ---- end-to-end: host buffers in, host result table out, through the public sweep API
-    pin_in = [torch.empty(B, dtype=torch.float64).pin_memory() for _ in range(2)]
-    pin_out = torch.empty((B, Y.size), dtype=torch.float64).pin_memory()
-    e2e_steps = max(1, min(args.steps, 4))
+    # ---- end-to-end: host buffers in, host result table out, through the reference-facing call
+    # (analysis.create_spectra semantics at N = 1; at N > 1 every rank delivers its shard of the table to pinned host
+    # memory, streamed out chunk by chunk under the compute)
+    e2e_steps = args.steps
 
     def e2e_step(s):
-        vw, an = batch_points(1000 + s, rank, world, B)
-        pin_in[0].copy_(torch.from_numpy(vw)); pin_in[1].copy_(torch.from_numpy(an))
-        vw_d = pin_in[0].to("cuda", non_blocking=True)
-        an_d = pin_in[1].to("cuda", non_blocking=True)
-        res = device_step(s, vw_d, an_d)
-        pin_out.copy_(res.table, non_blocking=True)
-        torch.cuda.synchronize()
-        return float(np.nanmax(pin_out.numpy()[:, 0]))
+        vw, an = step_points(1000 + s)
+        shard, host_table = sweep.sweep_omgw0_distributed(model, vw, an, y=Y, r_star=R_STAR, n_xi=N_XI, chunk=args.chunk,
+                                                          plan=plan, mem="host")
+        return float(np.nanmax(host_table[:, 0])) if len(shard) else 0.0
 
     e2e_step(0)
     barrier()
@@ -305,83 +327,88 @@ def gpu_arm(args):
 
     if rank == 0:
         value = B * world * args.steps / (dev_ms * 1e-3)
-        # roofline of the dominant kernel: algorithmic flops per launch / measured launch duration
         peak = engine.fp64_peak_flops()
-        n_sdv = plan.lookup_pass.z.size
-        n_launch_pts = min(args.chunk, B)
-        alg = {
-            # 10 flop per (z_i, T_j) lookup-and-accumulate
-            "spec_den_v": 10.0 * n_sdv * NPT[1] * n_launch_pts,
-            # 25 flop per (y_i, z_k) integrand with two lookups
-            "spec_den_gw": 25.0 * Y.size * plan.gw["n_int"] * n_launch_pts,
-        }
-        if "spec_den_gw_cells" in stage_ms:
-            # cell formulation: 2 mul + 4 fma per (wavenumber, cell, profile); the cells of a wavenumber are its
-            # segments of the first lookup plus the steps of the second one, counted from the plan's tables
-            _, nseg, meta, _ = engine.gw_cells(plan)
-            steps = sum(int(meta[i, 2:2 + int(n)].sum().item()) for i, n in enumerate(nseg.tolist()))
-            alg["spec_den_gw_cells"] = 10.0 * float(int(nseg.sum().item()) + steps) * n_launch_pts
-        if "spec_den_v_group" in stage_ms:
-            # banded matrix product: 2 flop per (z_i, knot, profile) MAC over the band + the weight build; per launch =
-            # one v_wall row of the grid (1000 profiles)
-            from pttools_b200.engine import _group_band
-            _, kw = _group_band(plan.lookup_pass, 0.5)
-            # one stage entry = the groups of one chunk (they run concurrently on side streams, fork -> join)
-            groups = max(1, n_launch_pts // GRID_N)
-            alg["spec_den_v_group"] = groups * (2.0 * n_sdv * kw * GRID_N + 10.0 * n_sdv * NPT[1])
-        # measured DRAM traffic per stage entry, from the committed ncu captures (profiles/r01_traffic.json)
-        traffic = {}
+        peaks_file = {}
         try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
-                tj = json.load(f)
-            per = lambda k: tj[k]["read"] + tj[k]["write"]
-            if args.path == "generic" and NPT == (2000, 10000, 10000):
-                traffic["spec_den_v_group"] = max(1, n_launch_pts // GRID_N) * (per("sdv_gemm_kernel") + per("sdv_weights_kernel"))
-                traffic["spec_den_gw_cells"] = (per("spec_den_gw_cells_kernel") + per("gw_table_kernel")) * n_launch_pts / 2000.0
-        except (OSError, KeyError, ValueError):
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks_file = json.load(f)
+        except (OSError, ValueError):
             pass
-        dom = max((k for k in stage_ms if k in alg), key=lambda k: stage_ms[k]["ms"], default=None)
-        roofline = None
-        if dom:
-            dur = stage_ms[dom]["ms"] / max(1, stage_ms[dom]["n"]) * 1e-3
-            ach = alg[dom] / dur / 1e12
-            # spec_den_v_group = weights kernel + banded matrix product on the FP64 tensor pipe (DMMA): "tensor";
-            # everything else on this path is FP64 FMA-pipe work, reported against the same measured FP64 peak
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak / 1e12, "unit": "TFLOP/s",
-                        "frac": ach / (peak / 1e12), "traffic": traffic.get(dom),
-                        "precision": "fp64 (DMMA m8n8k4)" if dom.startswith("spec_den_v_group") else "fp64 (FMA pipe)",
-                        "peak_source": "in-run FP64 FMA probe kernel (MEASURED_PEAKS.json has no FP64 entry); a DMMA-only "
-                                       "probe measures the same peak (37.0 TFLOP/s, engine.fp64_pipe_flops)",
-                        "share_of_step": stage_ms[dom]["ms"] / dev_ms}
+        hbm_peak = float(peaks_file.get("hbm_gbs", 6554.2))
+        agg["steps"] = args.steps
+        alg = _alg_work(plan, agg, B, n_samples)
+        traffic = {}
+        for fname in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", fname)) as f:
+                    tj = json.load(f)
+                per = lambda k: tj[k]["read"] + tj[k]["write"]
+                rows = max(1, min(args.chunk, B) // GRID_N)
+                traffic = {"spec_den_v_group": rows * (per("sdv_gemm_kernel") + per("sdv_weights_kernel")),
+                           "spec_den_gw_cells": (per("spec_den_gw_cells_kernel") + per("gw_table_kernel")) * min(args.chunk, B) / tj.get("gw_profiles_per_launch", 2000.0),
+                           "_source": "profiles/" + fname}
+                break
+            except (OSError, KeyError, ValueError):
+                continue
+        stages = []
+        for name, a in alg.items():
+            if name not in stage_ms:
+                continue
+            ms_step = stage_ms[name]["ms"] / args.steps
+            n_entries = max(1, stage_ms[name]["n"]) / args.steps
+            if a["bound"] == "hbm":
+                ach, pk, unit = a["bytes"] / (ms_step * 1e-3) / 1e9, hbm_peak, "GB/s"
+            else:
+                ach, pk, unit = a["flop"] / (ms_step * 1e-3) / 1e12, peak / 1e12, "TFLOP/s"
+            stages.append({"kernel": name, "bound": a["bound"], "achieved": ach, "peak": pk, "unit": unit, "frac": ach / pk,
+                           "traffic": traffic.get(name), "precision": a["precision"], "ms_per_step": ms_step,
+                           "entries_per_step": n_entries, "share_of_step": stage_ms[name]["ms"] / dev_ms})
+        stages.sort(key=lambda d: -d["share_of_step"])
+        roofline = dict(stages[0]) if stages else None
+        if roofline:
+            roofline["peak_source"] = ("in-run FP64 FMA probe kernel (MEASURED_PEAKS.json has no FP64 entry); a DMMA-only probe "
+                                       "measures the same peak (engine.fp64_pipe_flops)") if roofline["unit"] == "TFLOP/s" \
+                else "MEASURED_PEAKS.json hbm_gbs"
+            roofline["traffic_source"] = traffic.get("_source")
         cores = len(os.sched_getaffinity(0))
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            n_cpu = 4 * max(cores, 8)
-            vw, an = batch_points(0, 0, 1, B)
-            pick = np.linspace(0, B - 1, n_cpu).astype(int)
-            dt = cpu_run(list(zip(vw[pick], an[pick])), cores, args.path)
-            cpu = {"value": n_cpu / dt, "unit": "spectra/s", "cores": cores, "kind": "port",
-                   "sample": f"{n_cpu} points spread evenly over the batch of step 0 (same grid, same sizes), "
-                             f"fork pool of {cores} processes, {dt:.1f} s"}
+            cpu = cpu_baseline_leg(B, cores, args)
         out = {
             "metric": "bubble+GW spectra/sec", "value": value, "unit": "spectra/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.path], "batch_per_gpu_per_step": B, "chunk": args.chunk,
+            "config": {"workload": WORKLOADS["generic"], "batch_per_step": B * world, "batch_per_gpu_per_step": B,
+                       "chunk": args.chunk, "api": "sweep.sweep_omgw0_distributed -> ptt_sweep_spectra (one C call per rank and "
+                       "step); whole v_wall rows per rank, blocks sent to rank 0 as they finish",
                        "l2": "per-step working set (profiles + A2 + lookup tables, ~1 MB per point) exceeds the 126 MB L2; "
                              "every step uses fresh points",
-                       "valid_points_in_timed_region": n_ok, "per_step_ms": per_step_ms, "wall_ms_per_step": wall_ms / args.steps},
+                       "valid_points_in_timed_region_rank0": n_ok, "per_step_ms": per_step_ms,
+                       "wall_ms_per_step": wall_ms / args.steps, "retried_points_rank0": agg["retried"],
+                       "rescued_points_rank0": agg["rescued"]},
             "clocks": clocks,
-            "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "spectra/s", "h2d_bytes_per_step": 2 * 8 * B,
-                    "d2h_bytes_per_step": 8 * B * int(Y.size), "steps": e2e_steps},
+            "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "spectra/s", "h2d_bytes_per_step": (16 + 4 + 1) * 8 * B * world,
+                    "d2h_bytes_per_step": (8 * int(Y.size) + 32 * 8 + 4) * B * world, "steps": e2e_steps,
+                    "api": "sweep.sweep_omgw0_distributed(mem='host') -> ptt_sweep_spectra(PTT_MEM_HOST): numpy in, pinned numpy out"},
             "gpu_launches": launches,
             "stage_ms_per_step": {k: v["ms"] / args.steps for k, v in stage_ms.items()},
             "roofline": roofline,
+            "roofline_stages": stages,
             "cpu_baseline": cpu,
         }
         print(json.dumps(out), file=RESULT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline_leg(B, cores, args):
+    n_cpu = 4 * max(cores, 8)
+    vw, an = batch_points(0, 0, 1, B)
+    pick = np.linspace(0, B - 1, n_cpu).astype(int)
+    dt = cpu_run(list(zip(vw[pick], an[pick])), cores, "generic")
+    return {"value": n_cpu / dt, "unit": "spectra/s", "cores": cores, "kind": "port",
+            "sample": f"{n_cpu} points spread evenly over the batch of step 0 (same grid, same sizes), "
+                      f"fork pool of {cores} processes, {dt:.1f} s"}
 
 
 RESULT = sys.stdout
@@ -404,7 +431,8 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=64000)
     ap.add_argument("--chunk", type=int, default=8000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--path", default="generic", choices=["generic", "bag"])
+    ap.add_argument("--path", default="generic", choices=["generic"])
+    ap.add_argument("--pow-v", action="store_true", help="also compute pow_v (the y pass of spec_den_v)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     RESULT = _claim_stdout()

@@ -262,6 +262,144 @@ int ptt_profile_integrals_batch(int P, const double* rows_v, const double* rows_
                                 int64_t row_stride, const int32_t* off, const int32_t* npts, const double* pp2,
                                 double* out, void* stream);
 
+/* --- Seam B, the performance seam: a whole sweep in one call -------------------------------------------------
+ * create_spectra(model, v_walls, alpha_ns, spectrum_kwargs) / create_bubbles(...)     pttools/analysis/parallel.py:89-187
+ *   -> run_parallel: one future per (v_wall, alpha_n) point, pickled Bubble / Spectrum objects back
+ *                                                                                      pttools/speedup/parallel.py:67-196
+ * Here: per point Bubble(model, v_wall, alpha_n).solve() (bubble.py:232-352: sound_shell_generic, the reference's
+ * retries, the thermodynamic integrals), SSMSpectrum.compute (ssmtools/spectrum.py:96-136) and
+ * Spectrum.omgw0 (omgw0/omgw0_ssm.py:123-131), for all n points, chunked against device memory, with the groups of
+ * equal v_wall of K6' on side streams and the result tables streamed out per chunk.
+ *
+ * The plan is a POD of views: the four sub-plans of seam C plus the few host numbers the driver needs to lay out the
+ * bands of K6'.  ptt_ssm_plan_create() builds one (grids with the reference's expressions, spectrum.py:169-186,
+ * 503-515, 473; calculators.py:100,136-153); a caller that already holds the sub-plans may fill it in itself. */
+typedef struct ptt_sweep_plan {
+    ptt_a2_plan_t a2;          /* all lookup grids concatenated: [pass 0 | pass 1] */
+    int32_t n_pass;            /* 1 or 2; the LAST pass is the z_lookup pass that feeds the GW integral */
+    int32_t has_y_pass;        /* pass 0 evaluates spec_den_v on y itself (-> pow_v) */
+    ptt_sdv_plan_t sdv[2];
+    ptt_gw_plan_t gw;
+    ptt_gw_cells_t cells;      /* cells.cap == 0: no cell tables, the per-sample kernel is used */
+    const double* h_zterm[2];  /* HOST copies of sdv[i].zterm */
+    double lt_first[2], lt_last[2], dl[2];   /* LT[0], LT[nt-1], dlog10 of each pass */
+    int32_t seg[4];            /* start of each pass' grid in a2 (seg[n_pass] = a2.n_z) */
+} ptt_sweep_plan_t;
+
+/* Plan builder.  mode 0: the SSMSpectrum.compute chain (pass 0 on y -> pow_v and a2, z_lookup = gen_lookup(y, cs,
+ * n_z_lookup, eps=1e-8), pass 1 on z_lookup, GW integral on (z_lookup, y)); mode 1: power_gw_scaled_bag
+ * (spectrum.py:243-294: one pass on z_lookup).  ptt_ssm_plan_create_host builds the host arrays only (no CUDA call:
+ * usable without a device, e.g. to inspect the grids with ptt_ssm_plan_array); ptt_ssm_plan_upload puts them on the
+ * current device and builds the cell tables of the GW integral; ptt_ssm_plan_create does both. */
+#define PTT_PLAN_ONLY_FIRST_PASS 1   /* spec_den_v on y only (no z_lookup pass, no GW tables) */
+#define PTT_PLAN_ONLY_LOOKUP_PASS 2  /* skip the y pass (no pow_v) */
+#define PTT_PLAN_FORCE_DIRECT 4      /* exact sine transform with one sine per (z, xi) pair (validation) */
+#define PTT_PLAN_NO_GW_CELLS 8       /* GW integral by the per-sample kernel */
+typedef struct ptt_ssm_plan ptt_ssm_plan_t;
+typedef struct ptt_ssm_plan_desc {
+    int32_t n_y, nt, n_z_lookup, nxi;   /* defaults of the reference: 1000, 10000, 10000, 2000 (ssmtools/const.py:10-20) */
+    int32_t nuc_type;                   /* 0 exponential, 1 simultaneous (spectrum.py:189-205) */
+    int32_t mode;
+    int32_t phase_rule;                 /* -1: the mode's default (ptt_a2_plan_t.phase_rule) */
+    int32_t nz_int;                     /* 0: n_z_lookup */
+    int32_t flags, reserved;
+    double cs;                          /* sound speed of the GW integral */
+    double z_st_thresh;                 /* 0 -> 50 */
+    double nuc_a;                       /* nucleation parameter a (1) */
+    double gamma;                       /* 0 -> 4/3 (ssmtools/const.py:46) */
+} ptt_ssm_plan_desc_t;
+int ptt_ssm_plan_create_host(const ptt_ssm_plan_desc_t* desc, const double* y, ptt_ssm_plan_t** out);
+int ptt_ssm_plan_upload(ptt_ssm_plan_t* plan);
+int ptt_ssm_plan_create(const ptt_ssm_plan_desc_t* desc, const double* y, ptt_ssm_plan_t** out);
+int ptt_ssm_plan_destroy(ptt_ssm_plan_t* plan);
+/* the POD view ptt_sweep_spectra and the seam-C operators take (NULL before the upload) */
+const ptt_sweep_plan_t* ptt_ssm_plan_view(const ptt_ssm_plan_t* plan);
+/* host array by name ("y", "z_lookup", "z_all", "frac_all", "xi_re", "p<i>_{qT,z,zterm,T,LT,W,omega_ab}",
+ * "gw_{L1,L2,Z1,Z2,G,yterm}"): copies up to cap doubles into out (may be NULL) and returns the size, -1 if unknown */
+int64_t ptt_ssm_plan_array(const ptt_ssm_plan_t* plan, const char* name, double* out, int64_t cap);
+/* n_pass, seg[n_pass+1], z_tile[n_pass], win_entries[n_pass], scal[8] = {l0_0, dl_0, l0_1, dl_1, z_exact_max,
+ * gw prefactor, gw lrange, gw win_entries}; any pointer may be NULL */
+int ptt_ssm_plan_info(const ptt_ssm_plan_t* plan, int32_t* n_pass, int32_t* seg, int32_t* z_tile, int32_t* win, double* scal);
+
+#define PTT_SWEEP_NSCAL 32
+/* columns of the per-point result table scalars[n, PTT_SWEEP_NSCAL]:
+ *  0..13  vp, vm, vp_tilde, vm_tilde, v_sh, vm_sh, vm_tilde_sh, wp, wm, wm_sh, v_cj, wn, wn_estimate, solver_failed
+ *         (the 17-tuple of sound_shell_generic, fluid.py:1052)
+ *  14..29 va_kinetic_energy_density, va_trace_anomaly_diff, va_thermal_energy_density_diff, va_entropy_density_diff,
+ *         wbar, ebar, kinetic_energy_density, kinetic_energy_fraction, va_thermal_energy_density,
+ *         thermal_energy_density, va_enthalpy_density, kappa, omega, ubarf2, mean_adiabatic_index, nu_gdh2024
+ *         (cached properties of Bubble, bubble.py:377-632 / thermo.py)
+ *  30     source_lifetime_factor (spectrum.py:123-136)      31  number of profile samples */
+
+#define PTT_SWEEP_TIMING 1     /* opts.flags: bracket every stage with CUDA events (ptt_sweep_last_stats) */
+#define PTT_SWEEP_NO_RETRY 2   /* opts.flags: report points whose first root search fails as solver failures */
+
+typedef struct ptt_sweep_opts {
+    int32_t n_xi;              /* 0 -> 5000 (bubble/const.py:12) */
+    int32_t thin_shell_limit;  /* 0 -> 100  (const.py:26) */
+    int32_t chunk;             /* points per spectrum chunk, 0 -> 8000 */
+    int32_t shell_chunk;       /* points per shell solve, 0 -> from free device memory */
+    int32_t flags;
+    int32_t group_min;         /* smallest run of equal v_wall that goes through the banded matrix product K6'
+                                * (ptt_spec_den_v_group), 0 -> 24; shorter runs use the gather kernel */
+    double t_end;              /* 0 -> 50 (const.py:18) */
+    double wn_rtol;            /* 0 -> 1e-4 (fluid.py:650) */
+    double r_star;             /* <= 0: Spectrum without r_star (lifetime factor 1/(1+2 nu) only) */
+    double lifetime_multiplier;/* spectrum.py:123-136; may be +inf */
+} ptt_sweep_opts_t;
+
+typedef struct ptt_sweep_out {
+    double* pow_v;             /* [n, n_y] or NULL */
+    double* pow_gw;            /* [n, n_y] or NULL */
+    double* omgw0;             /* [n, n_y] or NULL (needs scale[n]) */
+    double* scalars;           /* [n, PTT_SWEEP_NSCAL] or NULL */
+    int32_t* status;           /* [n] PTT_ST_* */
+    double *rows_v, *rows_w, *rows_xi;   /* optional profiles [n, row_stride] (device memory only), with off/npts */
+    int64_t row_stride;
+    int32_t *off, *npts;
+} ptt_sweep_out_t;
+
+/* Called after the rows [row0, row1) of the result tables have been queued for delivery on `stream` (a cudaStream_t):
+ * whatever is ordered after that stream sees them complete.  Lets a caller overlap its own exchange step (e.g. the
+ * NCCL gather of a sharded sweep) with the chunks still being computed.  Only issued per chunk when the points come
+ * ordered by v_wall (otherwise once, for [0, n)). */
+typedef void (*ptt_chunk_cb)(void* user, int64_t row0, int64_t row1, void* stream);
+
+/* pg[n,16]: as ptt_sweep_shells_generic.  pm[n,4] = {a_s, a_b, T_ref, 0} of each point's model.
+ * scale[n] = r_star * F_gw0 * suppression(v_wall, alpha_n) (NULL: no omgw0).  Rows may come in any order; results are
+ * returned in the caller's order.  With PTT_MEM_HOST the call returns when all results are in the caller's buffers. */
+int ptt_sweep_spectra(const ptt_sweep_plan_t* plan, const ptt_sweep_opts_t* opts, int64_t n, const double* pg,
+                      const double* pm, const double* scale, const ptt_sweep_out_t* out, ptt_chunk_cb cb, void* user,
+                      int mem, void* stream);
+
+#define PTT_STAGE_SHELLS 0
+#define PTT_STAGE_RETRY 1
+#define PTT_STAGE_THERMO 2
+#define PTT_STAGE_A2 3
+#define PTT_STAGE_SDV_Y 4
+#define PTT_STAGE_SDV 5
+#define PTT_STAGE_GW 6
+#define PTT_STAGE_EMIT 7
+#define PTT_STAGE_RETRY_FOLD 8
+#define PTT_N_STAGES 12
+typedef struct ptt_sweep_stats {
+    double stage_ms[PTT_N_STAGES];     /* device time per stage (events on the launching stream; stages on different
+                                        * streams overlap, so the sum can exceed the duration of the call) */
+    int64_t stage_calls[PTT_N_STAGES];
+    int64_t launches;                  /* kernels launched */
+    int64_t retried, rescued;          /* points sent to / solved by the retry search */
+    int64_t group_profiles;            /* profiles multiplied in K6' (lookup pass), after trimming no-solution rows */
+    int64_t group_count;
+    int64_t group_kw_sum;              /* sum over those groups of the band width in knots */
+    int64_t group_macs;                /* multiply-adds of those matrix products: sum of n_z * band * profiles */
+    int64_t a2_profiles, gw_profiles;  /* profiles that went through A^2 / the GW integral */
+} ptt_sweep_stats_t;
+int ptt_sweep_last_stats(ptt_sweep_stats_t* out);
+/* frees the device / pinned workspace the sweep driver keeps between calls */
+int ptt_sweep_release(void);
+/* points per shell solve the driver would pick for `free_bytes` of device memory */
+int64_t ptt_sweep_shell_chunk(int n_xi, int64_t free_bytes);
+
 /* FP64 FMA throughput probe used by bench.py for the roofline denominator (not part of the reference). */
 int ptt_fp64_peak_probe(int iters, double* out_flops_per_s, void* stream);
 /* mode 0: DFMA only, 1: DMMA m8n8k4 only, 2: both interleaved - measures what the FP64 tensor pipe can deliver on this

@@ -49,6 +49,52 @@ class GwCells(C.Structure):
                 ("coef", C.c_void_p)]
 
 
+class SweepPlan(C.Structure):
+    _fields_ = [("a2", A2Plan), ("n_pass", C.c_int32), ("has_y_pass", C.c_int32), ("sdv", SdvPlan * 2), ("gw", GwPlan),
+                ("cells", GwCells), ("h_zterm", C.c_void_p * 2), ("lt_first", C.c_double * 2), ("lt_last", C.c_double * 2),
+                ("dl", C.c_double * 2), ("seg", C.c_int32 * 4)]
+
+
+class PlanDesc(C.Structure):
+    _fields_ = [("n_y", C.c_int32), ("nt", C.c_int32), ("n_z_lookup", C.c_int32), ("nxi", C.c_int32),
+                ("nuc_type", C.c_int32), ("mode", C.c_int32), ("phase_rule", C.c_int32), ("nz_int", C.c_int32),
+                ("flags", C.c_int32), ("reserved", C.c_int32), ("cs", C.c_double), ("z_st_thresh", C.c_double),
+                ("nuc_a", C.c_double), ("gamma", C.c_double)]
+
+
+class SweepOpts(C.Structure):
+    _fields_ = [("n_xi", C.c_int32), ("thin_shell_limit", C.c_int32), ("chunk", C.c_int32), ("shell_chunk", C.c_int32),
+                ("flags", C.c_int32), ("group_min", C.c_int32), ("t_end", C.c_double), ("wn_rtol", C.c_double),
+                ("r_star", C.c_double), ("lifetime_multiplier", C.c_double)]
+
+
+class SweepOut(C.Structure):
+    _fields_ = [("pow_v", C.c_void_p), ("pow_gw", C.c_void_p), ("omgw0", C.c_void_p), ("scalars", C.c_void_p),
+                ("status", C.c_void_p), ("rows_v", C.c_void_p), ("rows_w", C.c_void_p), ("rows_xi", C.c_void_p),
+                ("row_stride", C.c_int64), ("off", C.c_void_p), ("npts", C.c_void_p)]
+
+
+N_STAGES = 12
+STAGE_NAMES = ("shells_generic", "shells_retry", "thermo", "a2", "spec_den_v_group_y", "spec_den_v_group", "spec_den_gw_cells",
+               "emit", "retry_fold")
+SWEEP_NSCAL = 32
+SWEEP_SCALARS = ("vp", "vm", "vp_tilde", "vm_tilde", "v_sh", "vm_sh", "vm_tilde_sh", "wp", "wm", "wm_sh", "v_cj", "wn",
+                 "wn_estimate", "solver_failed", "va_kinetic_energy_density", "va_trace_anomaly_diff",
+                 "va_thermal_energy_density_diff", "va_entropy_density_diff", "wbar", "ebar", "kinetic_energy_density",
+                 "kinetic_energy_fraction", "va_thermal_energy_density", "thermal_energy_density", "va_enthalpy_density",
+                 "kappa", "omega", "ubarf2", "mean_adiabatic_index", "nu_gdh2024", "source_lifetime_factor", "npts")
+SWEEP_TIMING, SWEEP_NO_RETRY = 1, 2
+PLAN_ONLY_FIRST_PASS, PLAN_ONLY_LOOKUP_PASS, PLAN_FORCE_DIRECT, PLAN_NO_GW_CELLS = 1, 2, 4, 8
+
+
+class SweepStats(C.Structure):
+    _fields_ = [("stage_ms", C.c_double * N_STAGES), ("stage_calls", C.c_int64 * N_STAGES), ("launches", C.c_int64),
+                ("retried", C.c_int64), ("rescued", C.c_int64), ("group_profiles", C.c_int64), ("group_count", C.c_int64),
+                ("group_kw_sum", C.c_int64), ("group_macs", C.c_int64), ("a2_profiles", C.c_int64), ("gw_profiles", C.c_int64)]
+
+
+CHUNK_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p)
+
 # name -> (restype, argtypes); the test-suite checks that every symbol of include/pttools_b200.h is here and exported
 SIGNATURES = {
     "ptt_last_error": (C.c_char_p, []),
@@ -98,6 +144,18 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_profile_integrals_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ptt_ssm_plan_create_host": (C.c_int, [C.POINTER(PlanDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ptt_ssm_plan_upload": (C.c_int, [C.c_void_p]),
+    "ptt_ssm_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ptt_ssm_plan_destroy": (C.c_int, [C.c_void_p]),
+    "ptt_ssm_plan_view": (C.POINTER(SweepPlan), [C.c_void_p]),
+    "ptt_ssm_plan_array": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "ptt_ssm_plan_info": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ptt_sweep_spectra": (C.c_int, [C.POINTER(SweepPlan), C.POINTER(SweepOpts), C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.POINTER(SweepOut), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ptt_sweep_last_stats": (C.c_int, [C.POINTER(SweepStats)]),
+    "ptt_sweep_release": (C.c_int, []),
+    "ptt_sweep_shell_chunk": (C.c_int64, [C.c_int, C.c_int64]),
     "ptt_fp64_peak_probe": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     "ptt_fp64_pipe_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
 }

@@ -11,6 +11,7 @@ import numpy as np
 
 from . import bubble as bub
 from . import sweep
+from ._lib import SWEEP_SCALARS as _SWEEP_SCALARS
 from .models import CODE_SOL, Model, SolutionType
 
 
@@ -27,6 +28,25 @@ class BubbleView:
         self.solver_failed = st == 5
         self.no_solution_found = not self.solved
         self._prof = None
+        self._flags = None
+
+    NEEDS_SOLUTION = frozenset(_SWEEP_SCALARS) - {"wn", "v_cj"}
+
+    def _validity(self):
+        if self._flags is None:
+            BubbleView._cache_validity(self._b)
+            self._flags = {k: bool(v[self._i]) for k, v in self._b._validity.items()}
+        return self._flags
+
+    @staticmethod
+    def _cache_validity(batch):
+        if getattr(batch, "_validity", None) is None:
+            batch._validity = batch.validity()
+
+    numerical_error = property(lambda self: self._validity()["numerical_error"])
+    unphysical_alpha_plus = property(lambda self: self._validity()["unphysical_alpha_plus"])
+    negative_entropy_flux = property(lambda self: self._validity()["negative_entropy_flux"])
+    negative_net_entropy_change = property(lambda self: self._validity()["negative_net_entropy_change"])
 
     def _profile(self):
         if self._prof is None:
@@ -40,6 +60,8 @@ class BubbleView:
     def __getattr__(self, name):
         scal = self.__dict__["_b"].scal
         if name in scal:
+            if not self.__dict__.get("solved", False) and name in BubbleView.NEEDS_SOLUTION:
+                raise bub.NotYetSolvedError                       # bubble.py:377-632: cached properties of an unsolved bubble
             return float(scal[name][self.__dict__["_i"]])
         raise AttributeError(name)
 
@@ -47,85 +69,124 @@ class BubbleView:
 class SpectrumView:
     """Row of a spectrum sweep with the attribute names of pttools.omgw0.Spectrum."""
 
-    def __init__(self, res: sweep.SweepResult, i: int, bubble: tp.Optional[BubbleView], r_star):
+    def __init__(self, res: sweep.SweepResult, i: int, bubble: tp.Optional[BubbleView], r_star, Tn=None, g_star=None,
+                 gs_star=None):
+        from . import omgw0 as om
         self._r, self._i, self.bubble, self.r_star = res, i, bubble, r_star
         self.y = res.y
+        # both in-scope models have non-physical temperatures: the overrides of omgw0_ssm.py:62-112 apply
+        self.Tn = om.T_default if Tn is None else Tn
+        self.g_star = om.G_STAR_DEFAULT if g_star is None else gs_star           # sic: omgw0_ssm.py:74
+        self.gs_star = self.g_star if gs_star is None else gs_star
 
     pow_gw = property(lambda self: self._r.pow_gw[self._i].cpu().numpy())
     pow_v = property(lambda self: self._r.pow_v[self._i].cpu().numpy())
+    source_lifetime_factor = property(lambda self: float(self._r.scalars["source_lifetime_factor"][self._i]))
 
     def omgw0(self):
         return self._r.omgw0[self._i].cpu().numpy()
 
+    @property
+    def f_star0(self):
+        from . import omgw0 as om
+        return om.f_star0(Tn=self.Tn, g_star=self.g_star)
+
+    def f(self, z=None):
+        """omgw0_ssm.py:162-171."""
+        from . import omgw0 as om
+        return om.f(self.y if z is None else z, self.r_star, self.f_star0)
+
+    def omgw0_peak(self):
+        om_ = self.omgw0()
+        i = int(np.argmax(om_))
+        return self.f()[i], om_[i]
+
+
+def _rejected(model: Model, v_wall: float, alpha_n: float) -> Exception:
+    """The exception the reference's Bubble constructor raises for a point the sweep marked invalid (bubble.py:36-177)."""
+    if alpha_n < 0 or alpha_n < model.alpha_n_min:
+        return ValueError(f"Invalid alpha_n={alpha_n}. Minimum for the model: {model.alpha_n_min}")
+    return ValueError(f"Bubble(model={model.label_unicode}, v_wall={v_wall}, alpha_n={alpha_n}) is rejected by the "
+                      "constructor: no solution type, or T_nuc > T_crit")
+
+
+def _bubble_objects(model, batch: bub.BubbleBatch, shape, allow_bubble_failure: bool):
+    """Object array of BubbleView.  Like the reference's create_bubble (parallel.py:21-54): a point the Bubble constructor
+    rejects raises, or becomes None under allow_bubble_failure; a point whose solve fails is still returned, with
+    solved = False and no_solution_found = True."""
+    objs = np.empty(int(np.prod(shape)), dtype=object)
+    for i in range(objs.size):
+        if batch.invalid is not None and batch.invalid[i]:
+            if not allow_bubble_failure:
+                raise _rejected(model, float(batch.v_wall[i]), float(batch.alpha_n[i]))
+            objs[i] = None
+        else:
+            objs[i] = BubbleView(batch, i, model)
+    return objs
+
 
 def create_bubbles(model: Model, v_walls: np.ndarray, alpha_ns: np.ndarray, func: callable = None,
-                   log_progress_percentage: float = 5, max_workers: int = None, allow_bubble_failure: bool = False,
-                   kwargs: tp.Dict[str, tp.Any] = None, bubble_kwargs: tp.Dict[str, tp.Any] = None,
-                   bubble_func: callable = None):
-    """parallel.py:89-154: object array [n_alpha, n_vw] of bubbles (+ the outputs of `func`, applied on the host)."""
+                   log_progress_percentage: float = 5, max_workers: int = None, single_thread: bool = False,
+                   allow_bubble_failure: bool = False, kwargs: tp.Dict[str, tp.Any] = None,
+                   bubble_kwargs: tp.Dict[str, tp.Any] = None, bubble_func: callable = None):
+    """parallel.py:89-154: object array [n_alpha, n_vw] of bubbles (+ the outputs of `func`, applied on the host).
+    `kwargs` may carry allow_bubble_failure / use_bag_solver the way BubbleGridVWAlpha passes them (bubble_grid.py:66-69);
+    the remaining entries go to `func`."""
     v_walls, alpha_ns = np.asarray(v_walls, dtype=float), np.asarray(alpha_ns, dtype=float)
+    kwargs = dict(kwargs or {})
+    allow_bubble_failure = bool(kwargs.pop("allow_bubble_failure", allow_bubble_failure))
+    if kwargs.pop("use_bag_solver", False):
+        raise NotImplementedError("use_bag_solver is outside the hot path")
     vw, an = np.meshgrid(v_walls, alpha_ns)                     # params[i_alpha, i_vw], parallel.py:126-130
     bk = bubble_kwargs or {}
     batch = bub.sweep_bubbles(model, vw.ravel(), an.ravel(), n_xi=bk.get("n_xi", bub.N_XI_DEFAULT),
-                              t_end=bk.get("t_end", bub.T_END_DEFAULT))
-    objs = np.empty(vw.shape, dtype=object)
-    flat = objs.reshape(-1)
-    for i in range(flat.size):
-        view = BubbleView(batch, i, model)
-        if not view.solved:
-            if not allow_bubble_failure:
-                raise RuntimeError(f"Solver crashed with model={model.label_unicode}, v_wall={view.v_wall}, "
-                                   f"alpha_n={view.alpha_n}.")
-            view = None
-        flat[i] = view
+                              t_end=bk.get("t_end", bub.T_END_DEFAULT), allow_invalid=bk.get("allow_invalid", False))
+    flat = _bubble_objects(model, batch, vw.shape, allow_bubble_failure)
+    objs = flat.reshape(vw.shape)
     if func is None:
         return objs
-    return objs, _apply(func, flat, vw.shape, kwargs)
+    return (objs,) + _apply(func, flat, vw.shape, kwargs)
 
 
 def _apply(func, flat, shape, kwargs):
-    """Post-functions carry .return_type / .fail_value attributes (bubble_quantities.py:6-39)."""
+    """Post-functions carry .return_type / .fail_value attributes (bubble_quantities.py:6-39); a tuple return_type means
+    several output arrays (parallel.py:103-110)."""
+    if not hasattr(func, "return_type"):
+        raise ValueError("The function should have a return_type attribute for output array initialization")
     kwargs = kwargs or {}
-    fail = getattr(func, "fail_value", np.nan)
+    multiple = isinstance(func.return_type, tuple)
+    fail = getattr(func, "fail_value", (np.nan,) * len(func.return_type) if multiple else np.nan)
     vals = [fail if o is None else func(o, **kwargs) for o in flat]
-    return np.array(vals, dtype=getattr(func, "return_type", float)).reshape(shape)
+    if not multiple:
+        return (np.array(vals, dtype=func.return_type).reshape(shape),)
+    return tuple(np.array([v[k] for v in vals], dtype=t).reshape(shape) for k, t in enumerate(func.return_type))
 
 
 def create_spectra(model: Model, v_walls: np.ndarray, alpha_ns: np.ndarray, func: callable = None,
-                   log_progress_percentage: float = 5, max_workers: int = None, allow_bubble_failure: bool = False,
-                   kwargs: tp.Dict[str, tp.Any] = None, bubble_kwargs: tp.Dict[str, tp.Any] = None,
-                   spectrum_kwargs: tp.Dict[str, tp.Any] = None):
-    """parallel.py:157-187."""
+                   log_progress_percentage: float = 5, max_workers: int = None, single_thread: bool = False,
+                   allow_bubble_failure: bool = False, kwargs: tp.Dict[str, tp.Any] = None,
+                   bubble_kwargs: tp.Dict[str, tp.Any] = None, spectrum_kwargs: tp.Dict[str, tp.Any] = None):
+    """parallel.py:157-187: object array [n_alpha, n_vw] of spectra (+ the outputs of `func`)."""
     v_walls, alpha_ns = np.asarray(v_walls, dtype=float), np.asarray(alpha_ns, dtype=float)
-    # device order: v_wall-major and ascending (points that share v_wall are contiguous); objects go back into the
-    # reference's [i_alpha, i_vw] layout (parallel.py:126-130)
-    order_vw = np.argsort(v_walls, kind="stable")
-    vw = np.repeat(v_walls[order_vw], alpha_ns.size)
-    an = np.tile(alpha_ns, v_walls.size)
+    vw, an = np.meshgrid(v_walls, alpha_ns)                     # params[i_alpha, i_vw]: the order of the returned arrays
     sk = dict(spectrum_kwargs or {})
     bk = bubble_kwargs or {}
     nuc = sk.get("nuc_type", "exponential")
-    res = sweep.sweep_spectra(model, vw, an, y=sk.get("y"), r_star=sk.get("r_star"),
+    res = sweep.sweep_spectra(model, vw.ravel(), an.ravel(), y=sk.get("y"), r_star=sk.get("r_star"),
                               lifetime_multiplier=sk.get("lifetime_multiplier", 1.0),
                               nuc_type=str(getattr(nuc, "value", nuc)),
                               nt=sk.get("nt", 10000), n_z_lookup=sk.get("n_z_lookup", 10000),
                               z_st_thresh=sk.get("z_st_thresh", 50.0), n_xi=bk.get("n_xi", bub.N_XI_DEFAULT),
-                              Tn=sk.get("Tn"), g_star=sk.get("g_star"), gs_star=sk.get("gs_star"), keep_bubbles=True)
-    objs = np.empty((alpha_ns.size, v_walls.size), dtype=object)
-    k = 0
-    for bb in res.bubbles:
-        for j in range(len(bb)):
-            bview = BubbleView(bb, j, model)
-            if not bview.solved and not allow_bubble_failure:
-                raise RuntimeError(f"Solver crashed with v_wall={bview.v_wall}, alpha_n={bview.alpha_n}.")
-            i_vw, i_alpha = order_vw[k // alpha_ns.size], k % alpha_ns.size
-            objs[i_alpha, i_vw] = SpectrumView(res, k, bview, sk.get("r_star")) if bview.solved else None
-            k += 1
-    flat = objs.reshape(-1)
-    vw = objs          # only .shape is used below
+                              Tn=sk.get("Tn"), g_star=sk.get("g_star"), gs_star=sk.get("gs_star"), keep_bubbles=True,
+                              allow_invalid=bk.get("allow_invalid", False))
+    bubbles = _bubble_objects(model, res.bubbles, vw.shape, allow_bubble_failure)
+    flat = np.empty(bubbles.size, dtype=object)
+    for i, b in enumerate(bubbles):
+        flat[i] = None if b is None else SpectrumView(res, i, b, sk.get("r_star"), sk.get("Tn"), sk.get("g_star"), sk.get("gs_star"))
+    objs = flat.reshape(vw.shape)
     if func is None:
         return objs
-    return objs, _apply(func, flat, vw.shape, kwargs)
+    return (objs,) + _apply(func, flat, vw.shape, kwargs)
 
 
 class BubbleGridVWAlpha:
@@ -137,16 +198,34 @@ class BubbleGridVWAlpha:
             raise NotImplementedError("use_bag_solver is outside the hot path")
         self.model, self.v_walls, self.alpha_ns = model, v_walls, alpha_ns
         out = create_bubbles(model, v_walls, alpha_ns, func, allow_bubble_failure=True, **kw)
-        self.bubbles, self.data = (out if isinstance(out, tuple) else (out, None))
+        if isinstance(out, tuple):
+            self.bubbles = out[0]
+            self.data = out[1] if len(out) == 2 else out[1:]               # bubble_grid.py:70-74
+        else:
+            self.bubbles, self.data = out, None
 
-    def get_value(self, name: str) -> np.ndarray:
-        return np.array([[np.nan if b is None else getattr(b, name) for b in row] for row in self.bubbles])
+    def get_value(self, name: str, dtype=None) -> np.ndarray:
+        """bubble_grid.py:18-34: None (NaN for float dtypes) where there is no bubble or it has not been solved."""
+        def one(b):
+            if b is None or (not b.solved and name in BubbleView.NEEDS_SOLUTION):
+                return None
+            return getattr(b, name)
+        return np.array([[one(b) for b in row] for row in self.bubbles], dtype=dtype)
 
     def kappa(self):
-        return self.get_value("kappa")
+        return self.get_value("kappa", dtype=np.float64)
 
     def omega(self):
-        return self.get_value("omega")
+        return self.get_value("omega", dtype=np.float64)
 
     def numerical_error(self):
-        return np.array([[b is None for b in row] for row in self.bubbles])
+        return self.get_value("numerical_error", dtype=np.bool_)
+
+    def solver_failed(self):
+        return self.get_value("solver_failed", dtype=np.bool_)
+
+    def unphysical_alpha_plus(self):
+        return self.get_value("unphysical_alpha_plus", dtype=np.bool_)
+
+    def negative_net_entropy_change(self):
+        return self.get_value("negative_net_entropy_change", dtype=np.bool_)

@@ -172,7 +172,8 @@ def fluid_integrate_param(v0, w0, xi0, phase=-1., t_end=T_END_DEFAULT, n_xi=N_XI
 @dataclasses.dataclass
 class BubbleBatch:
     """Solved bubbles of a sweep, all on the device.  `scal` holds the reference's per-bubble scalars
-    (fluid.py:1052 and the cached properties of bubble.py:377-632) as [n] tensors."""
+    (fluid.py:1052 and the cached properties of bubble.py:377-632) as [n] tensors (columns of the result table of
+    ptt_sweep_spectra)."""
     model: tp.Union[Model, tp.Sequence[Model]]
     shells: engine.ShellBatch
     v_wall: tp.Any
@@ -183,7 +184,7 @@ class BubbleBatch:
     scal: tp.Dict[str, tp.Any]
     pp: tp.Any                # [n,8] parameters of ptt_a2_batch
     n_xi: int
-    retry_job: tp.Any = None  # sweep_bubbles(retry="async"): RetryJob still to be finished (finish_retry)
+    invalid: tp.Any = None    # host bool [n]: points the reference's Bubble constructor rejects
 
     def __len__(self):
         return self.v_wall.numel()
@@ -225,178 +226,91 @@ def _per_point(models, n, attr):
 
 
 @dataclasses.dataclass
-class RetryJob:
-    """The retry search (engine.generic_retry) of the points of a batch whose first root search failed, possibly still
-    running on a side stream."""
-    pos: np.ndarray           # positions in the batch
-    shells: engine.ShellBatch  # compact results
-    rescued: tp.Any
-    pg: tp.Any
-    stream: tp.Any
-    thermo: bool
+class PointTable:
+    """Host-side parameter rows of a sweep: what the model contributes per point (closed forms of models.py and the
+    starting guesses of the fluid-reference table).  pg / pm are the inputs of ptt_sweep_spectra."""
+    pg: np.ndarray            # [n,16]
+    pm: np.ndarray            # [n,4]
+    wn: np.ndarray
+    codes: np.ndarray         # solution type codes; -1 where the point is rejected
+    invalid: np.ndarray       # bool: rejected by the checks of the reference's Bubble constructor
 
 
-_RETRY_STREAM = None
-
-
-def _retry_stream():
-    global _RETRY_STREAM
-    if _RETRY_STREAM is None:
-        _RETRY_STREAM = engine._torch().cuda.Stream()
-    return _RETRY_STREAM
-
-
-def finish_retry(b: BubbleBatch):
-    """Waits for the retry search of `b`, writes the rescued points back into `b` (profiles, scalars, status,
-    thermodynamic quantities) and returns (sub, pos): the rescued points as a BubbleBatch of their own and their
-    positions in `b`; (None, empty) if there was nothing to do."""
-    torch = engine._torch()
-    job, b.retry_job = b.retry_job, None
-    none = (None, np.zeros(0, dtype=np.int64))
-    if job is None:
-        return none
-    if job.stream is not None:
-        # read the flags on the side stream: the host then waits for the retries only, not for whatever the current
-        # stream still has queued
-        with torch.cuda.stream(job.stream):
-            ok = job.rescued.cpu().numpy() != 0
-        torch.cuda.current_stream().wait_stream(job.stream)
-    else:
-        ok = job.rescued.cpu().numpy() != 0
-    if not ok.any():
-        return none
-    pos = job.pos[ok]
-    sel = torch.as_tensor(np.nonzero(ok)[0], device="cuda")
-    at = torch.as_tensor(pos, device="cuda", dtype=torch.int64)
-    sh = job.shells
-    sub_sh = engine.ShellBatch(sh.v_wall[sel], sh.alpha_n[sel], None, sh.sol_type[sel], sh.status[sel].contiguous(),
-                               sh.rows_v[sel], sh.rows_w[sel], sh.rows_xi[sel], sh.off[sel].contiguous(),
-                               sh.npts[sel].contiguous(), sh.scalars[sel].contiguous(), sh.n_xi)
-    model = b.model if isinstance(b.model, Model) else [b.model[int(i)] for i in pos]
-    n = pos.size
-    scal = {name: sub_sh.scalars[:, k] for k, name in enumerate(engine.GEN_SCALARS)}
-    sub = BubbleBatch(model, sub_sh, b.v_wall[at].contiguous(), b.alpha_n[at].contiguous(), b.wn[at].contiguous(),
-                      sub_sh.sol_type, sub_sh.status, scal, b.pp[at].contiguous(), b.n_xi)
-    if job.thermo:
-        add_thermo(sub, engine.dev_f64(1 + 1 / _per_point(model, n, "css2")),
-                   engine.dev_f64(1 + 1 / _per_point(model, n, "csb2")))
-    # write back
-    for dst, src in ((b.shells.rows_v, sub_sh.rows_v), (b.shells.rows_w, sub_sh.rows_w), (b.shells.rows_xi, sub_sh.rows_xi),
-                     (b.shells.off, sub_sh.off), (b.shells.npts, sub_sh.npts), (b.shells.scalars, sub_sh.scalars),
-                     (b.shells.status, sub_sh.status)):
-        dst.index_copy_(0, at, src)
-    for k, v in sub.scal.items():
-        if k not in engine.GEN_SCALARS and k in b.scal:        # the solver's scalars are views of shells.scalars
-            b.scal[k].index_copy_(0, at, v)
-    return sub, pos
-
-
-def sweep_bubbles(model, v_wall, alpha_n, sol_type=None, n_xi=N_XI_DEFAULT, t_end=T_END_DEFAULT,
-                  thin_shell_limit=THIN_SHELL_T_POINTS_MIN, wn_rtol=1e-4, thermo=True, retry="sync") -> BubbleBatch:
-    """Bubble(model, v_wall, alpha_n).solve() for every point of a sweep (bubble.py:232-352, fluid.py:848-1052).
-    `model` is one Model or a sequence with one Model per point.
-    retry: what to do with the points whose root search did not converge, for which the reference varies the start
-    (fsolve_vary) and scans (hybrids): "sync" = retry and patch before returning; "async" = queue the retries on a side
-    stream and leave `retry_job` set (the caller ends with finish_retry); "off" = report them as solver failures."""
-    torch = engine._torch()
+def point_table(model, v_wall, alpha_n, sol_type=None, allow_invalid=False) -> PointTable:
+    """Per-point inputs of the shell solver for Bubble(model, v_wall, alpha_n) (bubble.py:36-177, fluid.py:890-949).
+    Points the reference's constructor rejects -- alpha_n < model.alpha_n_min (model.py:813-823), T_n > T_crit
+    (bubble.py:97-101), no solution type (transition.py:47-69), wn not found -- get solution type -1: the device
+    reports them as PTT_ST_INVALID_INPUT with NaN outputs."""
     vw = np.asarray(v_wall, dtype=float).reshape(-1)
     an = np.asarray(alpha_n, dtype=float).reshape(-1)
     n = vw.size
     single = isinstance(model, Model)
-    if single:
-        wn = np.asarray(model.wn(an), dtype=float).reshape(-1)
-        if sol_type is None:
-            codes = model.solution_type_codes(vw, an, wn)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if single:
+            wn = np.asarray(model.wn(an), dtype=float).reshape(-1)
+            codes = model.solution_type_codes(vw, an, wn) if sol_type is None else \
+                np.asarray(sol_type, dtype=np.int32).reshape(-1)
+            v_cj = np.asarray(model.v_chapman_jouguet(an, wn), dtype=float).reshape(-1)
+            an_min = np.full(n, model.alpha_n_min)
+            tn = np.asarray(model.temp(wn, Phase.SYMMETRIC), dtype=float).reshape(-1)
+            t_crit = np.full(n, model.T_crit)
         else:
-            codes = np.asarray(sol_type, dtype=np.int32).reshape(-1)
-        v_cj = np.asarray(model.v_chapman_jouguet(an, wn), dtype=float).reshape(-1)
-    else:
-        wn = np.array([m.wn(a) for m, a in zip(model, an)], dtype=float)
-        codes = np.array([SOL_CODE[m.solution_type(v, a, w)] for m, v, a, w in zip(model, vw, an, wn)], dtype=np.int32) \
-            if sol_type is None else np.asarray(sol_type, dtype=np.int32).reshape(-1)
-        v_cj = np.array([m.v_chapman_jouguet(a, w) for m, a, w in zip(model, an, wn)], dtype=float)
-    guesses = fluid_reference.ref().get_batch(vw, an, codes)      # [n,6] vp, vm, vp_tilde, vm_tilde, wp, wm
-    pg = torch.zeros((n, 16), dtype=torch.float64, device="cuda")
-    wn_d = engine.dev_f64(wn)
-    pg[:, 0], pg[:, 1], pg[:, 2] = engine.dev_f64(vw), engine.dev_f64(an), engine.dev_f64(codes.astype(float))
-    pg[:, 3], pg[:, 4] = wn_d, engine.dev_f64(v_cj)
+            wn = np.array([m.wn(a) for m, a in zip(model, an)], dtype=float)
+            codes = np.array([SOL_CODE[m.solution_type(v, a, w)] for m, v, a, w in zip(model, vw, an, wn)],
+                             dtype=np.int32) if sol_type is None else np.asarray(sol_type, dtype=np.int32).reshape(-1)
+            v_cj = np.array([m.v_chapman_jouguet(a, w) for m, a, w in zip(model, an, wn)], dtype=float)
+            an_min = _per_point(model, n, "alpha_n_min")
+            tn = np.array([m.temp(w, Phase.SYMMETRIC) for m, w in zip(model, wn)], dtype=float)
+            t_crit = _per_point(model, n, "T_crit")
+        codes = np.array(codes, dtype=np.int32)
+        invalid = ~np.isfinite(wn) | (codes < 0) | (vw < 0) | (vw > 1)
+        if not allow_invalid:
+            invalid |= (an < 0) | (an < an_min) | (tn > t_crit)
+    codes[invalid] = -1
+    guesses = fluid_reference.ref().get_batch(vw, an, np.where(invalid, 0, codes)).cpu().numpy()   # vp, vm, vp~, vm~, wp, wm
+    pg = np.zeros((n, 16))
+    pg[:, 0], pg[:, 1], pg[:, 2], pg[:, 3], pg[:, 4] = vw, an, codes, wn, v_cj
     pg[:, 5], pg[:, 6] = guesses[:, 0], guesses[:, 2]
-    pg[:, 7] = guesses[:, 4] * wn_d                       # fluid.py:939-941
-    wm_g = guesses[:, 5] * wn_d
-    pg[:, 8] = torch.where(torch.isnan(wm_g), 0.3 * wn_d, wm_g)   # fluid.py:942-949
+    pg[:, 7] = guesses[:, 4] * wn                         # fluid.py:939-941
+    wm_g = guesses[:, 5] * wn
+    pg[:, 8] = np.where(np.isnan(wm_g), 0.3 * wn, wm_g)   # fluid.py:942-949
     for col, attr in ((9, "css2"), (10, "csb2"), (11, "V_s"), (12, "V_b")):
-        pg[:, col] = engine.dev_f64(_per_point(model, n, attr))
-    pg[:, 13] = engine.dev_f64(np.array([1.0 if m.name == "bag" else 0.0 for m in ([model] * n if single else model)]))
+        pg[:, col] = _per_point(model, n, attr)
+    pg[:, 13] = [1.0 if m.name == "bag" else 0.0 for m in ([model] * n if single else model)]
     # entropy density s(w) = coef * w^(1 - 1/mu) per phase (s = w / T): the retry search applies the reference's
     # entropy-flux test to its scan starts
     a_s_, a_b_, t0 = (_per_point(model, n, k) for k in ("a_s", "a_b", "T_ref"))
-    mus, mub = 1 + 1 / _per_point(model, n, "css2"), 1 + 1 / _per_point(model, n, "csb2")
-    pg[:, 14] = engine.dev_f64((mus * a_s_) ** (1 / mus) * t0 ** (4 / mus - 1))
-    pg[:, 15] = engine.dev_f64((mub * a_b_) ** (1 / mub) * t0 ** (4 / mub - 1))
-    shells = engine.sweep_shells_generic(pg, n_xi, t_end, thin_shell_limit, wn_rtol)
-    scal = {name: shells.scalars[:, k] for k, name in enumerate(engine.GEN_SCALARS)}
-    mu_s = engine.dev_f64(1 + 1 / _per_point(model, n, "css2"))
-    mu_b = engine.dev_f64(1 + 1 / _per_point(model, n, "csb2"))
-    V_s, V_b = pg[:, 11], pg[:, 12]
-    cs_b = torch.sqrt(pg[:, 10])
-    pp = engine.point_params(pg[:, 0], cs_b, 1 - 1 / mu_s, 1 - 1 / mu_b, V_s, V_b)
-    batch = BubbleBatch(model, shells, pg[:, 0].contiguous(), pg[:, 1].contiguous(), wn_d, shells.sol_type,
-                        shells.status, scal, pp, n_xi)
-    if retry not in ("sync", "async", "off"):
-        raise ValueError(f"retry={retry!r}")
-    if retry != "off":
-        st_host = shells.status.cpu().numpy()
-        pos = np.nonzero(((st_host == _lib.ST_SOLVER_FAILED) | (st_host == _lib.ST_ROOT_NOT_CONVERGED)) &
-                         ((codes == 0) | (codes == 1)))[0]
-        if pos.size:
-            stream = _retry_stream() if retry == "async" else None
-            sub_sh, rescued = engine.generic_retry(pg, pos, n_xi, t_end, thin_shell_limit, wn_rtol, stream=stream)
-            batch.retry_job = RetryJob(pos, sub_sh, rescued, pg, stream, thermo)
-    if thermo:
-        add_thermo(batch, mu_s, mu_b)
-    if retry == "sync":
-        finish_retry(batch)
-    return batch
+    mus, mub = 1 + 1 / pg[:, 9], 1 + 1 / pg[:, 10]
+    pg[:, 14] = (mus * a_s_) ** (1 / mus) * t0 ** (4 / mus - 1)
+    pg[:, 15] = (mub * a_b_) ** (1 / mub) * t0 ** (4 / mub - 1)
+    pm = np.zeros((n, 4))
+    pm[:, 0], pm[:, 1], pm[:, 2] = a_s_, a_b_, t0
+    return PointTable(pg, pm, wn, codes, invalid)
 
 
-def add_thermo(b: BubbleBatch, mu_s, mu_b):
-    """The volume-averaged thermodynamic quantities of thermo.py from the K4 integrals."""
+def sweep_bubbles(model, v_wall, alpha_n, sol_type=None, n_xi=N_XI_DEFAULT, t_end=T_END_DEFAULT,
+                  thin_shell_limit=THIN_SHELL_T_POINTS_MIN, wn_rtol=1e-4, thermo=True, retry="sync",
+                  allow_invalid=False) -> BubbleBatch:
+    """Bubble(model, v_wall, alpha_n).solve() for every point of a sweep (bubble.py:232-352, fluid.py:848-1052) through
+    ptt_sweep_spectra (shells, retries, thermodynamic scalars; no spectra).  `model` is one Model or a sequence with
+    one Model per point.  retry: "sync" = the reference's retries (fsolve_vary, backup scan) for the points whose first
+    root search fails; "off" = report them as solver failures.  Profiles stay on the device (`shells`)."""
     torch = engine._torch()
-    n = len(b)
-    model = b.model
-    pp2 = torch.zeros((n, 12), dtype=torch.float64, device="cuda")
-    pp2[:, 0], pp2[:, 1], pp2[:, 2] = b.v_wall, mu_s, mu_b
-    pp2[:, 3], pp2[:, 4] = b.pp[:, 4], b.pp[:, 5]
-    pp2[:, 5] = engine.dev_f64(_per_point(model, n, "a_s"))
-    pp2[:, 6] = engine.dev_f64(_per_point(model, n, "a_b"))
-    pp2[:, 7] = engine.dev_f64(_per_point(model, n, "T_ref"))
-    pp2[:, 8] = 1.0                                               # props.find_phase
-    I = engine.profile_integrals(b.shells, pp2)
-    s = b.scal
-    four_pi_3 = 4 * np.pi / 3
-    vw3 = b.v_wall ** 3
-    wn = b.wn
-    s["va_kinetic_energy_density"] = four_pi_3 * I[:, 0]                                  # thermo.py:169-181
-    s["va_trace_anomaly_diff"] = four_pi_3 * I[:, 1]                                      # :213-221
-    s["va_thermal_energy_density_diff"] = four_pi_3 * 0.75 * I[:, 2]                      # :206-210
-    s["va_entropy_density_diff"] = four_pi_3 * I[:, 3]                                    # :156-166
-    s["wbar"] = I[:, 4]                                                                   # :139-149
-    s["ebar"] = (1 - 1 / mu_s) * wn + b.pp[:, 4]                                          # :89-91 e(wn, symmetric)
-    s["kinetic_energy_density"] = 3 / (4 * np.pi * vw3) * s["va_kinetic_energy_density"]  # :42-46
-    s["kinetic_energy_fraction"] = s["kinetic_energy_density"] / s["ebar"]               # :49-53
-    s["va_thermal_energy_density"] = np.pi * wn * s["v_sh"] ** 3 - s["va_kinetic_energy_density"] \
-        - s["va_trace_anomaly_diff"]                                                     # :191-195
-    s["thermal_energy_density"] = 3 / (4 * np.pi * vw3) * s["va_thermal_energy_density"]  # :56-60
-    s["va_enthalpy_density"] = 4 / 3 * s["thermal_energy_density"]                        # :153-155
-    s["kappa"] = s["va_kinetic_energy_density"] / torch.abs(s["va_trace_anomaly_diff"])   # :94-106
-    s["omega"] = s["va_thermal_energy_density_diff"] / torch.abs(s["va_trace_anomaly_diff"])   # :122-133
-    s["ubarf2"] = s["kinetic_energy_density"] / I[:, 7]                                   # :136 (w[-1])
-    s["mean_adiabatic_index"] = s["wbar"] / s["ebar"]
-    # nu of Giombi et al. at the volume-averaged enthalpy, broken phase (models/model.py:688-698)
-    wq = s["va_enthalpy_density"]
-    om = (wq / mu_b - b.pp[:, 5]) / ((1 - 1 / mu_b) * wq + b.pp[:, 5])
-    s["nu_gdh2024"] = (1 - 3 * om) / (1 + 3 * om)
-    return b
+    if retry not in ("sync", "off"):
+        raise ValueError(f"retry={retry!r}")
+    pt = point_table(model, v_wall, alpha_n, sol_type, allow_invalid)
+    n = pt.wn.size
+    out = engine.sweep_c(None, engine.dev_f64(pt.pg), engine.dev_f64(pt.pm), n_xi=n_xi, t_end=t_end,
+                         thin_shell_limit=thin_shell_limit, wn_rtol=wn_rtol, rows=True, retry=retry == "sync")
+    pg = engine.dev_f64(pt.pg)
+    sol = torch.as_tensor(pt.codes, dtype=torch.int32, device="cuda")
+    shells = engine.ShellBatch(pg[:, 0].contiguous(), pg[:, 1].contiguous(), None, sol, out.status, out.rows[0],
+                               out.rows[1], out.rows[2], out.off, out.npts, out.scalars, n_xi)
+    scal = {name: out.scalars[:, k] for k, name in enumerate(_lib.SWEEP_SCALARS)}
+    mu_s, mu_b = 1 + 1 / pg[:, 9], 1 + 1 / pg[:, 10]
+    pp = engine.point_params(pg[:, 0], torch.sqrt(pg[:, 10]), 1 - 1 / mu_s, 1 - 1 / mu_b, pg[:, 11], pg[:, 12])
+    return BubbleBatch(model, shells, shells.v_wall, shells.alpha_n, engine.dev_f64(pt.wn), sol, out.status, scal, pp,
+                       n_xi, invalid=pt.invalid)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -40,10 +40,12 @@ class _Stages:
         self.enabled = False
         self.launches = 0
         self._ev = []
+        self.c_stage_ms = {}        # stage times reported by the C sweep driver (ptt_sweep_last_stats)
 
     def enable(self, on: bool):
         self.enabled = on
         self._ev = []
+        self.c_stage_ms = {}
 
     class _Ctx:
         def __init__(self, outer, name, launches):
@@ -75,6 +77,10 @@ class _Stages:
             d = out.setdefault(name, {"ms": 0.0, "n": 0})
             d["ms"] += a.elapsed_time(b)
             d["n"] += 1
+        for name, v in self.c_stage_ms.items():
+            d = out.setdefault(name, {"ms": 0.0, "n": 0})
+            d["ms"] += v["ms"]
+            d["n"] += v["n"]
         return out
 
 
@@ -303,6 +309,117 @@ def generic_retry(pg, idx_host, n_xi=N_XI_DEFAULT, t_end=50.0, thin_shell_limit=
     return sub, rescued
 
 
+class SweepOutput:
+    """Result tables of ptt_sweep_spectra: torch tensors (mem="device") or pinned numpy arrays (mem="host")."""
+
+    def __init__(self):
+        self.pow_v = self.pow_gw = self.omgw0 = self.scalars = self.status = None
+        self.rows = self.off = self.npts = None
+        self.stats = None
+        self._keep = []
+
+    def scal(self, name):
+        return self.scalars[:, _lib.SWEEP_SCALARS.index(name)]
+
+
+_LIVE_CALLBACKS = []
+
+
+def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_shell_limit=100, wn_rtol=1e-4, r_star=None,
+            lifetime_multiplier=1.0, chunk=8000, shell_chunk=0, want=("pow_v", "pow_gw", "omgw0"), scalars=True,
+            rows=False, mem="device", retry=True, timing=False, on_chunk=None, out=None) -> SweepOutput:
+    """The whole sweep in one C call (ptt_sweep_spectra, csrc/ptt_sweep.cu): shells, the reference's retries,
+    thermodynamic scalars, A^2, spec_den_v, spec_den_gw, pow_gw, omgw0.  pg[n,16], pm[n,4] as in the C header (host
+    numpy arrays or device tensors according to `mem`); plan: SsmPlan / CPlan or None (shells only).
+    on_chunk(row0, row1, cuda_stream_ptr) is called as chunks are queued for delivery; out: dict of preallocated
+    destination tables (same kind as `mem`) to write into instead of fresh ones."""
+    torch = _torch()
+    lib = _lib.load()
+    host = mem == "host"
+    if mem not in ("host", "device"):
+        raise ValueError(mem)
+    res = SweepOutput()
+    if host:
+        pg_a = np.ascontiguousarray(pg, dtype=np.float64)
+        pm_a = np.ascontiguousarray(pm, dtype=np.float64)
+        sc_a = None if scale is None else np.ascontiguousarray(scale, dtype=np.float64)
+        n = pg_a.shape[0]
+        ptr = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+
+        def alloc(shape, dtype=torch.float64):
+            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+            res._keep.append(t)
+            return t.numpy()
+    else:
+        pg_a, pm_a = dev_f64(pg), dev_f64(pm)
+        sc_a = None if scale is None else dev_f64(scale).reshape(-1)
+        n = pg_a.shape[0]
+        ptr = lambda a: None if a is None else C.c_void_p(a.data_ptr())
+
+        def alloc(shape, dtype=torch.float64):
+            return torch.empty(shape, dtype=dtype, device="cuda")
+    view = None if plan is None else plan.sweep_view()
+    want = tuple(want) if plan is not None else ()
+    if "pow_v" in want and not (view.n_pass == 2 and view.has_y_pass):
+        want = tuple(w for w in want if w != "pow_v")
+    if "omgw0" in want and sc_a is None:
+        want = tuple(w for w in want if w != "omgw0")
+    n_y = int(view.gw.n_y) if view is not None else 0
+    out = out or {}
+    o = _lib.SweepOut()
+    for name in ("pow_v", "pow_gw", "omgw0"):
+        if name in want:
+            t = out.get(name)
+            if t is None:
+                t = alloc((n, n_y))
+            setattr(res, name, t)
+            setattr(o, name, ptr(t))
+    res.status = out.get("status")
+    if res.status is None:
+        res.status = alloc((n,), torch.int32)
+    o.status = ptr(res.status)
+    if scalars:
+        res.scalars = out.get("scalars")
+        if res.scalars is None:
+            res.scalars = alloc((n, _lib.SWEEP_NSCAL))
+        o.scalars = ptr(res.scalars)
+    if rows:
+        if host:
+            raise ValueError("profile rows are returned in device memory only")
+        cap = lib.ptt_generic_row_capacity(n_xi)
+        res.rows = [torch.empty((n, cap), dtype=torch.float64, device="cuda") for _ in range(3)]
+        res.off = torch.empty(n, dtype=torch.int32, device="cuda")
+        res.npts = torch.empty(n, dtype=torch.int32, device="cuda")
+        o.rows_v, o.rows_w, o.rows_xi = (ptr(r) for r in res.rows)
+        o.row_stride = cap
+        o.off, o.npts = ptr(res.off), ptr(res.npts)
+    opts = _lib.SweepOpts(n_xi=int(n_xi), thin_shell_limit=int(thin_shell_limit), chunk=int(chunk),
+                          shell_chunk=int(shell_chunk or 0),
+                          flags=(_lib.SWEEP_TIMING if timing else 0) | (0 if retry else _lib.SWEEP_NO_RETRY),
+                          group_min=int(GROUP_MIN) if USE_GROUPED_SDV else 1 << 30,
+                          t_end=float(t_end), wn_rtol=float(wn_rtol), r_star=-1.0 if r_star is None else float(r_star),
+                          lifetime_multiplier=float(lifetime_multiplier))
+    cb = None
+    if on_chunk is not None:
+        cb = _lib.CHUNK_CB(lambda user, r0, r1, stream: on_chunk(int(r0), int(r1), stream))
+    rc = lib.ptt_sweep_spectra(C.byref(view) if view is not None else None, C.byref(opts), n, ptr(pg_a), ptr(pm_a),
+                               ptr(sc_a), C.byref(o), C.cast(cb, C.c_void_p) if cb is not None else None, None,
+                               _lib.MEM_HOST if host else _lib.MEM_DEVICE, _stream_ptr(torch))
+    _lib.check(rc, "ptt_sweep_spectra")
+    st = _lib.SweepStats()
+    lib.ptt_sweep_last_stats(C.byref(st))
+    res.stats = st
+    STAGES.launches += int(st.launches)
+    if timing:
+        for i, name in enumerate(_lib.STAGE_NAMES):
+            if st.stage_calls[i]:
+                d = STAGES.c_stage_ms.setdefault(name, {"ms": 0.0, "n": 0})
+                d["ms"] += st.stage_ms[i]
+                d["n"] += int(st.stage_calls[i])
+    res._keep += [pg_a, pm_a, sc_a]
+    return res
+
+
 def shell_wall_values(shells: ShellBatch):
     """props.v_and_w_from_solution for a batch of bag shells -> [n,8] = vp, vm, vp_tilde, vm_tilde, wp, wm, wn, 0."""
     torch = _torch()
@@ -515,6 +632,92 @@ class SsmPlan:
     @property
     def n_a2(self):
         return int(self.z_all.size)
+
+    def sweep_view(self) -> "_lib.SweepPlan":
+        """The POD view of this plan that ptt_sweep_spectra takes (include/pttools_b200.h, ptt_sweep_plan_t)."""
+        if self.gw is None:
+            raise ValueError("a sweep needs a plan with the z_lookup pass and the GW tables")
+        v = getattr(self, "_sweep_view", None)
+        if v is not None:
+            return v
+        v = _lib.SweepPlan()
+        v.a2 = self.a2_plan
+        v.n_pass = len(self.passes)
+        v.has_y_pass = int(self.has_y_pass)
+        self._h_zterm = [np.ascontiguousarray(p.zterm, dtype=np.float64) for p in self.passes]
+        for i, p in enumerate(self.passes):
+            v.sdv[i] = self.sdv_plans[i]
+            v.h_zterm[i] = self._h_zterm[i].ctypes.data
+            v.lt_first[i], v.lt_last[i], v.dl[i] = float(p.LT[0]), float(p.LT[-1]), float(p.dl)
+        for i, sg in enumerate(self.seg):
+            v.seg[i] = int(sg)
+        v.gw = self.gw_plan
+        tabs = gw_cells(self) if USE_GW_CELLS else False
+        if tabs:
+            v.cells = tabs[0]
+        self._sweep_view = v
+        return v
+
+
+class CPlan:
+    """A plan built by the library itself (ptt_ssm_plan_create, csrc/ptt_plan.cu): what a C caller of ptt_sweep_spectra
+    uses.  Same grids as SsmPlan to rounding (tests/test_plan_cabi.py)."""
+
+    def __init__(self, y, cs=CS0, nt=NT_DEFAULT, n_z_lookup=NZ_LOOKUP_DEFAULT, nxi=NXI_DEFAULT, z_st_thresh=Z_ST_THRESH,
+                 nuc_type="exponential", a=1.0, gamma=GAMMA_DEFAULT, mode="ssm", phase_rule=-1, nz_int=0, flags=0,
+                 upload=True):
+        lib = _lib.load()
+        self.y = np.ascontiguousarray(y, dtype=np.float64)
+        if nuc_type not in ("exponential", "simultaneous"):
+            raise ValueError("Nucleation type not recognized")
+        d = _lib.PlanDesc(n_y=self.y.size, nt=int(nt), n_z_lookup=int(n_z_lookup), nxi=int(nxi),
+                          nuc_type=int(nuc_type == "simultaneous"), mode={"ssm": 0, "bag": 1}[mode], phase_rule=int(phase_rule),
+                          nz_int=int(nz_int or 0), flags=int(flags), cs=float(cs), z_st_thresh=float(z_st_thresh),
+                          nuc_a=float(a), gamma=float(gamma))
+        self._h = C.c_void_p()
+        if upload:
+            _torch()
+            _lib.check(lib.ptt_ssm_plan_create(C.byref(d), self.y.ctypes.data, C.byref(self._h)), "ptt_ssm_plan_create")
+        else:
+            _lib.check(lib.ptt_ssm_plan_create_host(C.byref(d), self.y.ctypes.data, C.byref(self._h)),
+                       "ptt_ssm_plan_create_host")
+        self.uploaded = upload
+
+    def array(self, name: str) -> np.ndarray:
+        lib = _lib.load()
+        n = lib.ptt_ssm_plan_array(self._h, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype=np.float64)
+        lib.ptt_ssm_plan_array(self._h, name.encode(), out.ctypes.data, n)
+        return out
+
+    def info(self):
+        lib = _lib.load()
+        n_pass = C.c_int32()
+        seg, zt, win, sc = (C.c_int32 * 4)(), (C.c_int32 * 2)(), (C.c_int32 * 2)(), (C.c_double * 8)()
+        _lib.check(lib.ptt_ssm_plan_info(self._h, C.byref(n_pass), seg, zt, win, sc), "ptt_ssm_plan_info")
+        return {"n_pass": n_pass.value, "seg": list(seg)[: n_pass.value + 1], "z_tile": list(zt)[: n_pass.value],
+                "win_entries": list(win)[: n_pass.value], "l0_dl": list(sc)[:4], "z_exact_max": sc[4],
+                "gw_prefactor": sc[5], "gw_lrange": sc[6], "gw_win_entries": int(sc[7])}
+
+    def sweep_view(self) -> "_lib.SweepPlan":
+        ptr = _lib.load().ptt_ssm_plan_view(self._h)
+        if not ptr:
+            raise _lib.PttError("the plan has not been uploaded")
+        return ptr.contents
+
+    @property
+    def has_y_pass(self):
+        return bool(self.sweep_view().has_y_pass)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().ptt_ssm_plan_destroy(h)
+            except Exception:       # interpreter shutdown
+                pass
 
 
 def build_gw_tables(z_lookup, y, cs, gamma=GAMMA_DEFAULT, nz_int=None):

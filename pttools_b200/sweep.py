@@ -31,22 +31,31 @@ class SweepResult:
     omgw0: tp.Any = None
     scalars: tp.Dict[str, tp.Any] = dataclasses.field(default_factory=dict)
 
+    invalid: tp.Any = None
+    stats: tp.Any = None
+
+    def take(self, rows):
+        """The given rows (host int array) as a SweepResult of their own."""
+        def tk(x):
+            if x is None:
+                return None
+            if hasattr(x, "cpu"):
+                import torch
+                return x[torch.as_tensor(np.asarray(rows), device=x.device, dtype=torch.int64)]
+            return np.asarray(x)[rows]
+        r = SweepResult(tk(self.v_wall), tk(self.alpha_n), tk(self.sol_type), tk(self.status), tk(self.alpha_plus), self.y,
+                        pow_gw=tk(self.pow_gw), pow_v=tk(self.pow_v), omgw0=tk(self.omgw0),
+                        scalars={k: tk(v) for k, v in self.scalars.items()})
+        r.invalid = None if self.invalid is None else np.asarray(self.invalid)[rows]
+        return r
+
     def numpy(self):
         def cv(x):
             return x.cpu().numpy() if hasattr(x, "cpu") else x
-        return SweepResult(**{f.name: (cv(getattr(self, f.name)) if f.name != "scalars"
-                                        else {k: cv(v) for k, v in self.scalars.items()})
+        return SweepResult(**{f.name: (cv(getattr(self, f.name)) if f.name not in ("scalars", "stats", "y")
+                                        else ({k: cv(v) for k, v in self.scalars.items()} if f.name == "scalars"
+                                              else getattr(self, f.name)))
                               for f in dataclasses.fields(self)})
-
-
-def shard_indices(n: int, rank: int, world: int, sol_type: tp.Optional[np.ndarray] = None) -> np.ndarray:
-    """Static partition of the points of a sweep over ranks.  Points are dealt cyclically WITHIN each solution-type
-    bucket so that expensive hybrids/deflagrations and cheap detonations are balanced."""
-    idx = np.arange(n)
-    if sol_type is None:
-        return idx[rank::world]
-    order = np.argsort(sol_type, kind="stable")
-    return np.sort(order[rank::world])
 
 
 def bag_classify_host(v_wall: np.ndarray, alpha_n: np.ndarray, an_max: np.ndarray) -> np.ndarray:
@@ -98,231 +107,286 @@ def power_gw_scaled_bag_sweep(v_wall, alpha_n, z, npt=(engine.NXI_DEFAULT, engin
     return SweepResult(vw, an, st, status, ap, z, pow_gw=pow_gw)
 
 
-def shell_chunk_points(n_xi: int, budget_bytes: float = 24e9) -> int:
-    """How many shells to solve per launch: bounded by the profile rows (3 arrays of row_capacity doubles each)."""
-    cap = 5002 + n_xi + 2
+def shell_chunk_points(n_xi: int, budget_bytes: tp.Optional[float] = None) -> int:
+    """How many bag shells to solve per launch: bounded by the profile rows (3 arrays of row_capacity doubles each)
+    against a share of the free device memory."""
+    from . import _lib
+    torch = engine._torch()
+    cap = _lib.load().ptt_profile_row_capacity(n_xi)
+    if budget_bytes is None:
+        budget_bytes = 0.3 * torch.cuda.mem_get_info()[0]
     return int(max(1024, min(65536, budget_bytes // (3 * 8 * cap))))
+
+
+def omgw0_scale(v_wall, alpha_n, r_star, g_star=None, gs_star=None, suppression="default") -> np.ndarray:
+    """Per-point factor r_star * F_gw0 * suppression(v_wall, alpha_n) of Spectrum.omgw0 (omgw0_ssm.py:62-131).  Both
+    in-scope models have non-physical temperatures, so the overrides of the reference apply (g_star_override takes
+    gs_star when g_star is given: omgw0_ssm.py:74, sic)."""
+    from . import omgw0 as om
+    g_eff = om.G_STAR_DEFAULT if g_star is None else gs_star
+    gs_eff = g_eff if gs_star is None else gs_star
+    fgw0 = om.F_gw0(g_star=g_eff, gs_star=gs_eff)
+    if suppression == "default":
+        sup = om.DEFAULT_SUPPRESSION.points(v_wall, alpha_n)
+    elif suppression is None:
+        sup = np.ones_like(v_wall)
+    else:
+        sup = suppression.points(v_wall, alpha_n)
+    return r_star * fgw0 * sup
 
 
 def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multiplier=1.0, nuc_type="exponential",
                   nt=engine.NT_DEFAULT, n_z_lookup=engine.NZ_LOOKUP_DEFAULT, z_st_thresh=engine.Z_ST_THRESH,
                   n_xi=engine.N_XI_DEFAULT, Tn=None, g_star=None, gs_star=None, suppression="default",
-                  chunk=4096, shell_chunk=None, want_pow_v=True, keep_bubbles=False, plan=None) -> SweepResult:
+                  chunk=8000, shell_chunk=None, want_pow_v=True, keep_bubbles=False, plan=None, mem="device",
+                  allow_invalid=False, on_chunk=None, timing=False, out=None, sol_type=None) -> SweepResult:
     """Spectrum(Bubble(model, v_wall, alpha_n), y, r_star=...) for every point of a sweep: the model-independent shell
     solve, the thermodynamic scalars, the SSM chain and Omega_gw,0 (pttools/analysis/parallel.py:157-187 ->
-    bubble.py:232-352 -> ssmtools/spectrum.py:96-115 -> omgw0/omgw0_ssm.py:123-131), one model for all points."""
+    bubble.py:232-352 -> ssmtools/spectrum.py:96-115 -> omgw0/omgw0_ssm.py:123-131) in ONE call of the C ABI
+    (ptt_sweep_spectra).  `model`: one Model, or a sequence with one Model per point that share csb2 (the sound speed of
+    the GW integral, spectrum.py:99).  mem="device": result tables are torch tensors; "host": pinned numpy arrays,
+    streamed out per chunk while the sweep runs.  Points the reference's Bubble constructor rejects come back with
+    status PTT_ST_INVALID_INPUT and NaN rows (`invalid` marks them)."""
     from . import bubble as bub
-    from . import omgw0 as om
+    from .models import Model
     torch = engine._torch()
     to_np = lambda a: a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a, dtype=float)
     vw = to_np(v_wall).astype(float).reshape(-1)
     an = to_np(alpha_n).astype(float).reshape(-1)
-    n = vw.size
-    # Points that share v_wall share the lifetime-convolution weights (K6'): process the sweep sorted by v_wall and
-    # undo the permutation on the way out.
-    perm = np.argsort(vw, kind="stable")
-    sorted_already = bool(np.all(perm == np.arange(n)))
-    if not sorted_already:
-        vw, an = vw[perm], an[perm]
     y = engine.Y_DEFAULT if y is None else np.asarray(y, dtype=float)
-    cs = float(np.sqrt(model.csb2))                                   # spectrum.py:99 (cs2 is constant per phase)
+    if isinstance(model, Model):
+        csb2 = float(model.csb2)
+    else:
+        csb2s = {float(m.csb2) for m in model}
+        if len(csb2s) != 1:
+            raise ValueError("the models of one sweep must share csb2 (it fixes the grids of the GW integral)")
+        csb2 = csb2s.pop()
+    cs = float(np.sqrt(csb2))                                         # spectrum.py:99 (cs2 is constant per phase)
     if plan is None:
         plan = engine.SsmPlan(y, cs=cs, nt=nt, n_z_lookup=n_z_lookup, z_st_thresh=z_st_thresh, nuc_type=nuc_type,
                               a=1.0, mode="ssm", only_lookup_pass=not want_pow_v)
     want_pow_v = want_pow_v and plan.has_y_pass
-    scale = None
-    if r_star is not None:
-        # omgw0_ssm.py:62-131: model temperatures are not physical for both in-scope models -> the overrides apply
-        g_eff = om.G_STAR_DEFAULT if g_star is None else gs_star
-        gs_eff = g_eff if gs_star is None else gs_star
-        fgw0 = om.F_gw0(g_star=g_eff, gs_star=gs_eff)
-        if suppression == "default":
-            sup = om.DEFAULT_SUPPRESSION.points(vw, an)
-        elif suppression is None:
-            sup = np.ones_like(vw)
-        else:
-            sup = suppression.points(vw, an)
-        scale = engine.dev_f64(r_star * fgw0 * sup)
-    dev = "cuda"
-    pow_gw = torch.empty((n, y.size), dtype=torch.float64, device=dev)
-    pow_v = torch.empty((n, y.size), dtype=torch.float64, device=dev) if want_pow_v else None
-    omgw0 = torch.empty((n, y.size), dtype=torch.float64, device=dev) if scale is not None else None
-    status = torch.empty(n, dtype=torch.int32, device=dev)
-    st = torch.empty(n, dtype=torch.int32, device=dev)
-    scal: tp.Dict[str, tp.Any] = {}
-    if shell_chunk is None:
-        shell_chunk = max(chunk, min(n, int(24e9 // (3 * 8 * (2 * n_xi + 4)))))
-    bubbles = []
-    for s0 in range(0, n, shell_chunk):
-        e0 = min(n, s0 + shell_chunk)
-        # Points whose root search fails are retried the way the reference does (varied starts, backup scan); the
-        # retries run on a side stream under the spectrum stages of the other points and are folded in below.
-        bb = bub.sweep_bubbles(model, vw[s0:e0], an[s0:e0], n_xi=n_xi, retry="async")
-        status[s0:e0], st[s0:e0] = bb.status, bb.sol_type
-        for k, v in bb.scal.items():
-            scal.setdefault(k, torch.empty(n, dtype=torch.float64, device=dev))[s0:e0] = v
-
-        def lifetime_factor(b):
-            # source lifetime factor, spectrum.py:123-136
-            nu_ = b.scal["nu_gdh2024"]
-            f = 1 / (1 + 2 * nu_)
-            if r_star is not None and not np.isinf(lifetime_multiplier):
-                f = f * (1 - (1 + lifetime_multiplier * 2 * r_star / torch.sqrt(b.scal["kinetic_energy_fraction"]))
-                         ** (-1 - 2 * nu_))
-            return f
-
-        slf = lifetime_factor(bb)
-        valid = bb.shells.npts.cpu().numpy() >= 3        # has a profile (points flagged solver_failed do, like the reference)
-
-        def run_chunk(s):
-            e = min(e0, s + chunk)
-            sub = bb.shells.slice(s - s0, e - s0)
-            res = engine.spectra_from_shells(plan, sub, bb.pp[s - s0:e - s0].contiguous(),
-                                             slf=slf[s - s0:e - s0].contiguous(),
-                                             scale=None if scale is None else scale[s:e].contiguous(),
-                                             v_wall_host=vw[s:e], valid_host=valid[s - s0:e - s0])
-            pow_gw[s:e] = res.pow_gw
-            if want_pow_v:
-                pow_v[s:e] = res.pow_v
-            if omgw0 is not None:
-                omgw0[s:e] = res.omgw0
-
-        starts = list(range(s0, e0, chunk))
-        n_free = 1
-        if bb.retry_job is not None and len(starts) > 1:
-            # Chunks without retried points go first (at least one chunk does): the retries finish under them and are
-            # written into the batch before the chunks that hold such points start, so only the rescued points of chunks
-            # that have already run need a pass of their own - normally none.
-            where = bb.retry_job.pos + s0
-            cnt = [np.count_nonzero((where >= s) & (where < s + chunk)) for s in starts]
-            order = np.argsort(cnt, kind="stable")
-            starts = [starts[i] for i in order]
-            n_free = max(1, int(np.count_nonzero(np.asarray(cnt) == 0)))
-        for s in starts[:n_free]:
-            run_chunk(s)
-        _, pos = bub.finish_retry(bb)                    # rescued profiles, scalars, status now sit in bb
-        if pos.size:
-            at = torch.as_tensor(pos + s0, device=dev, dtype=torch.int64)
-            here = torch.as_tensor(pos, device=dev, dtype=torch.int64)
-            status[at] = bb.status[here]
-            for k, v in bb.scal.items():
-                scal[k][at] = v[here]
-            slf = lifetime_factor(bb)
-            valid[pos] = True
-        for s in starts[n_free:]:
-            run_chunk(s)
-        done_early = np.zeros(pos.shape, dtype=bool)
-        for s in starts[:n_free]:
-            done_early |= (pos + s0 >= s) & (pos + s0 < s + chunk)
-        late = pos[done_early]
-        if late.size:
-            here = torch.as_tensor(late, device=dev, dtype=torch.int64)
-            at = here + s0
-            res = engine.spectra_from_shells(plan, bb.shells.take(here), bb.pp[here].contiguous(),
-                                             slf=slf[here].contiguous(),
-                                             scale=None if scale is None else scale[at].contiguous(),
-                                             v_wall_host=vw[late + s0], valid_host=np.ones(late.size, dtype=bool))
-            pow_gw[at] = res.pow_gw
-            if want_pow_v:
-                pow_v[at] = res.pow_v
-            if omgw0 is not None:
-                omgw0[at] = res.omgw0
-        if keep_bubbles:
-            bubbles.append(bb)
-    if not sorted_already:
-        if keep_bubbles:
-            raise NotImplementedError("keep_bubbles needs points ordered by v_wall (grid sweeps are)")
-        inv = torch.as_tensor(np.argsort(perm), device=dev)
-        unperm = lambda t: None if t is None else t[inv]
-        pow_gw, pow_v, omgw0, status, st = (unperm(t) for t in (pow_gw, pow_v, omgw0, status, st))
-        scal = {k: v[inv] for k, v in scal.items()}
-        vw, an = vw[np.argsort(perm)], an[np.argsort(perm)]
-    out = SweepResult(engine.dev_f64(vw), engine.dev_f64(an), st, status, None, y, pow_gw=pow_gw, pow_v=pow_v,
-                      omgw0=omgw0, scalars=scal)
+    pt = bub.point_table(model, vw, an, sol_type=sol_type, allow_invalid=allow_invalid)
+    scale = None if r_star is None else omgw0_scale(vw, an, r_star, g_star, gs_star, suppression)
+    want = (("pow_v",) if want_pow_v else ()) + ("pow_gw",) + (("omgw0",) if scale is not None else ())
+    if mem == "device":
+        pg_in, pm_in = engine.dev_f64(pt.pg), engine.dev_f64(pt.pm)
+        sc_in = None if scale is None else engine.dev_f64(scale)
+    else:
+        pg_in, pm_in, sc_in = pt.pg, pt.pm, scale
+    res = engine.sweep_c(plan, pg_in, pm_in, sc_in, n_xi=n_xi, r_star=r_star, lifetime_multiplier=lifetime_multiplier,
+                         chunk=chunk, shell_chunk=shell_chunk or 0, want=want, rows=keep_bubbles, mem=mem,
+                         on_chunk=on_chunk, timing=timing, out=out)
+    from . import _lib
+    scal = {name: res.scalars[:, k] for k, name in enumerate(_lib.SWEEP_SCALARS)}
+    asdev = (lambda a: a) if mem == "host" else engine.dev_f64
+    codes = pt.codes if mem == "host" else torch.as_tensor(pt.codes, dtype=torch.int32, device="cuda")
+    out_ = SweepResult(asdev(vw), asdev(an), codes, res.status, None, y, pow_gw=res.pow_gw, pow_v=res.pow_v,
+                       omgw0=res.omgw0, scalars=scal)
+    out_.invalid = pt.invalid
+    out_.stats = res.stats
+    out_._keep = res
     if keep_bubbles:
-        out.bubbles = bubbles
-    return out
+        pg = engine.dev_f64(pt.pg)
+        sol = torch.as_tensor(pt.codes, dtype=torch.int32, device="cuda")
+        shells = engine.ShellBatch(pg[:, 0].contiguous(), pg[:, 1].contiguous(), None, sol, res.status, res.rows[0],
+                                   res.rows[1], res.rows[2], res.off, res.npts, res.scalars, n_xi)
+        out_.bubbles = bub.BubbleBatch(model, shells, shells.v_wall, shells.alpha_n, engine.dev_f64(pt.wn), sol,
+                                       res.status, scal, None, n_xi, invalid=pt.invalid)
+    return out_
 
 
 def sweep_models(models, v_walls, alpha_ns, y=None, rank: int = 0, world: int = 1, **kw) -> tp.List[tp.Dict[str, tp.Any]]:
     """Spectra for several models on one (v_wall, alpha_n) grid - the multi-model sweeps of the reference's
     examples/const_cs/const_cs_gw.py:153-187 (create_spectra once per model).  Per model the grid is restricted to
-    alpha_n >= model.alpha_n_min (Bubble raises below it, model.py:813-823); points are ordered v_wall-major so that
-    the grouped spec_den_v path applies; plans are shared between models with the same broken-phase sound speed.
-    With world > 1 the MODELS are dealt over the ranks (each model's sweep stays on one GPU).
-    Returns one dict per model of this rank: {"model", "index", "mask" [n_alpha, n_vw], "result" SweepResult with rows
-    in v_wall-major order of the masked grid, "i_alpha", "i_vw" row -> grid indices}."""
+    alpha_n >= model.alpha_n_min (Bubble raises below it, model.py:813-823).  Models that share the broken-phase sound
+    speed share the grids of the spectrum chain AND the lifetime-convolution weights of K6' (they depend on v_wall and
+    csb2 only), so each such family runs as ONE sweep ordered by v_wall: a group of K6' then holds the profiles of all
+    its models.  With world > 1 the v_wall rows of every family are dealt over the ranks.
+    Returns one dict per model: {"model", "index", "mask" [n_alpha, n_vw], "result" SweepResult with rows in v_wall-major
+    order of the masked grid (None if the model has no point on this rank), "i_alpha", "i_vw" row -> grid indices}."""
     v_walls = np.asarray(v_walls, dtype=float)
     alpha_ns = np.asarray(alpha_ns, dtype=float)
     y = engine.Y_DEFAULT if y is None else np.asarray(y, dtype=float)
-    plans: tp.Dict[tp.Tuple, engine.SsmPlan] = {}
-    out = []
-    for im, model in enumerate(models):
-        if im % world != rank:
+    my_vw = np.arange(v_walls.size)[rank::world]
+    families: tp.Dict[float, tp.List[int]] = {}
+    for im, m in enumerate(models):
+        families.setdefault(round(float(m.csb2), 15), []).append(im)
+    out = [None] * len(models)
+    for _, members in families.items():
+        blocks = []
+        for im in members:
+            ok_alpha = np.nonzero(alpha_ns >= models[im].alpha_n_min)[0]
+            i_vw, i_al = np.meshgrid(my_vw, ok_alpha, indexing="ij")                  # v_wall-major
+            blocks.append((im, i_vw.ravel(), i_al.ravel()))
+        im_all = np.concatenate([np.full(b[1].size, b[0]) for b in blocks])
+        ivw_all = np.concatenate([b[1] for b in blocks])
+        ial_all = np.concatenate([b[2] for b in blocks])
+        if im_all.size == 0:
+            for im, i_vw, i_al in blocks:
+                out[im] = {"model": models[im], "index": im, "mask": np.zeros((alpha_ns.size, v_walls.size), bool),
+                           "result": None, "i_alpha": i_al, "i_vw": i_vw}
             continue
-        ok_alpha = alpha_ns >= model.alpha_n_min
-        i_vw, i_al = np.meshgrid(np.arange(v_walls.size), np.nonzero(ok_alpha)[0], indexing="ij")     # v_wall-major
-        i_vw, i_al = i_vw.ravel(), i_al.ravel()
-        key = (round(float(model.csb2), 15), kw.get("nt", engine.NT_DEFAULT), kw.get("n_z_lookup", engine.NZ_LOOKUP_DEFAULT),
-               kw.get("z_st_thresh", engine.Z_ST_THRESH), kw.get("nuc_type", "exponential"))
-        if key not in plans:
-            plans[key] = engine.SsmPlan(y, cs=float(np.sqrt(model.csb2)), nt=key[1], n_z_lookup=key[2], z_st_thresh=key[3],
-                                        nuc_type=key[4], a=1.0, mode="ssm",
-                                        only_lookup_pass=not kw.get("want_pow_v", True))
-        res = sweep_spectra(model, v_walls[i_vw], alpha_ns[i_al], y=y, plan=plans[key], **kw) if i_vw.size else None
-        mask = np.zeros((alpha_ns.size, v_walls.size), dtype=bool)
-        mask[i_al, i_vw] = True
-        out.append({"model": model, "index": im, "mask": mask, "result": res, "i_alpha": i_al, "i_vw": i_vw})
+        order = np.argsort(v_walls[ivw_all], kind="stable")       # all models' profiles of one wall speed together
+        per_point = [models[i] for i in im_all[order]]
+        res = sweep_spectra(per_point, v_walls[ivw_all[order]], alpha_ns[ial_all[order]], y=y, **kw)
+        inv = np.empty_like(order)
+        inv[order] = np.arange(order.size)
+        start = 0
+        for im, i_vw, i_al in blocks:
+            rows = inv[start:start + i_vw.size]
+            start += i_vw.size
+            mask = np.zeros((alpha_ns.size, v_walls.size), dtype=bool)
+            mask[i_al, i_vw] = True
+            out[im] = {"model": models[im], "index": im, "mask": mask, "result": res.take(rows) if rows.size else None,
+                       "i_alpha": i_al, "i_vw": i_vw}
     return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# Multi-GPU: static sharding, no collective in the solve, one gather of the result table at the end
+# Multi-GPU: whole v_wall rows per rank, no collective in the solve, result blocks sent to the root as they finish
 # ---------------------------------------------------------------------------------------------------------------
 
-def distributed_table(compute: tp.Callable[[np.ndarray], "np.ndarray | tp.Any"], n_points: int, n_cols: int,
-                      sol_type: tp.Optional[np.ndarray] = None, device: str = "cuda", dst: int = 0):
-    """Runs `compute(indices) -> [len(indices), n_cols] float64 tensor` on this rank's shard of range(n_points) and
-    gathers the full [n_points, n_cols] table on rank `dst` (None elsewhere).
+def shard_rows(v_wall: np.ndarray, cost: tp.Optional[np.ndarray], world: int) -> tp.List[np.ndarray]:
+    """Static partition of the points of a sweep over `world` ranks by WHOLE v_wall ROWS: all points that share a wall
+    speed stay on one rank, because they share the lifetime-convolution weights of K6' (one banded matrix product per
+    wall speed).  Rows are dealt greedily, most expensive first, to the least loaded rank (cost[i] = estimated cost of
+    point i; None = 1).  Returns per rank the point indices, ordered by (v_wall, original index)."""
+    v_wall = np.asarray(v_wall, dtype=float).reshape(-1)
+    n = v_wall.size
+    cost = np.ones(n) if cost is None else np.asarray(cost, dtype=float).reshape(-1)
+    uniq, inv = np.unique(v_wall, return_inverse=True)
+    row_cost = np.bincount(inv, weights=cost, minlength=uniq.size)
+    owner = np.empty(uniq.size, dtype=np.int64)
+    load = np.zeros(world)
+    for r in np.argsort(-row_cost, kind="stable"):
+        k = int(np.argmin(load))
+        owner[r] = k
+        load[k] += row_cost[r]
+    point_owner = owner[inv]
+    order = np.lexsort((np.arange(n), v_wall))
+    return [order[point_owner[order] == k] for k in range(world)]
 
-    Every (v_wall, alpha_n, model) point is independent (the reference maps one future per point,
-    speedup/parallel.py:134-137), so the ranks never talk during the solve; the only exchange step is the final
-    gather (NCCL over NVLink on a GPU box, gloo in the CPU tests).  Works without torch.distributed initialised
-    (single process)."""
+
+def point_cost(codes: np.ndarray) -> np.ndarray:
+    """Relative cost of a point from its solution type code: points without a solution (-1) skip the spectrum chain."""
+    return np.where(np.asarray(codes) < 0, 0.05, 1.0)
+
+
+def distributed_table(local_compute: tp.Callable, shards: tp.List[np.ndarray], n_cols: int, block: int, device="cuda",
+                      dst: int = 0, dtype=None):
+    """Runs `local_compute(idx, out, on_chunk)` on this rank's shard and assembles the full [n_points, n_cols] table on
+    rank `dst` (None elsewhere).  `local_compute` fills out[r0:r1] for row ranges of its shard in any order and calls
+    on_chunk(r0, r1, cuda_stream_ptr_or_None) when a range has been queued; ranges never straddle a multiple of
+    `block`.  Completed blocks are sent to `dst` while the rest of the shard is still being computed (point-to-point,
+    NCCL over NVLink on a GPU box, gloo in the CPU tests): the exchange hides under the compute except for the last
+    block.  Every (v_wall, alpha_n, model) point is independent (the reference maps one future per point,
+    speedup/parallel.py:134-137), so there is no other communication."""
     import torch
     import torch.distributed as dist
+    dtype = dtype or torch.float64
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
-    mine = shard_indices(n_points, rank, world, sol_type)
-    block = compute(mine)
-    block = torch.as_tensor(block, dtype=torch.float64, device=device).reshape(len(mine), n_cols)
-    if world == 1:
-        out = torch.empty((n_points, n_cols), dtype=torch.float64, device=device)
-        out[torch.as_tensor(mine, device=device)] = block
-        return out
-    # shards differ by at most one row: pad to a common size so that a plain gather can be used
-    rows = (n_points + world - 1) // world
-    padded = torch.zeros((rows, n_cols), dtype=torch.float64, device=device)
-    padded[: len(mine)] = block
-    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
-    dist.gather(padded, bufs, dst=dst)
+    mine = shards[rank]
+    n_points = int(sum(len(s) for s in shards))
+    local = torch.empty((len(mine), n_cols), dtype=dtype, device=device)
+    blocks = lambda m: [(a, min(a + block, m)) for a in range(0, m, block)]
+    works = []
+    recv = {}
+    use_cuda = torch.device(device).type == "cuda"
+    if world > 1 and rank == dst:
+        # post every receive up front, block by block round-robin over the senders
+        recv = {r: torch.empty((len(shards[r]), n_cols), dtype=dtype, device=device) for r in range(world) if r != dst}
+        todo = {r: blocks(len(shards[r])) for r in recv}
+        k = 0
+        while any(k < len(b) for b in todo.values()):
+            for r, b in todo.items():
+                if k < len(b):
+                    works.append(dist.irecv(recv[r][b[k][0]:b[k][1]], src=r))
+            k += 1
+    my_blocks = blocks(len(mine))
+    done = np.zeros(len(my_blocks), dtype=np.int64)      # rows delivered per block
+    next_block = [0]
+
+    def on_chunk(r0, r1, stream):
+        if world == 1 or rank == dst:
+            return
+        done[r0 // block] += r1 - r0
+        while next_block[0] < len(my_blocks):
+            a, b = my_blocks[next_block[0]]
+            if done[next_block[0]] < b - a:
+                break
+            if use_cuda and stream:
+                with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+                    works.append(dist.isend(local[a:b], dst=dst))
+            else:
+                works.append(dist.isend(local[a:b], dst=dst))
+            next_block[0] += 1
+
+    local_compute(mine, local, on_chunk)
+    if world > 1 and rank != dst:
+        # whatever the callbacks have not covered (a compute that never called back) goes now
+        while next_block[0] < len(my_blocks):
+            a, b = my_blocks[next_block[0]]
+            works.append(dist.isend(local[a:b], dst=dst))
+            next_block[0] += 1
+    for w in works:
+        w.wait()
     if rank != dst:
         return None
-    out = torch.empty((n_points, n_cols), dtype=torch.float64, device=device)
-    for r in range(world):
-        idx = shard_indices(n_points, r, world, sol_type)
-        out[torch.as_tensor(idx, device=device)] = bufs[r][: len(idx)]
+    out = torch.empty((n_points, n_cols), dtype=dtype, device=device)
+    out[torch.as_tensor(mine, device=device)] = local
+    for r, buf in recv.items():
+        out[torch.as_tensor(shards[r], device=device)] = buf
     return out
 
 
-def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, **kw):
-    """10^6-point style sweep sharded over the ranks of torch.distributed: Omega_gw,0(f) table [n, n_y] on rank 0."""
+LAST_LOCAL: tp.Dict[str, tp.Any] = {}      # the SweepResult of this rank's shard of the last distributed sweep (statistics)
+
+
+def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, chunk=8000, dst=0, table="omgw0", mem="device",
+                            **kw):
+    """The 10^6-point sweep of BASELINE.json config 5, sharded over the ranks of torch.distributed (one process per
+    GPU): Omega_gw,0(f) table [n, n_y] on rank `dst` with rows in the order of the input points (None on the other
+    ranks).  Whole v_wall rows per rank (shard_rows), cost-balanced by the closed-form solution types; finished chunks
+    travel to `dst` while the next ones are computed.
+    mem="host": no exchange; every rank returns (indices of its shard, its [n_shard, n_y] block in pinned host memory),
+    streamed out of the device chunk by chunk -- the host-side form of a sharded table."""
+    from . import bubble as bub
+    from .models import Model
     vw = np.asarray(v_wall, dtype=float).reshape(-1)
     an = np.asarray(alpha_n, dtype=float).reshape(-1)
     y = engine.Y_DEFAULT if y is None else np.asarray(y, dtype=float)
-    codes = model.solution_type_codes(vw, an, np.asarray(model.wn(an), dtype=float))
+    single = isinstance(model, Model)
+    if single:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            codes = np.array(model.solution_type_codes(vw, an, np.asarray(model.wn(an), dtype=float)), dtype=np.int64)
+        codes[(an < model.alpha_n_min)] = -1
+        cost = point_cost(codes)
+    else:
+        cost = None
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    shards = shard_rows(vw, cost, world)
+    torch = engine._torch()
+    # shell chunks that are multiples of the spectrum chunk keep every delivered range inside one block of `chunk` rows
+    from . import _lib
+    sc = int(_lib.load().ptt_sweep_shell_chunk(kw.get("n_xi", engine.N_XI_DEFAULT), int(torch.cuda.mem_get_info()[0])))
+    sc = max(chunk, sc // chunk * chunk)
 
-    def compute(idx):
-        return sweep_spectra(model, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False, **kw).omgw0
+    def local_compute(idx, out, on_chunk):
+        if len(idx) == 0:
+            return
+        m = model if single else [model[i] for i in idx]
+        LAST_LOCAL["result"] = sweep_spectra(m, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False, chunk=chunk,
+                                             shell_chunk=sc, on_chunk=on_chunk, out={table: out}, **kw)
 
-    return distributed_table(compute, vw.size, y.size, sol_type=codes)
+    if mem == "host":
+        rank = dist.get_rank() if world > 1 else 0
+        idx = shards[rank]
+        m = model if single else [model[i] for i in idx]
+        res = sweep_spectra(m, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False, chunk=chunk, shell_chunk=sc,
+                            mem="host", **kw)
+        LAST_LOCAL["result"] = res
+        return idx, getattr(res, table)
+    return distributed_table(local_compute, shards, y.size, chunk, dst=dst)

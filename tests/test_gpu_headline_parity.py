@@ -1,0 +1,129 @@
+"""GPU parity on the bench workload itself, against the REAL reference (imported in the build container, default
+LSODA and tight LSODA side by side: tools/make_golden.py::headline_grid / config3_grid).
+
+* 256 points of the 1000 x 1000 grid of BASELINE.json configs 2/5, BagModel(alpha_n_min=0.005), Bubble +
+  Spectrum(r_star=0.1) at the reference's default sizes;
+* config 3: 4 x 16 points of ConstCSModel(css2, csb2, a_s=5, a_b=1, V_s=1, alpha_n_min=0.05), Spectrum(r_star=0.1,
+  Tn=200) (examples/const_cs/const_cs_gw.py:138-184).
+
+Bars (north star): profiles and shell scalars 1e-6, spectra and omgw0 1e-5.  The reference's own results move when its
+LSODA tolerance is tightened (its integrator noise) -- recorded per point and per quantity in the
+fixture.  A point may exceed a bar only up to TWICE that measured noise; every such point is listed in the audit
+(gpurun_out/r02_parity_audit*.json, copied to profiles/)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from util_compare import curve_errors
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+PROFILE_TOL, SPEC_TOL = 1e-6, 1e-5
+# shell scalars that are differences of nearly equal numbers amplify the 1e-7 profile agreement (w_n / (w - w_n)): they
+# are held to the same rule, their noise is in the fixture
+SCALARS_1E6 = ("wn", "vp", "vm", "vp_tilde", "vm_tilde", "v_sh", "wp", "wm", "kappa", "kinetic_energy_fraction",
+               "va_enthalpy_density", "ubarf2", "wbar", "omega")
+
+
+def _audit(name, model, d, prefix, spectrum_kwargs, audit):
+    from pttools_b200 import sweep
+    pts = d[f"{prefix}points"]
+    names = list(d[f"{prefix}scalar_names"])
+    ydec = int(d["y_dec"][0])
+    res = sweep.sweep_spectra(model, pts[:, 0], pts[:, 1], keep_bubbles=True, **spectrum_kwargs)
+    bb = res.bubbles
+    r = res.numpy()
+    err, flags, noise = d[f"{prefix}err"], d[f"{prefix}flags"], d[f"{prefix}noise"]
+    entry = {"points": int(len(pts)), "reference_rejects": int((err == 1).sum()), "reference_no_solution": int((err == 2).sum()),
+             "flag_mismatches": [], "npts_mismatches": [], "over_bar_within_2x_noise": [], "violations": [],
+             "worst": {"curve_v": 0.0, "curve_w": 0.0, "scalar": 0.0, "pow_v": 0.0, "pow_gw": 0.0, "omgw0": 0.0}}
+
+    def check(i, what, dev, tol, ns):
+        key = what.split(":")[0]
+        entry["worst"][key] = max(entry["worst"].get(key, 0.0), float(dev))
+        if dev <= tol:
+            return
+        rec = {"point": [float(pts[i, 0]), float(pts[i, 1])], "what": what, "deviation": float(dev), "bar": tol,
+               "reference_noise": None if not np.isfinite(ns) else float(ns)}
+        if np.isfinite(ns) and dev <= 2 * ns:
+            entry["over_bar_within_2x_noise"].append(rec)
+        else:
+            entry["violations"].append(rec)
+
+    for i, (vw, an) in enumerate(pts):
+        if err[i] == 1:            # the reference's constructor raises
+            assert r.invalid[i] and r.status[i] == 4, (vw, an)
+            continue
+        solved = r.status[i] in (0, 5)
+        if err[i] == 2 or not solved:
+            if (err[i] == 2) != (not solved):
+                entry["flag_mismatches"].append({"point": [float(vw), float(an)], "ours_status": int(r.status[i]),
+                                                 "reference_err": float(err[i])})
+            continue
+        fl = flags[i]
+        assert int(r.sol_type[i]) == int(fl[0])
+        if bool(fl[1]) != (r.status[i] == 5):
+            entry["flag_mismatches"].append({"point": [float(vw), float(an)], "ours_solver_failed": bool(r.status[i] == 5),
+                                             "reference_solver_failed": bool(fl[1])})
+        if int(fl[7]) != int(r.scalars["npts"][i]):
+            entry["npts_mismatches"].append({"point": [float(vw), float(an)], "ours": int(r.scalars["npts"][i]),
+                                             "reference": int(fl[7]), "reference_tight_differs": bool(noise[i, 6])})
+        gv, gw, gx = bb.shells.profile(i)
+        ev, ew = curve_errors(gx, gv, gw, d[f"{prefix}xi_{i}"], d[f"{prefix}v_{i}"], d[f"{prefix}w_{i}"], vw)
+        check(i, "curve_v", ev, PROFILE_TOL, noise[i, 3])
+        check(i, "curve_w", ew, PROFILE_TOL, noise[i, 4])
+        sc_noise = d[f"{prefix}scal_noise_{i}"] if f"{prefix}scal_noise_{i}" in d else np.full(len(names), np.nan)
+        ref_sc = dict(zip(names, d[f"{prefix}scal"][i]))
+        for k, nm in enumerate(names):
+            if nm not in SCALARS_1E6 or ref_sc[nm] == 0:
+                continue
+            check(i, f"scalar:{nm}", abs(float(r.scalars[nm][i]) / ref_sc[nm] - 1), PROFILE_TOL, sc_noise[k])
+        for k, nm in enumerate(("pow_v", "pow_gw", "omgw0")):
+            ref = d[f"{prefix}{nm}_{i}"]
+            got = getattr(r, nm)[i][::ydec]
+            if not np.all(np.isfinite(ref)):        # outside the suppression data (NaN in the reference too)
+                assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+                continue
+            check(i, nm, float(np.max(np.abs(got / ref - 1))), SPEC_TOL, noise[i, k])
+    audit[name] = entry
+    return entry
+
+
+def _write(audit, fname):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, fname), "w") as f:
+        json.dump(audit, f, indent=1)
+
+
+def test_headline_grid_against_the_reference():
+    from pttools_b200.models import BagModel
+    d = np.load(os.path.join(GOLDEN, "ref_headline_grid.npz"))
+    model = BagModel(alpha_n_min=0.005)
+    np.testing.assert_allclose([model.a_s, model.a_b, model.V_s, model.V_b], d["model"], rtol=1e-14)
+    audit = {}
+    e = _audit("headline_grid", model, d, "", {"r_star": 0.1}, audit)
+    _write(audit, "r02_parity_audit_headline.json")
+    print(json.dumps({k: v for k, v in e.items() if k != "over_bar_within_2x_noise"}, indent=1))
+    print("over the bar but within 2x the reference's own noise:", len(e["over_bar_within_2x_noise"]))
+    assert not e["violations"], e["violations"][:5]
+    assert len(e["flag_mismatches"]) <= 2, e["flag_mismatches"]
+
+
+def test_config3_grid_against_the_reference():
+    from pttools_b200.models import ConstCSModel
+    d = np.load(os.path.join(GOLDEN, "ref_config3_grid.npz"))
+    audit = {}
+    for im in range(4):
+        mm = d[f"m{im}__model"]
+        model = ConstCSModel(css2=mm[0], csb2=mm[1], a_s=5, a_b=1, V_s=1, alpha_n_min=0.05)
+        np.testing.assert_allclose([model.a_s, model.a_b, model.V_s, model.V_b, model.T_ref, model.alpha_n_min], mm[2:], rtol=1e-9)
+        e = _audit(f"config3_model{im}_css2={mm[0]:.4f}_csb2={mm[1]:.4f}", model, d, f"m{im}__", {"r_star": 0.1, "Tn": 200}, audit)
+        print(json.dumps({k: v for k, v in e.items() if k != "over_bar_within_2x_noise"}, indent=1))
+    _write(audit, "r02_parity_audit_config3.json")
+    for name, e in audit.items():
+        assert not e["violations"], (name, e["violations"][:5])
+        assert not e["flag_mismatches"], (name, e["flag_mismatches"])

@@ -267,6 +267,151 @@ TASKS.update({"retry_points": retry_points, "constcs_alpha_n_min": constcs_alpha
               "generic_spectra": generic_spectra, "suppression_ssm": suppression_ssm})
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Round 2: the bench grid itself (config 2/5) and config 3, default LSODA and tight LSODA side by side
+# ---------------------------------------------------------------------------------------------------------------
+
+GRID_SCALARS = ["wn", "vp", "vm", "vp_tilde", "vm_tilde", "v_sh", "wp", "wm", "kappa", "omega", "kinetic_energy_fraction",
+                "va_enthalpy_density", "ubarf2", "wbar"]
+Y_DEC = 4            # spectra are stored at y[::Y_DEC]
+PROFILE_DEC = 24     # profiles are stored at every PROFILE_DEC-th sample (probes against the other curve)
+
+
+class _tight_lsoda:
+    """Runs the reference with scipy.integrate.odeint at rtol = atol = 1e-12 instead of its default 1.49e-8 (the
+    reference passes no tolerances, bubble/integrate.py:180): the difference to the default run estimates the
+    reference's own integrator noise."""
+
+    def __enter__(self):
+        import scipy.integrate as spi
+        self.spi, self.orig = spi, spi.odeint
+
+        def tight(func, y0, t, args=(), **kw):
+            kw.setdefault("rtol", 1e-12)
+            kw.setdefault("atol", 1e-12)
+            kw.setdefault("mxstep", 50000)
+            return self.orig(func, y0, t, args=args, **kw)
+        spi.odeint = tight
+        from pttools.bubble import boundary
+        boundary.solve_junction_internal.cache_clear()
+        return self
+
+    def __exit__(self, *exc):
+        self.spi.odeint = self.orig
+        return False
+
+
+def _decimate(a, step=PROFILE_DEC):
+    idx = np.unique(np.concatenate([np.arange(0, a.size, step), np.arange(min(4, a.size)), np.arange(max(0, a.size - 4), a.size)]))
+    return idx
+
+
+def _one_point(model, vw, an, spectrum_kwargs):
+    """The reference's Bubble + Spectrum at one point -> dict (or {"err": code})."""
+    from pttools.bubble import Bubble
+    from pttools.omgw0 import Spectrum
+    codes = {"Subsonic deflagration": 0, "Hybrid": 1, "Detonation": 2}
+    try:
+        b = Bubble(model, vw, an)
+    except Exception as e:      # noqa: BLE001 - the constructor rejects the point (alpha_n range, solution type)
+        return {"err": 1.0, "msg": type(e).__name__}
+    if not b.solved:
+        return {"err": 2.0}
+    s = Spectrum(b, **spectrum_kwargs)
+    return {"flags": np.array([codes[b.sol_type.value], b.solver_failed, b.no_solution_found, b.numerical_error,
+                               b.unphysical_alpha_plus, b.negative_entropy_flux, b.negative_net_entropy_change,
+                               b.v.size], dtype=float),
+            "scal": np.array([float(getattr(b, k)) for k in GRID_SCALARS]),
+            "v": b.v, "w": b.w, "xi": b.xi, "pow_v": s.pow_v, "pow_gw": s.pow_gw, "omgw0": s.omgw0(),
+            "misc": np.array([s.cs, s.source_lifetime_factor, s.F_gw0(), s.f_star0, s.suppression_factor()])}
+
+
+def _grid_fixture(model, points, spectrum_kwargs, prefix, d):
+    """Default-LSODA and tight-LSODA runs of the reference at `points`; stores the default run (decimated) and, per
+    point, how far the tight run is from it (= the reference's own integrator noise)."""
+    import logging
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT), ""))
+    from util_compare import curve_errors
+    logging.disable(logging.CRITICAL)
+    n = len(points)
+    d[f"{prefix}points"] = np.array(points)
+    d[f"{prefix}scalar_names"] = np.array(GRID_SCALARS)
+    err = np.zeros(n)
+    flags = np.full((n, 8), np.nan)
+    scal = np.full((n, len(GRID_SCALARS)), np.nan)
+    misc = np.full((n, 5), np.nan)
+    noise = np.full((n, 8), np.nan)   # pow_v, pow_gw, omgw0, curve v, curve w, scalars(max), npts differs, flags differ
+    for i, (vw, an) in enumerate(points):
+        r = _one_point(model, vw, an, spectrum_kwargs)
+        if "err" in r:
+            err[i] = r["err"]
+            print(prefix, i, vw, an, "no bubble", r)
+            continue
+        with _tight_lsoda():
+            t = _one_point(model, vw, an, spectrum_kwargs)
+        from pttools.bubble import boundary
+        boundary.solve_junction_internal.cache_clear()
+        flags[i], scal[i], misc[i] = r["flags"], r["scal"], r["misc"]
+        idx = _decimate(r["v"])
+        for k in ("v", "w", "xi"):
+            d[f"{prefix}{k}_{i}"] = r[k][idx]
+        for k in ("pow_v", "pow_gw", "omgw0"):
+            d[f"{prefix}{k}_{i}"] = r[k][::Y_DEC]
+        if "err" in t:
+            noise[i, 7] = 1.0
+            print(prefix, i, vw, an, "tight run has no bubble")
+            continue
+        rel = lambda a, b: float(np.nanmax(np.abs(a / b - 1))) if np.all(np.isfinite(b)) else np.nan
+        ev, ew = curve_errors(t["xi"], t["v"], t["w"], r["xi"], r["v"], r["w"], vw)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            noise[i] = [rel(t["pow_v"], r["pow_v"]), rel(t["pow_gw"], r["pow_gw"]), rel(t["omgw0"], r["omgw0"]), ev, ew,
+                        float(np.nanmax(np.abs(t["scal"] / r["scal"] - 1))), float(t["flags"][7] != r["flags"][7]),
+                        float(np.any(t["flags"][:7] != r["flags"][:7]))]
+            d[f"{prefix}scal_noise_{i}"] = np.abs(t["scal"] / r["scal"] - 1)
+        print(prefix, i, f"{vw:.4f} {an:.4f}", int(r["flags"][0]), int(r["flags"][7]), "noise", " ".join(f"{x:.1e}" for x in noise[i]),
+              flush=True)
+    d[f"{prefix}err"], d[f"{prefix}flags"], d[f"{prefix}scal"], d[f"{prefix}misc"], d[f"{prefix}noise"] = err, flags, scal, misc, noise
+    logging.disable(logging.NOTSET)
+
+
+def headline_grid():
+    """256 points of the bench grid (BASELINE.json configs 2/5): v_wall = linspace(0.05, 0.95, 1000)[iv] x
+    alpha_n = linspace(0.005, 0.5, 1000)[ia], a 16 x 16 sub-lattice that includes the edges of the grid;
+    BagModel(alpha_n_min=0.005), Bubble + Spectrum(r_star=0.1) at the reference's default sizes."""
+    from pttools.models import BagModel
+    model = BagModel(alpha_n_min=0.005)
+    v_walls, alpha_ns = np.linspace(0.05, 0.95, 1000), np.linspace(0.005, 0.5, 1000)
+    iv = np.linspace(0, 999, 16).astype(int)
+    ia = np.linspace(0, 999, 16).astype(int)
+    pts = [(float(v_walls[a]), float(alpha_ns[b])) for a in iv for b in ia]
+    d = {"iv": iv, "ia": ia, "y_dec": np.array([Y_DEC]), "model": np.array([model.a_s, model.a_b, model.V_s, model.V_b])}
+    _grid_fixture(model, pts, {"r_star": 0.1}, "", d)
+    np.savez_compressed(os.path.join(OUT, "ref_headline_grid.npz"), **d)
+    print("ref_headline_grid.npz", len(pts))
+
+
+def config3_grid():
+    """Config 3 as the reference's example builds it (examples/const_cs/const_cs_gw.py:138-184):
+    ConstCSModel(css2, csb2, a_s=5, a_b=1, V_s=1, alpha_n_min=0.05) for css2, csb2 in {1/3, 1/4}, Spectrum(r_star=0.1,
+    Tn=200); 4 models x 16 points of the 128 x 128 grid v_wall = linspace(0.05, 0.95, 128) x alpha_n = linspace(0.05,
+    0.5, 128)."""
+    from pttools.models import ConstCSModel
+    v_walls, alpha_ns = np.linspace(0.05, 0.95, 128), np.linspace(0.05, 0.5, 128)
+    iv = np.array([3, 40, 77, 120])
+    ia = np.array([0, 30, 70, 127])
+    d = {"iv": iv, "ia": ia, "y_dec": np.array([Y_DEC])}
+    for im, (css2, csb2) in enumerate(((1 / 3, 1 / 3), (1 / 3, 1 / 4), (1 / 4, 1 / 3), (1 / 4, 1 / 4))):
+        model = ConstCSModel(css2=css2, csb2=csb2, a_s=5, a_b=1, V_s=1, alpha_n_min=0.05)
+        d[f"m{im}__model"] = np.array([css2, csb2, model.a_s, model.a_b, model.V_s, model.V_b, model.T_ref, model.alpha_n_min])
+        pts = [(float(v_walls[a]), float(alpha_ns[b])) for a in iv for b in ia]
+        _grid_fixture(model, pts, {"r_star": 0.1, "Tn": 200}, f"m{im}__", d)
+    np.savez_compressed(os.path.join(OUT, "ref_config3_grid.npz"), **d)
+    print("ref_config3_grid.npz")
+
+
+TASKS.update({"headline_grid": headline_grid, "config3_grid": config3_grid})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
