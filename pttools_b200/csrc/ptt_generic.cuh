@@ -77,12 +77,13 @@ struct GenericShockLocator {
     int found;          // i_shock (> 0) or 0 = not found
     int last_i;
     int first_close;    // first sample close to (cs_n, 0)
+    int first_above;    // first sample with xi > cs_n (-1: none so far)
     bool turned;
     State cur, prev, prev2, close_prev;     // close_prev: the sample before first_close
 
     PTT_HD void reset(const EosDev& m_, const double v_wall_, const double cs_n_, const bool full_) {
         m = m_; v_wall = v_wall_; cs_n = cs_n_; full = full_;
-        found = 0; last_i = -1; first_close = -1; turned = false;
+        found = 0; last_i = -1; first_close = -1; first_above = -1; turned = false;
     }
     PTT_HD bool behind(const State& y) const {
         if (m.bag_name) return (y.xi > v_wall) && (y.v <= v_shock_bag(y.xi));          // shock.py:63-66
@@ -97,22 +98,23 @@ struct GenericShockLocator {
         return !full && !behind(y_end) && !near_cs(y_end) && (last_i < 0 || y_end.xi > prev.xi);
     }
     PTT_HD bool visit(const int i, const State& y) {
+        if (first_above < 0 && y.xi > cs_n) first_above = i;                // i_cs_n = argmax(xi > cs_n), shock.py:112
         if (i > 0) {
+            if (first_close < 0 && near_cs(y)) {
+                first_close = i; close_prev = prev;
+                // shock.py:109-121: the first sample close to (cs_n, 0) IS the shock index when the curve has not been
+                // above cs_n before it -- decided before the shock curve is looked at, whatever follows (xi that
+                // wiggles by an ulp around the fixed point, v that rounds to -1e-17)
+                if (!m.bag_name && (first_above < 0 || first_above >= i)) { found = i; cur = y; return false; }
+            }
             if (behind(y)) { found = i; cur = y; return false; }
-            if (first_close < 0 && near_cs(y)) { first_close = i; close_prev = prev; }
-            if (!m.bag_name) {
-                if (y.xi > cs_n && first_close > 0) {                                                // shock.py:114-121
-                    found = first_close; cur = y; prev = close_prev;
-                    return false;
-                }
-                if (y.xi < prev.xi) {
-                    // the curve turned back before reaching the shock curve: i_right = argmax(xi) (shock.py:134-141)
-                    turned = true;
-                    found = last_i;
-                    cur = prev;
-                    prev = prev2;
-                    return false;
-                }
+            if (!m.bag_name && y.xi < prev.xi) {
+                // the curve turned back before reaching the shock curve: i_right = argmax(xi) (shock.py:134-141)
+                turned = true;
+                found = last_i;
+                cur = prev;
+                prev = prev2;
+                return false;
             }
         }
         prev2 = prev;

@@ -364,7 +364,7 @@ def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, chunk=80
         codes[(an < model.alpha_n_min)] = -1
         cost = point_cost(codes)
     else:
-        cost = None
+        cost = codes = None
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     shards = shard_rows(vw, cost, world)
@@ -379,14 +379,15 @@ def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, chunk=80
             return
         m = model if single else [model[i] for i in idx]
         LAST_LOCAL["result"] = sweep_spectra(m, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False, chunk=chunk,
-                                             shell_chunk=sc, on_chunk=on_chunk, out={table: out}, **kw)
+                                             shell_chunk=sc, on_chunk=on_chunk, out={table: out},
+                                             sol_type=None if codes is None else codes[idx], **kw)
 
     if mem == "host":
         rank = dist.get_rank() if world > 1 else 0
         idx = shards[rank]
         m = model if single else [model[i] for i in idx]
         res = sweep_spectra(m, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False, chunk=chunk, shell_chunk=sc,
-                            mem="host", **kw)
+                            mem="host", sol_type=None if codes is None else codes[idx], **kw)
         LAST_LOCAL["result"] = res
         return idx, getattr(res, table)
     return distributed_table(local_compute, shards, y.size, chunk, dst=dst)

@@ -38,7 +38,7 @@ def _audit(name, model, d, prefix, spectrum_kwargs, audit):
     r = res.numpy()
     err, flags, noise = d[f"{prefix}err"], d[f"{prefix}flags"], d[f"{prefix}noise"]
     entry = {"points": int(len(pts)), "reference_rejects": int((err == 1).sum()), "reference_no_solution": int((err == 2).sum()),
-             "flag_mismatches": [], "npts_mismatches": [], "over_bar_within_2x_noise": [], "violations": [],
+             "flag_mismatches": [], "both_solver_failed": 0, "npts_mismatches": [], "over_bar_within_2x_noise": [], "violations": [],
              "worst": {"curve_v": 0.0, "curve_w": 0.0, "scalar": 0.0, "pow_v": 0.0, "pow_gw": 0.0, "omgw0": 0.0}}
 
     def check(i, what, dev, tol, ns):
@@ -68,6 +68,13 @@ def _audit(name, model, d, prefix, spectrum_kwargs, audit):
         if bool(fl[1]) != (r.status[i] == 5):
             entry["flag_mismatches"].append({"point": [float(vw), float(an)], "ours_solver_failed": bool(r.status[i] == 5),
                                              "reference_solver_failed": bool(fl[1])})
+            continue
+        if bool(fl[1]):
+            # solver_failed in the reference AND here: the root search did not converge, the returned profile is the
+            # last iterate of whatever path the root finder took (Bubble.solver_failed, bubble.py:123-131) -- the flag
+            # is the result, the numbers are not compared
+            entry["both_solver_failed"] += 1
+            continue
         if int(fl[7]) != int(r.scalars["npts"][i]):
             entry["npts_mismatches"].append({"point": [float(vw), float(an)], "ours": int(r.scalars["npts"][i]),
                                              "reference": int(fl[7]), "reference_tight_differs": bool(noise[i, 6])})
