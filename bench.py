@@ -272,7 +272,9 @@ def gpu_arm(args):
         sampler.mark_start()
     engine.STAGES.enable(True)
     launches0 = engine.STAGES.launches
-    agg = {k: 0 for k in ("group_macs", "group_count", "group_profiles", "gw_profiles", "a2_profiles", "retried", "rescued")}
+    agg = {k: 0 for k in ("group_macs", "group_count", "group_profiles", "gw_profiles", "a2_profiles", "retried", "rescued",
+                          "chunks_before_fold", "chunks_after_fold")}
+    waits = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     ev0.record()
@@ -283,6 +285,8 @@ def gpu_arm(args):
         st = sweep.LAST_LOCAL["result"]
         for k in agg:
             agg[k] += int(getattr(st.stats, k))
+        waits.append((round(st.stats.host_wait_shells_ms, 1), round(st.stats.host_wait_retry_ms, 1), int(st.stats.retried),
+                      int(st.stats.chunks_before_fold)))
         n_samples += float(torch.nan_to_num(st.scalars["npts"]).sum())
         n_ok += int((st.status == 0).sum())
         step_ev.append(torch.cuda.Event(enable_timing=True))
@@ -385,7 +389,9 @@ def gpu_arm(args):
                              "every step uses fresh points",
                        "valid_points_in_timed_region_rank0": n_ok, "per_step_ms": per_step_ms,
                        "wall_ms_per_step": wall_ms / args.steps, "retried_points_rank0": agg["retried"],
-                       "rescued_points_rank0": agg["rescued"]},
+                       "rescued_points_rank0": agg["rescued"],
+                       "host_waits_rank0": {"per_step": waits, "columns": ["wait_shells_ms", "wait_retry_ms", "retried_points",
+                                                                           "chunks_before_fold"]}},
             "clocks": clocks,
             "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "spectra/s", "h2d_bytes_per_step": (16 + 4 + 1) * 8 * B * world,
                     "d2h_bytes_per_step": (8 * int(Y.size) + 32 * 8 + 4) * B * world, "steps": e2e_steps,

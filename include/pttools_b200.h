@@ -123,6 +123,14 @@ int ptt_generic_rescue(int n_f, const int32_t* idx, const double* pg, int n_xi, 
                        double wn_rtol, double* rows_v, double* rows_w, double* rows_xi, int64_t row_stride, int32_t* off,
                        int32_t* npts, double* scalars, int32_t* status, int32_t* rescued, void* stream);
 
+/* Starting guesses: nearest valid entry of the fluid-reference table with the same solution type, for a batch
+ * (FluidReference.get -> NearestNDInterpolator, pttools/bubble/fluid_reference.py:60-62, 152-163).  The table entries
+ * of set s are cx/cy[set_off[s] .. set_off[s+1]); sel[i] picks the set of query i.  out_idx[i] = index of the nearest
+ * entry (squared Euclidean distance in (v_wall, alpha_n), first one on ties), -1 for an empty or unknown set.
+ * Device pointers. */
+int ptt_nearest_batch(int n, const double* qx, const double* qy, const int32_t* sel, int n_sets, const int32_t* set_off,
+                      const double* cx, const double* cy, int32_t* out_idx, void* stream);
+
 /* props.v_and_w_from_solution for a batch of bag shells (pttools/bubble/props.py:52-87): the entries of the
  * fluid-reference starting-guess table (fluid_reference.py:166-196).  Device pointers.
  * out[n,8] = {vp, vm, vp_tilde, vm_tilde, wp, wm, wn, 0}. */
@@ -393,6 +401,9 @@ typedef struct ptt_sweep_stats {
     int64_t group_kw_sum;              /* sum over those groups of the band width in knots */
     int64_t group_macs;                /* multiply-adds of those matrix products: sum of n_z * band * profiles */
     int64_t a2_profiles, gw_profiles;  /* profiles that went through A^2 / the GW integral */
+    int64_t chunks_before_fold, chunks_after_fold;   /* spectrum chunks queued before / after the retries were folded in */
+    double host_wait_retry_ms;         /* host time spent waiting for the retry search (the device may idle meanwhile) */
+    double host_wait_shells_ms;        /* host time spent waiting for the status of a shell chunk */
 } ptt_sweep_stats_t;
 int ptt_sweep_last_stats(ptt_sweep_stats_t* out);
 /* frees the device / pinned workspace the sweep driver keeps between calls */

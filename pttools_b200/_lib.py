@@ -90,7 +90,9 @@ PLAN_ONLY_FIRST_PASS, PLAN_ONLY_LOOKUP_PASS, PLAN_FORCE_DIRECT, PLAN_NO_GW_CELLS
 class SweepStats(C.Structure):
     _fields_ = [("stage_ms", C.c_double * N_STAGES), ("stage_calls", C.c_int64 * N_STAGES), ("launches", C.c_int64),
                 ("retried", C.c_int64), ("rescued", C.c_int64), ("group_profiles", C.c_int64), ("group_count", C.c_int64),
-                ("group_kw_sum", C.c_int64), ("group_macs", C.c_int64), ("a2_profiles", C.c_int64), ("gw_profiles", C.c_int64)]
+                ("group_kw_sum", C.c_int64), ("group_macs", C.c_int64), ("a2_profiles", C.c_int64), ("gw_profiles", C.c_int64),
+                ("chunks_before_fold", C.c_int64), ("chunks_after_fold", C.c_int64), ("host_wait_retry_ms", C.c_double),
+                ("host_wait_shells_ms", C.c_double)]
 
 
 CHUNK_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p)
@@ -140,6 +142,8 @@ SIGNATURES = {
     "ptt_generic_rescue": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    "ptt_nearest_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
     "ptt_shell_wall_values": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_profile_integrals_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,

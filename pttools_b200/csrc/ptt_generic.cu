@@ -177,9 +177,42 @@ __global__ void wall_values_kernel(const int n, const double* __restrict__ rows_
     o[6] = w[N - 1]; o[7] = 0.0;
 }
 
+// Nearest table entry of the same set for every query point (brute force, no temporaries): the batched form of the
+// NearestNDInterpolator lookups of FluidReference.get (fluid_reference.py:60-62, 152-163).  Ties: the first entry.
+__global__ void nearest_kernel(const int n, const double* __restrict__ qx, const double* __restrict__ qy,
+                               const int* __restrict__ sel, const int n_sets, const int* __restrict__ set_off,
+                               const double* __restrict__ cx, const double* __restrict__ cy, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = sel[i];
+    int best = -1;
+    if (s >= 0 && s < n_sets) {
+        const double x = qx[i], y = qy[i];
+        double d_best = INFINITY;
+        for (int k = set_off[s]; k < set_off[s + 1]; ++k) {
+            const double dx = x - cx[k], dy = y - cy[k];
+            const double d = dx * dx + dy * dy;
+            if (d < d_best) { d_best = d; best = k; }
+        }
+    }
+    out[i] = best;
+}
+
 }  // namespace ptt
 
 using namespace ptt;
+
+extern "C" int ptt_nearest_batch(int n, const double* qx, const double* qy, const int32_t* sel, int n_sets,
+                                 const int32_t* set_off, const double* cx, const double* cy, int32_t* out_idx,
+                                 void* stream_) {
+    if (n == 0) return PTT_OK;
+    if (n < 0 || n_sets < 0 || !qx || !qy || !sel || !set_off || !out_idx || (n_sets > 0 && (!cx || !cy)))
+        return set_error(PTT_E_ARG, "ptt_nearest_batch: null pointer or bad size");
+    nearest_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(n, qx, qy, sel, n_sets, set_off, cx, cy, out_idx);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error("nearest_kernel", e);
+    return PTT_OK;
+}
 
 extern "C" int ptt_generic_row_capacity(int n_xi) { return gen_row_capacity(n_xi); }
 

@@ -7,8 +7,10 @@
 // Host C++ only drives: ordering by v_wall, chunking against device memory, the K6' groups on side streams, the retry
 // search folded in under the spectrum stages, results streamed out per chunk.  All arithmetic is in the kernels.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <numeric>
 #include <vector>
@@ -328,13 +330,20 @@ struct Timer {
         recs.push_back({stage, a, b});
     }
     void collect(ptt_sweep_stats_t& st) {
+        const char* trace = getenv("PTT_SWEEP_TRACE");       // diagnostics: timeline of the stages on stderr
         for (const Rec& r : recs) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
                 st.stage_ms[r.stage] += ms;
                 st.stage_calls[r.stage] += 1;
             }
+            if (trace && !recs.empty()) {
+                float t0 = 0.f;
+                cudaEventElapsedTime(&t0, recs[0].a, r.a);
+                fprintf(stderr, "[ptt trace] stage %d start %9.3f ms dur %8.3f ms\n", r.stage, t0, ms);
+            }
         }
+        if (trace) fprintf(stderr, "[ptt trace] end\n");
     }
 };
 
@@ -553,13 +562,17 @@ int Sweep::launch_retry(const long long c, const std::vector<int>& failed) {
     ShellSlot& sl = ws.slot[c & 1];
     const long long s0 = c * shell_chunk;
     const int n_f = (int)failed.size();
-    int* h_idx = sl.h_idx.get<int>(n_f); SW_ALLOC(h_idx);
-    SW_ALLOC(sl.h_rescued.get<int>(n_f));
+    // capacity in entries: generous and doubling, so that the buffers are (re)allocated practically never -- cudaFree /
+    // cudaMalloc / cudaHostAlloc in the middle of a sweep stall the host for tens of milliseconds each
+    size_t cap_f = 256;
+    while (cap_f < (size_t)n_f) cap_f *= 2;
+    int* h_idx = sl.h_idx.get<int>(cap_f); SW_ALLOC(h_idx);
+    SW_ALLOC(sl.h_rescued.get<int>(cap_f));
     memcpy(h_idx, failed.data(), n_f * sizeof(int));
-    for (int k = 0; k < 3; ++k) SW_ALLOC(sl.c_rows[k].get<double>((size_t)n_f * cap));
-    SW_ALLOC(sl.c_off.get<int>(n_f)); SW_ALLOC(sl.c_npts.get<int>(n_f)); SW_ALLOC(sl.c_scal.get<double>((size_t)n_f * SW_GS));
-    SW_ALLOC(sl.c_status.get<int>(n_f)); SW_ALLOC(sl.c_rescued.get<int>(n_f)); SW_ALLOC(sl.c_idx.get<int>(n_f));
-    SW_ALLOC(sl.c_I.get<double>((size_t)n_f * 8)); SW_ALLOC(sl.c_pp2.get<double>((size_t)n_f * 12));
+    for (int k = 0; k < 3; ++k) SW_ALLOC(sl.c_rows[k].get<double>(cap_f * cap));
+    SW_ALLOC(sl.c_off.get<int>(cap_f)); SW_ALLOC(sl.c_npts.get<int>(cap_f)); SW_ALLOC(sl.c_scal.get<double>(cap_f * SW_GS));
+    SW_ALLOC(sl.c_status.get<int>(cap_f)); SW_ALLOC(sl.c_rescued.get<int>(cap_f)); SW_ALLOC(sl.c_idx.get<int>(cap_f));
+    SW_ALLOC(sl.c_I.get<double>(cap_f * 8)); SW_ALLOC(sl.c_pp2.get<double>(cap_f * 12));
     cudaStream_t s = ws.s_retry;
     SW_CUDA(cudaStreamWaitEvent(s, sl.solved, 0));
     SW_CUDA(cudaMemcpyAsync(sl.c_idx.p, h_idx, n_f * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -605,7 +618,11 @@ int Sweep::fold(const long long c, const std::vector<int>& failed, std::vector<c
     ShellSlot& sl = ws.slot[c & 1];
     const long long s0 = c * shell_chunk;
     const int n_f = (int)failed.size();
-    SW_CUDA(cudaEventSynchronize(sl.retried));
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        SW_CUDA(cudaEventSynchronize(sl.retried));
+        stats.host_wait_retry_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
     const int* h_resc = sl.h_rescued.as<int>();
     int n_r = 0;
     for (int f = 0; f < n_f; ++f)
@@ -825,7 +842,11 @@ int Sweep::run() {
     for (long long c = 0; c < n_shell_chunks; ++c) {
         ShellSlot& sl = ws.slot[c & 1];
         const long long s0 = c * shell_chunk, e0 = std::min(n, s0 + shell_chunk), S = e0 - s0;
-        SW_CUDA(cudaEventSynchronize(sl.solved));
+        {
+            const auto t0 = std::chrono::steady_clock::now();
+            SW_CUDA(cudaEventSynchronize(sl.solved));
+            stats.host_wait_shells_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
         const int* h_status = sl.h_status.as<int>();
         const int* h_npts = sl.h_npts.as<int>();
         std::vector<int> failed;
@@ -855,6 +876,8 @@ int Sweep::run() {
             for (const auto& ch : chunks) SW_RC(spectra_chunk(c, ch.first, ch.second, valid));
             if (!folded) { SW_RC(fold(c, failed, valid)); folded = true; }
             for (const auto& ch : later) SW_RC(spectra_chunk(c, ch.first, ch.second, valid));
+            stats.chunks_before_fold += (long long)chunks.size();
+            stats.chunks_after_fold += (long long)later.size();
         }
         if (!folded) SW_RC(fold(c, failed, valid));
         SW_RC(finish_shell_chunk(c));

@@ -39,29 +39,32 @@ class FluidReference:
         self.data = data.reshape(n_alpha_n, n_v_wall, 6)
         self.sol_type = sol_type.reshape(n_alpha_n, n_v_wall)
         self.vp, self.vm, self.vp_tilde, self.vm_tilde, self.wp, self.wm = (self.data[:, :, k] for k in range(6))
-        # device copies for batched nearest-neighbour queries
-        self._coords = {}
-        for code in (0, 1, 2):
-            sel = np.nonzero(sol_type == code)[0]
-            self._coords[code] = (torch.as_tensor(np.stack([vw_f[sel], an_f[sel]], axis=1), device="cuda"),
-                                  torch.as_tensor(data[sel], device="cuda"))
+        # device copies for batched nearest-neighbour queries: the valid entries of the three solution types back to back
+        sets = [np.nonzero(sol_type == code)[0] for code in (0, 1, 2)]
+        self._set_off = torch.as_tensor(np.cumsum([0] + [s.size for s in sets]).astype(np.int32), device="cuda")
+        order = np.concatenate(sets)
+        self._cx = torch.as_tensor(np.ascontiguousarray(vw_f[order]), device="cuda")
+        self._cy = torch.as_tensor(np.ascontiguousarray(an_f[order]), device="cuda")
+        self._vals = torch.as_tensor(np.ascontiguousarray(data[order]), device="cuda")
 
     def get_batch(self, v_wall, alpha_n, sol_type):
         """Nearest valid table entry of the same solution type for every point: tensor [n, 6]
-        (vp, vm, vp_tilde, vm_tilde, wp, wm), like NearestNDInterpolator in fluid_reference.py:60-62,152-163."""
+        (vp, vm, vp_tilde, vm_tilde, wp, wm), like NearestNDInterpolator in fluid_reference.py:60-62,152-163; NaN rows
+        for points without a solution type."""
+        import ctypes as C
+        from . import _lib
         torch = engine._torch()
+        lib = _lib.load()
         v_wall, alpha_n = engine.dev_f64(v_wall).reshape(-1), engine.dev_f64(alpha_n).reshape(-1)
-        st = torch.as_tensor(sol_type, device=v_wall.device).reshape(-1)
-        out = torch.full((v_wall.numel(), 6), float("nan"), dtype=torch.float64, device=v_wall.device)
-        for code in (0, 1, 2):
-            idx = torch.nonzero(st == code).reshape(-1)
-            coords, vals = self._coords[code]
-            if idx.numel() == 0 or coords.shape[0] == 0:
-                continue
-            for s in range(0, idx.numel(), 32768):
-                ii = idx[s:s + 32768]
-                d2 = (v_wall[ii, None] - coords[None, :, 0]) ** 2 + (alpha_n[ii, None] - coords[None, :, 1]) ** 2
-                out[ii] = vals[torch.argmin(d2, dim=1)]
+        st = torch.as_tensor(np.asarray(sol_type), device=v_wall.device).reshape(-1).to(torch.int32).contiguous()
+        n = v_wall.numel()
+        idx = torch.empty(n, dtype=torch.int32, device=v_wall.device)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(lib.ptt_nearest_batch(n, p(v_wall), p(alpha_n), p(st), 3, p(self._set_off), p(self._cx), p(self._cy),
+                                         p(idx), engine._stream_ptr(torch)), "ptt_nearest_batch")
+        idx = idx.long()
+        out = self._vals[idx.clamp(min=0)]
+        out[idx < 0] = float("nan")
         return out
 
     def get(self, v_wall, alpha_n, sol_type):

@@ -138,7 +138,8 @@ def omgw0_scale(v_wall, alpha_n, r_star, g_star=None, gs_star=None, suppression=
 def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multiplier=1.0, nuc_type="exponential",
                   nt=engine.NT_DEFAULT, n_z_lookup=engine.NZ_LOOKUP_DEFAULT, z_st_thresh=engine.Z_ST_THRESH,
                   n_xi=engine.N_XI_DEFAULT, Tn=None, g_star=None, gs_star=None, suppression="default",
-                  chunk=8000, shell_chunk=None, want_pow_v=True, keep_bubbles=False, plan=None, mem="device",
+                  chunk=8000, shell_chunk=None, want_pow_v=True, want_pow_gw=True, keep_bubbles=False, plan=None,
+                  mem="device",
                   allow_invalid=False, on_chunk=None, timing=False, out=None, sol_type=None) -> SweepResult:
     """Spectrum(Bubble(model, v_wall, alpha_n), y, r_star=...) for every point of a sweep: the model-independent shell
     solve, the thermodynamic scalars, the SSM chain and Omega_gw,0 (pttools/analysis/parallel.py:157-187 ->
@@ -168,7 +169,8 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
     want_pow_v = want_pow_v and plan.has_y_pass
     pt = bub.point_table(model, vw, an, sol_type=sol_type, allow_invalid=allow_invalid)
     scale = None if r_star is None else omgw0_scale(vw, an, r_star, g_star, gs_star, suppression)
-    want = (("pow_v",) if want_pow_v else ()) + ("pow_gw",) + (("omgw0",) if scale is not None else ())
+    want = (("pow_v",) if want_pow_v else ()) + (("pow_gw",) if want_pow_gw or scale is None else ()) + \
+        (("omgw0",) if scale is not None else ())
     if mem == "device":
         pg_in, pm_in = engine.dev_f64(pt.pg), engine.dev_f64(pt.pm)
         sc_in = None if scale is None else engine.dev_f64(scale)
@@ -334,6 +336,8 @@ def distributed_table(local_compute: tp.Callable, shards: tp.List[np.ndarray], n
         w.wait()
     if rank != dst:
         return None
+    if world == 1 and np.array_equal(mine, np.arange(n_points)):
+        return local                      # one rank, points already in processing order: the shard IS the table
     out = torch.empty((n_points, n_cols), dtype=dtype, device=device)
     out[torch.as_tensor(mine, device=device)] = local
     for r, buf in recv.items():
@@ -378,7 +382,8 @@ def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, chunk=80
         if len(idx) == 0:
             return
         m = model if single else [model[i] for i in idx]
-        LAST_LOCAL["result"] = sweep_spectra(m, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False, chunk=chunk,
+        LAST_LOCAL["result"] = sweep_spectra(m, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False,
+                                             want_pow_gw=table == "pow_gw", chunk=chunk,
                                              shell_chunk=sc, on_chunk=on_chunk, out={table: out},
                                              sol_type=None if codes is None else codes[idx], **kw)
 
@@ -386,8 +391,8 @@ def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, chunk=80
         rank = dist.get_rank() if world > 1 else 0
         idx = shards[rank]
         m = model if single else [model[i] for i in idx]
-        res = sweep_spectra(m, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False, chunk=chunk, shell_chunk=sc,
-                            mem="host", sol_type=None if codes is None else codes[idx], **kw)
+        res = sweep_spectra(m, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False, want_pow_gw=table == "pow_gw",
+                            chunk=chunk, shell_chunk=sc, mem="host", sol_type=None if codes is None else codes[idx], **kw)
         LAST_LOCAL["result"] = res
         return idx, getattr(res, table)
     return distributed_table(local_compute, shards, y.size, chunk, dst=dst)

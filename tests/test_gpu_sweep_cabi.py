@@ -119,10 +119,11 @@ def test_invalid_points_are_marked_not_solved():
     with pytest.raises(ValueError):
         analysis.create_spectra(model, np.array([0.5]), np.array([0.01, 0.1]), spectrum_kwargs={k: v for k, v in SMALL.items() if k != "n_xi"})
     objs = analysis.create_spectra(model, np.array([0.5, 0.7]), np.array([0.01, 0.1]), allow_bubble_failure=True,
-                                   spectrum_kwargs={k: v for k, v in SMALL.items() if k != "n_xi"})
+                                   spectrum_kwargs={k: v for k, v in SMALL.items() if k != "n_xi"},
+                                   bubble_kwargs={"n_xi": SMALL["n_xi"]})
     assert objs.shape == (2, 2) and objs[0, 0] is None and objs[0, 1] is None and objs[1, 0].bubble.solved
-    big = res.pow_gw[1] > 1e-3 * res.pow_gw[1].max()
-    np.testing.assert_allclose(objs[1, 0].pow_gw[big], res.pow_gw[1][big], rtol=1e-3)     # n_xi differs (default vs 1500)
+    np.testing.assert_allclose(objs[1, 0].pow_gw, res.pow_gw[1], rtol=1e-10)
+    assert objs[1, 0].bubble.v_wall == 0.5 and objs[1, 1].bubble.v_wall == 0.7 and objs[1, 1].bubble.alpha_n == 0.1
 
 
 def _host_call(name, *args):
