@@ -174,7 +174,9 @@ typedef struct ptt_a2_plan {
 
 /* a2_e_conserving / a2_e_conserving_bag                                       pttools/ssmtools/ssm.py:35-140
  * per-point params pp[P,8] = {v_wall, cs, e_coef_s, e_coef_b, V_s, V_b, 0, 0} with e(w,phase) = e_coef*w + V.
- * work: [P, 2*row_cap + 2*nxi + 32] doubles of scratch.  Outputs a2/fp2_2/lam2: [P, n_z] (the last two may be NULL). */
+ * work: [P, work_stride] doubles of scratch with work_stride >= ptt_a2_work_stride(row_stride, nxi, n_z) (weighted
+ * profiles, resampled lambda, envelopes, moment pyramids, f and l per wavenumber).  Outputs a2/fp2_2/lam2: [P, n_z] (the
+ * last two may be NULL).  Any batch size (batches above 65535 profiles are processed in slices). */
 int ptt_a2_batch(const ptt_a2_plan_t* plan, int P, const double* rows_v, const double* rows_w, const double* rows_xi,
                  int64_t row_stride, const int32_t* off, const int32_t* npts, const double* pp,
                  double* work, int64_t work_stride, double* a2, double* fp2_2, double* lam2, void* stream);
@@ -232,6 +234,14 @@ typedef struct ptt_gw_plan {
  * (omgw0_ssm.py:123-131) or NULL.  Outputs [P, n_y]: sd_gw (may be NULL), pow_gw, omgw0 (NULL if scale NULL). */
 int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const double* pv, int64_t pv_stride, const double* slf,
                           const double* scale, double* sd_gw, double* pow_gw, double* omgw0, void* stream);
+
+/* spec_den_gw_scaled on an arbitrary ascending z_lookup and any y (np.interp by binary search per sample; the general
+ * form of spectrum.py:402-430 -- the log-uniform grids of gen_lookup / np.logspace take the two entries around this one).
+ * Z1[n_int] = zeta_k, Z2 = zeta_+ + zeta_- - zeta_k, G = trapezoid weight * integrand kernel, as in ptt_gw_plan_t. */
+int ptt_spec_den_gw_general_batch(int n_zl, const double* z_lookup, int n_y, const double* y, int n_int, const double* Z1,
+                                  const double* Z2, const double* G, double prefactor, int P, const double* pv,
+                                  int64_t pv_stride, const double* slf, const double* scale, double* sd_gw, double* pow_gw,
+                                  double* omgw0, void* stream);
 
 /* spec_den_gw_scaled, cell formulation for large batches (same trapezoid sum over the same samples, regrouped by runs of
  * samples that share both np.interp segments and collected per segment of the first lookup; spectrum.py:327-368).
@@ -365,6 +375,9 @@ typedef struct ptt_sweep_out {
     double *rows_v, *rows_w, *rows_xi;   /* optional profiles [n, row_stride] (device memory only), with off/npts */
     int64_t row_stride;
     int32_t *off, *npts;
+    double* snr;               /* [n, n_snr] or NULL: signal-to-noise ratios of omgw0 (needs omgw0's scale and snr_weight) */
+    const double* snr_weight;  /* DEVICE [n_snr, n_y], see ptt_snr_batch */
+    int32_t n_snr, reserved;
 } ptt_sweep_out_t;
 
 /* Called after the rows [row0, row1) of the result tables have been queued for delivery on `stream` (a cudaStream_t):
@@ -410,6 +423,20 @@ int ptt_sweep_last_stats(ptt_sweep_stats_t* out);
 int ptt_sweep_release(void);
 /* points per shell solve the driver would pick for `free_bytes` of device memory */
 int64_t ptt_sweep_shell_chunk(int n_xi, int64_t free_bytes);
+
+/* --- Post-processing epilogues (device pointers, enqueued on `stream`) ---------------------------------------
+ * Suppression factor of Omega_gw,0: piecewise-linear interpolation of the simulation-measured table on its Delaunay
+ * triangulation, NaN outside the hull (Suppression.suppression -> scipy griddata(method="linear"),
+ * pttools/omgw0/suppression/suppression.py:53-96).  tri[n_tri,6] = (x0,y0,x1,y1,x2,y2) of each triangle in
+ * (v_wall, alpha_n), val[n_tri,3] the table values at its vertices (the triangulation is built once on the host).
+ * mode 0 = SuppressionMethod.NO_EXT, 1 = EXT_CONSTANT (1 below alpha_min). */
+int ptt_suppression_batch(int n, const double* v_wall, const double* alpha_n, int n_tri, const double* tri,
+                          const double* val, int mode, double alpha_min, double* out, void* stream);
+/* signal_to_noise_ratio(f, signal, noise) = sqrt(T_obs * trapezoid(signal^2 / noise^2, f)) for P spectra that share f
+ * (pttools/omgw0/noise.py:7-52; Spectrum.signal_to_noise_ratio[_instrument], omgw0_ssm.py:143-147), for n_w <= 4 noise
+ * curves at once: weight[n_w, n_y] = T_obs * trapezoid weight(f) / noise^2, out[P, n_w]. */
+int ptt_snr_batch(int P, int n_y, const double* signal, int64_t stride, int n_w, const double* weight, double* out,
+                  void* stream);
 
 /* FP64 FMA throughput probe used by bench.py for the roofline denominator (not part of the reference). */
 int ptt_fp64_peak_probe(int iters, double* out_flops_per_s, void* stream);

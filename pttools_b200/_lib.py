@@ -71,7 +71,8 @@ class SweepOpts(C.Structure):
 class SweepOut(C.Structure):
     _fields_ = [("pow_v", C.c_void_p), ("pow_gw", C.c_void_p), ("omgw0", C.c_void_p), ("scalars", C.c_void_p),
                 ("status", C.c_void_p), ("rows_v", C.c_void_p), ("rows_w", C.c_void_p), ("rows_xi", C.c_void_p),
-                ("row_stride", C.c_int64), ("off", C.c_void_p), ("npts", C.c_void_p)]
+                ("row_stride", C.c_int64), ("off", C.c_void_p), ("npts", C.c_void_p), ("snr", C.c_void_p),
+                ("snr_weight", C.c_void_p), ("n_snr", C.c_int32), ("reserved", C.c_int32)]
 
 
 N_STAGES = 12
@@ -127,6 +128,9 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ptt_spec_den_gw_batch": (C.c_int, [C.POINTER(GwPlan), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ptt_spec_den_gw_general_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_gw_cells_capacity": (C.c_int, [C.c_int, C.c_int, C.c_double]),
     "ptt_gw_cells_coef_capacity": (C.c_int, [C.c_int]),
     "ptt_gw_cells_build": (C.c_int, [C.POINTER(GwPlan), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -160,6 +164,9 @@ SIGNATURES = {
     "ptt_sweep_last_stats": (C.c_int, [C.POINTER(SweepStats)]),
     "ptt_sweep_release": (C.c_int, []),
     "ptt_sweep_shell_chunk": (C.c_int64, [C.c_int, C.c_int64]),
+    "ptt_suppression_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                        C.c_void_p, C.c_void_p]),
+    "ptt_snr_batch": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_fp64_peak_probe": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     "ptt_fp64_pipe_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
 }

@@ -101,6 +101,22 @@ class SpectrumView:
         i = int(np.argmax(om_))
         return self.f()[i], om_[i]
 
+    def noise(self):
+        from . import noise
+        return noise.omega_noise(self.f())                    # omgw0_ssm.py:117-118
+
+    def noise_ins(self):
+        from . import noise
+        return noise.omega_ins(self.f())                      # omgw0_ssm.py:120-121
+
+    def signal_to_noise_ratio(self) -> float:
+        from . import noise
+        return float(noise.signal_to_noise_ratio(f=self.f(), signal=self.omgw0(), noise=self.noise()))      # :143-144
+
+    def signal_to_noise_ratio_instrument(self) -> float:
+        from . import noise
+        return float(noise.signal_to_noise_ratio(f=self.f(), signal=self.omgw0(), noise=self.noise_ins()))  # :146-147
+
 
 def _rejected(model: Model, v_wall: float, alpha_n: float) -> Exception:
     """The exception the reference's Bubble constructor raises for a point the sweep marked invalid (bubble.py:36-177)."""

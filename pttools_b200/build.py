@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpttools_b200.so")
-SOURCES = ["ptt_api.cu", "ptt_shell.cu", "ptt_ssm.cu", "ptt_thermo.cu", "ptt_generic.cu", "ptt_sdv_gemm.cu", "ptt_gw_cells.cu", "ptt_sweep.cu", "ptt_plan.cu"]
+SOURCES = ["ptt_api.cu", "ptt_shell.cu", "ptt_ssm.cu", "ptt_thermo.cu", "ptt_generic.cu", "ptt_sdv_gemm.cu", "ptt_gw_cells.cu", "ptt_sweep.cu", "ptt_plan.cu", "ptt_post.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",

@@ -918,12 +918,20 @@ static int check_launch(const char* what) {
     return PTT_OK;
 }
 
+// The batch index of these operators is gridDim.y (limit 65535): larger batches are processed in slices.
+constexpr int MAX_BATCH_SLICE = 65535;
+
 extern "C" int ptt_sin_transform_batch(int P, const double* xi, const double* f, int64_t stride, const int32_t* off,
                                        const int32_t* npts, int n_z, const double* z, const double* frac,
                                        double* out, void* stream_) {
     if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (P < 0 || n_z < 0 || !xi || !f || !off || !npts || !z || !frac || !out)
         return set_error(PTT_E_ARG, "ptt_sin_transform_batch: null pointer or bad size");
+    for (int p0 = 0; P > MAX_BATCH_SLICE && p0 < P; p0 += MAX_BATCH_SLICE) {
+        const int rc = ptt_sin_transform_batch(min(MAX_BATCH_SLICE, P - p0), xi + (size_t)p0 * stride, f + (size_t)p0 * stride,
+                                               stride, off + p0, npts + p0, n_z, z, frac, out + (size_t)p0 * n_z, stream_);
+        if (rc != PTT_OK || p0 + MAX_BATCH_SLICE >= P) return rc;
+    }
     if (P == 0 || n_z == 0) return PTT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     double* g = nullptr;
@@ -948,6 +956,12 @@ extern "C" int ptt_sin_transform_unit_batch(int P, const double* xi, const doubl
     if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (P < 0 || n_z < 0 || !xi || !f || !off || !npts || !z || !frac || !out)
         return set_error(PTT_E_ARG, "ptt_sin_transform_unit_batch: null pointer or bad size");
+    for (int p0 = 0; P > MAX_BATCH_SLICE && p0 < P; p0 += MAX_BATCH_SLICE) {
+        const int rc = ptt_sin_transform_unit_batch(min(MAX_BATCH_SLICE, P - p0), xi + (size_t)p0 * stride,
+                                                    f + (size_t)p0 * stride, stride, off + p0, npts + p0, n_z, z, frac,
+                                                    out + (size_t)p0 * n_z, stream_);
+        if (rc != PTT_OK || p0 + MAX_BATCH_SLICE >= P) return rc;
+    }
     if (P == 0 || n_z == 0) return PTT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     double* g = nullptr;
@@ -979,6 +993,14 @@ extern "C" int ptt_a2_batch(const ptt_a2_plan_t* plan, int P, const double* rows
     if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (!plan || P < 0 || !rows_v || !rows_w || !rows_xi || !off || !npts || !pp || !work || !a2)
         return set_error(PTT_E_ARG, "ptt_a2_batch: null pointer or bad size");
+    for (int p0 = 0; P > MAX_BATCH_SLICE && p0 < P; p0 += MAX_BATCH_SLICE) {
+        const size_t o = (size_t)p0;
+        const int rc = ptt_a2_batch(plan, min(MAX_BATCH_SLICE, P - p0), rows_v + o * row_stride, rows_w + o * row_stride,
+                                    rows_xi + o * row_stride, row_stride, off + p0, npts + p0, pp + o * 8,
+                                    work + o * work_stride, work_stride, a2 + o * plan->n_z,
+                                    fp2_2 ? fp2_2 + o * plan->n_z : nullptr, lam2 ? lam2 + o * plan->n_z : nullptr, stream_);
+        if (rc != PTT_OK || p0 + MAX_BATCH_SLICE >= P) return rc;
+    }
     if (P == 0) return PTT_OK;
     WorkLayout lay;
     lay.row_cap = (int)row_stride;
@@ -1022,6 +1044,11 @@ extern "C" int ptt_spec_den_v_batch(const ptt_sdv_plan_t* plan, int P, const dou
     if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (!plan || P < 0 || !a2 || !v_wall || !out || plan->z_tile < 1)
         return set_error(PTT_E_ARG, "ptt_spec_den_v_batch: null pointer or bad size");
+    for (int p0 = 0; P > MAX_BATCH_SLICE && p0 < P; p0 += MAX_BATCH_SLICE) {
+        const int rc = ptt_spec_den_v_batch(plan, min(MAX_BATCH_SLICE, P - p0), a2 + (size_t)p0 * a2_stride, a2_stride,
+                                            v_wall + p0, out + (size_t)p0 * out_stride, out_stride, stream_);
+        if (rc != PTT_OK || p0 + MAX_BATCH_SLICE >= P) return rc;
+    }
     if (P == 0) return PTT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int smem = plan->smem_bytes;
@@ -1042,6 +1069,13 @@ extern "C" int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const dou
     if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (!plan || P < 0 || !pv || !slf || plan->y_tile < 1 || plan->y_tile % GW_R != 0)
         return set_error(PTT_E_ARG, "ptt_spec_den_gw_batch: null pointer or bad size (y_tile must be a multiple of 4)");
+    for (int p0 = 0; P > MAX_BATCH_SLICE && p0 < P; p0 += MAX_BATCH_SLICE) {
+        const size_t o = (size_t)p0 * plan->n_y;
+        const int rc = ptt_spec_den_gw_batch(plan, min(MAX_BATCH_SLICE, P - p0), pv + (size_t)p0 * pv_stride, pv_stride,
+                                             slf + p0, scale ? scale + p0 : nullptr, sd_gw ? sd_gw + o : nullptr,
+                                             pow_gw ? pow_gw + o : nullptr, omgw0 ? omgw0 + o : nullptr, stream_);
+        if (rc != PTT_OK || p0 + MAX_BATCH_SLICE >= P) return rc;
+    }
     if (P == 0) return PTT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int smem = plan->smem_bytes;
@@ -1057,10 +1091,81 @@ extern "C" int ptt_spec_den_gw_batch(const ptt_gw_plan_t* plan, int P, const dou
     return check_launch("spec_den_gw_kernel");
 }
 
+// spec_den_gw_scaled on an ARBITRARY ascending z_lookup (and any order of y): np.interp by binary search per sample
+// (spectrum.py:327-368, 361-363).  The log-uniform grids the reference itself always passes take the arithmetic-index
+// kernels above; this is the general form of the operator.  CTA = one (wavenumber, profile) pair.
+__device__ __forceinline__ double interp_search(const double x, const int n, const double* __restrict__ xp,
+                                                const double* __restrict__ fp) {
+    if (!(x > xp[0])) return (x != x) ? x : fp[0];           // np.interp: left clamp (NaN stays NaN)
+    if (x >= xp[n - 1]) return fp[n - 1];
+    int lo = 0, hi = n - 1;                                   // xp[lo] <= x < xp[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (xp[mid] <= x) lo = mid; else hi = mid;
+    }
+    const double x0 = xp[lo], f0 = fp[lo];
+    return fma((fp[lo + 1] - f0) / (xp[lo + 1] - x0), x - x0, f0);
+}
+
+__global__ void __launch_bounds__(128) spec_den_gw_search_kernel(
+    const int n_zl, const int n_y, const int n_int, const double* __restrict__ z_lookup, const double* __restrict__ y,
+    const double* __restrict__ Z1, const double* __restrict__ Z2, const double* __restrict__ G, const double prefactor,
+    const double* __restrict__ pv, const long long pv_stride, const double* __restrict__ slf,
+    const double* __restrict__ scale, double* __restrict__ sd_gw, double* __restrict__ pow_gw, double* __restrict__ omgw0) {
+    __shared__ double s_red[128];
+    const int i = blockIdx.x;
+    const size_t p = blockIdx.y;
+    const double* fp = pv + p * pv_stride;
+    const double yi = y[i];
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < n_int; k += blockDim.x) {
+        const double p1 = interp_search(yi * Z1[k], n_zl, z_lookup, fp);
+        const double p2 = interp_search(yi * Z2[k], n_zl, z_lookup, fp);
+        acc = fma(G[k] * p1, p2, acc);
+    }
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double sd = prefactor * yi * yi * s_red[0] * slf[p];
+        const size_t o = p * n_y + i;
+        if (sd_gw) sd_gw[o] = sd;
+        const double pw = yi * yi * yi / (2.0 * M_PI * M_PI) * sd;
+        if (pow_gw) pow_gw[o] = pw;
+        if (omgw0 && scale) omgw0[o] = scale[p] * pw;
+    }
+}
+
+extern "C" int ptt_spec_den_gw_general_batch(int n_zl, const double* z_lookup, int n_y, const double* y, int n_int,
+                                             const double* Z1, const double* Z2, const double* G, double prefactor, int P,
+                                             const double* pv, int64_t pv_stride, const double* slf, const double* scale,
+                                             double* sd_gw, double* pow_gw, double* omgw0, void* stream_) {
+    if (P == 0 || n_y == 0) return PTT_OK;
+    if (P < 0 || n_y < 0 || n_zl < 2 || n_int < 2 || !z_lookup || !y || !Z1 || !Z2 || !G || !pv || !slf || pv_stride < n_zl)
+        return set_error(PTT_E_ARG, "ptt_spec_den_gw_general_batch: null pointer or bad size");
+    for (int p0 = 0; p0 < P; p0 += MAX_BATCH_SLICE) {
+        const int np_ = min(MAX_BATCH_SLICE, P - p0);
+        const size_t o = (size_t)p0 * n_y;
+        spec_den_gw_search_kernel<<<dim3(n_y, np_), 128, 0, (cudaStream_t)stream_>>>(
+            n_zl, n_y, n_int, z_lookup, y, Z1, Z2, G, prefactor, pv + (size_t)p0 * pv_stride, pv_stride, slf + p0,
+            scale ? scale + p0 : nullptr, sd_gw ? sd_gw + o : nullptr, pow_gw ? pow_gw + o : nullptr,
+            omgw0 ? omgw0 + o : nullptr);
+    }
+    return check_launch("spec_den_gw_search_kernel");
+}
+
 extern "C" int ptt_pow_spec_batch(int P, int n_z, const double* z, const double* spec_den, int64_t stride, double* out,
                                   void* stream_) {
     if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (P < 0 || n_z < 0 || !z || !spec_den || !out) return set_error(PTT_E_ARG, "ptt_pow_spec_batch: null pointer");
+    for (int p0 = 0; P > MAX_BATCH_SLICE && p0 < P; p0 += MAX_BATCH_SLICE) {
+        const int rc = ptt_pow_spec_batch(min(MAX_BATCH_SLICE, P - p0), n_z, z, spec_den + (size_t)p0 * stride, stride,
+                                          out + (size_t)p0 * stride, stream_);
+        if (rc != PTT_OK || p0 + MAX_BATCH_SLICE >= P) return rc;
+    }
     if (P == 0 || n_z == 0) return PTT_OK;
     dim3 grid((n_z + 255) / 256, P);
     pow_spec_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(n_z, z, spec_den, stride, out);
@@ -1098,7 +1203,10 @@ extern "C" int ptt_fp64_pipe_probe(int mode, int iters, double* out_flops_per_s,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     double* sink = nullptr;
-    cudaMalloc((void**)&sink, sizeof(double));
+    {
+        const cudaError_t e = cudaMalloc((void**)&sink, sizeof(double));
+        if (e != cudaSuccess) return set_cuda_error("fp64 probe: cudaMalloc", e);
+    }
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
@@ -1129,7 +1237,10 @@ extern "C" int ptt_fp64_peak_probe(int iters, double* out_flops_per_s, void* str
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     double* sink = nullptr;
-    cudaMalloc((void**)&sink, sizeof(double));
+    {
+        const cudaError_t e = cudaMalloc((void**)&sink, sizeof(double));
+        if (e != cudaSuccess) return set_cuda_error("fp64 probe: cudaMalloc", e);
+    }
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);

@@ -99,15 +99,15 @@ __global__ void thermo_finish_kernel(const int n, const double* __restrict__ pg,
 template <class T>
 __global__ void scatter_rows_kernel(const int n_col, const T* __restrict__ src, const long long src_stride,
                                     const long long* __restrict__ row, T* __restrict__ dst, const long long dst_stride) {
-    const int f = blockIdx.y;
-    const T* s = src + (size_t)f * src_stride;
-    T* d = dst + (size_t)(row ? row[f] : f) * dst_stride;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_col; c += gridDim.x * blockDim.x) d[c] = s[c];
+    const size_t f = blockIdx.x;                 // rows on grid.x (no 65535 limit), column blocks on grid.y
+    const T* s = src + f * src_stride;
+    T* d = dst + (size_t)(row ? row[f] : (long long)f) * dst_stride;
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < n_col; c += gridDim.y * blockDim.x) d[c] = s[c];
 }
 
 __global__ void fill_rows_kernel(const int n_col, double* __restrict__ dst, const long long stride, const double value) {
-    double* d = dst + (size_t)blockIdx.y * stride;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_col; c += gridDim.x * blockDim.x) d[c] = value;
+    double* d = dst + (size_t)blockIdx.x * stride;
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < n_col; c += gridDim.y * blockDim.x) d[c] = value;
 }
 
 // dst[r, :] = src[idx[r], :]
@@ -204,7 +204,7 @@ struct Workspace {
     cudaStream_t s_shell = nullptr, s_retry = nullptr, s_copy = nullptr, s_side[2] = {nullptr, nullptr};
     ShellSlot slot[2];
     DevBuf pg, pm, scale, perm, stage_in, a2, work, pv_y, pv_l, omega[2], ebase, gw_table, out[2][3], full[3], full_scal,
-        full_status, vw_tmp;
+        full_status, vw_tmp, snr, snr_perm;
     PinBuf h_pg, h_ebase, h_scal, h_status;
     cudaEvent_t out_free[2] = {nullptr, nullptr}, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_tmp = nullptr,
                 ev_emit = nullptr;
@@ -219,7 +219,7 @@ struct Workspace {
     std::vector<DevBuf*> dev() {
         return {&pg, &pm, &scale, &perm, &stage_in, &a2, &work, &pv_y, &pv_l, &omega[0], &omega[1], &ebase, &gw_table,
                 &out[0][0], &out[0][1], &out[0][2], &out[1][0], &out[1][1], &out[1][2], &full[0], &full[1], &full[2],
-                &full_scal, &full_status, &vw_tmp};
+                &full_scal, &full_status, &vw_tmp, &snr, &snr_perm};
     }
     int init() {
         int dev_now = 0;
@@ -379,6 +379,7 @@ struct Sweep {
     double* d_full[3] = {nullptr, nullptr, nullptr};
     double* d_full_scal = nullptr;
     int* d_full_status = nullptr;
+    double* d_snr = nullptr;     // [n, n_snr] in processing order
     long long emitted = 0;      // spectrum chunks emitted so far (selects the output slot)
     bool out_used[2] = {false, false};
 
@@ -508,6 +509,7 @@ int Sweep::setup(const long long n_, const double* pg, const double* pm, const d
             if (user_tab[k] && host && !sorted) { d_full[k] = ws.full[k].get<double>(nn * n_y); SW_ALLOC(d_full[k]); }
         }
     }
+    if (out.snr && want_spec) { d_snr = ws.snr.get<double>(nn * out.n_snr); SW_ALLOC(d_snr); }
     if (host && !sorted) {
         if (out.scalars) { d_full_scal = ws.full_scal.get<double>(nn * SW_NS); SW_ALLOC(d_full_scal); }
         d_full_status = ws.full_status.get<int>(nn); SW_ALLOC(d_full_status);
@@ -697,7 +699,7 @@ int Sweep::sdv_pass(const int ip, const long long c, const long long s, const lo
         stats.launches += 1;
     }
     for (const auto& nf : nanfill) {
-        fill_rows_kernel<<<dim3(4, (unsigned)(nf.second - nf.first)), 256, 0, s_main>>>(n_z, out_pv + (size_t)(nf.first - s) * n_z, n_z, NAN);
+        fill_rows_kernel<<<dim3((unsigned)(nf.second - nf.first), 4), 256, 0, s_main>>>(n_z, out_pv + (size_t)(nf.first - s) * n_z, n_z, NAN);
         SW_LAUNCHED("fill_rows_kernel");
         stats.launches += 1;
     }
@@ -767,6 +769,10 @@ int Sweep::spectra_chunk(const long long c, const long long s, const long long e
                                     scale_c ? o_tab[b][2] : nullptr, s_main));
         stats.launches += 1;
     }
+    if (d_snr && scale_c) {
+        SW_RC(ptt_snr_batch(P, n_y, o_tab[b][2], n_y, out.n_snr, out.snr_weight, d_snr + (size_t)s * out.n_snr, s_main));
+        stats.launches += 1;
+    }
     timer.end(PTT_STAGE_GW, t0, s_main);
     // ---- deliver: the copy stream takes over, the compute stream goes on with the next chunk
     SW_CUDA(cudaEventRecord(ws.ev_emit, s_main));
@@ -781,7 +787,7 @@ int Sweep::spectra_chunk(const long long c, const long long s, const long long e
                                     host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ws.s_copy));
         } else {
             double* dst = host ? d_full[k] : user_tab[k];
-            scatter_rows_kernel<double><<<dim3(4, P), 256, 0, ws.s_copy>>>(n_y, o_tab[b][k], n_y, d_perm + s, dst, n_y);
+            scatter_rows_kernel<double><<<dim3(P, 4), 256, 0, ws.s_copy>>>(n_y, o_tab[b][k], n_y, d_perm + s, dst, n_y);
             SW_LAUNCHED("scatter_rows_kernel");
             stats.launches += 1;
         }
@@ -805,11 +811,11 @@ int Sweep::finish_shell_chunk(const long long c) {
         if (out.scalars) SW_CUDA(cudaMemcpyAsync(out.scalars + (size_t)s0 * SW_NS, sl.table.p, S * SW_NS * sizeof(double), kind, s));
     } else {
         int* st_dst = host ? d_full_status : out.status;
-        scatter_rows_kernel<int><<<dim3(1, (unsigned)S), 32, 0, s>>>(1, sl.gstatus.as<int>(), 1, d_perm + s0, st_dst, 1);
+        scatter_rows_kernel<int><<<dim3((unsigned)S, 1), 32, 0, s>>>(1, sl.gstatus.as<int>(), 1, d_perm + s0, st_dst, 1);
         SW_LAUNCHED("scatter_rows_kernel");
         if (out.scalars) {
             double* sc_dst = host ? d_full_scal : out.scalars;
-            scatter_rows_kernel<double><<<dim3(1, (unsigned)S), 32, 0, s>>>(SW_NS, sl.table.as<double>(), SW_NS, d_perm + s0, sc_dst, SW_NS);
+            scatter_rows_kernel<double><<<dim3((unsigned)S, 1), 32, 0, s>>>(SW_NS, sl.table.as<double>(), SW_NS, d_perm + s0, sc_dst, SW_NS);
             SW_LAUNCHED("scatter_rows_kernel");
         }
     }
@@ -820,7 +826,7 @@ int Sweep::finish_shell_chunk(const long long c) {
                                                   sl.rows[k].p, cap * sizeof(double), cap * sizeof(double), (size_t)S,
                                                   cudaMemcpyDeviceToDevice, s));
             else {
-                scatter_rows_kernel<double><<<dim3(8, (unsigned)S), 256, 0, s>>>((int)cap, sl.rows[k].as<double>(), cap, d_perm + s0, dst[k], out.row_stride);
+                scatter_rows_kernel<double><<<dim3((unsigned)S, 8), 256, 0, s>>>((int)cap, sl.rows[k].as<double>(), cap, d_perm + s0, dst[k], out.row_stride);
                 SW_LAUNCHED("scatter_rows_kernel");
             }
         }
@@ -828,8 +834,8 @@ int Sweep::finish_shell_chunk(const long long c) {
             SW_CUDA(cudaMemcpyAsync(out.off + s0, sl.off.p, S * sizeof(int), cudaMemcpyDeviceToDevice, s));
             SW_CUDA(cudaMemcpyAsync(out.npts + s0, sl.npts.p, S * sizeof(int), cudaMemcpyDeviceToDevice, s));
         } else {
-            scatter_rows_kernel<int><<<dim3(1, (unsigned)S), 32, 0, s>>>(1, sl.off.as<int>(), 1, d_perm + s0, out.off, 1);
-            scatter_rows_kernel<int><<<dim3(1, (unsigned)S), 32, 0, s>>>(1, sl.npts.as<int>(), 1, d_perm + s0, out.npts, 1);
+            scatter_rows_kernel<int><<<dim3((unsigned)S, 1), 32, 0, s>>>(1, sl.off.as<int>(), 1, d_perm + s0, out.off, 1);
+            scatter_rows_kernel<int><<<dim3((unsigned)S, 1), 32, 0, s>>>(1, sl.npts.as<int>(), 1, d_perm + s0, out.npts, 1);
             SW_LAUNCHED("scatter_rows_kernel");
         }
     }
@@ -893,6 +899,17 @@ int Sweep::run() {
         SW_CUDA(cudaMemcpyAsync(out.status, d_full_status, nn * sizeof(int), cudaMemcpyDeviceToHost, s_main));
         if (out.scalars) SW_CUDA(cudaMemcpyAsync(out.scalars, d_full_scal, nn * SW_NS * sizeof(double), cudaMemcpyDeviceToHost, s_main));
     }
+    if (d_snr) {
+        const size_t cnt = (size_t)n * out.n_snr;
+        const double* src = d_snr;
+        if (!sorted) {
+            double* t = ws.snr_perm.get<double>(cnt); SW_ALLOC(t);
+            scatter_rows_kernel<double><<<dim3((unsigned)n, 1), 32, 0, s_main>>>(out.n_snr, d_snr, out.n_snr, d_perm, t, out.n_snr);
+            SW_LAUNCHED("scatter_rows_kernel");
+            src = t;
+        }
+        SW_CUDA(cudaMemcpyAsync(out.snr, src, cnt * sizeof(double), host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s_main));
+    }
     if (cb && !sorted) cb(user, 0, n, s_main);
     if (host || timer.on) {
         SW_CUDA(cudaStreamSynchronize(s_main));
@@ -939,6 +956,8 @@ extern "C" int ptt_sweep_spectra(const ptt_sweep_plan_t* plan, const ptt_sweep_o
     if (want_spec && (plan->n_pass < 1 || plan->n_pass > 2 || !plan->h_zterm[plan->n_pass - 1]))
         return set_error(PTT_E_ARG, "ptt_sweep_spectra: malformed plan");
     if (out->omgw0 && !scale) return set_error(PTT_E_ARG, "ptt_sweep_spectra: omgw0 needs scale[n]");
+    if (out->snr && (!out->omgw0 || !out->snr_weight || out->n_snr < 1 || out->n_snr > 4))
+        return set_error(PTT_E_ARG, "ptt_sweep_spectra: snr needs omgw0, snr_weight and 1 <= n_snr <= 4");
     if (out->pow_v && !(plan->n_pass == 2 && plan->has_y_pass))
         return set_error(PTT_E_ARG, "ptt_sweep_spectra: pow_v needs a plan with the y pass");
     const bool want_rows = out->rows_v || out->rows_w || out->rows_xi;

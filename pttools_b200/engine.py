@@ -314,7 +314,7 @@ class SweepOutput:
 
     def __init__(self):
         self.pow_v = self.pow_gw = self.omgw0 = self.scalars = self.status = None
-        self.rows = self.off = self.npts = None
+        self.rows = self.off = self.npts = self.snr = None
         self.stats = None
         self._keep = []
 
@@ -327,7 +327,7 @@ _LIVE_CALLBACKS = []
 
 def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_shell_limit=100, wn_rtol=1e-4, r_star=None,
             lifetime_multiplier=1.0, chunk=8000, shell_chunk=0, want=("pow_v", "pow_gw", "omgw0"), scalars=True,
-            rows=False, mem="device", retry=True, timing=False, on_chunk=None, out=None) -> SweepOutput:
+            rows=False, mem="device", retry=True, timing=False, on_chunk=None, out=None, snr_weights=None) -> SweepOutput:
     """The whole sweep in one C call (ptt_sweep_spectra, csrc/ptt_sweep.cu): shells, the reference's retries,
     thermodynamic scalars, A^2, spec_den_v, spec_den_gw, pow_gw, omgw0.  pg[n,16], pm[n,4] as in the C header (host
     numpy arrays or device tensors according to `mem`); plan: SsmPlan / CPlan or None (shells only).
@@ -383,6 +383,11 @@ def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_she
         if res.scalars is None:
             res.scalars = alloc((n, _lib.SWEEP_NSCAL))
         o.scalars = ptr(res.scalars)
+    if snr_weights is not None and "omgw0" in want:
+        w = dev_f64(np.ascontiguousarray(snr_weights, dtype=np.float64))
+        res._keep.append(w)
+        res.snr = alloc((n, w.shape[0]))
+        o.snr, o.snr_weight, o.n_snr = ptr(res.snr), C.c_void_p(w.data_ptr()), int(w.shape[0])
     if rows:
         if host:
             raise ValueError("profile rows are returned in device memory only")
@@ -753,24 +758,31 @@ def make_gw_plan(g, t, n_zl, n_y):
 
 
 class GwOnlyPlan:
-    """Plan for spec_den_gw_scaled on a user-supplied log-uniform z_lookup (spectrum.py:402-430)."""
+    """Plan for spec_den_gw_scaled on a user-supplied z_lookup (spectrum.py:402-430).  Log-uniform z_lookup with ascending
+    y (what gen_lookup / np.logspace give, and what the reference itself always passes) runs on the arithmetic-index
+    kernels; any other ascending z_lookup, or unordered y, on the binary-search kernel (`general`)."""
 
     def __init__(self, z_lookup, y, cs=CS0, gamma=GAMMA_DEFAULT, nz_int=None):
         torch = _torch()
         z_lookup = np.asarray(z_lookup, dtype=np.float64)
         y = np.asarray(y, dtype=np.float64)
+        if z_lookup.size < 2 or np.any(np.diff(z_lookup) <= 0):
+            raise ValueError("z_lookup must be strictly ascending (np.interp needs it)")
         lz = np.log10(z_lookup)
-        if z_lookup.size < 2 or not np.allclose(lz, np.linspace(lz[0], lz[-1], z_lookup.size), rtol=0, atol=1e-9):
-            raise NotImplementedError("spec_den_gw_scaled: z_lookup must be log-uniform (gen_lookup / np.logspace)")
-        if np.any(np.diff(y) < 0):
-            raise NotImplementedError("spec_den_gw_scaled: y must be ascending")
+        uniform = np.all(z_lookup > 0) and np.allclose(lz, np.linspace(lz[0], lz[-1], z_lookup.size), rtol=0, atol=1e-9)
+        self.general = not (uniform and np.all(np.diff(y) >= 0))
         self.y, self.z_lookup = y, z_lookup
-        self.gw = build_gw_tables(z_lookup, y, cs, gamma, nz_int)
         up = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
         self._t = {"z_lookup": up(z_lookup), "y": up(y)}
+        if self.general:
+            # the same zeta tables; the log-index tables are not used by the search kernel
+            grid = np.logspace(0, 12, 16)
+            self.gw = build_gw_tables(grid, np.array([1.0, 1.0]), cs, gamma, z_lookup.size if nz_int is None else nz_int)
+        else:
+            self.gw = build_gw_tables(z_lookup, y, cs, gamma, nz_int)
         for k in ("L1", "L2", "Z1", "Z2", "G", "yterm"):
             self._t["gw_" + k] = up(self.gw[k])
-        self.gw_plan = make_gw_plan(self.gw, self._t, z_lookup.size, y.size)
+        self.gw_plan = None if self.general else make_gw_plan(self.gw, self._t, z_lookup.size, y.size)
 
 
 class A2OnlyPlan:
@@ -1025,6 +1037,15 @@ def spec_den_gw_batch(plan: SsmPlan, pv, slf=None, scale=None, want_sd=True, cel
     sd = torch.empty((P, n_y), dtype=torch.float64, device=dev) if want_sd else None
     pw = torch.empty((P, n_y), dtype=torch.float64, device=dev)
     om = torch.empty((P, n_y), dtype=torch.float64, device=dev) if scale_t is not None else None
+    if getattr(plan, "general", False):
+        with STAGES.stage("spec_den_gw_general", 1):
+            t = plan._t
+            _lib.check(lib.ptt_spec_den_gw_general_batch(int(plan.z_lookup.size), _ptr(t["z_lookup"]), n_y, _ptr(t["y"]),
+                                                         int(plan.gw["n_int"]), _ptr(t["gw_Z1"]), _ptr(t["gw_Z2"]),
+                                                         _ptr(t["gw_G"]), float(plan.gw["prefactor"]), P, _ptr(pv),
+                                                         pv.shape[1], _ptr(slf_t), _ptr(scale_t), _ptr(sd), _ptr(pw),
+                                                         _ptr(om), _stream_ptr(torch)), "ptt_spec_den_gw_general_batch")
+        return sd, pw, om
     if cells is None:
         cells = USE_GW_CELLS and P >= GW_CELLS_MIN
     tabs = gw_cells(plan) if cells else False

@@ -9,6 +9,7 @@ import os
 
 import numpy as np
 
+from . import noise
 from . import ssmtools as ssm
 from .bubble import Bubble
 from .models import Phase
@@ -58,6 +59,8 @@ class Suppression:
         return self._interp
 
     def suppression(self, v_wall, alpha_n, method=SuppressionMethod.DEFAULT, interpolation="linear"):
+        if interpolation != "linear":
+            raise NotImplementedError("only the reference's default interpolation='linear' is implemented")
         scalar = np.isscalar(v_wall) and np.isscalar(alpha_n)
         if method == SuppressionMethod.NONE:
             return 1. if scalar else np.ones(np.broadcast(v_wall, alpha_n).shape)
@@ -74,6 +77,36 @@ class Suppression:
             sup[an_m < self.alpha_n_min] = 1
         sup[an_m > alpha_n_max_approx(vw_m)] = np.nan
         return sup
+
+    def _triangles(self):
+        """The Delaunay triangulation griddata builds (scipy.spatial.Delaunay = Qhull), as flat vertex / value tables."""
+        if getattr(self, "_tri", None) is None:
+            from scipy.spatial import Delaunay
+            pts = np.stack([self.v_walls, self.alpha_ns], axis=1)
+            simplices = Delaunay(pts).simplices
+            self._tri = (np.ascontiguousarray(pts[simplices].reshape(-1, 6)), np.ascontiguousarray(self.suppressions[simplices]))
+        return self._tri
+
+    def points_device(self, v_wall, alpha_n, method=SuppressionMethod.DEFAULT):
+        """points() on the device (ptt_suppression_batch): device tensors in, device tensor out."""
+        import ctypes as C
+        from . import _lib, engine
+        torch = engine._torch()
+        v_wall, alpha_n = engine.dev_f64(v_wall).reshape(-1), engine.dev_f64(alpha_n).reshape(-1)
+        if method == SuppressionMethod.NONE:
+            return torch.ones_like(v_wall)
+        if method not in (SuppressionMethod.NO_EXT, SuppressionMethod.EXT_CONSTANT):
+            raise ValueError(f"Got invalid suppression method: {method}")
+        if getattr(self, "_tri_dev", None) is None:
+            tri, val = self._triangles()
+            self._tri_dev = (engine.dev_f64(tri), engine.dev_f64(val))
+        tri, val = self._tri_dev
+        out = torch.empty_like(v_wall)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(_lib.load().ptt_suppression_batch(v_wall.numel(), p(v_wall), p(alpha_n), tri.shape[0], p(tri), p(val),
+                                                     int(method == SuppressionMethod.EXT_CONSTANT), float(self.alpha_n_min),
+                                                     p(out), engine._stream_ptr(torch)), "ptt_suppression_batch")
+        return out
 
     def points(self, v_wall, alpha_n, method=SuppressionMethod.DEFAULT):
         """Pointwise version for sweeps: suppression factor for matching arrays of (v_wall, alpha_n)."""
@@ -182,3 +215,19 @@ class Spectrum(ssm.SSMSpectrum):
         om = self.omgw0(**kw)
         i = int(np.argmax(om))
         return self.f()[i], om[i]
+
+    def noise(self):
+        """omgw0_ssm.py:117-118."""
+        return noise.omega_noise(self.f())
+
+    def noise_ins(self):
+        """omgw0_ssm.py:120-121."""
+        return noise.omega_ins(self.f())
+
+    def signal_to_noise_ratio(self) -> float:
+        """omgw0_ssm.py:143-144."""
+        return float(noise.signal_to_noise_ratio(f=self.f(), signal=self.omgw0(), noise=self.noise()))
+
+    def signal_to_noise_ratio_instrument(self) -> float:
+        """omgw0_ssm.py:146-147."""
+        return float(noise.signal_to_noise_ratio(f=self.f(), signal=self.omgw0(), noise=self.noise_ins()))

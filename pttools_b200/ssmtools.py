@@ -147,8 +147,8 @@ def spec_den_v_bag(z: np.ndarray, params, npt=NPTDEFAULT, z_st_thresh=Z_ST_THRES
 
 def spec_den_gw_scaled(z_lookup: np.ndarray, P_v_lookup: np.ndarray, y: np.ndarray = None, cs: float = CS0,
                        Gamma: float = GAMMA, source_lifetime_factor: float = 1., nz_int: int = None):
-    """spectrum.py:402-430.  z_lookup must be the log-uniform grid the reference itself always passes
-    (gen_lookup / np.logspace); anything else raises NotImplementedError rather than silently differing."""
+    """spectrum.py:402-430.  Any ascending z_lookup: the log-uniform grids the reference itself passes
+    (gen_lookup / np.logspace) take the arithmetic-index kernel, anything else np.interp by binary search."""
     z_lookup = np.asarray(z_lookup, dtype=float)
     P_v_lookup = np.asarray(P_v_lookup, dtype=float)
     if z_lookup.shape != P_v_lookup.shape:

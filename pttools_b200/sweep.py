@@ -33,6 +33,7 @@ class SweepResult:
 
     invalid: tp.Any = None
     stats: tp.Any = None
+    snr: tp.Any = None        # [n, 2]: signal_to_noise_ratio, signal_to_noise_ratio_instrument (sweep_spectra(snr=True))
 
     def take(self, rows):
         """The given rows (host int array) as a SweepResult of their own."""
@@ -118,7 +119,7 @@ def shell_chunk_points(n_xi: int, budget_bytes: tp.Optional[float] = None) -> in
     return int(max(1024, min(65536, budget_bytes // (3 * 8 * cap))))
 
 
-def omgw0_scale(v_wall, alpha_n, r_star, g_star=None, gs_star=None, suppression="default") -> np.ndarray:
+def omgw0_scale(v_wall, alpha_n, r_star, g_star=None, gs_star=None, suppression="default", device=False):
     """Per-point factor r_star * F_gw0 * suppression(v_wall, alpha_n) of Spectrum.omgw0 (omgw0_ssm.py:62-131).  Both
     in-scope models have non-physical temperatures, so the overrides of the reference apply (g_star_override takes
     gs_star when g_star is given: omgw0_ssm.py:74, sic)."""
@@ -126,12 +127,13 @@ def omgw0_scale(v_wall, alpha_n, r_star, g_star=None, gs_star=None, suppression=
     g_eff = om.G_STAR_DEFAULT if g_star is None else gs_star
     gs_eff = g_eff if gs_star is None else gs_star
     fgw0 = om.F_gw0(g_star=g_eff, gs_star=gs_eff)
-    if suppression == "default":
-        sup = om.DEFAULT_SUPPRESSION.points(v_wall, alpha_n)
-    elif suppression is None:
-        sup = np.ones_like(v_wall)
+    table = om.DEFAULT_SUPPRESSION if isinstance(suppression, str) and suppression == "default" else suppression
+    if table is None:
+        sup = engine.dev_f64(np.ones_like(v_wall)) if device else np.ones_like(v_wall)
+    elif device:
+        sup = table.points_device(v_wall, alpha_n)           # ptt_suppression_batch: interpolated on the device
     else:
-        sup = suppression.points(v_wall, alpha_n)
+        sup = table.points(v_wall, alpha_n)
     return r_star * fgw0 * sup
 
 
@@ -140,14 +142,17 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
                   n_xi=engine.N_XI_DEFAULT, Tn=None, g_star=None, gs_star=None, suppression="default",
                   chunk=8000, shell_chunk=None, want_pow_v=True, want_pow_gw=True, keep_bubbles=False, plan=None,
                   mem="device",
-                  allow_invalid=False, on_chunk=None, timing=False, out=None, sol_type=None) -> SweepResult:
+                  allow_invalid=False, on_chunk=None, timing=False, out=None, sol_type=None, snr=False) -> SweepResult:
     """Spectrum(Bubble(model, v_wall, alpha_n), y, r_star=...) for every point of a sweep: the model-independent shell
     solve, the thermodynamic scalars, the SSM chain and Omega_gw,0 (pttools/analysis/parallel.py:157-187 ->
     bubble.py:232-352 -> ssmtools/spectrum.py:96-115 -> omgw0/omgw0_ssm.py:123-131) in ONE call of the C ABI
     (ptt_sweep_spectra).  `model`: one Model, or a sequence with one Model per point that share csb2 (the sound speed of
     the GW integral, spectrum.py:99).  mem="device": result tables are torch tensors; "host": pinned numpy arrays,
     streamed out per chunk while the sweep runs.  Points the reference's Bubble constructor rejects come back with
-    status PTT_ST_INVALID_INPUT and NaN rows (`invalid` marks them)."""
+    status PTT_ST_INVALID_INPUT and NaN rows (`invalid` marks them).
+    snr=True (needs r_star): additionally the LISA signal-to-noise ratios of every point, Spectrum.signal_to_noise_ratio()
+    and .signal_to_noise_ratio_instrument() (omgw0_ssm.py:143-147), as `snr[n, 2]`; the frequencies are
+    f = y / r_star * f_star0(Tn, g_star) (omgw0_ssm.py:162-188)."""
     from . import bubble as bub
     from .models import Model
     torch = engine._torch()
@@ -168,17 +173,26 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
                               a=1.0, mode="ssm", only_lookup_pass=not want_pow_v)
     want_pow_v = want_pow_v and plan.has_y_pass
     pt = bub.point_table(model, vw, an, sol_type=sol_type, allow_invalid=allow_invalid)
-    scale = None if r_star is None else omgw0_scale(vw, an, r_star, g_star, gs_star, suppression)
+    scale = None if r_star is None else omgw0_scale(vw, an, r_star, g_star, gs_star, suppression, device=mem == "device")
+    snr_w = None
+    if snr:
+        if r_star is None:
+            raise ValueError("snr needs r_star (the frequencies today depend on it)")
+        from . import noise as nz
+        from . import omgw0 as om
+        g_eff = om.G_STAR_DEFAULT if g_star is None else gs_star                 # sic: omgw0_ssm.py:74
+        f = om.f(y, r_star, om.f_star0(om.T_default if Tn is None else Tn, g_eff))
+        snr_w = nz.snr_weights(f, (nz.omega_noise(f), nz.omega_ins(f)))
     want = (("pow_v",) if want_pow_v else ()) + (("pow_gw",) if want_pow_gw or scale is None else ()) + \
         (("omgw0",) if scale is not None else ())
     if mem == "device":
         pg_in, pm_in = engine.dev_f64(pt.pg), engine.dev_f64(pt.pm)
-        sc_in = None if scale is None else engine.dev_f64(scale)
+        sc_in = scale
     else:
         pg_in, pm_in, sc_in = pt.pg, pt.pm, scale
     res = engine.sweep_c(plan, pg_in, pm_in, sc_in, n_xi=n_xi, r_star=r_star, lifetime_multiplier=lifetime_multiplier,
                          chunk=chunk, shell_chunk=shell_chunk or 0, want=want, rows=keep_bubbles, mem=mem,
-                         on_chunk=on_chunk, timing=timing, out=out)
+                         on_chunk=on_chunk, timing=timing, out=out, snr_weights=snr_w)
     from . import _lib
     scal = {name: res.scalars[:, k] for k, name in enumerate(_lib.SWEEP_SCALARS)}
     asdev = (lambda a: a) if mem == "host" else engine.dev_f64
@@ -187,6 +201,7 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
                        omgw0=res.omgw0, scalars=scal)
     out_.invalid = pt.invalid
     out_.stats = res.stats
+    out_.snr = res.snr
     out_._keep = res
     if keep_bubbles:
         pg = engine.dev_f64(pt.pg)

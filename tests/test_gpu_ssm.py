@@ -317,3 +317,35 @@ def test_bubble_txt_through_the_kernels():
             prof = sb.sound_shell_bag(vw[i], alpha[i], 10000)
             t = ssm.a2_e_conserving_bag(z, vw[i], alpha[i], npt=(10000, 1000), profile=prof)
         np.testing.assert_allclose(got[i, 1:], [x.sum() for x in t], rtol=2e-6)
+
+
+def test_spec_den_gw_scaled_on_an_arbitrary_lookup_grid():
+    """spec_den_gw_scaled takes any ascending z_lookup (np.interp, spectrum.py:361-363): a non-uniform grid and unordered
+    y through the binary-search kernel, against the oracle; and the same kernel against the arithmetic-index kernel on a
+    log-uniform grid."""
+    import torch
+    from pttools_b200 import engine, ssmtools
+    rng = np.random.default_rng(21)
+    cs = 0.55
+    z_lookup = np.sort(np.concatenate([np.logspace(-2, 4, 700), rng.uniform(0.5, 50, 300)]))
+    z_lookup = z_lookup[np.concatenate(([True], np.diff(z_lookup) > 0))]
+    pv = z_lookup ** 3 / (1 + (z_lookup / 7) ** 7) * (1 + 0.2 * np.sin(2 * np.log(z_lookup)))
+    y = np.array([30.0, 0.7, 5.0, 120.0, 2.2])                 # not ordered
+    got, y_out = ssmtools.spec_den_gw_scaled(z_lookup, pv, y, cs=cs, source_lifetime_factor=0.8, nz_int=900)
+    want = ssm.spec_den_gw_scaled(z_lookup, pv, y, cs, source_lifetime_factor=0.8, nz_int=900)[0]
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    np.testing.assert_array_equal(y_out, y)
+    # y = None: the reference builds it from the lookup range
+    got2, y2 = ssmtools.spec_den_gw_scaled(z_lookup, pv, cs=cs)
+    want2, y2_ref = ssm.spec_den_gw_scaled(z_lookup, pv, None, cs)
+    np.testing.assert_allclose(y2, y2_ref, rtol=1e-13)
+    np.testing.assert_allclose(got2, want2, rtol=1e-9)
+    # both kernels on a log-uniform grid
+    zl = np.logspace(-2, 4, 1500)
+    pv2 = torch.as_tensor((zl ** 3 / (1 + (zl / 7) ** 7))[None, :].repeat(3, 0), device="cuda")
+    yy = np.logspace(-0.5, 2, 40)
+    a = engine.spec_den_gw_batch(engine.GwOnlyPlan(zl, yy, cs=cs), pv2, cells=False)[0].cpu().numpy()
+    plan_g = engine.GwOnlyPlan(zl, yy, cs=cs)
+    plan_g.general = True
+    b = engine.spec_den_gw_batch(plan_g, pv2)[0].cpu().numpy()
+    np.testing.assert_allclose(b, a, rtol=1e-10)

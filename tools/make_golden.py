@@ -409,7 +409,33 @@ def config3_grid():
     print("ref_config3_grid.npz")
 
 
-TASKS.update({"headline_grid": headline_grid, "config3_grid": config3_grid})
+def noise_snr():
+    """LISA noise curves (omgw0/noise.py) on a frequency grid and Spectrum.signal_to_noise_ratio[_instrument]
+    (omgw0_ssm.py:143-147) for bag bubbles, Spectrum(r_star=0.1) and Spectrum(r_star=0.01, Tn=500)."""
+    from pttools.omgw0 import noise, Spectrum
+    from pttools.models import BagModel
+    from pttools.bubble import Bubble
+    f = np.logspace(-5, 0, 200)
+    d = {"f": f}
+    for name in ("omega_noise", "omega_ins", "omega_gb", "omega_eb", "S_AE", "S_gb", "P_acc", "S_AE_approx"):
+        d[name] = getattr(noise, name)(f)
+    d["consts"] = np.array([noise.FT_LISA, noise.F2_LISA, noise.P_oms(), noise.N_acc()])
+    model = BagModel(a_s=1.1, a_b=1, V_s=1)
+    pts = [(0.5, 0.1), (0.7, 0.1), (0.9, 0.1), (0.62, 0.15)]
+    d["points"] = np.array(pts)
+    rows = []
+    for vw, an in pts:
+        b = Bubble(model, vw, an)
+        for kw in ({"r_star": 0.1}, {"r_star": 0.01, "Tn": 500}):
+            s = Spectrum(b, **kw)
+            rows.append([vw, an, kw["r_star"], kw.get("Tn", 100), s.signal_to_noise_ratio(), s.signal_to_noise_ratio_instrument(),
+                         s.f()[0], s.f()[-1]])
+            print(rows[-1])
+    d["snr"] = np.array(rows)
+    np.savez_compressed(os.path.join(OUT, "ref_noise_snr.npz"), **d)
+
+
+TASKS.update({"headline_grid": headline_grid, "config3_grid": config3_grid, "noise_snr": noise_snr})
 
 
 if __name__ == "__main__":
