@@ -76,7 +76,7 @@ def _cpu_setup(path):
     warnings.filterwarnings("ignore")
     from oracle import models, shell_generic as sg
     _CPU["path"] = path
-    if path == "generic":
+    if path in ("generic", "shells"):
         _CPU["model"] = models.bag_model(a_s=1.0 / (1 - 3 * 0.005 * 0.999), a_b=1.0, V_s=1.0)
         _CPU["ref"] = sg.FluidReference(dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_fluid_reference.npz"))))
 
@@ -84,8 +84,15 @@ def _cpu_setup(path):
 def _cpu_point(args):
     vw, an = args
     from oracle import shell_bag as sb, shell_generic as sg, ssm
-    if sb.identify_solution_type(vw, an) == sb.ERROR:
+    if not _CPU.get("skip_bag_type") and sb.identify_solution_type(vw, an) == sb.ERROR:
         return 0
+    if _CPU["path"] == "shells":
+        try:
+            sol = sg.sound_shell_generic(_CPU["model"], vw, an, _CPU["ref"])
+            sg.bubble_scalars(_CPU["model"], sol, vw)
+        except (ValueError, RuntimeError, IndexError):
+            return 0
+        return 1
     if _CPU["path"] == "bag":
         ssm.power_gw_scaled_bag(Y, (vw, an), NPT)
         return 1
@@ -268,6 +275,9 @@ def gpu_arm(args):
     for s in range(args.warmup):
         device_step(s)
     barrier()
+    import gc
+    gc.collect()
+    gc.disable()          # no collector pauses inside the timed regions (re-enabled below)
     if sampler:
         sampler.mark_start()
     engine.STAGES.enable(True)
@@ -328,6 +338,7 @@ def gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
+    gc.enable()
 
     if rank == 0:
         value = B * world * args.steps / (dev_ms * 1e-3)
@@ -417,6 +428,300 @@ def cpu_baseline_leg(B, cores, args):
                       f"fork pool of {cores} processes, {dt:.1f} s"}
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# The other configurations of BASELINE.json (1 GPU): --workload config3 | config2-shells | config4
+# ---------------------------------------------------------------------------------------------------------------
+
+def _timed(step, steps, warmup):
+    """warmup untimed calls of step(s), then `steps` timed ones: device ms (CUDA events on the launching stream) and wall ms."""
+    import torch
+    for s in range(warmup):
+        step(s)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    per = []
+    for s in range(warmup, warmup + steps):
+        t1 = time.perf_counter()
+        step(s)
+        torch.cuda.synchronize()
+        per.append(1e3 * (time.perf_counter() - t1))
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b), 1e3 * (time.perf_counter() - t0), per
+
+
+def _peaks(engine):
+    hbm = 6554.2
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm = float(json.load(f).get("hbm_gbs", hbm))
+    except (OSError, ValueError):
+        pass
+    return engine.fp64_peak_flops() / 1e12, hbm
+
+
+def _emit(out, sampler):
+    out["clocks"] = sampler.stop() if sampler else None
+    print(json.dumps(out), file=RESULT, flush=True)
+
+
+def config3_models():
+    """Config 3: ConstCSModel(css2, csb2, a_s=5, a_b=1, V_s=1, alpha_n_min=0.05) for css2, csb2 in linspace(1/4, 1/3, 8)
+    (the reference's example uses the corners {1/3, 1/4}^2, examples/const_cs/const_cs_gw.py:153-157), grouped by csb2.
+    Combinations for which the reference's parameter search raises are left out (counted)."""
+    import logging
+    from pttools_b200.models import ConstCSModel
+    logging.disable(logging.CRITICAL)
+    vals = np.linspace(0.25, 1 / 3, 8)
+    fams, skipped = [], 0
+    for csb2 in vals:
+        fam = []
+        for css2 in vals:
+            try:
+                fam.append(ConstCSModel(css2=float(css2), csb2=float(csb2), a_s=5, a_b=1, V_s=1, alpha_n_min=0.05))
+            except Exception:       # noqa: BLE001 - the reference's constructor rejects the combination
+                skipped += 1
+        fams.append(fam)
+    logging.disable(logging.NOTSET)
+    return fams, skipped
+
+
+def workload_config3(args):
+    import torch
+    from pttools_b200 import engine, fluid_reference, sweep
+    torch.cuda.set_device(0)
+    fluid_reference.ref()
+    fams, skipped = config3_models()
+    v_walls, alpha_ns = np.linspace(0.05, 0.95, 128), np.linspace(0.05, 0.5, 128)
+    kw = dict(y=Y, r_star=R_STAR, Tn=200, n_xi=N_XI, want_pow_v=False, chunk=args.chunk)
+    counts = {}
+
+    def step(s, mem="device"):
+        fam = fams[s % len(fams)]
+        res = sweep.sweep_models(fam, v_walls, alpha_ns, mem=mem, timing=mem == "device", **kw)
+        counts[s % len(fams)] = sum(int(r["mask"].sum()) for r in res)
+        return res
+
+    sampler = ClockSampler(0)
+    for s in range(len(fams)):       # every family once: plans, cell tables, point counts
+        step(s)
+    sampler.mark_start()
+    engine.STAGES.enable(True)
+    dev_ms, wall_ms, per = _timed(step, args.steps, args.warmup)
+    stage_ms = engine.STAGES.summary()
+    engine.STAGES.enable(False)
+    n_pts = sum(counts[s % len(fams)] for s in range(args.warmup, args.warmup + args.steps))
+    e2e_ms, _, _ = _timed(lambda s: step(s, mem="host"), args.steps, 1)
+    peak, hbm = _peaks(engine)
+    cores = len(os.sched_getaffinity(0))
+    cpu = None
+    if not args.no_cpu_baseline:
+        m = fams[-1][-1]
+        n_cpu = 2 * max(cores, 8)
+        iv = np.linspace(0, 127, n_cpu).astype(int)
+        pts = [(float(v_walls[i]), float(alpha_ns[(37 * k) % 128])) for k, i in enumerate(iv)]
+        dt = cpu_run_model(pts, cores, (m.css2, m.csb2, m.a_s, m.a_b, m.V_s))
+        cpu = {"value": n_cpu / dt, "unit": "spectra/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} points of the 128x128 grid for the model (css2, csb2) = ({m.css2:.4f}, {m.csb2:.4f}), fork pool, {dt:.1f} s"}
+    _emit({"metric": "bubble+GW spectra/sec", "value": n_pts / (dev_ms * 1e-3), "unit": "spectra/s", "n_gpus": 1,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "config3: 64 ConstCSModel(css2, csb2, a_s=5, a_b=1, V_s=1, alpha_n_min=0.05), css2, csb2 in "
+                                  "linspace(1/4, 1/3, 8); v_wall=linspace(0.05,0.95,128) x alpha_n=linspace(0.05,0.5,128) restricted "
+                                  "to alpha_n >= model.alpha_n_min; Spectrum(r_star=0.1, Tn=200) at the default sizes; one step = the "
+                                  "8 models that share csb2 in ONE sweep ordered by v_wall",
+                      "models_skipped_by_constructor": skipped, "points_per_family": [counts[k] for k in sorted(counts)],
+                      "per_step_wall_ms": per, "l2": "working set per step far above the 126 MB L2"},
+           "e2e": {"value": n_pts / (e2e_ms * 1e-3), "unit": "spectra/s", "steps": args.steps,
+                   "h2d_bytes_per_step": 21 * 8 * n_pts // args.steps, "d2h_bytes_per_step": (8 * Y.size + 260) * n_pts // args.steps},
+           "gpu_launches": int(engine.STAGES.launches), "stage_ms_per_step": {k: v["ms"] / args.steps for k, v in stage_ms.items()},
+           "roofline": None, "cpu_baseline": cpu}, sampler)
+
+
+def workload_config2_shells(args):
+    import torch
+    from pttools_b200 import bubble, engine, fluid_reference
+    from pttools_b200.models import BagModel
+    torch.cuda.set_device(0)
+    model = BagModel(alpha_n_min=0.005)
+    fluid_reference.ref()
+    B = args.batch
+    sampler = ClockSampler(0)
+    stats = {"samples": 0.0, "ok": 0, "n": 0}
+    tables = {}
+
+    def prep(s):
+        if s not in tables:
+            vw, an = batch_points(s, 0, 1, B)
+            pt = bubble.point_table(model, vw, an)
+            tables[s] = (vw, an, pt, engine.dev_f64(pt.pg), engine.dev_f64(pt.pm))
+        return tables[s]
+
+    def step_generic(s, count=True):
+        vw, an, pt, pg, pm = prep(s)
+        out = engine.sweep_c(None, pg, pm, n_xi=N_XI, rows=False, timing=True)
+        if count:
+            stats["samples"] += float(torch.nan_to_num(out.scalars[:, 31]).sum())
+            stats["ok"] += int((out.status == 0).sum())
+            stats["n"] += B
+        return out
+
+    def step_bag(s):
+        vw, an, *_ = prep(s)
+        return engine.sweep_shells_bag(vw, an, n_xi=N_XI)
+
+    def step_host(s):
+        vw, an, pt, *_ = prep(s)
+        return engine.sweep_c(None, pt.pg, pt.pm, n_xi=N_XI, mem="host")
+
+    total = args.warmup + args.steps
+    for s in range(total):
+        prep(s)
+    sampler.mark_start()
+    engine.STAGES.enable(True)
+    dev_ms, wall_ms, per = _timed(step_generic, args.steps, args.warmup)
+    stage_ms = engine.STAGES.summary()
+    engine.STAGES.enable(False)
+    bag_ms, _, _ = _timed(step_bag, args.steps, args.warmup)
+    bag = step_bag(args.warmup)
+    bag_samples = float(bag.npts[bag.status == 0].sum())
+    e2e_ms, _, _ = _timed(step_host, args.steps, 1)
+    # per solution type: pure batches of one type drawn from the grid
+    per_type = {}
+    v_walls, alpha_ns = np.linspace(0.05, 0.95, GRID_N), np.linspace(0.005, 0.5, GRID_N)
+    vw_all, an_all = np.repeat(v_walls, 40), np.tile(alpha_ns[::25], GRID_N)
+    codes = model.solution_type_codes(vw_all, an_all, np.asarray(model.wn(an_all)))
+    for code, name in ((0, "sub_def"), (1, "hybrid"), (2, "detonation")):
+        sel = np.nonzero(codes == code)[0][:16000]
+        pt = bubble.point_table(model, vw_all[sel], an_all[sel])
+        pg, pm = engine.dev_f64(pt.pg), engine.dev_f64(pt.pm)
+        ms, _, _ = _timed(lambda s: engine.sweep_c(None, pg, pm, n_xi=N_XI), 3, 2)
+        per_type[name] = {"points": int(sel.size), "shells_per_s": sel.size * 3 / (ms * 1e-3)}
+    peak, hbm = _peaks(engine)
+    k3 = stage_ms.get("shells_generic", {"ms": 0.0})["ms"] / args.steps
+    bytes_step = 24.0 * stats["samples"] / args.steps
+    roof = {"kernel": "shells_generic", "bound": "hbm", "achieved": bytes_step / (k3 * 1e-3) / 1e9 if k3 else None, "peak": hbm,
+            "unit": "GB/s", "frac": (bytes_step / (k3 * 1e-3) / 1e9 / hbm) if k3 else None, "traffic": None,
+            "ms_per_step": k3, "note": "one thread per point, latency bound: the profile rows (3 x 8 B per sample) are the only "
+            "algorithmic HBM traffic"}
+    cores = len(os.sched_getaffinity(0))
+    cpu = None
+    if not args.no_cpu_baseline:
+        n_cpu = 16 * max(cores, 8)
+        vw, an = batch_points(0, 0, 1, B)
+        pick = np.linspace(0, B - 1, n_cpu).astype(int)
+        dt = cpu_run(list(zip(vw[pick], an[pick])), cores, "shells")
+        cpu = {"value": n_cpu / dt, "unit": "shells/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} points of the batch of step 0 through the port of sound_shell_generic, fork pool, {dt:.1f} s"}
+    _emit({"metric": "fluid shells/sec", "value": B * args.steps / (dev_ms * 1e-3), "unit": "shells/s", "n_gpus": 1,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "config2-shells: BagModel(alpha_n_min=0.005) grid v_wall=linspace(0.05,0.95,1000) x "
+                                  "alpha_n=linspace(0.005,0.5,1000), n_xi=5000; value = Bubble(model, v_wall, alpha_n).solve() "
+                                  "(model-independent solver + the reference's retries + thermodynamic scalars, ptt_sweep_spectra "
+                                  "without spectra), inputs resident in HBM",
+                      "batch_per_step": B, "valid_fraction": stats["ok"] / max(1, stats["n"]),
+                      "profile_samples_per_shell": stats["samples"] / max(1, stats["ok"]), "per_step_wall_ms": per,
+                      "variants": {"sound_shell_bag (old API, ptt_sweep_shells_bag)": {
+                          "shells_per_s": B * args.steps / (bag_ms * 1e-3), "ms_per_step": bag_ms / args.steps,
+                          "hbm_write_GBps": 24.0 * bag_samples / (bag_ms / args.steps * 1e-3) / 1e9},
+                          "per_solution_type (generic solver, pure batches)": per_type}},
+           "e2e": {"value": B * args.steps / (e2e_ms * 1e-3), "unit": "shells/s", "steps": args.steps,
+                   "h2d_bytes_per_step": 20 * 8 * B, "d2h_bytes_per_step": 260 * B},
+           "gpu_launches": int(engine.STAGES.launches), "stage_ms_per_step": {k: v["ms"] / args.steps for k, v in stage_ms.items()},
+           "roofline": roof, "cpu_baseline": cpu}, sampler)
+
+
+def workload_config4(args):
+    """Config 4: batched sin_transform, 10^4 profiles x 4096 wavenumbers x 8192 xi (f_p = max(0, cos(xi + phi_p)) on
+    [xi_a, xi_b], numpy default_rng(0): generalises tests/test_performance.py:76-87 of the reference), then
+    spec_den_gw_scaled with z_lookup[10^4] and y[4096] for the same number of profiles."""
+    import torch
+    from pttools_b200 import engine
+    torch.cuda.set_device(0)
+    P, n_z, n_xi = 10000, 4096, 8192
+    rng = np.random.default_rng(0)
+    phi, xa = rng.uniform(0, 1, P), rng.uniform(0.05, 0.5, P)
+    xb = xa + rng.uniform(0.05, 0.45, P)
+    xi = np.linspace(0, 1, n_xi)
+    f = np.maximum(0, np.cos(xi[None, :] + phi[:, None])) * ((xi[None, :] > xa[:, None]) & (xi[None, :] < xb[:, None]))
+    xi_h = np.broadcast_to(xi, (P, n_xi)).copy()
+    xi_d, f_d = engine.dev_f64(xi_h), engine.dev_f64(f)
+    off, npts = np.zeros(P, np.int32), np.full(P, n_xi, np.int32)
+    z_mixed = np.logspace(-1, 3, n_z)
+    z_exact = np.logspace(-1, np.log10(50), n_z)
+    sampler = ClockSampler(0)
+    sampler.mark_start()
+    ms_mixed, _, per = _timed(lambda s: engine.sin_transform_batch(z_mixed, xi_d, f_d, off, npts, method="moments"), args.steps, args.warmup)
+    ms_exact, _, _ = _timed(lambda s: engine.sin_transform_batch(z_exact, xi_d, f_d, off, npts, method="moments"), args.steps, args.warmup)
+    pin_x, pin_f = torch.from_numpy(xi_h).pin_memory(), torch.from_numpy(f).pin_memory()
+    pin_o = torch.empty((P, n_z), dtype=torch.float64).pin_memory()
+
+    def e2e(s):
+        r = engine.sin_transform_batch(z_mixed, pin_x.to("cuda", non_blocking=True), pin_f.to("cuda", non_blocking=True), off, npts,
+                                       method="moments")
+        pin_o.copy_(r, non_blocking=True)
+    e2e_ms, _, _ = _timed(e2e, args.steps, 1)
+    # GW integral on the same scale
+    y4 = np.logspace(-1, 3, 4096)
+    gplan = engine.GwOnlyPlan(10.0 ** np.linspace(np.log10(y4.min() * 0.5 * (1 - engine.CS0) / engine.CS0 - 1e-8),
+                                                  np.log10(y4.max() * 0.5 * (1 + engine.CS0) / engine.CS0 + 1e-8), 10000), y4)
+    zl = gplan.z_lookup
+    pv = engine.dev_f64((zl ** 3 / (1 + (zl / 10) ** 8))[None, :] * rng.uniform(0.5, 2, (2000, 1)))
+    ms_gw, _, _ = _timed(lambda s: engine.spec_den_gw_batch(gplan, pv, want_sd=False), 3, 2)
+    peak, hbm = _peaks(engine)
+    n_lo = int((z_mixed <= 50).sum())
+    blocks = np.minimum(128.0, 2.0 ** np.ceil(np.log2(np.maximum(z_mixed[z_mixed <= 50] / 0.4, 1.0))))
+    flop = P * (22.0 * blocks.sum() + 60.0 * (n_z - n_lo) + 24.0 * n_xi)
+    byts = P * (2.0 * n_xi + n_z) * 8
+    dur = ms_mixed / args.steps * 1e-3
+    roof = {"kernel": "sin_transform (block moments)", "bound": "hbm", "achieved": byts / dur / 1e9, "peak": hbm, "unit": "GB/s",
+            "frac": byts / dur / 1e9 / hbm, "traffic": None, "fp64_TFLOPs": flop / dur / 1e12, "fp64_frac": flop / dur / 1e12 / peak,
+            "note": "algorithmic bytes = profiles in (xi, f) + transform out; flops = 22 per (exact wavenumber, block) + 24 per sample"}
+    cores = len(os.sched_getaffinity(0))
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import ssm
+        n_cpu = 8
+        t0 = time.perf_counter()
+        for p in range(n_cpu):
+            ssm.sin_transform(z_mixed, xi, f[p])
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_cpu / dt, "unit": "profiles/s", "cores": 1, "kind": "port",
+               "sample": f"{n_cpu} profiles through the numpy port of sin_transform (one thread), {dt:.1f} s"}
+    _emit({"metric": "sin_transform profiles/sec", "value": P * args.steps / (ms_mixed * 1e-3), "unit": "profiles/s", "n_gpus": 1,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_mixed / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "config4: sin_transform of 10^4 profiles x 4096 wavenumbers z=logspace(-1,3) (mixed exact / asymptotic) "
+                                  "x 8192 xi samples, inputs resident in HBM (1.3 GB, above the L2)",
+                      "all_exact_z_ms_per_step": ms_exact / args.steps, "per_step_wall_ms": per,
+                      "sine_products_per_s_equivalent": P * n_lo * n_xi / dur,
+                      "spec_den_gw_scaled": {"profiles": 2000, "n_y": 4096, "n_z_lookup": 10000, "ms": ms_gw / 3,
+                                             "profiles_per_s": 2000 * 3 / (ms_gw * 1e-3)}},
+           "e2e": {"value": P * args.steps / (e2e_ms * 1e-3), "unit": "profiles/s", "steps": args.steps,
+                   "h2d_bytes_per_step": int(P * 2 * n_xi * 8), "d2h_bytes_per_step": int(P * n_z * 8)},
+           "gpu_launches": 3 * (2 * args.steps + 2 * args.warmup), "roofline": roof, "cpu_baseline": cpu}, sampler)
+
+
+def cpu_run_model(points, cores, model_params):
+    import multiprocessing as mp
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import models, shell_generic as sg
+    css2, csb2, a_s, a_b, V_s = model_params
+    _CPU["path"] = "generic"
+    _CPU["model"] = models.const_cs_model(css2, csb2, a_s, a_b, V_s)
+    _CPU["ref"] = sg.FluidReference(dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_fluid_reference.npz"))))
+    _CPU["skip_bag_type"] = True
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_point, points, chunksize=1)
+    _CPU.pop("skip_bag_type", None)
+    return time.perf_counter() - t0
+
+
 RESULT = sys.stdout
 
 
@@ -438,11 +743,17 @@ if __name__ == "__main__":
     ap.add_argument("--chunk", type=int, default=8000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="generic", choices=["generic"])
+    ap.add_argument("--workload", default="headline", choices=["headline", "config3", "config2-shells", "config4"],
+                    help="headline = configs 2/5 of BASELINE.json (the metric's configuration); the others are extra lines")
     ap.add_argument("--pow-v", action="store_true", help="also compute pow_v (the y pass of spec_den_v)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     RESULT = _claim_stdout()
     if a.impl == "reference":
         reference_arm(a)
-    else:
+    elif a.workload == "headline":
         gpu_arm(a)
+    else:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            sys.exit("the extra workloads run on one GPU")
+        {"config3": workload_config3, "config2-shells": workload_config2_shells, "config4": workload_config4}[a.workload](a)

@@ -244,47 +244,47 @@ def point_table(model, v_wall, alpha_n, sol_type=None, allow_invalid=False) -> P
     vw = np.asarray(v_wall, dtype=float).reshape(-1)
     an = np.asarray(alpha_n, dtype=float).reshape(-1)
     n = vw.size
-    single = isinstance(model, Model)
+    if not isinstance(model, Model):
+        # one model per point: the closed forms are vectorised per distinct model, then put back in place
+        models = list(model)
+        if len(models) != n:
+            raise ValueError("one model per point is needed")
+        pg, pm = np.zeros((n, 16)), np.zeros((n, 4))
+        wn, codes, invalid = np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=bool)
+        ids = np.array([id(m) for m in models])
+        st = None if sol_type is None else np.asarray(sol_type, dtype=np.int32).reshape(-1)
+        for uid in np.unique(ids):
+            sel = np.nonzero(ids == uid)[0]
+            sub = point_table(models[sel[0]], vw[sel], an[sel], None if st is None else st[sel], allow_invalid)
+            pg[sel], pm[sel], wn[sel], codes[sel], invalid[sel] = sub.pg, sub.pm, sub.wn, sub.codes, sub.invalid
+        return PointTable(pg, pm, wn, codes, invalid)
     with np.errstate(invalid="ignore", divide="ignore"):
-        if single:
-            wn = np.asarray(model.wn(an), dtype=float).reshape(-1)
-            codes = model.solution_type_codes(vw, an, wn) if sol_type is None else \
-                np.asarray(sol_type, dtype=np.int32).reshape(-1)
-            v_cj = np.asarray(model.v_chapman_jouguet(an, wn), dtype=float).reshape(-1)
-            an_min = np.full(n, model.alpha_n_min)
-            tn = np.asarray(model.temp(wn, Phase.SYMMETRIC), dtype=float).reshape(-1)
-            t_crit = np.full(n, model.T_crit)
-        else:
-            wn = np.array([m.wn(a) for m, a in zip(model, an)], dtype=float)
-            codes = np.array([SOL_CODE[m.solution_type(v, a, w)] for m, v, a, w in zip(model, vw, an, wn)],
-                             dtype=np.int32) if sol_type is None else np.asarray(sol_type, dtype=np.int32).reshape(-1)
-            v_cj = np.array([m.v_chapman_jouguet(a, w) for m, a, w in zip(model, an, wn)], dtype=float)
-            an_min = _per_point(model, n, "alpha_n_min")
-            tn = np.array([m.temp(w, Phase.SYMMETRIC) for m, w in zip(model, wn)], dtype=float)
-            t_crit = _per_point(model, n, "T_crit")
+        wn = np.asarray(model.wn(an), dtype=float).reshape(-1)
+        codes = model.solution_type_codes(vw, an, wn) if sol_type is None else \
+            np.asarray(sol_type, dtype=np.int32).reshape(-1)
+        v_cj = np.asarray(model.v_chapman_jouguet(an, wn), dtype=float).reshape(-1)
+        tn = np.asarray(model.temp(wn, Phase.SYMMETRIC), dtype=float).reshape(-1)
         codes = np.array(codes, dtype=np.int32)
         invalid = ~np.isfinite(wn) | (codes < 0) | (vw < 0) | (vw > 1)
         if not allow_invalid:
-            invalid |= (an < 0) | (an < an_min) | (tn > t_crit)
+            invalid |= (an < 0) | (an < model.alpha_n_min) | (tn > model.T_crit)
     codes[invalid] = -1
-    guesses = fluid_reference.ref().get_batch(vw, an, np.where(invalid, 0, codes)).cpu().numpy()   # vp, vm, vp~, vm~, wp, wm
+    guesses = fluid_reference.ref().get_batch(vw, an, codes).cpu().numpy()   # vp, vm, vp~, vm~, wp, wm
     pg = np.zeros((n, 16))
     pg[:, 0], pg[:, 1], pg[:, 2], pg[:, 3], pg[:, 4] = vw, an, codes, wn, v_cj
     pg[:, 5], pg[:, 6] = guesses[:, 0], guesses[:, 2]
     pg[:, 7] = guesses[:, 4] * wn                         # fluid.py:939-941
     wm_g = guesses[:, 5] * wn
     pg[:, 8] = np.where(np.isnan(wm_g), 0.3 * wn, wm_g)   # fluid.py:942-949
-    for col, attr in ((9, "css2"), (10, "csb2"), (11, "V_s"), (12, "V_b")):
-        pg[:, col] = _per_point(model, n, attr)
-    pg[:, 13] = [1.0 if m.name == "bag" else 0.0 for m in ([model] * n if single else model)]
+    pg[:, 9], pg[:, 10], pg[:, 11], pg[:, 12] = model.css2, model.csb2, model.V_s, model.V_b
+    pg[:, 13] = 1.0 if model.name == "bag" else 0.0
     # entropy density s(w) = coef * w^(1 - 1/mu) per phase (s = w / T): the retry search applies the reference's
     # entropy-flux test to its scan starts
-    a_s_, a_b_, t0 = (_per_point(model, n, k) for k in ("a_s", "a_b", "T_ref"))
-    mus, mub = 1 + 1 / pg[:, 9], 1 + 1 / pg[:, 10]
-    pg[:, 14] = (mus * a_s_) ** (1 / mus) * t0 ** (4 / mus - 1)
-    pg[:, 15] = (mub * a_b_) ** (1 / mub) * t0 ** (4 / mub - 1)
+    mus, mub = 1 + 1 / model.css2, 1 + 1 / model.csb2
+    pg[:, 14] = (mus * model.a_s) ** (1 / mus) * model.T_ref ** (4 / mus - 1)
+    pg[:, 15] = (mub * model.a_b) ** (1 / mub) * model.T_ref ** (4 / mub - 1)
     pm = np.zeros((n, 4))
-    pm[:, 0], pm[:, 1], pm[:, 2] = a_s_, a_b_, t0
+    pm[:, 0], pm[:, 1], pm[:, 2] = model.a_s, model.a_b, model.T_ref
     return PointTable(pg, pm, wn, codes, invalid)
 
 
