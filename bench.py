@@ -258,12 +258,15 @@ def gpu_arm(args):
         parts = [batch_points(s, r, world, B) for r in range(world)]
         return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
 
+    # the result table of a step: on rank 0, written by all ranks (CUDA IPC, peer stores over NVLink); allocated once
+    shared = sweep.SharedTable(B * world, Y.size) if world > 1 else None
+
     def device_step(s):
         """One pass of the hot path through the product's sweep API: rank 0 ends with the Omega_gw,0 table of all
         world x B points in HBM, in the order of the input points (config 5 of BASELINE.json)."""
         vw, an = step_points(s)
         return sweep.sweep_omgw0_distributed(model, vw, an, y=Y, r_star=R_STAR, n_xi=N_XI, chunk=args.chunk, plan=plan,
-                                             timing=True)
+                                             timing=True, shared=shared)
 
     def barrier():
         if world > 1:
@@ -395,7 +398,8 @@ def gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS["generic"], "batch_per_step": B * world, "batch_per_gpu_per_step": B,
                        "chunk": args.chunk, "api": "sweep.sweep_omgw0_distributed -> ptt_sweep_spectra (one C call per rank and "
-                       "step); whole v_wall rows per rank, blocks sent to rank 0 as they finish",
+                       "step); whole v_wall rows per rank; every rank writes its rows into the table on rank 0 (CUDA IPC, peer "
+                       "stores over NVLink) chunk by chunk as they are produced",
                        "l2": "per-step working set (profiles + A2 + lookup tables, ~1 MB per point) exceeds the 126 MB L2; "
                              "every step uses fresh points",
                        "valid_points_in_timed_region_rank0": n_ok, "per_step_ms": per_step_ms,
@@ -415,6 +419,9 @@ def gpu_arm(args):
         }
         print(json.dumps(out), file=RESULT, flush=True)
     if world > 1:
+        dist.barrier()
+        if shared is not None:
+            shared.close()
         dist.destroy_process_group()
 
 

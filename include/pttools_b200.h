@@ -375,6 +375,10 @@ typedef struct ptt_sweep_out {
     double *rows_v, *rows_w, *rows_xi;   /* optional profiles [n, row_stride] (device memory only), with off/npts */
     int64_t row_stride;
     int32_t *off, *npts;
+    const int64_t* table_rows; /* HOST [n] or NULL (PTT_MEM_DEVICE only): row of point i in pow_v / pow_gw / omgw0, for tables
+                                * larger than this call's n -- e.g. the shard of a sweep writing straight into the full
+                                * table, which may live on ANOTHER GPU of the box (peer memory opened with ptt_ipc_open:
+                                * the rows then travel over NVLink as they are produced, no collective) */
     double* snr;               /* [n, n_snr] or NULL: signal-to-noise ratios of omgw0 (needs omgw0's scale and snr_weight) */
     const double* snr_weight;  /* DEVICE [n_snr, n_y], see ptt_snr_batch */
     int32_t n_snr, reserved;
@@ -421,6 +425,13 @@ typedef struct ptt_sweep_stats {
 int ptt_sweep_last_stats(ptt_sweep_stats_t* out);
 /* frees the device / pinned workspace the sweep driver keeps between calls */
 int ptt_sweep_release(void);
+/* Device buffers that other processes of the box can map (CUDA IPC): the result table of a sharded sweep lives on one
+ * GPU, every rank's sweep writes its rows into it through ptt_sweep_out_t.table_rows.  handle: 64 bytes to hand to the
+ * other processes (any transport); ptt_ipc_open maps it there (peer access over NVLink / NVSwitch is enabled lazily). */
+int ptt_ipc_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int ptt_ipc_open(const unsigned char* handle64, void** ptr);
+int ptt_ipc_close(void* ptr);
+int ptt_ipc_free(void* ptr);
 /* points per shell solve the driver would pick for `free_bytes` of device memory */
 int64_t ptt_sweep_shell_chunk(int n_xi, int64_t free_bytes);
 

@@ -71,7 +71,8 @@ class SweepOpts(C.Structure):
 class SweepOut(C.Structure):
     _fields_ = [("pow_v", C.c_void_p), ("pow_gw", C.c_void_p), ("omgw0", C.c_void_p), ("scalars", C.c_void_p),
                 ("status", C.c_void_p), ("rows_v", C.c_void_p), ("rows_w", C.c_void_p), ("rows_xi", C.c_void_p),
-                ("row_stride", C.c_int64), ("off", C.c_void_p), ("npts", C.c_void_p), ("snr", C.c_void_p),
+                ("row_stride", C.c_int64), ("off", C.c_void_p), ("npts", C.c_void_p), ("table_rows", C.c_void_p),
+                ("snr", C.c_void_p),
                 ("snr_weight", C.c_void_p), ("n_snr", C.c_int32), ("reserved", C.c_int32)]
 
 
@@ -161,6 +162,10 @@ SIGNATURES = {
     "ptt_ssm_plan_info": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_sweep_spectra": (C.c_int, [C.POINTER(SweepPlan), C.POINTER(SweepOpts), C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(SweepOut), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ptt_ipc_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "ptt_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ptt_ipc_close": (C.c_int, [C.c_void_p]),
+    "ptt_ipc_free": (C.c_int, [C.c_void_p]),
     "ptt_sweep_last_stats": (C.c_int, [C.POINTER(SweepStats)]),
     "ptt_sweep_release": (C.c_int, []),
     "ptt_sweep_shell_chunk": (C.c_int64, [C.c_int, C.c_int64]),

@@ -204,7 +204,7 @@ struct Workspace {
     cudaStream_t s_shell = nullptr, s_retry = nullptr, s_copy = nullptr, s_side[2] = {nullptr, nullptr};
     ShellSlot slot[2];
     DevBuf pg, pm, scale, perm, stage_in, a2, work, pv_y, pv_l, omega[2], ebase, gw_table, out[2][3], full[3], full_scal,
-        full_status, vw_tmp, snr, snr_perm;
+        full_status, vw_tmp, snr, snr_perm, trows;
     PinBuf h_pg, h_ebase, h_scal, h_status;
     cudaEvent_t out_free[2] = {nullptr, nullptr}, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_tmp = nullptr,
                 ev_emit = nullptr;
@@ -219,7 +219,7 @@ struct Workspace {
     std::vector<DevBuf*> dev() {
         return {&pg, &pm, &scale, &perm, &stage_in, &a2, &work, &pv_y, &pv_l, &omega[0], &omega[1], &ebase, &gw_table,
                 &out[0][0], &out[0][1], &out[0][2], &out[1][0], &out[1][1], &out[1][2], &full[0], &full[1], &full[2],
-                &full_scal, &full_status, &vw_tmp, &snr, &snr_perm};
+                &full_scal, &full_status, &vw_tmp, &snr, &snr_perm, &trows};
     }
     int init() {
         int dev_now = 0;
@@ -380,6 +380,7 @@ struct Sweep {
     double* d_full_scal = nullptr;
     int* d_full_status = nullptr;
     double* d_snr = nullptr;     // [n, n_snr] in processing order
+    long long* d_trows = nullptr;   // destination row of every sorted position in the spectrum tables (out.table_rows)
     long long emitted = 0;      // spectrum chunks emitted so far (selects the output slot)
     bool out_used[2] = {false, false};
 
@@ -508,6 +509,13 @@ int Sweep::setup(const long long n_, const double* pg, const double* pm, const d
             for (int b = 0; b < 2; ++b) { o_tab[b][k] = ws.out[b][k].get<double>((size_t)C * n_y); SW_ALLOC(o_tab[b][k]); }
             if (user_tab[k] && host && !sorted) { d_full[k] = ws.full[k].get<double>(nn * n_y); SW_ALLOC(d_full[k]); }
         }
+    }
+    if (out.table_rows && want_spec) {
+        std::vector<long long> tr(nn);
+        for (size_t i = 0; i < nn; ++i) tr[i] = (long long)out.table_rows[sorted ? i : (size_t)perm[i]];
+        d_trows = ws.trows.get<long long>(nn); SW_ALLOC(d_trows);
+        SW_CUDA(cudaMemcpyAsync(d_trows, tr.data(), nn * sizeof(long long), cudaMemcpyHostToDevice, s_main));
+        SW_CUDA(cudaStreamSynchronize(s_main));      // tr is a local
     }
     if (out.snr && want_spec) { d_snr = ws.snr.get<double>(nn * out.n_snr); SW_ALLOC(d_snr); }
     if (host && !sorted) {
@@ -782,7 +790,11 @@ int Sweep::spectra_chunk(const long long c, const long long s, const long long e
     for (int k = 0; k < 3; ++k) {
         if (!user_tab[k]) continue;
         const size_t bytes = (size_t)P * n_y * sizeof(double);
-        if (sorted) {
+        if (d_trows) {
+            scatter_rows_kernel<double><<<dim3(P, 4), 256, 0, ws.s_copy>>>(n_y, o_tab[b][k], n_y, d_trows + s, user_tab[k], n_y);
+            SW_LAUNCHED("scatter_rows_kernel");
+            stats.launches += 1;
+        } else if (sorted) {
             SW_CUDA(cudaMemcpyAsync(user_tab[k] + (size_t)s * n_y, o_tab[b][k], bytes,
                                     host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ws.s_copy));
         } else {
@@ -924,6 +936,45 @@ int Sweep::run() {
 
 using namespace ptt;
 
+extern "C" int ptt_ipc_alloc(int64_t bytes, void** ptr, unsigned char* handle64) {
+    if (bytes <= 0 || !ptr || !handle64) return set_error(PTT_E_ARG, "ptt_ipc_alloc: null pointer or bad size");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) return set_cuda_error("ptt_ipc_alloc: cudaMalloc", e);
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return set_cuda_error("ptt_ipc_alloc: cudaIpcGetMemHandle", e); }
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return PTT_OK;
+}
+
+extern "C" int ptt_ipc_open(const unsigned char* handle64, void** ptr) {
+    if (!handle64 || !ptr) return set_error(PTT_E_ARG, "ptt_ipc_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return set_cuda_error("ptt_ipc_open: cudaIpcOpenMemHandle", e);
+    *ptr = p;
+    return PTT_OK;
+}
+
+extern "C" int ptt_ipc_close(void* ptr) {
+    if (!ptr) return PTT_OK;
+    const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    if (e != cudaSuccess) return set_cuda_error("ptt_ipc_close", e);
+    return PTT_OK;
+}
+
+extern "C" int ptt_ipc_free(void* ptr) {
+    if (!ptr) return PTT_OK;
+    const cudaError_t e = cudaFree(ptr);
+    if (e != cudaSuccess) return set_cuda_error("ptt_ipc_free", e);
+    return PTT_OK;
+}
+
 extern "C" int ptt_sweep_release(void) {
     std::lock_guard<std::mutex> lock(g_ws.mu);
     g_ws.release();
@@ -969,6 +1020,8 @@ extern "C" int ptt_sweep_spectra(const ptt_sweep_plan_t* plan, const ptt_sweep_o
                                     "ptt_generic_row_capacity(n_xi)");
     if (want_rows && mem != PTT_MEM_DEVICE)
         return set_error(PTT_E_ARG, "ptt_sweep_spectra: profile rows are returned in device memory only");
+    if (out->table_rows && mem != PTT_MEM_DEVICE)
+        return set_error(PTT_E_ARG, "ptt_sweep_spectra: table_rows needs device tables");
     std::lock_guard<std::mutex> lock(g_ws.mu);
     SW_RC(g_ws.init());
     g_ws.timing_used = 0;

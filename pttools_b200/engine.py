@@ -327,7 +327,8 @@ _LIVE_CALLBACKS = []
 
 def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_shell_limit=100, wn_rtol=1e-4, r_star=None,
             lifetime_multiplier=1.0, chunk=8000, shell_chunk=0, want=("pow_v", "pow_gw", "omgw0"), scalars=True,
-            rows=False, mem="device", retry=True, timing=False, on_chunk=None, out=None, snr_weights=None) -> SweepOutput:
+            rows=False, mem="device", retry=True, timing=False, on_chunk=None, out=None, snr_weights=None,
+            table_rows=None, out_rows=None) -> SweepOutput:
     """The whole sweep in one C call (ptt_sweep_spectra, csrc/ptt_sweep.cu): shells, the reference's retries,
     thermodynamic scalars, A^2, spec_den_v, spec_den_gw, pow_gw, omgw0.  pg[n,16], pm[n,4] as in the C header (host
     numpy arrays or device tensors according to `mem`); plan: SsmPlan / CPlan or None (shells only).
@@ -371,7 +372,7 @@ def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_she
         if name in want:
             t = out.get(name)
             if t is None:
-                t = alloc((n, n_y))
+                t = alloc((n if table_rows is None else int(out_rows or n), n_y))
             setattr(res, name, t)
             setattr(o, name, ptr(t))
     res.status = out.get("status")
@@ -383,6 +384,14 @@ def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_she
         if res.scalars is None:
             res.scalars = alloc((n, _lib.SWEEP_NSCAL))
         o.scalars = ptr(res.scalars)
+    if table_rows is not None:
+        if host:
+            raise ValueError("table_rows needs device tables")
+        tr = np.ascontiguousarray(table_rows, dtype=np.int64)
+        if tr.shape != (n,):
+            raise ValueError("table_rows: one destination row per point")
+        res._keep.append(tr)
+        o.table_rows = C.c_void_p(tr.ctypes.data)
     if snr_weights is not None and "omgw0" in want:
         w = dev_f64(np.ascontiguousarray(snr_weights, dtype=np.float64))
         res._keep.append(w)

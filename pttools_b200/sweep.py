@@ -142,7 +142,8 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
                   n_xi=engine.N_XI_DEFAULT, Tn=None, g_star=None, gs_star=None, suppression="default",
                   chunk=8000, shell_chunk=None, want_pow_v=True, want_pow_gw=True, keep_bubbles=False, plan=None,
                   mem="device",
-                  allow_invalid=False, on_chunk=None, timing=False, out=None, sol_type=None, snr=False) -> SweepResult:
+                  allow_invalid=False, on_chunk=None, timing=False, out=None, sol_type=None, snr=False,
+                  table_rows=None, out_rows=None) -> SweepResult:
     """Spectrum(Bubble(model, v_wall, alpha_n), y, r_star=...) for every point of a sweep: the model-independent shell
     solve, the thermodynamic scalars, the SSM chain and Omega_gw,0 (pttools/analysis/parallel.py:157-187 ->
     bubble.py:232-352 -> ssmtools/spectrum.py:96-115 -> omgw0/omgw0_ssm.py:123-131) in ONE call of the C ABI
@@ -192,7 +193,8 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
         pg_in, pm_in, sc_in = pt.pg, pt.pm, scale
     res = engine.sweep_c(plan, pg_in, pm_in, sc_in, n_xi=n_xi, r_star=r_star, lifetime_multiplier=lifetime_multiplier,
                          chunk=chunk, shell_chunk=shell_chunk or 0, want=want, rows=keep_bubbles, mem=mem,
-                         on_chunk=on_chunk, timing=timing, out=out, snr_weights=snr_w)
+                         on_chunk=on_chunk, timing=timing, out=out, snr_weights=snr_w, table_rows=table_rows,
+                         out_rows=out_rows)
     from . import _lib
     scal = {name: res.scalars[:, k] for k, name in enumerate(_lib.SWEEP_SCALARS)}
     asdev = (lambda a: a) if mem == "host" else engine.dev_f64
@@ -267,21 +269,31 @@ def sweep_models(models, v_walls, alpha_ns, y=None, rank: int = 0, world: int = 
 def shard_rows(v_wall: np.ndarray, cost: tp.Optional[np.ndarray], world: int) -> tp.List[np.ndarray]:
     """Static partition of the points of a sweep over `world` ranks by WHOLE v_wall ROWS: all points that share a wall
     speed stay on one rank, because they share the lifetime-convolution weights of K6' (one banded matrix product per
-    wall speed).  Rows are dealt greedily, most expensive first, to the least loaded rank (cost[i] = estimated cost of
-    point i; None = 1).  Returns per rank the point indices, ordered by (v_wall, original index)."""
+    wall speed).  cost = None: the rows, ordered by v_wall, are dealt cyclically -- neighbouring wall speeds have nearly
+    the same mix of solution types, so the shards are balanced without looking at the points; with cost[i] (estimated
+    cost of point i) rows are dealt greedily, most expensive first, to the least loaded rank.  Returns per rank the
+    point indices, ordered by (v_wall, original index)."""
     v_wall = np.asarray(v_wall, dtype=float).reshape(-1)
     n = v_wall.size
-    cost = np.ones(n) if cost is None else np.asarray(cost, dtype=float).reshape(-1)
-    uniq, inv = np.unique(v_wall, return_inverse=True)
-    row_cost = np.bincount(inv, weights=cost, minlength=uniq.size)
-    owner = np.empty(uniq.size, dtype=np.int64)
-    load = np.zeros(world)
-    for r in np.argsort(-row_cost, kind="stable"):
-        k = int(np.argmin(load))
-        owner[r] = k
-        load[k] += row_cost[r]
+    if n and np.all(v_wall[1:] >= v_wall[:-1]):            # already ordered (grid sweeps are): rows are runs
+        order = np.arange(n)
+        inv = np.concatenate(([0], np.cumsum(v_wall[1:] != v_wall[:-1])))
+        n_rows = int(inv[-1]) + 1
+    else:
+        uniq, inv = np.unique(v_wall, return_inverse=True)
+        n_rows = uniq.size
+        order = np.lexsort((np.arange(n), v_wall))
+    if cost is None:
+        owner = np.arange(n_rows) % world
+    else:
+        row_cost = np.bincount(inv, weights=np.asarray(cost, dtype=float).reshape(-1), minlength=n_rows)
+        owner = np.empty(n_rows, dtype=np.int64)
+        load = np.zeros(world)
+        for r in np.argsort(-row_cost, kind="stable"):
+            k = int(np.argmin(load))
+            owner[r] = k
+            load[k] += row_cost[r]
     point_owner = owner[inv]
-    order = np.lexsort((np.arange(n), v_wall))
     return [order[point_owner[order] == k] for k in range(world)]
 
 
@@ -363,51 +375,112 @@ def distributed_table(local_compute: tp.Callable, shards: tp.List[np.ndarray], n
 LAST_LOCAL: tp.Dict[str, tp.Any] = {}      # the SweepResult of this rank's shard of the last distributed sweep (statistics)
 
 
+class SharedTable:
+    """A [n_rows, n_cols] float64 table in the memory of ONE GPU (rank `dst`) that every rank of the box can write:
+    allocated by the library on `dst` (ptt_ipc_alloc), mapped by the other processes through CUDA IPC (ptt_ipc_open; peer
+    access over NVLink / NVSwitch).  Collective over torch.distributed: every rank constructs it at the same point.
+    `tensor`: torch view of the table (on rank dst its own memory, elsewhere the peer mapping)."""
+
+    def __init__(self, n_rows: int, n_cols: int, dst: int = 0):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib
+        torch = engine._torch()
+        lib = _lib.load()
+        self.shape, self.dst = (int(n_rows), int(n_cols)), dst
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self._ptr = C.c_void_p()
+        self._owner = self.rank == dst
+        nbytes = 8 * self.shape[0] * self.shape[1]
+        handle = (C.c_ubyte * 64)()
+        if self._owner:
+            _lib.check(lib.ptt_ipc_alloc(nbytes, C.byref(self._ptr), handle), "ptt_ipc_alloc")
+        if self.world > 1:
+            box = [bytes(handle) if self._owner else None]
+            dist.broadcast_object_list(box, src=dst)
+            if not self._owner:
+                buf = (C.c_ubyte * 64).from_buffer_copy(box[0])
+                _lib.check(lib.ptt_ipc_open(buf, C.byref(self._ptr)), "ptt_ipc_open")
+
+        class _Iface:
+            pass
+        holder = _Iface()
+        holder.__cuda_array_interface__ = {"shape": self.shape, "typestr": "<f8", "data": (int(self._ptr.value), False),
+                                           "version": 3, "strides": None}
+        self._holder = holder
+        self.tensor = torch.as_tensor(holder, device="cuda")
+
+    def close(self):
+        from . import _lib
+        ptr, self._ptr = getattr(self, "_ptr", None), None
+        if ptr is None or not ptr.value:
+            return
+        self.tensor = None
+        lib = _lib.load()
+        (lib.ptt_ipc_free if self._owner else lib.ptt_ipc_close)(ptr)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown
+            pass
+
+
 def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, chunk=8000, dst=0, table="omgw0", mem="device",
-                            **kw):
+                            shared: tp.Optional[SharedTable] = None, transport: str = "auto", **kw):
     """The 10^6-point sweep of BASELINE.json config 5, sharded over the ranks of torch.distributed (one process per
     GPU): Omega_gw,0(f) table [n, n_y] on rank `dst` with rows in the order of the input points (None on the other
-    ranks).  Whole v_wall rows per rank (shard_rows), cost-balanced by the closed-form solution types; finished chunks
-    travel to `dst` while the next ones are computed.
+    ranks).  Whole v_wall rows per rank (shard_rows); every rank's sweep writes its rows STRAIGHT INTO the table on
+    `dst`, chunk by chunk as they are produced: the table is shared through CUDA IPC (SharedTable) and the rows travel as
+    peer stores over NVLink / NVSwitch under the compute of the next chunk -- no collective, no SM of the receiving GPU
+    involved; one barrier at the end.  shared: a SharedTable([n, n_y]) to write into (reuse it across sweeps of one
+    shape; without it a table is allocated and mapped per call).  transport="sendrecv": point-to-point messages of
+    torch.distributed instead (distributed_table; what the CPU tests run over gloo).
     mem="host": no exchange; every rank returns (indices of its shard, its [n_shard, n_y] block in pinned host memory),
     streamed out of the device chunk by chunk -- the host-side form of a sharded table."""
-    from . import bubble as bub
     from .models import Model
+    import torch.distributed as dist
     vw = np.asarray(v_wall, dtype=float).reshape(-1)
     an = np.asarray(alpha_n, dtype=float).reshape(-1)
     y = engine.Y_DEFAULT if y is None else np.asarray(y, dtype=float)
     single = isinstance(model, Model)
-    if single:
-        with np.errstate(invalid="ignore", divide="ignore"):
-            codes = np.array(model.solution_type_codes(vw, an, np.asarray(model.wn(an), dtype=float)), dtype=np.int64)
-        codes[(an < model.alpha_n_min)] = -1
-        cost = point_cost(codes)
-    else:
-        cost = codes = None
-    import torch.distributed as dist
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    shards = shard_rows(vw, cost, world)
+    rank = dist.get_rank() if world > 1 else 0
+    shards = shard_rows(vw, None, world)
     torch = engine._torch()
     # shell chunks that are multiples of the spectrum chunk keep every delivered range inside one block of `chunk` rows
     from . import _lib
     sc = int(_lib.load().ptt_sweep_shell_chunk(kw.get("n_xi", engine.N_XI_DEFAULT), int(torch.cuda.mem_get_info()[0])))
     sc = max(chunk, sc // chunk * chunk)
-
-    def local_compute(idx, out, on_chunk):
-        if len(idx) == 0:
-            return
-        m = model if single else [model[i] for i in idx]
-        LAST_LOCAL["result"] = sweep_spectra(m, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False,
-                                             want_pow_gw=table == "pow_gw", chunk=chunk,
-                                             shell_chunk=sc, on_chunk=on_chunk, out={table: out},
-                                             sol_type=None if codes is None else codes[idx], **kw)
-
+    idx = shards[rank]
+    m = model if single else [model[i] for i in idx]
+    common = dict(y=y, r_star=r_star, want_pow_v=False, want_pow_gw=table == "pow_gw", chunk=chunk, shell_chunk=sc, **kw)
     if mem == "host":
-        rank = dist.get_rank() if world > 1 else 0
-        idx = shards[rank]
-        m = model if single else [model[i] for i in idx]
-        res = sweep_spectra(m, vw[idx], an[idx], y=y, r_star=r_star, want_pow_v=False, want_pow_gw=table == "pow_gw",
-                            chunk=chunk, shell_chunk=sc, mem="host", sol_type=None if codes is None else codes[idx], **kw)
+        res = sweep_spectra(m, vw[idx], an[idx], mem="host", **common)
         LAST_LOCAL["result"] = res
         return idx, getattr(res, table)
-    return distributed_table(local_compute, shards, y.size, chunk, dst=dst)
+    if world == 1:
+        res = sweep_spectra(model, vw, an, out=None if shared is None else {table: shared.tensor}, **common)
+        LAST_LOCAL["result"] = res
+        return getattr(res, table)
+    if transport == "sendrecv":
+        def local_compute(ids, out, on_chunk):
+            if len(ids):
+                LAST_LOCAL["result"] = sweep_spectra(m, vw[ids], an[ids], on_chunk=on_chunk, out={table: out}, **common)
+        return distributed_table(local_compute, shards, y.size, chunk, dst=dst)
+    own = shared is None
+    if own:
+        shared = SharedTable(vw.size, y.size, dst=dst)
+    if shared.shape != (vw.size, y.size):
+        raise ValueError(f"shared table has shape {shared.shape}, the sweep needs {(vw.size, y.size)}")
+    if len(idx):
+        LAST_LOCAL["result"] = sweep_spectra(m, vw[idx], an[idx], out={table: shared.tensor}, table_rows=idx, **common)
+    torch.cuda.current_stream().synchronize()      # this rank's rows are in the table on `dst`
+    dist.barrier()
+    result = shared.tensor if rank == dst else None
+    if own and rank != dst:
+        shared.close()
+    if own and rank == dst:
+        result._shared = shared                       # keeps the allocation alive as long as the tensor
+    return result

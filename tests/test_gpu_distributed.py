@@ -30,10 +30,19 @@ def _worker(rank, world, port, q):
     from pttools_b200.models import BagModel
     vw, an = _grid()
     model = BagModel(a_s=1.1, a_b=1, V_s=1)
-    out = sweep.sweep_omgw0_distributed(model, vw, an, y=Y, chunk=64, **KW)
+    out = sweep.sweep_omgw0_distributed(model, vw, an, y=Y, chunk=64, **KW)          # table shared through CUDA IPC
+    out = None if out is None else out.cpu().numpy()
+    shared = sweep.SharedTable(vw.size, Y.size)                                        # the same, table reused
+    for _ in range(2):
+        out2 = sweep.sweep_omgw0_distributed(model, vw, an, y=Y, chunk=64, shared=shared, **KW)
+    out2 = None if out2 is None else out2.cpu().numpy()
+    out3 = sweep.sweep_omgw0_distributed(model, vw, an, y=Y, chunk=64, transport="sendrecv", **KW)   # NCCL messages
+    out3 = None if out3 is None else out3.cpu().numpy()
     shard, host = sweep.sweep_omgw0_distributed(model, vw, an, y=Y, chunk=64, mem="host", **KW)
     torch.cuda.synchronize()
-    q.put({"rank": rank, "out": None if out is None else out.cpu().numpy(), "shard": np.asarray(shard), "host": np.asarray(host)})
+    dist.barrier()
+    shared.close()
+    q.put({"rank": rank, "out": out, "out2": out2, "out3": out3, "shard": np.asarray(shard), "host": np.asarray(host)})
     dist.barrier()
     dist.destroy_process_group()
 
@@ -60,8 +69,9 @@ def test_two_rank_nccl_sweep_equals_single_gpu_sweep():
         assert p.exitcode == 0
     vw, an = _grid()
     one = sweep.sweep_spectra(BagModel(a_s=1.1, a_b=1, V_s=1), vw, an, y=Y, want_pow_v=False, **KW).numpy()
-    assert res[1]["out"] is None
-    np.testing.assert_allclose(res[0]["out"], one.omgw0, rtol=1e-10, equal_nan=True)
+    assert res[1]["out"] is None and res[1]["out2"] is None and res[1]["out3"] is None
+    for key in ("out", "out2", "out3"):
+        np.testing.assert_allclose(res[0][key], one.omgw0, rtol=1e-10, equal_nan=True)
     assert np.isfinite(one.omgw0).all(axis=1).sum() > 150
     # host-side form: every rank holds its shard; together they are the table
     full = np.full_like(one.omgw0, -1.0)
