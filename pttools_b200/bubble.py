@@ -236,11 +236,12 @@ class PointTable:
     invalid: np.ndarray       # bool: rejected by the checks of the reference's Bubble constructor
 
 
-def point_table(model, v_wall, alpha_n, sol_type=None, allow_invalid=False) -> PointTable:
+def point_table(model, v_wall, alpha_n, sol_type=None, allow_invalid=False, device=False) -> PointTable:
     """Per-point inputs of the shell solver for Bubble(model, v_wall, alpha_n) (bubble.py:36-177, fluid.py:890-949).
     Points the reference's constructor rejects -- alpha_n < model.alpha_n_min (model.py:813-823), T_n > T_crit
     (bubble.py:97-101), no solution type (transition.py:47-69), wn not found -- get solution type -1: the device
-    reports them as PTT_ST_INVALID_INPUT with NaN outputs."""
+    reports them as PTT_ST_INVALID_INPUT with NaN outputs.  device=True: `pg` and `pm` are assembled as CUDA tensors (the
+    starting guesses come from the device table), the rest stays numpy."""
     vw = np.asarray(v_wall, dtype=float).reshape(-1)
     an = np.asarray(alpha_n, dtype=float).reshape(-1)
     n = vw.size
@@ -257,6 +258,8 @@ def point_table(model, v_wall, alpha_n, sol_type=None, allow_invalid=False) -> P
             sel = np.nonzero(ids == uid)[0]
             sub = point_table(models[sel[0]], vw[sel], an[sel], None if st is None else st[sel], allow_invalid)
             pg[sel], pm[sel], wn[sel], codes[sel], invalid[sel] = sub.pg, sub.pm, sub.wn, sub.codes, sub.invalid
+        if device:
+            pg, pm = engine.dev_f64(pg), engine.dev_f64(pm)
         return PointTable(pg, pm, wn, codes, invalid)
     with np.errstate(invalid="ignore", divide="ignore"):
         wn = np.asarray(model.wn(an), dtype=float).reshape(-1)
@@ -269,20 +272,36 @@ def point_table(model, v_wall, alpha_n, sol_type=None, allow_invalid=False) -> P
         if not allow_invalid:
             invalid |= (an < 0) | (an < model.alpha_n_min) | (tn > model.T_crit)
     codes[invalid] = -1
-    guesses = fluid_reference.ref().get_batch(vw, an, codes).cpu().numpy()   # vp, vm, vp~, vm~, wp, wm
-    pg = np.zeros((n, 16))
-    pg[:, 0], pg[:, 1], pg[:, 2], pg[:, 3], pg[:, 4] = vw, an, codes, wn, v_cj
-    pg[:, 5], pg[:, 6] = guesses[:, 0], guesses[:, 2]
-    pg[:, 7] = guesses[:, 4] * wn                         # fluid.py:939-941
-    wm_g = guesses[:, 5] * wn
-    pg[:, 8] = np.where(np.isnan(wm_g), 0.3 * wn, wm_g)   # fluid.py:942-949
-    pg[:, 9], pg[:, 10], pg[:, 11], pg[:, 12] = model.css2, model.csb2, model.V_s, model.V_b
-    pg[:, 13] = 1.0 if model.name == "bag" else 0.0
     # entropy density s(w) = coef * w^(1 - 1/mu) per phase (s = w / T): the retry search applies the reference's
     # entropy-flux test to its scan starts
     mus, mub = 1 + 1 / model.css2, 1 + 1 / model.csb2
-    pg[:, 14] = (mus * model.a_s) ** (1 / mus) * model.T_ref ** (4 / mus - 1)
-    pg[:, 15] = (mub * model.a_b) ** (1 / mub) * model.T_ref ** (4 / mub - 1)
+    s_coef_s = (mus * model.a_s) ** (1 / mus) * model.T_ref ** (4 / mus - 1)
+    s_coef_b = (mub * model.a_b) ** (1 / mub) * model.T_ref ** (4 / mub - 1)
+    consts = (model.css2, model.csb2, model.V_s, model.V_b, 1.0 if model.name == "bag" else 0.0, s_coef_s, s_coef_b)
+    guesses = fluid_reference.ref().get_batch(vw, an, codes)                 # device [n,6]: vp, vm, vp~, vm~, wp, wm
+    if device:
+        # assemble the rows where the starting guesses already are: on the device
+        torch = engine._torch()
+        up = torch.as_tensor(np.stack([vw, an, codes.astype(float), wn, v_cj]), device="cuda")     # [5, n]
+        wn_d = up[3]
+        wm_g = guesses[:, 5] * wn_d
+        cols = [up[0], up[1], up[2], wn_d, up[4], guesses[:, 0], guesses[:, 2], guesses[:, 4] * wn_d,    # fluid.py:939-941
+                torch.where(torch.isnan(wm_g), 0.3 * wn_d, wm_g)]                                      # fluid.py:942-949
+        cols += [torch.full_like(wn_d, c) for c in consts]
+        pg = torch.stack(cols, dim=1).contiguous()
+        pm = torch.zeros((n, 4), dtype=torch.float64, device="cuda")
+        pm[:, 0], pm[:, 1], pm[:, 2] = model.a_s, model.a_b, model.T_ref
+        return PointTable(pg, pm, wn, codes, invalid)
+    guesses = guesses.cpu().numpy()
+    pgT = np.empty((16, n))                               # filled row-wise (contiguous), transposed once
+    pgT[0], pgT[1], pgT[2], pgT[3], pgT[4] = vw, an, codes, wn, v_cj
+    pgT[5], pgT[6] = guesses[:, 0], guesses[:, 2]
+    pgT[7] = guesses[:, 4] * wn                           # fluid.py:939-941
+    wm_g = guesses[:, 5] * wn
+    pgT[8] = np.where(np.isnan(wm_g), 0.3 * wn, wm_g)     # fluid.py:942-949
+    for k, c in enumerate(consts):
+        pgT[9 + k] = c
+    pg = np.ascontiguousarray(pgT.T)
     pm = np.zeros((n, 4))
     pm[:, 0], pm[:, 1], pm[:, 2] = model.a_s, model.a_b, model.T_ref
     return PointTable(pg, pm, wn, codes, invalid)

@@ -173,7 +173,7 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
         plan = engine.SsmPlan(y, cs=cs, nt=nt, n_z_lookup=n_z_lookup, z_st_thresh=z_st_thresh, nuc_type=nuc_type,
                               a=1.0, mode="ssm", only_lookup_pass=not want_pow_v)
     want_pow_v = want_pow_v and plan.has_y_pass
-    pt = bub.point_table(model, vw, an, sol_type=sol_type, allow_invalid=allow_invalid)
+    pt = bub.point_table(model, vw, an, sol_type=sol_type, allow_invalid=allow_invalid, device=mem == "device")
     scale = None if r_star is None else omgw0_scale(vw, an, r_star, g_star, gs_star, suppression, device=mem == "device")
     snr_w = None
     if snr:
@@ -186,11 +186,7 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
         snr_w = nz.snr_weights(f, (nz.omega_noise(f), nz.omega_ins(f)))
     want = (("pow_v",) if want_pow_v else ()) + (("pow_gw",) if want_pow_gw or scale is None else ()) + \
         (("omgw0",) if scale is not None else ())
-    if mem == "device":
-        pg_in, pm_in = engine.dev_f64(pt.pg), engine.dev_f64(pt.pm)
-        sc_in = scale
-    else:
-        pg_in, pm_in, sc_in = pt.pg, pt.pm, scale
+    pg_in, pm_in, sc_in = pt.pg, pt.pm, scale
     res = engine.sweep_c(plan, pg_in, pm_in, sc_in, n_xi=n_xi, r_star=r_star, lifetime_multiplier=lifetime_multiplier,
                          chunk=chunk, shell_chunk=shell_chunk or 0, want=want, rows=keep_bubbles, mem=mem,
                          on_chunk=on_chunk, timing=timing, out=out, snr_weights=snr_w, table_rows=table_rows,

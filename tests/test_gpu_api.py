@@ -13,7 +13,10 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def test_xi_v_plane_golden_through_fluid_integrate_param():
     """tests/paper/test_plane.py of the reference: 9 deflagration curves, tau = -+100, 1000 samples, summed.  The
-    reference accepts other integrators at 8e-4 ... 2e-2 against its odeint golden; here 1e-5."""
+    reference pins its own odeint at 1e-7 and accepts other integrators at 8e-4 ... 2e-2 against that golden.  The golden
+    carries odeint's error at its default tolerance (1.49e-8 per step, accumulated over tau = 100): the kernel is held to
+    1e-7 against the same integration with tight LSODA tolerances, and to the golden within twice the distance between
+    the two (the golden's own integrator noise, measured here)."""
     from pttools_b200.bubble import fluid_integrate_param
     golden = np.load(os.path.join(GOLDEN, "ref_goldens.npz"))["xi_v_plane"]
     n_xi = 1000
@@ -27,8 +30,20 @@ def test_xi_v_plane_golden_through_fluid_integrate_param():
             vb[vb < sb.v_shock_bag(xb)] = np.nan
         data[:, i, :] = [vb, wb, xb, vf, wf, xf]
     got = np.nansum(data, axis=2)
-    np.testing.assert_allclose(got[1:], golden[1:], rtol=1e-5)
-    np.testing.assert_allclose(got[0, :2], golden[0, :2], rtol=1e-5)
+    tight = np.zeros((6, 9, n_xi))
+    for i, xi0 in enumerate(np.linspace(1 / 10, 1 - 1 / 10, 9)):
+        vb, wb, xb, _ = sb.integrate(xi0, 1, xi0, 0.0, -100.0, n_xi, rtol=1e-12, atol=1e-13)
+        vf, wf, xf, _ = sb.integrate(xi0, 1, xi0, 0.0, 100.0, n_xi, rtol=1e-12, atol=1e-13)
+        vb = vb.copy()
+        with np.errstate(invalid="ignore"):
+            vb[vb < sb.v_shock_bag(xb)] = np.nan
+        tight[:, i, :] = [vb, wb, xb, vf, wf, xf]
+    tight = np.nansum(tight, axis=2)
+    for sel in ((slice(1, None), slice(None)), (0, slice(0, 2))):      # row 0: only the unmasked curves (oracle test)
+        g, t, ref = got[sel], tight[sel], golden[sel]
+        np.testing.assert_allclose(g, t, rtol=1e-7)
+        noise = np.abs(t / ref - 1)
+        assert np.all(np.abs(g / ref - 1) <= np.maximum(1e-7, 2 * noise)), (np.abs(g / ref - 1).max(), noise.max())
 
 
 def test_old_bag_api_functions():

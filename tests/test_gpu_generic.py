@@ -26,10 +26,35 @@ def test_fluid_reference_table_matches_reference():
         a, b = getattr(ref, k), tab[k]
         both = np.isfinite(a) & np.isfinite(b)
         assert both.sum() > 0.9 * np.isfinite(b).sum()
-        # hybrids: vm / wm are read one tau-step behind the wall, where the curve leaves the sonic point with
-        # infinite slope: agreement is limited by the reference's own LSODA noise there
-        np.testing.assert_allclose(a[both], b[both], rtol=2e-5 if k in ("vm", "vm_tilde", "wm") else 2e-6, atol=1e-7)
+        if k in ("vm", "vm_tilde", "wm"):
+            continue
+        np.testing.assert_allclose(a[both], b[both], rtol=2e-6, atol=1e-7)
     assert (np.isfinite(ref.vp) != np.isfinite(tab["vp"])).mean() < 0.01
+    # vm, vm_tilde, wm of hybrids are read one tau-step behind the wall, where the curve leaves the sonic point with
+    # infinite slope: the reference's own LSODA noise is largest there.  Rule: 2e-6 where the table is not noise-limited;
+    # elsewhere within twice the distance between the table and the reference algorithm run with tight LSODA tolerances
+    # (measured here on the 40 entries that deviate most).
+    from oracle import shell_bag as sb
+    from oracle import shell_generic as sg
+    for k in ("vm", "vm_tilde", "wm"):
+        a, b = getattr(ref, k), tab[k]
+        both = np.isfinite(a) & np.isfinite(b)
+        dev = np.where(both, np.abs(a - b) / np.maximum(np.abs(b), 1e-7 / 2e-6), 0.0)
+        worst = np.argsort(dev.ravel())[::-1][:40]
+        for flat in worst:
+            ia, iv = np.unravel_index(flat, dev.shape)
+            if dev[ia, iv] <= 2e-6:
+                break
+            vw, an = float(tab["v_wall"][iv]), float(tab["alpha_n"][ia])
+            with sb.lsoda_tolerances(1e-12, 1e-13):
+                v_, w_, xi_ = sb.sound_shell_bag(vw, an)
+                vals = sg.v_and_w_from_solution(v_, w_, xi_, vw, sb.identify_solution_type(vw, an))
+            tight = dict(zip(("vp", "vm", "vp_tilde", "vm_tilde", "wp", "wm"), vals))[k]
+            noise = abs(tight / b[ia, iv] - 1)
+            assert dev[ia, iv] <= max(2e-6, 2 * noise), (k, vw, an, dev[ia, iv], noise)
+        rest = np.ones(dev.size, dtype=bool)
+        rest[worst] = False
+        assert dev.ravel()[rest].max() <= max(2e-6, dev.ravel()[worst[-1]])
 
 
 @pytest.mark.parametrize("mname", ["bag", "cs_quarter_third", "cs_third_quarter", "cs_032_third"])
@@ -45,6 +70,24 @@ def test_generic_bubbles_match_reference_runs(mname):
     an = np.array([p[1] for _, p in pts])
     batch = bubble.sweep_bubbles(model, vw, an)
     assert np.all(batch.status.cpu().numpy() == 0)
+    # the reference's own integrator noise on the difference-type integrals, measured with the restatement of its
+    # algorithm run with tight LSODA tolerances (oracle pinned to the reference: tests/test_hostemu_generic.py)
+    from oracle import models as omodels, shell_bag as sb, shell_generic as sg
+    import warnings
+    omodel = {"bag": omodels.bag_model(1.1, 1, 1), "cs_quarter_third": omodels.const_cs_model(1 / 4, 1 / 3, 1.5, 1, 1),
+              "cs_third_quarter": omodels.const_cs_model(1 / 3, 1 / 4, 5, 1, 1),
+              "cs_032_third": omodels.const_cs_model(1 / 3 - 0.01, 1 / 3, 1.5, 1, 1)}[mname]
+    oref = sg.FluidReference(dict(np.load(os.path.join(GOLDEN, "ref_fluid_reference.npz"))))
+    tight_cache = {}
+
+    def tight_scalars(k):
+        if k not in tight_cache:
+            with warnings.catch_warnings(), sb.lsoda_tolerances(1e-12, 1e-13):
+                warnings.simplefilter("ignore")
+                sol = sg.sound_shell_generic(omodel, vw[k], an[k], oref)
+                tight_cache[k] = sg.bubble_scalars(omodel, sol, vw[k])
+        return tight_cache[k]
+
     for k, (i, _) in enumerate(pts):
         v, w, xi = d[f"{mname}__v_{i}"], d[f"{mname}__w_{i}"], d[f"{mname}__xi_{i}"]
         sc = dict(zip(names, d[f"{mname}__scal_{i}"]))
@@ -65,8 +108,13 @@ def test_generic_bubbles_match_reference_runs(mname):
             # omega, the thermal-energy and the entropy differences integrate w - w_n (or s - s_n), small differences
             # of large numbers: they amplify the ~1e-7 profile differences (the reference's own LSODA noise) by
             # w_n / (w - w_n) ~ 30-100
-            rtol = 3e-5 if name in ("va_entropy_density_diff", "omega", "va_thermal_energy_density_diff") else 2e-6
-            np.testing.assert_allclose(float(batch.scal[name][k]), sc[name], rtol=rtol, err_msg=name)
+            got = float(batch.scal[name][k])
+            if abs(got / sc[name] - 1) <= 2e-6:
+                continue
+            assert name in ("va_entropy_density_diff", "omega", "va_thermal_energy_density_diff"), (name, got, sc[name])
+            # over the bar: allowed up to twice the reference's own noise on this quantity at this point
+            noise = abs(tight_scalars(k)[name] / sc[name] - 1)
+            assert abs(got / sc[name] - 1) <= max(2e-6, 2 * noise), (name, vw[k], an[k], got, sc[name], noise)
 
 
 def test_bubble_object_config1():

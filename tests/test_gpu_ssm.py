@@ -90,6 +90,7 @@ def test_a2_spec_den_and_gw_bag_chain(mode):
                 prof = sb.sound_shell_bag(a, b, npt[0])
                 tight[i] = {nuc: ssm.power_gw_scaled_bag(z, (a, b, nuc, (1.,)), npt, profile=prof)
                             for nuc in ("exponential", "simultaneous")}
+                tight[i]["pow_v"] = ssm.power_v_bag(z, (a, b, "exponential", (1.,)), npt, profile=prof)
     for nuc in ("exponential", "simultaneous"):
         plan = engine.SsmPlan(z, cs=sb.CS0, nt=npt[1], n_z_lookup=npt[2], nxi=npt[0], nuc_type=nuc, mode="bag")
         res = engine.spectra_from_shells(plan, shells, pp, keep=True)
@@ -107,7 +108,14 @@ def test_a2_spec_den_and_gw_bag_chain(mode):
     res = engine.spectra_from_shells(plan, shells, pp, keep=True)
     pow_v = res.pow_v.cpu().numpy()
     for i in range(len(pts)):
-        np.testing.assert_allclose(pow_v[i], d[f"pow_v_exp_{i}"], rtol=tol if mode != "gpu_profiles" else 1e-4)
+        ref = d[f"pow_v_exp_{i}"]
+        if mode == "gpu_profiles":
+            # same rule as for pow_gw: 1e-5 against the noise-free restatement, the fixture within twice its own noise
+            np.testing.assert_allclose(pow_v[i], tight[i]["pow_v"], rtol=SPEC_RTOL)
+            noise = np.max(np.abs(tight[i]["pow_v"] / ref - 1))
+            np.testing.assert_allclose(pow_v[i], ref, rtol=max(SPEC_RTOL, 2 * noise))
+        else:
+            np.testing.assert_allclose(pow_v[i], ref, rtol=tol)
 
 
 def test_a2_parts_against_reference_fixture():
@@ -311,12 +319,16 @@ def test_bubble_txt_through_the_kernels():
     got = np.stack([np.full(6, z.sum()), a2.sum(1).cpu().numpy(), fp2.sum(1).cpu().numpy(), lam2.sum(1).cpu().numpy()], axis=1)
     print("relative deviations from bubble.txt:", np.abs(got / ref - 1).max(axis=1))
     np.testing.assert_allclose(got[3:], ref[3:], rtol=2e-6)
-    np.testing.assert_allclose(got[:3], ref[:3], rtol=3e-5)
     for i in range(3):
+        # weak shells: 2e-6 against the restatement run with tight LSODA tolerances, and the table within twice the
+        # distance of that restatement from it (the reference's own integrator noise, measured here)
         with sb.lsoda_tolerances(1e-12, 1e-13):
             prof = sb.sound_shell_bag(vw[i], alpha[i], 10000)
             t = ssm.a2_e_conserving_bag(z, vw[i], alpha[i], npt=(10000, 1000), profile=prof)
-        np.testing.assert_allclose(got[i, 1:], [x.sum() for x in t], rtol=2e-6)
+        tight = np.array([x.sum() for x in t])
+        np.testing.assert_allclose(got[i, 1:], tight, rtol=2e-6)
+        noise = np.abs(tight / ref[i, 1:] - 1)
+        assert np.all(np.abs(got[i, 1:] / ref[i, 1:] - 1) <= np.maximum(2e-6, 2 * noise)), (i, noise)
 
 
 def test_spec_den_gw_scaled_on_an_arbitrary_lookup_grid():
