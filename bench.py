@@ -11,8 +11,9 @@ result block is gathered on rank 0 over NCCL, as a sharded sweep would do.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
 
-prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the CPU oracle port of the same
-workload on the host cores (the reference itself is python and cannot travel to the GPU box).
+prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the reference's own CPU implementation of the
+same workload on the host cores: the unmodified package staged under oracle/_ref by build() (cpu_baseline.kind =
+"reference"), or the oracle port when that does not import on the box ("port", with the reason in `sample`).
 """
 import argparse
 import datetime
@@ -107,13 +108,107 @@ def _cpu_point(args):
     return 1
 
 
-def cpu_run(points, cores, path):
-    import multiprocessing as mp
-    _cpu_setup(path)          # before the fork: workers inherit the model and the starting-guess table
-    t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_cpu_point, points, chunksize=1)
-    return time.perf_counter() - t0
+def _ref_setup(path):
+    """The REAL reference (oracle/_ref: the unmodified pttools package staged by oracle/build_ref.py, numba-jitted) when it
+    imports here; returns None on success, else the reason (the caller then falls back to the oracle port and says so).
+    The jitted helpers are compiled in the parent, before the fork, by solving one point of each solution type."""
+    if "ref_reason" in _CPU:
+        return _CPU["ref_reason"]
+    from oracle import build_ref
+    dst = build_ref.build()
+    reason = None
+    if dst is None:
+        reason = "oracle/_ref not staged (build() did not see /root/reference)"
+    else:
+        os.environ.setdefault("NUMBA_THREADING_LAYER", "workqueue")
+        os.environ.setdefault("NUMBA_NUM_THREADS", "1")      # one process per core, as the reference's own run_parallel
+        added = [dst, os.path.join(ROOT, "tools", "refenv", "stubs")]
+        sys.path[:0] = added
+        try:
+            import logging
+            import warnings
+            warnings.filterwarnings("ignore")
+            logging.getLogger("pttools").setLevel(logging.CRITICAL)
+            from pttools.models import BagModel
+            from pttools.bubble import Bubble
+            from pttools.omgw0 import Spectrum
+            logging.getLogger("pttools").setLevel(logging.CRITICAL)
+            _CPU["refmod"] = {"Bubble": Bubble, "Spectrum": Spectrum, "model": BagModel(alpha_n_min=0.005)}
+            _CPU["path"] = path
+            t0 = time.perf_counter()
+            for pt in ((0.5, 0.1), (0.62, 0.1), (0.9, 0.05)):       # deflagration, hybrid, detonation
+                _ref_point(pt)
+            _CPU["ref_jit_s"] = time.perf_counter() - t0
+        except Exception as e:      # noqa: BLE001 - numba / scipy missing or incompatible on this box
+            for a in added:
+                if a in sys.path:
+                    sys.path.remove(a)
+            reason = f"reference not importable here: {type(e).__name__}: {e}"
+    _CPU["ref_reason"] = reason
+    return reason
+
+
+def _ref_point(args):
+    """One grid point through the reference's own public API: Bubble(model, v_wall, alpha_n) [+ Spectrum(...).omgw0()]."""
+    vw, an = args
+    R = _CPU["refmod"]
+    try:
+        b = R["Bubble"](R["model"], float(vw), float(an))
+    except (ValueError, RuntimeError):       # the constructor rejects the point (no solution type, alpha_n range)
+        return 0
+    if not b.solved:
+        return 0
+    if _CPU["path"] == "shells":
+        return 1
+    R["Spectrum"](b, r_star=R_STAR).omgw0()
+    return 1
+
+
+class CpuPool:
+    """Fork pool over the host cores, created once and reused across steps.  kind = "reference" (the real reference from
+    oracle/_ref) when it imports on this box and the path is one it covers, else "port" (the oracle restatement)."""
+
+    def __init__(self, cores, path, prefer_reference=True):
+        import multiprocessing as mp
+        self.kind, self.note = "port", ""
+        if prefer_reference and path in ("generic", "shells"):
+            reason = _ref_setup(path)
+            if reason is None:
+                self.kind = "reference"
+                self.note = f"; the unmodified reference from oracle/_ref (numba {_numba_version()}, jit warm-up " \
+                            f"{_CPU['ref_jit_s']:.0f} s before the fork, not timed)"
+            else:
+                self.note = f"; oracle port, because: {reason}"
+        if self.kind == "port":
+            _cpu_setup(path)      # before the fork: workers inherit the model and the starting-guess table
+        _CPU["path"] = path
+        self.fn = _ref_point if self.kind == "reference" else _cpu_point
+        self.pool = mp.get_context("fork").Pool(cores)
+
+    def run(self, points):
+        t0 = time.perf_counter()
+        self.pool.map(self.fn, points, chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def _numba_version():
+    try:
+        import numba
+        return numba.__version__
+    except ImportError:
+        return "?"
+
+
+def cpu_run(points, cores, path, prefer_reference=False):
+    pool = CpuPool(cores, path, prefer_reference)
+    try:
+        return pool.run(points)
+    finally:
+        pool.close()
 
 
 def reference_arm(args):
@@ -123,23 +218,25 @@ def reference_arm(args):
     cores = len(os.sched_getaffinity(0))
     per_step = 2 * max(cores, 8)
     times = []
+    pool = CpuPool(cores, args.path, prefer_reference=not args.cpu_port)
     for s in range(args.warmup + args.steps):
         vw, an = batch_points(s, 0, 1, args.batch)
         pick = np.linspace(0, vw.size - 1, per_step).astype(int)      # spread over the rows and strengths of the batch
         vw, an = vw[pick], an[pick]
-        dt = cpu_run(list(zip(vw, an)), cores, args.path)
+        dt = pool.run(list(zip(vw, an)))
         if s >= args.warmup:
             times.append(dt)
+    pool.close()
     total = float(np.sum(times))
     value = per_step * args.steps / total
     sample = (f"{per_step} grid points per step spread evenly over the GPU arm's batch of the same step, "
-              f"{args.steps} steps, fork pool of {cores} processes")
+              f"{args.steps} steps, one fork pool of {cores} processes" + pool.note)
     print(json.dumps({
         "impl": "reference", "metric": "bubble+GW spectra/sec", "value": value, "unit": "spectra/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.path], "batch_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": "spectra/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "spectra/s", "cores": cores, "kind": pool.kind, "sample": sample},
         "e2e": {"value": value, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), file=RESULT, flush=True)
 
@@ -429,10 +526,12 @@ def cpu_baseline_leg(B, cores, args):
     n_cpu = 4 * max(cores, 8)
     vw, an = batch_points(0, 0, 1, B)
     pick = np.linspace(0, B - 1, n_cpu).astype(int)
-    dt = cpu_run(list(zip(vw[pick], an[pick])), cores, "generic")
-    return {"value": n_cpu / dt, "unit": "spectra/s", "cores": cores, "kind": "port",
+    pool = CpuPool(cores, "generic", prefer_reference=not args.cpu_port)
+    dt = pool.run(list(zip(vw[pick], an[pick])))
+    pool.close()
+    return {"value": n_cpu / dt, "unit": "spectra/s", "cores": cores, "kind": pool.kind,
             "sample": f"{n_cpu} points spread evenly over the batch of step 0 (same grid, same sizes), "
-                      f"fork pool of {cores} processes, {dt:.1f} s"}
+                      f"fork pool of {cores} processes, {dt:.1f} s" + pool.note}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -754,6 +853,8 @@ if __name__ == "__main__":
                     help="headline = configs 2/5 of BASELINE.json (the metric's configuration); the others are extra lines")
     ap.add_argument("--pow-v", action="store_true", help="also compute pow_v (the y pass of spec_den_v)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-port", action="store_true", help="CPU arm / cpu_baseline: the oracle port even when the real "
+                    "reference (oracle/_ref) imports")
     a = ap.parse_args()
     RESULT = _claim_stdout()
     if a.impl == "reference":
