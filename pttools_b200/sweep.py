@@ -262,35 +262,60 @@ def sweep_models(models, v_walls, alpha_ns, y=None, rank: int = 0, world: int = 
 # Multi-GPU: whole v_wall rows per rank, no collective in the solve, result blocks sent to the root as they finish
 # ---------------------------------------------------------------------------------------------------------------
 
-def shard_rows(v_wall: np.ndarray, cost: tp.Optional[np.ndarray], world: int) -> tp.List[np.ndarray]:
+def shard_rows(v_wall: np.ndarray, cost: tp.Optional[np.ndarray], world: int,
+               only: tp.Optional[int] = None) -> tp.List[np.ndarray]:
     """Static partition of the points of a sweep over `world` ranks by WHOLE v_wall ROWS: all points that share a wall
     speed stay on one rank, because they share the lifetime-convolution weights of K6' (one banded matrix product per
     wall speed).  cost = None: the rows, ordered by v_wall, are dealt cyclically -- neighbouring wall speeds have nearly
     the same mix of solution types, so the shards are balanced without looking at the points; with cost[i] (estimated
     cost of point i) rows are dealt greedily, most expensive first, to the least loaded rank.  Returns per rank the
-    point indices, ordered by (v_wall, original index)."""
+    point indices, ordered by (v_wall, original index).  only=k: only the shard of rank k is built (the others are None)."""
     v_wall = np.asarray(v_wall, dtype=float).reshape(-1)
     n = v_wall.size
-    if n and np.all(v_wall[1:] >= v_wall[:-1]):            # already ordered (grid sweeps are): rows are runs
-        order = np.arange(n)
-        inv = np.concatenate(([0], np.cumsum(v_wall[1:] != v_wall[:-1])))
-        n_rows = int(inv[-1]) + 1
-    else:
-        uniq, inv = np.unique(v_wall, return_inverse=True)
-        n_rows = uniq.size
-        order = np.lexsort((np.arange(n), v_wall))
-    if cost is None:
-        owner = np.arange(n_rows) % world
-    else:
-        row_cost = np.bincount(inv, weights=np.asarray(cost, dtype=float).reshape(-1), minlength=n_rows)
+    ranks = range(world) if only is None else (only,)
+    out: tp.List[tp.Optional[np.ndarray]] = [None] * world
+
+    def deal(n_rows, row_cost):
+        if row_cost is None:
+            return np.arange(n_rows) % world
         owner = np.empty(n_rows, dtype=np.int64)
         load = np.zeros(world)
         for r in np.argsort(-row_cost, kind="stable"):
             k = int(np.argmin(load))
             owner[r] = k
             load[k] += row_cost[r]
-    point_owner = owner[inv]
-    return [order[point_owner[order] == k] for k in range(world)]
+        return owner
+
+    if n:
+        # grid sweeps arrive as runs of equal wall speed: if every wall speed forms ONE run (in whatever order the runs
+        # come), the rows are the runs, only the run values need sorting and a shard is a concatenation of index ranges
+        starts = np.concatenate(([0], np.nonzero(v_wall[1:] != v_wall[:-1])[0] + 1))
+        by_value = np.argsort(v_wall[starts], kind="stable")
+        sorted_vals = v_wall[starts][by_value]
+        if starts.size * 8 <= n and np.all(sorted_vals[1:] > sorted_vals[:-1]):
+            lengths = np.diff(np.concatenate((starts, [n])))
+            r_start, r_len = starts[by_value], lengths[by_value]          # rows in v_wall order
+            row_cost = None if cost is None else \
+                np.add.reduceat(np.asarray(cost, dtype=float).reshape(-1), starts)[by_value]
+            owner = deal(starts.size, row_cost)
+            for k in ranks:
+                rs, rl = r_start[owner == k], r_len[owner == k]
+                offs = np.concatenate(([0], np.cumsum(rl)[:-1]))
+                out[k] = np.repeat(rs - offs, rl) + np.arange(int(rl.sum()))
+            return out
+    uniq, inv = np.unique(v_wall, return_inverse=True)
+    order = np.lexsort((np.arange(n), v_wall))
+    row_cost = None if cost is None else \
+        np.bincount(inv, weights=np.asarray(cost, dtype=float).reshape(-1), minlength=uniq.size)
+    owner = deal(uniq.size, row_cost)
+    # split `order` by owner, keeping the order inside every shard: one stable radix sort on a 16-bit key instead of a
+    # mask per rank
+    key = owner[inv][order].astype(np.uint16 if world <= 65535 else np.int64)
+    by_owner = order[np.argsort(key, kind="stable")]
+    ends = np.cumsum(np.bincount(key, minlength=world))
+    for k in ranks:
+        out[k] = by_owner[(ends[k - 1] if k else 0):ends[k]]
+    return out
 
 
 def point_cost(codes: np.ndarray) -> np.ndarray:
@@ -443,7 +468,8 @@ def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, chunk=80
     single = isinstance(model, Model)
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
-    shards = shard_rows(vw, None, world)
+    # only the sendrecv transport needs the other ranks' shards (rank `dst` posts the receives)
+    shards = shard_rows(vw, None, world, only=None if transport == "sendrecv" else rank)
     torch = engine._torch()
     # shell chunks that are multiples of the spectrum chunk keep every delivered range inside one block of `chunk` rows
     from . import _lib
