@@ -317,13 +317,14 @@ def _alg_work(plan, stats, n_points_step, n_samples_step):
     _, nseg, meta, _ = engine.gw_cells(plan)
     cells = float(int(nseg.sum().item()) + sum(int(meta[i, 2:2 + int(n)].sum().item()) for i, n in enumerate(nseg.tolist())))
     w["spec_den_gw_cells"] = {"flop": 10.0 * cells * stats["gw_profiles"] / steps, "bound": "fp64", "precision": "fp64 (FMA pipe)"}
-    # K5: block-moment sine transform: 2^l blocks x 22 flop x 2 functions per exact wavenumber (2^l >= z / 0.4, l <= 7),
-    # 12 moments x 2 flop x 2 functions per profile sample for the finest level, ~60 flop per asymptotic wavenumber
+    # K5: block-moment sine transform: 2^l blocks x 39 flop (16 moments: 14 fma Horner, 5 flop combine, 6 flop rotation)
+    # x 2 functions per exact wavenumber (2^l >= z / 1.6, l <= 5), 16 moments x 2 flop x 2 functions per profile sample
+    # for the finest level, ~60 flop per asymptotic wavenumber
     z, fr = plan.z_all, plan.frac_all
     zl = z[fr < 1.0]
-    blocks = np.minimum(128.0, 2.0 ** np.ceil(np.log2(np.maximum(zl / 0.4, 1.0))))
-    per_profile = 44.0 * blocks.sum() + 60.0 * np.count_nonzero(fr > 0.0)
-    w["a2"] = {"flop": (per_profile * stats["a2_profiles"] + 48.0 * (n_samples_step + 2000.0 * stats["a2_profiles"])) / steps,
+    blocks = np.minimum(32.0, 2.0 ** np.ceil(np.log2(np.maximum(zl / 1.6, 1.0))))
+    per_profile = 78.0 * blocks.sum() + 60.0 * np.count_nonzero(fr > 0.0)
+    w["a2"] = {"flop": (per_profile * stats["a2_profiles"] + 64.0 * (n_samples_step + 2000.0 * stats["a2_profiles"])) / steps,
                "bound": "fp64", "precision": "fp64 (FMA pipe)"}
     # K3: one thread per point, latency bound; its roofline is the HBM write of the materialised profiles,
     # 3 arrays x 8 B per sample
@@ -379,19 +380,21 @@ def gpu_arm(args):
     for s in list(range(total_steps)) + [1000 + k for k in range(args.steps + 1)]:
         step_points(s)
     sampler = ClockSampler(local) if rank == 0 else None
-    for s in range(args.warmup):
-        device_step(s)
-    barrier()
     import gc
     gc.collect()
     gc.disable()          # no collector pauses inside the timed regions (re-enabled below)
+    engine.STAGES.enable(True)          # the warm-up steps run exactly what the timed steps run
+    for s in range(args.warmup):
+        device_step(s)
+    barrier()
+    engine.STAGES.enable(True)          # resets the stage times of the warm-up
     if sampler:
         sampler.mark_start()
-    engine.STAGES.enable(True)
     launches0 = engine.STAGES.launches
     agg = {k: 0 for k in ("group_macs", "group_count", "group_profiles", "gw_profiles", "a2_profiles", "retried", "rescued",
                           "chunks_before_fold", "chunks_after_fold")}
-    waits = []
+    waits, step_stages = [], []
+    from pttools_b200 import _lib
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     ev0.record()
@@ -404,6 +407,8 @@ def gpu_arm(args):
             agg[k] += int(getattr(st.stats, k))
         waits.append((round(st.stats.host_wait_shells_ms, 1), round(st.stats.host_wait_retry_ms, 1), int(st.stats.retried),
                       int(st.stats.chunks_before_fold)))
+        step_stages.append({name: round(float(st.stats.stage_ms[i]), 1) for i, name in enumerate(_lib.STAGE_NAMES)
+                            if st.stats.stage_calls[i]})
         n_samples += float(torch.nan_to_num(st.scalars["npts"]).sum())
         n_ok += int((st.status == 0).sum())
         step_ev.append(torch.cuda.Event(enable_timing=True))
@@ -507,7 +512,8 @@ def gpu_arm(args):
                        "l2": "per-step working set (profiles + A2 + lookup tables, ~1 MB per point) exceeds the 126 MB L2; "
                              "every step uses fresh points",
                        "valid_points_in_timed_region_rank0": n_ok, "per_step_ms": per_step_ms,
-                       "wall_ms_per_step": wall_ms / args.steps, "retried_points_rank0": agg["retried"],
+                       "wall_ms_per_step": wall_ms / args.steps, "stage_ms_by_step_rank0": step_stages,
+                       "retried_points_rank0": agg["retried"],
                        "rescued_points_rank0": agg["rescued"],
                        "host_waits_rank0": {"per_step": waits, "columns": ["wait_shells_ms", "wait_retry_ms", "retried_points",
                                                                            "chunks_before_fold"]}},

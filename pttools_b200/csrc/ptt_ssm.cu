@@ -13,15 +13,16 @@ namespace ptt {
 
 constexpr int ENV_SIZE = 16;   // xi1, xi_w, xi2, f1, f_m, f_p, f2, valid, ...
 // Block-moment representation of a sampled function for the exact part of the sine transform (see K5b').
-constexpr int MOM_NB = 128;                    // blocks over xi in [0, 1]
-constexpr int MOM_J = 12;                      // moments per block: sum_k g_k delta_k^j / j!,  j = 0..11
+constexpr int MOM_NB = 32;                     // blocks over xi in [0, 1]
+constexpr int MOM_J = 16;                      // moments per block: sum_k g_k delta_k^j / j!,  j = 0..15
 constexpr int MOM_HDR = 8;                     // {b_lo, b_hi, ...}
-constexpr int MOM_LEVELS = 8;                  // level l: 2^l blocks of width 2^-l; level 7 is the finest (MOM_NB)
+constexpr int MOM_LEVELS = 6;                  // level l: 2^l blocks of width 2^-l; level 5 is the finest (MOM_NB)
 constexpr int MOM_BLOCKS = 2 * MOM_NB - 1;     // pyramid, level l starts at block 2^l - 1
 constexpr int MOM_SIZE = MOM_HDR + MOM_BLOCKS * MOM_J;
 constexpr double MOM_W = 1.0 / MOM_NB;
-constexpr double MOM_ZW = 0.4;                 // a block of width W serves z W <= 0.4
-constexpr double MOM_ZMAX = 51.2;              // (z W / 2)^12 / 12! < 1e-17 for z <= 51.2
+constexpr double MOM_ZW = 1.6;                 // a block of width W serves z W <= 1.6
+constexpr double MOM_ZMAX = 51.2;              // (z W / 2)^16 / 16! < 1.4e-15 for z <= 51.2 = MOM_ZW * MOM_NB
+static_assert(MOM_NB == 1 << (MOM_LEVELS - 1) && MOM_J % 2 == 0, "pyramid shape");
 constexpr double FOUR_PI = 12.566370614359172953850573533118;
 
 // --- block-wide helpers -------------------------------------------------------------------------------------
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(ST_THREADS) sin_transform_kernel(
 // xi_k = c_b + delta_k inside block b (centre c_b, |delta_k| <= W/2):
 //     sum_{k in b} g_k sin(z xi_k) = sin(z c_b) C_b(z) + cos(z c_b) S_b(z),
 //     C_b = sum_m (-1)^m z^{2m}   M_{b,2m},     S_b = sum_m (-1)^m z^{2m+1} M_{b,2m+1},     M_{b,j} = sum_k g_k delta_k^j / j!
-// The moments do not depend on z, the series converges to 1e-17 for z W / 2 <= 0.2, and sin/cos(z c_b) advance by a
+// The moments do not depend on z, 16 of them carry the series to 1.4e-15 for z W / 2 <= 0.8, and sin/cos(z c_b) advance by a
 // constant rotation.  Same sum, ~N_xi / 6 times fewer flops than one sine per (z, xi) pair.
 __device__ void block_moments(const double* __restrict__ xi, const double* __restrict__ g, const int n,
                               double* __restrict__ mom /* MOM_SIZE, global */, double* s_pyr /* MOM_BLOCKS*MOM_J shared */,
@@ -370,34 +371,32 @@ __device__ void block_moments(const double* __restrict__ xi, const double* __res
 #pragma unroll
     for (int j = 0; j < MOM_J; ++j) m[j] = 0.0;
     int cur = -1;                                      // warp-uniform: block whose moments sit in m
-    static_assert(MOM_J == 12, "the butterfly below folds 12 -> 6 -> 3 -> 2 -> 1 values per lane");
+    static_assert(MOM_J == 16, "the butterfly below folds 16 -> 8 -> 4 -> 2 -> 1 values per lane");
     auto flush = [&]() {
         if (cur < 0) return;
-        // Butterfly that halves the values per lane at every step (13 shuffles instead of 60): afterwards lane L holds
-        // the warp total of moment j(L) = bit1 + 2 bit2 + 3 bit3 + 6 bit4 (bit1 + 2 bit2 == 3 is padding).
+        // Butterfly that halves the values per lane at every step (15 shuffles instead of 80): afterwards lane L holds
+        // the warp total of moment j(L) = bit1 + 2 bit2 + 4 bit3 + 8 bit4 of the lane index (bit0: a duplicate).
         const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
-        double a6[6], a3[4], a2[2];
+        double a8[8], a4[4], a2[2];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const double send = h4 ? m[i] : m[i + 6], keep = h4 ? m[i + 6] : m[i];
-            a6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        for (int i = 0; i < 8; ++i) {
+            const double send = h4 ? m[i] : m[i + 8], keep = h4 ? m[i + 8] : m[i];
+            a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const double send = h3 ? a6[i] : a6[i + 3], keep = h3 ? a6[i + 3] : a6[i];
-            a3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        for (int i = 0; i < 4; ++i) {
+            const double send = h3 ? a8[i] : a8[i + 4], keep = h3 ? a8[i + 4] : a8[i];
+            a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
         }
-        a3[3] = 0.0;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const double send = h2 ? a3[i] : a3[i + 2], keep = h2 ? a3[i + 2] : a3[i];
+            const double send = h2 ? a4[i] : a4[i + 2], keep = h2 ? a4[i + 2] : a4[i];
             a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
         }
         const double send = h1 ? a2[0] : a2[1], keep = h1 ? a2[1] : a2[0];
         double tot = keep + __shfl_xor_sync(0xffffffffu, send, 2);
         tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-        const int jl = (h1 ? 1 : 0) + (h2 ? 2 : 0);
-        if (!(lane & 1) && jl < 3) atomicAdd(&s_m[cur * MOM_J + jl + (h3 ? 3 : 0) + (h4 ? 6 : 0)], tot);
+        if (!(lane & 1)) atomicAdd(&s_m[cur * MOM_J + (h1 ? 1 : 0) + (h2 ? 2 : 0) + (h3 ? 4 : 0) + (h4 ? 8 : 0)], tot);
 #pragma unroll
         for (int j = 0; j < MOM_J; ++j) m[j] = 0.0;
         if (lane == 0) { atomicMin(&s_lohi[0], cur); atomicMax(&s_lohi[1], cur); }
@@ -501,12 +500,9 @@ __device__ __forceinline__ double moment_transform(const double* __restrict__ mo
     for (int b = b_lo; b <= b_hi; ++b) {
         const double* m = lev + b * MOM_J;
         // Horner in -z^2: even and odd moments
-        double C = m[10], S = m[11];
-        C = fma(C, z2, m[8]);  S = fma(S, z2, m[9]);
-        C = fma(C, z2, m[6]);  S = fma(S, z2, m[7]);
-        C = fma(C, z2, m[4]);  S = fma(S, z2, m[5]);
-        C = fma(C, z2, m[2]);  S = fma(S, z2, m[3]);
-        C = fma(C, z2, m[0]);  S = fma(S, z2, m[1]);
+        double C = m[MOM_J - 2], S = m[MOM_J - 1];
+#pragma unroll
+        for (int j = MOM_J - 4; j >= 0; j -= 2) { C = fma(C, z2, m[j]); S = fma(S, z2, m[j + 1]); }
         acc = fma(sb, C, acc);
         acc = fma(cb * z, S, acc);
         const double sn = fma(sb, cw, cb * sw);
@@ -539,22 +535,17 @@ __device__ __forceinline__ void moment_transform2(const double* __restrict__ mom
     sincos(zb * W, &swb, &cwb);
     for (int b = b_lo; b <= b_hi; ++b) {
         const double* m = lev + b * MOM_J;
-        const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5], m6 = m[6], m7 = m[7],
-                     m8 = m[8], m9 = m[9], m10 = m[10], m11 = m[11];
-        double C = m10, S = m11;
-        C = fma(C, za2, m8);  S = fma(S, za2, m9);
-        C = fma(C, za2, m6);  S = fma(S, za2, m7);
-        C = fma(C, za2, m4);  S = fma(S, za2, m5);
-        C = fma(C, za2, m2);  S = fma(S, za2, m3);
-        C = fma(C, za2, m0);  S = fma(S, za2, m1);
+        double mj[MOM_J];
+#pragma unroll
+        for (int j = 0; j < MOM_J; ++j) mj[j] = m[j];
+        double C = mj[MOM_J - 2], S = mj[MOM_J - 1];
+#pragma unroll
+        for (int j = MOM_J - 4; j >= 0; j -= 2) { C = fma(C, za2, mj[j]); S = fma(S, za2, mj[j + 1]); }
         ra = fma(sa, C, ra);
         ra = fma(ca * za, S, ra);
-        C = m10; S = m11;
-        C = fma(C, zb2, m8);  S = fma(S, zb2, m9);
-        C = fma(C, zb2, m6);  S = fma(S, zb2, m7);
-        C = fma(C, zb2, m4);  S = fma(S, zb2, m5);
-        C = fma(C, zb2, m2);  S = fma(S, zb2, m3);
-        C = fma(C, zb2, m0);  S = fma(S, zb2, m1);
+        C = mj[MOM_J - 2]; S = mj[MOM_J - 1];
+#pragma unroll
+        for (int j = MOM_J - 4; j >= 0; j -= 2) { C = fma(C, zb2, mj[j]); S = fma(S, zb2, mj[j + 1]); }
         rb = fma(sb, C, rb);
         rb = fma(cb * zb, S, rb);
         double sn = fma(sa, cwa, ca * swa);
