@@ -57,6 +57,17 @@ class BubbleView:
     w = property(lambda self: self._profile()[1])
     xi = property(lambda self: self._profile()[2])
 
+    @property
+    def alpha_theta_bar_n(self) -> float:
+        return float(self.model.alpha_theta_bar_n_from_alpha_n(self.alpha_n, wn=self.wn))
+
+    @property
+    def kappa_giese(self) -> float:
+        """bubble.py:539-543: 4 e_K / (3 alpha_theta_bar_n w_n)."""
+        if not self.solved:
+            raise bub.NotYetSolvedError
+        return 4 * self.kinetic_energy_density / (3 * self.alpha_theta_bar_n * self.wn)
+
     def __getattr__(self, name):
         scal = self.__dict__["_b"].scal
         if name in scal:
@@ -223,7 +234,7 @@ class BubbleGridVWAlpha:
     def get_value(self, name: str, dtype=None) -> np.ndarray:
         """bubble_grid.py:18-34: None (NaN for float dtypes) where there is no bubble or it has not been solved."""
         def one(b):
-            if b is None or (not b.solved and name in BubbleView.NEEDS_SOLUTION):
+            if b is None or (not b.solved and (name in BubbleView.NEEDS_SOLUTION or name == "kappa_giese")):
                 return None
             return getattr(b, name)
         return np.array([[one(b) for b in row] for row in self.bubbles], dtype=dtype)
@@ -233,6 +244,9 @@ class BubbleGridVWAlpha:
 
     def omega(self):
         return self.get_value("omega", dtype=np.float64)
+
+    def kappa_giese(self):
+        return self.get_value("kappa_giese", dtype=np.float64)
 
     def numerical_error(self):
         return self.get_value("numerical_error", dtype=np.bool_)

@@ -435,6 +435,13 @@ class Bubble:
     def vp_tilde_sh(self):
         return self.v_sh
 
+    @property
+    def kappa_giese(self) -> float:
+        """bubble.py:539-543."""
+        if not self.solved:
+            raise NotYetSolvedError
+        return 4 * self.kinetic_energy_density / (3 * self.alpha_theta_bar_n * self.wn)
+
     def export(self, path: str = None):
         data = {"model": self.model.export(), "v_wall": self.v_wall, "alpha_n": self.alpha_n, "sol_type": self.sol_type,
                 "t_end": self.t_end, "n_xi": self.n_xi, "thin_shell_limit": self.thin_shell_t_points_min, "v": self.v,

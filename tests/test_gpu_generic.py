@@ -173,6 +173,60 @@ def test_create_spectra_grid_api():
     assert np.all(np.isfinite(objs[0, 1].pow_gw)) and objs[0, 1].omgw0().shape == (100,)
 
 
+def test_grid_facade_values_against_the_reference():
+    """create_spectra / create_bubbles / BubbleGridVWAlpha (analysis/parallel.py:89-187, bubble_grid.py:57-80) on a 4 x 4
+    sub-lattice of the bench grid, against the reference's own Bubble + Spectrum objects at those points
+    (ref_headline_grid.npz): array layout [i_alpha_n, i_v_wall], omgw0 1e-5 (or twice the reference's own LSODA noise
+    recorded in the fixture), kappa / omega 1e-6 (same rule), post-functions, None for points the constructor rejects."""
+    from pttools_b200 import analysis
+    from pttools_b200.models import BagModel
+    d = np.load(os.path.join(GOLDEN, "ref_headline_grid.npz"))
+    model = BagModel(alpha_n_min=0.005)
+    v_all, a_all = np.linspace(0.05, 0.95, 1000), np.linspace(0.005, 0.5, 1000)
+    sel_v, sel_a = [2, 6, 9, 14], [0, 3, 7, 12]                 # positions in the fixture's 16 x 16 lattice
+    v_walls, alpha_ns = v_all[d["iv"][sel_v]], a_all[d["ia"][sel_a]]
+    ydec = int(d["y_dec"][0])
+    names = list(d["scalar_names"])
+
+    def peak(s):
+        return float(np.nanmax(s.omgw0()))
+    peak.return_type, peak.fail_value = np.float64, np.nan
+
+    objs, peaks = analysis.create_spectra(model, v_walls, alpha_ns, func=peak, allow_bubble_failure=True,
+                                          spectrum_kwargs={"r_star": 0.1})
+    assert objs.shape == peaks.shape == (4, 4)
+    grid = analysis.BubbleGridVWAlpha(model, v_walls, alpha_ns)
+    kappa, omega, kg = grid.kappa(), grid.omega(), grid.kappa_giese()
+    n_checked = 0
+    for ja, ka in enumerate(sel_a):
+        for jv, kv in enumerate(sel_v):
+            i = kv * 16 + ka                                      # fixture order: v_wall-major
+            np.testing.assert_allclose(d["points"][i], [v_walls[jv], alpha_ns[ja]], rtol=1e-14)
+            s = objs[ja, jv]
+            if d["err"][i] == 1:                                  # the reference's constructor raises
+                assert s is None and np.isnan(peaks[ja, jv]) and grid.bubbles[ja, jv] is None and np.isnan(kappa[ja, jv])
+                continue
+            assert s.bubble.v_wall == v_walls[jv] and s.bubble.alpha_n == alpha_ns[ja]
+            if d["err"][i] == 2 or d["flags"][i][1]:
+                continue
+            noise = d["noise"][i]
+            ref = d[f"omgw0_{i}"]
+            got = s.omgw0()[::ydec]
+            if np.all(np.isfinite(ref)):
+                assert np.max(np.abs(got / ref - 1)) <= max(1e-5, 2 * noise[2]), (v_walls[jv], alpha_ns[ja])
+                np.testing.assert_allclose(peaks[ja, jv], np.nanmax(s.omgw0()), rtol=0)
+            sc = dict(zip(names, d["scal"][i]))
+            sn = dict(zip(names, d[f"scal_noise_{i}"]))
+            for nm, arr in (("kappa", kappa), ("omega", omega)):
+                assert abs(arr[ja, jv] / sc[nm] - 1) <= max(1e-6, 2 * sn[nm]), (nm, v_walls[jv], alpha_ns[ja])
+            b = grid.bubbles[ja, jv]
+            np.testing.assert_allclose(kg[ja, jv], 4 * b.kinetic_energy_density / (3 * b.alpha_theta_bar_n * b.wn), rtol=1e-14)
+            n_checked += 1
+    assert n_checked >= 10
+    with pytest.raises(ValueError):                               # without allow_bubble_failure the rejection propagates
+        analysis.create_bubbles(model, v_walls[:1], np.array([0.001]))
+
+
 def test_spectrum_chain_through_grouped_matrix_product():
     """Same fixtures as above with the banded-GEMM spec_den_v forced on (runs of equal v_wall of any length)."""
     from pttools_b200 import engine, sweep
