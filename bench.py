@@ -400,22 +400,28 @@ def gpu_arm(args):
     ev0.record()
     n_ok, n_samples = 0, 0.0
     step_ev = [ev0]
+    per_step = []                   # results of the timed steps: reduced AFTER the timed region (no host sync inside it)
     for s in range(args.warmup, total_steps):
         table = device_step(s)
         st = sweep.LAST_LOCAL["result"]
-        for k in agg:
-            agg[k] += int(getattr(st.stats, k))
-        waits.append((round(st.stats.host_wait_shells_ms, 1), round(st.stats.host_wait_retry_ms, 1), int(st.stats.retried),
-                      int(st.stats.chunks_before_fold)))
-        step_stages.append({name: round(float(st.stats.stage_ms[i]), 1) for i, name in enumerate(_lib.STAGE_NAMES)
-                            if st.stats.stage_calls[i]})
-        n_samples += float(torch.nan_to_num(st.scalars["npts"]).sum())
-        n_ok += int((st.status == 0).sum())
+        per_step.append((getattr(st._keep, "stats_box", st._keep), st.scalars["npts"], st.status))
         step_ev.append(torch.cuda.Event(enable_timing=True))
         step_ev[-1].record()
     ev1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall
+    engine.finish_timing()          # the last step's stage times (read from its events)
+    for keep, npts, status in per_step:
+        stats = keep.stats
+        for k in agg:
+            agg[k] += int(getattr(stats, k))
+        waits.append((round(stats.host_wait_shells_ms, 1), round(stats.host_wait_retry_ms, 1), int(stats.retried),
+                      int(stats.chunks_before_fold)))
+        step_stages.append({name: round(float(stats.stage_ms[i]), 1) for i, name in enumerate(_lib.STAGE_NAMES)
+                            if stats.stage_calls[i]})
+        n_samples += float(torch.nan_to_num(npts).sum())
+        n_ok += int((status == 0).sum())
+    del per_step
     dev_ms = ev0.elapsed_time(ev1)
     per_step_ms = [a.elapsed_time(b) for a, b in zip(step_ev[:-1], step_ev[1:])]
     stage_ms = engine.STAGES.summary()

@@ -423,6 +423,9 @@ typedef struct ptt_sweep_stats {
     double host_wait_shells_ms;        /* host time spent waiting for the status of a shell chunk */
 } ptt_sweep_stats_t;
 int ptt_sweep_last_stats(ptt_sweep_stats_t* out);
+/* With PTT_MEM_DEVICE a timed sweep (PTT_SWEEP_TIMING) returns with its last chunks in flight and stage_ms not yet read
+ * from the events: this waits for them and completes the stats ptt_sweep_last_stats returns (the next sweep does it too). */
+int ptt_sweep_timing_sync(void);
 /* frees the device / pinned workspace the sweep driver keeps between calls */
 int ptt_sweep_release(void);
 /* Device buffers that other processes of the box can map (CUDA IPC): the result table of a sharded sweep lives on one

@@ -167,6 +167,7 @@ SIGNATURES = {
     "ptt_ipc_close": (C.c_int, [C.c_void_p]),
     "ptt_ipc_free": (C.c_int, [C.c_void_p]),
     "ptt_sweep_last_stats": (C.c_int, [C.POINTER(SweepStats)]),
+    "ptt_sweep_timing_sync": (C.c_int, []),
     "ptt_sweep_release": (C.c_int, []),
     "ptt_sweep_shell_chunk": (C.c_int64, [C.c_int, C.c_int64]),
     "ptt_suppression_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double,

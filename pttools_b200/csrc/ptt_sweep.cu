@@ -198,6 +198,8 @@ struct ShellSlot {
     std::vector<PinBuf*> pin() { return {&h_status, &h_npts, &h_rescued, &h_idx}; }
 };
 
+struct TimingRec { int stage; cudaEvent_t a, b; };
+
 struct Workspace {
     int device = -1;
     std::mutex mu;
@@ -210,6 +212,7 @@ struct Workspace {
                 ev_emit = nullptr;
     std::vector<cudaEvent_t> timing;
     size_t timing_used = 0;
+    std::vector<TimingRec> pending_timing;      // stage events of the last device-table sweep, not read yet
 
     std::vector<cudaStream_t*> streams() { return {&s_shell, &s_retry, &s_copy, &s_side[0], &s_side[1]}; }
     std::vector<cudaEvent_t*> events() {
@@ -258,6 +261,7 @@ struct Workspace {
         for (cudaEvent_t e : timing) cudaEventDestroy(e);
         timing.clear();
         timing_used = 0;
+        pending_timing.clear();
         device = -1;
     }
 };
@@ -313,7 +317,7 @@ static int group_band(const ptt_sweep_plan_t& pl, const int ip, const double v_w
 struct Timer {
     Workspace& ws;
     bool on;
-    struct Rec { int stage; cudaEvent_t a, b; };
+    typedef TimingRec Rec;
     std::vector<Rec> recs;
     Timer(Workspace& w, const bool enabled) : ws(w), on(enabled) {}
     cudaEvent_t begin(cudaStream_t s) {
@@ -329,7 +333,8 @@ struct Timer {
         cudaEventRecord(b, s);
         recs.push_back({stage, a, b});
     }
-    void collect(ptt_sweep_stats_t& st) {
+    void collect(ptt_sweep_stats_t& st) { collect_recs(recs, st); }
+    static void collect_recs(const std::vector<Rec>& recs, ptt_sweep_stats_t& st) {
         const char* trace = getenv("PTT_SWEEP_TRACE");       // diagnostics: timeline of the stages on stderr
         for (const Rec& r : recs) {
             float ms = 0.f;
@@ -923,12 +928,16 @@ int Sweep::run() {
         SW_CUDA(cudaMemcpyAsync(out.snr, src, cnt * sizeof(double), host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s_main));
     }
     if (cb && !sorted) cb(user, 0, n, s_main);
-    if (host || timer.on) {
+    if (host) {
         SW_CUDA(cudaStreamSynchronize(s_main));
         SW_CUDA(cudaStreamSynchronize(ws.s_shell));
         SW_CUDA(cudaStreamSynchronize(ws.s_retry));
+        timer.collect(stats);
+    } else if (timer.on) {
+        // device tables: the call returns with its last chunks still in flight (the caller's next host work overlaps
+        // them); the stage times are read from the events when somebody asks (ptt_sweep_timing_sync, or the next sweep)
+        ws.pending_timing.swap(timer.recs);
     }
-    timer.collect(stats);
     return PTT_OK;
 }
 
@@ -981,6 +990,23 @@ extern "C" int ptt_sweep_release(void) {
     return PTT_OK;
 }
 
+// stage times of a device-table sweep are read from its events on demand: waits for the sweep to finish
+static int timing_sync_locked() {
+    if (g_ws.pending_timing.empty()) return PTT_OK;
+    for (const TimingRec& r : g_ws.pending_timing) {
+        const cudaError_t e = cudaEventSynchronize(r.b);
+        if (e != cudaSuccess) { g_ws.pending_timing.clear(); return set_cuda_error("ptt_sweep_timing_sync", e); }
+    }
+    Timer::collect_recs(g_ws.pending_timing, g_stats);
+    g_ws.pending_timing.clear();
+    return PTT_OK;
+}
+
+extern "C" int ptt_sweep_timing_sync(void) {
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    return timing_sync_locked();
+}
+
 extern "C" int ptt_sweep_last_stats(ptt_sweep_stats_t* out) {
     if (!out) return set_error(PTT_E_ARG, "ptt_sweep_last_stats: null pointer");
     *out = g_stats;
@@ -1024,6 +1050,7 @@ extern "C" int ptt_sweep_spectra(const ptt_sweep_plan_t* plan, const ptt_sweep_o
         return set_error(PTT_E_ARG, "ptt_sweep_spectra: table_rows needs device tables");
     std::lock_guard<std::mutex> lock(g_ws.mu);
     SW_RC(g_ws.init());
+    SW_RC(timing_sync_locked());      // the events are reused: read the previous sweep's first (it has to be over anyway)
     g_ws.timing_used = 0;
     Sweep sw(g_ws, plan, *opts, *out, cb, user, mem, (cudaStream_t)stream_);
     int rc = sw.setup(n, pg, pm, scale);

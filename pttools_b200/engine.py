@@ -43,6 +43,7 @@ class _Stages:
         self.c_stage_ms = {}        # stage times reported by the C sweep driver (ptt_sweep_last_stats)
 
     def enable(self, on: bool):
+        finish_timing()
         self.enabled = on
         self._ev = []
         self.c_stage_ms = {}
@@ -71,6 +72,7 @@ class _Stages:
 
     def summary(self):
         import torch
+        finish_timing()
         torch.cuda.synchronize()
         out = {}
         for name, a, b in self._ev:
@@ -416,6 +418,7 @@ def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_she
     cb = None
     if on_chunk is not None:
         cb = _lib.CHUNK_CB(lambda user, r0, r1, stream: on_chunk(int(r0), int(r1), stream))
+    finish_timing()
     rc = lib.ptt_sweep_spectra(C.byref(view) if view is not None else None, C.byref(opts), n, ptr(pg_a), ptr(pm_a),
                                ptr(sc_a), C.byref(o), C.cast(cb, C.c_void_p) if cb is not None else None, None,
                                _lib.MEM_HOST if host else _lib.MEM_DEVICE, _stream_ptr(torch))
@@ -425,13 +428,50 @@ def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_she
     res.stats = st
     STAGES.launches += int(st.launches)
     if timing:
-        for i, name in enumerate(_lib.STAGE_NAMES):
-            if st.stage_calls[i]:
-                d = STAGES.c_stage_ms.setdefault(name, {"ms": 0.0, "n": 0})
-                d["ms"] += st.stage_ms[i]
-                d["n"] += int(st.stage_calls[i])
+        if host:
+            _add_stage_times(st)
+        else:
+            # device tables: the call has returned with its last chunks in flight; the stage times are read from the
+            # events when somebody asks for them (finish_timing) or when the next sweep starts
+            res.stats_box = _StatsBox(res)
+            _PENDING_TIMING.append(res.stats_box)
     res._keep += [pg_a, pm_a, sc_a]
     return res
+
+
+class _StatsBox:
+    """Where the completed stats of a timed device-table sweep arrive (does not keep the result tables alive)."""
+
+    def __init__(self, res):
+        import weakref
+        self.stats, self._res = res.stats, weakref.ref(res)
+
+
+_PENDING_TIMING = []
+
+
+def _add_stage_times(st):
+    for i, name in enumerate(_lib.STAGE_NAMES):
+        if st.stage_calls[i]:
+            d = STAGES.c_stage_ms.setdefault(name, {"ms": 0.0, "n": 0})
+            d["ms"] += st.stage_ms[i]
+            d["n"] += int(st.stage_calls[i])
+
+
+def finish_timing():
+    """Completes the stage times of the last timed device-table sweep (waits for it to finish)."""
+    while _PENDING_TIMING:
+        box = _PENDING_TIMING.pop()
+        lib = _lib.load()
+        _lib.check(lib.ptt_sweep_timing_sync(), "ptt_sweep_timing_sync")
+        st = _lib.SweepStats()
+        lib.ptt_sweep_last_stats(C.byref(st))
+        box.stats = st
+        res = box._res()
+        if res is not None:
+            res.stats = st
+        if STAGES.enabled:
+            _add_stage_times(st)
 
 
 def shell_wall_values(shells: ShellBatch):

@@ -187,15 +187,20 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
     want = (("pow_v",) if want_pow_v else ()) + (("pow_gw",) if want_pow_gw or scale is None else ()) + \
         (("omgw0",) if scale is not None else ())
     pg_in, pm_in, sc_in = pt.pg, pt.pm, scale
+    if mem == "host":
+        vw_out, an_out, codes = vw, an, pt.codes
+    else:
+        # before the call: with device tables the sweep returns with its last chunks in flight, and an upload from
+        # pageable memory after it would wait for them
+        vw_out, an_out = pt.pg[:, 0].contiguous(), pt.pg[:, 1].contiguous()
+        codes = pt.pg[:, 2].to(torch.int32)
     res = engine.sweep_c(plan, pg_in, pm_in, sc_in, n_xi=n_xi, r_star=r_star, lifetime_multiplier=lifetime_multiplier,
                          chunk=chunk, shell_chunk=shell_chunk or 0, want=want, rows=keep_bubbles, mem=mem,
                          on_chunk=on_chunk, timing=timing, out=out, snr_weights=snr_w, table_rows=table_rows,
                          out_rows=out_rows)
     from . import _lib
     scal = {name: res.scalars[:, k] for k, name in enumerate(_lib.SWEEP_SCALARS)}
-    asdev = (lambda a: a) if mem == "host" else engine.dev_f64
-    codes = pt.codes if mem == "host" else torch.as_tensor(pt.codes, dtype=torch.int32, device="cuda")
-    out_ = SweepResult(asdev(vw), asdev(an), codes, res.status, None, y, pow_gw=res.pow_gw, pow_v=res.pow_v,
+    out_ = SweepResult(vw_out, an_out, codes, res.status, None, y, pow_gw=res.pow_gw, pow_v=res.pow_v,
                        omgw0=res.omgw0, scalars=scal)
     out_.invalid = pt.invalid
     out_.stats = res.stats
