@@ -147,9 +147,11 @@ __global__ void __launch_bounds__(GC_WARPS * 32, PTT_GC_MINB) spec_den_gw_cells_
     const double* __restrict__ scale, double* __restrict__ sd_gw, double* __restrict__ pow_gw,
     double* __restrict__ omgw0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.y * GC_WARPS + warp;
+    // wavenumber blocks are the fast grid index: the CTAs resident together walk the rows of two or three profile
+    // groups (tens of MB, L2-resident) instead of a window of every group (more than the L2 holds)
+    const int i = blockIdx.x * GC_WARPS + warp;
     if (i >= n_y) return;
-    const int p0 = blockIdx.x * GC_PPW + lane;
+    const int p0 = blockIdx.y * GC_PPW + lane;
     const int nc = ncell[i];
     const int* __restrict__ mt = meta + (long long)i * (cap + 2);
     const double2* __restrict__ cp = reinterpret_cast<const double2*>(coef + (long long)i * cap_c * 2);
@@ -286,7 +288,7 @@ extern "C" int ptt_spec_den_gw_cells_batch(const ptt_gw_plan_t* plan, const ptt_
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return set_cuda_error("gw_table_kernel", e);
     }
-    dim3 grid(n_groups, (plan->n_y + GC_WARPS - 1) / GC_WARPS);
+    dim3 grid((plan->n_y + GC_WARPS - 1) / GC_WARPS, n_groups);
     spec_den_gw_cells_kernel<<<grid, GC_WARPS * 32, 0, stream>>>(plan->n_y, P, Ppad, plan->y, cells->cap,
                                                                  ptt_gw_cells_coef_capacity(cells->cap), cells->ncell,
                                                                  cells->meta, cells->coef, table, plan->prefactor, slf,

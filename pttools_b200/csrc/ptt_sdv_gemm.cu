@@ -32,6 +32,12 @@ __global__ void sdv_recip_kernel(const int n_q, const double* __restrict__ qT, d
     if (k < n_q) inv_q[k] = 1.0 / qT[k];
 }
 
+constexpr int WT_KPT = 4;                      // knots per thread
+constexpr int WT_SPAN = 256 * WT_KPT;         // knots per CTA (one row of Omega)
+
+// One CTA = one row i of Omega and WT_SPAN consecutive knots; thread t handles knots e0 + t + 256 k, k < WT_KPT, so the
+// per-row quantities (s_i, zterm_i + shift, the reciprocal spacing of LT) are formed once for four entries and the
+// stores of a warp stay coalesced.
 __global__ void __launch_bounds__(256) sdv_weights_kernel(
     const int n_q, const int n_z, const int nt, const double* __restrict__ qT, const double* __restrict__ z,
     const double* __restrict__ zterm, const double* __restrict__ T, const double* __restrict__ LT,
@@ -39,68 +45,75 @@ __global__ void __launch_bounds__(256) sdv_weights_kernel(
     const int* __restrict__ e_base, const double* __restrict__ inv_dq, const double* __restrict__ inv_q,
     const double2* __restrict__ omega_ab, double* __restrict__ omega) {
     const int i = blockIdx.y;
-    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
-    __shared__ double s_scale;
-    if (threadIdx.x == 64) s_scale = z[i] / bv;                      // one division per row, not per knot
+    const int kk0 = blockIdx.x * WT_SPAN;                            // first entry of this CTA within the band
+    const double s = z[i] / bv;
     const double ub = zterm[i] + shift;
-    const int e0 = e_base[i / GM_BM] + blockIdx.x * blockDim.x;      // knot of thread 0
-    const int e = e0 + threadIdx.x;
-    double acc = 0.0;
+    const int e0 = e_base[i / GM_BM] + kk0;                          // knot of entry kk0
     const double lt0 = LT[0];
     const double inv_dlt = (nt > 1) ? (double)(nt - 1) / (LT[nt - 1] - lt0) : 0.0;     // LT is a linspace
     // number of kinks LT_j below x(knot) = knot - (zterm_i + shift): x moves by exactly one per knot, so the three counts
-    // a knot needs (at x - 1, x, x + 1) are the counts of its neighbours: one per thread + a halo of two, through shared
+    // a knot needs (at x - 1, x, x + 1) are the counts of its neighbours: one per entry + a halo of two, through shared
     // memory
-    __shared__ int s_cnt[256 + 2];
-    auto count_below = [&](const int knot) {
-        const double yy = ((double)knot - ub - lt0) * inv_dlt;
+    __shared__ int s_cnt[WT_SPAN + 2];
+    auto count_below = [&](const int d) {                            // knot e0 + d
+        const double yy = ((double)(e0 + d) - ub - lt0) * inv_dlt;
         const int c = (yy > 0.0) ? __double2int_ru(yy) : 0;
         return min(c, nt);
     };
     if (omega_ab) {
-        s_cnt[threadIdx.x + 1] = count_below(e);
-        if (threadIdx.x == 0) s_cnt[0] = count_below(e0 - 1);
-        if (threadIdx.x == 32) s_cnt[blockDim.x + 1] = count_below(e0 + (int)blockDim.x);
+#pragma unroll
+        for (int k = 0; k < WT_KPT; ++k) s_cnt[threadIdx.x + 256 * k + 1] = count_below(threadIdx.x + 256 * k);
+        if (threadIdx.x == 0) s_cnt[0] = count_below(-1);
+        if (threadIdx.x == 32) s_cnt[WT_SPAN + 1] = count_below(WT_SPAN);
     }
     __syncthreads();
-    const double s = s_scale;
-    if (kk >= kw) return;
-    if (omega_ab && e > 0 && e < n_q - 1) {
-        // Closed form.  As a function of x = e - (zterm_i + shift) the weight of an interior knot is
-        //     omega(x) = alpha_p + beta_p * (s_i / qT[e])
-        // on every piece p between two consecutive kinks LT_j - 1, LT_j, LT_j + 1 (the set of contributing samples is
-        // fixed there and np.interp's weight (X - x0)/(x1 - x0) on a log grid is linear in X / qT[e]); the plan
-        // carries (alpha, beta) per piece, and the piece index is the number of kinks below x.
-        const int piece = s_cnt[threadIdx.x] + s_cnt[threadIdx.x + 1] + s_cnt[threadIdx.x + 2];
-        const double2 ab = omega_ab[piece];
-        acc = fma(ab.y, s * inv_q[e], ab.x);
-    } else if (e < n_q) {
-        int j = 0;
-        if (e > 0) {
-            const double jf = ((double)(e - 1) - ub - lt0) * inv_dlt;
-            j = (jf > 1.0) ? ((jf < (double)nt) ? (int)jf - 1 : nt) : 0;
-        }
-        for (; j < nt; ++j) {
-            const int er = __double2int_rd(ub + LT[j]);
-            const double wj = W[j];
-            int eff;
-            double w0, w1;
-            if (er < 0) { eff = 0; w0 = wj; w1 = 0.0; }                          // np.interp left clamp
-            else if (er >= n_q - 1) { eff = n_q - 2; w0 = 0.0; w1 = wj; }          // right clamp: all on the last knot
-            else {
-                // the arithmetic index may be off by one on a razor edge: the weights then extrapolate the
-                // neighbouring segment by ~1e-12 of its length, i.e. the same value (continuous interpolant)
-                eff = er;
-                const double t = (s * T[j] - qT[er]) * inv_dq[er];
-                w0 = wj * (1.0 - t);
-                w1 = wj * t;
+    double* __restrict__ row = omega + (size_t)i * kw;
+#pragma unroll
+    for (int k = 0; k < WT_KPT; ++k) {
+        const int d = threadIdx.x + 256 * k;
+        const int kk = kk0 + d, e = e0 + d;
+        if (kk >= kw) break;
+        double acc = 0.0;
+        if (omega_ab && e > 0 && e < n_q - 1) {
+            // Closed form.  As a function of x = e - (zterm_i + shift) the weight of an interior knot is
+            //     omega(x) = alpha_p + beta_p * (s_i / qT[e])
+            // on every piece p between two consecutive kinks LT_j - 1, LT_j, LT_j + 1 (the set of contributing samples
+            // is fixed there and np.interp's weight (X - x0)/(x1 - x0) on a log grid is linear in X / qT[e]); the plan
+            // carries (alpha, beta) per piece, and the piece index is the number of kinks below x.
+            const int piece = s_cnt[d] + s_cnt[d + 1] + s_cnt[d + 2];
+            const double2 ab = __ldg(omega_ab + piece);
+            acc = fma(ab.y, s * __ldg(inv_q + e), ab.x);
+        } else if (e < n_q) {
+            // np.interp's end clamps put the whole weight of a sample on knot 0 (left) or knot n_q - 1 (right): these
+            // two knots (and every knot of a plan without pieces) walk their samples, found arithmetically (LT is a
+            // linspace) and confirmed with the same floor() test as the gather kernel
+            int j = 0;
+            if (e > 0) {
+                const double jf = ((double)(e - 1) - ub - lt0) * inv_dlt;
+                j = (jf > 1.0) ? ((jf < (double)nt) ? (int)jf - 1 : nt) : 0;
             }
-            if (eff > e) break;                 // eff is non-decreasing in j
-            if (eff == e) acc += w0;
-            else if (eff == e - 1) acc += w1;
+            for (; j < nt; ++j) {
+                const int er = __double2int_rd(ub + LT[j]);
+                const double wj = W[j];
+                int eff;
+                double w0, w1;
+                if (er < 0) { eff = 0; w0 = wj; w1 = 0.0; }                          // np.interp left clamp
+                else if (er >= n_q - 1) { eff = n_q - 2; w0 = 0.0; w1 = wj; }          // right clamp: all on the last knot
+                else {
+                    // the arithmetic index may be off by one on a razor edge: the weights then extrapolate the
+                    // neighbouring segment by ~1e-12 of its length, i.e. the same value (continuous interpolant)
+                    eff = er;
+                    const double t = (s * T[j] - qT[er]) * inv_dq[er];
+                    w0 = wj * (1.0 - t);
+                    w1 = wj * t;
+                }
+                if (eff > e) break;                 // eff is non-decreasing in j
+                if (eff == e) acc += w0;
+                else if (eff == e - 1) acc += w1;
+            }
         }
+        row[kk] = acc;
     }
-    omega[(size_t)i * kw + kk] = acc;
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
@@ -228,7 +241,7 @@ extern "C" int ptt_spec_den_v_group(const ptt_sdv_plan_t* plan, int n_p, const d
     double* inv_dq = omega + (size_t)n_tiles * GM_BM * (size_t)kw;
     double* inv_q = inv_dq + plan->n_q;
     sdv_recip_kernel<<<(plan->n_q + 255) / 256, 256, 0, stream>>>(plan->n_q, plan->qT, inv_dq, inv_q);
-    sdv_weights_kernel<<<dim3((kw + 255) / 256, plan->n_z), 256, 0, stream>>>(
+    sdv_weights_kernel<<<dim3((kw + WT_SPAN - 1) / WT_SPAN, plan->n_z), 256, 0, stream>>>(
         plan->n_q, plan->n_z, plan->nt, plan->qT, plan->z, plan->zterm, plan->T, plan->LT, plan->W, bv,
         -log10(bv) * plan->inv_dlog, kw, e_base, inv_dq, inv_q,
         reinterpret_cast<const double2*>(plan->omega_ab), omega);
