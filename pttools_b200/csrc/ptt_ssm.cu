@@ -912,6 +912,22 @@ static int check_launch(const char* what) {
 // The batch index of these operators is gridDim.y (limit 65535): larger batches are processed in slices.
 constexpr int MAX_BATCH_SLICE = 65535;
 
+// The array operators take their scratch from the device's default memory pool (stream-ordered).  By default the pool
+// hands freed memory back to the driver at every synchronisation, so each call would pay a fresh allocation of hundreds
+// of MB: keep it (once per device).
+static void keep_pool_memory() {
+    static int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    done_for = dev;
+}
+
 extern "C" int ptt_sin_transform_batch(int P, const double* xi, const double* f, int64_t stride, const int32_t* off,
                                        const int32_t* npts, int n_z, const double* z, const double* frac,
                                        double* out, void* stream_) {
@@ -927,6 +943,7 @@ extern "C" int ptt_sin_transform_batch(int P, const double* xi, const double* f,
     cudaStream_t stream = (cudaStream_t)stream_;
     double* g = nullptr;
     double* env = nullptr;
+    keep_pool_memory();
     cudaError_t e = cudaMallocAsync((void**)&g, sizeof(double) * (size_t)P * (size_t)stride, stream);
     if (e != cudaSuccess) return set_cuda_error("ptt_sin_transform_batch alloc", e);
     e = cudaMallocAsync((void**)&env, sizeof(double) * (size_t)P * ENV_SIZE, stream);
@@ -958,6 +975,7 @@ extern "C" int ptt_sin_transform_unit_batch(int P, const double* xi, const doubl
     double* g = nullptr;
     double* env = nullptr;
     double* mom = nullptr;
+    keep_pool_memory();
     cudaError_t e = cudaMallocAsync((void**)&g, sizeof(double) * (size_t)P * (size_t)stride, stream);
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&env, sizeof(double) * (size_t)P * ENV_SIZE, stream);
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&mom, sizeof(double) * (size_t)P * MOM_SIZE, stream);
