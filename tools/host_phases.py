@@ -30,3 +30,18 @@ for s in range(6):
     t6 = time.perf_counter()
     print(f"step {s}: shard {1e3*(t1-t0):.1f}  mem_get_info {1e3*(t2-t1):.1f}  point_table {1e3*(t3-t2):.1f}  scale {1e3*(t4-t3):.1f}  "
           f"sweep_spectra call {1e3*(t5-t4):.1f}  tail sync {1e3*(t6-t5):.1f} ms")
+
+print("--- mem='host' (the e2e path)")
+for s in range(5):
+    vw, an = bench.batch_points(100 + s, 0, 1, 64000)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pt = bubble.point_table(model, vw, an, device=False)
+    t1 = time.perf_counter()
+    sc = sweep.omgw0_scale(vw, an, 0.1, None, None, "default", device=False)
+    t2 = time.perf_counter()
+    res = sweep.sweep_spectra(model, vw, an, y=bench.Y, r_star=0.1, want_pow_v=False, want_pow_gw=False, chunk=8000, plan=plan, mem="host")
+    t3 = time.perf_counter()
+    st = res.stats
+    print(f"step {s}: point_table {1e3*(t1-t0):.1f}  scale {1e3*(t2-t1):.1f}  sweep_spectra(host) call {1e3*(t3-t2):.1f} ms "
+          f"(includes its own point_table + scale); wait_shells {st.host_wait_shells_ms:.1f}")
