@@ -93,6 +93,20 @@ def _stream_ptr(torch):
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_PREP_STREAMS = {}
+
+
+def prep_stream():
+    """High-priority side stream for the small device work that PREPARES a sweep (alpha_n_max per wall speed, starting
+    guesses, suppression factors, parameter rows).  A device-table sweep returns with its last chunks in flight; on the
+    main stream the next sweep's preparation -- which ends in host reads -- would queue behind them."""
+    torch = _torch()
+    dev = torch.cuda.current_device()
+    if dev not in _PREP_STREAMS:
+        _PREP_STREAMS[dev] = torch.cuda.Stream(device=dev, priority=-1)
+    return _PREP_STREAMS[dev]
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 

@@ -173,8 +173,22 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
         plan = engine.SsmPlan(y, cs=cs, nt=nt, n_z_lookup=n_z_lookup, z_st_thresh=z_st_thresh, nuc_type=nuc_type,
                               a=1.0, mode="ssm", only_lookup_pass=not want_pow_v)
     want_pow_v = want_pow_v and plan.has_y_pass
-    pt = bub.point_table(model, vw, an, sol_type=sol_type, allow_invalid=allow_invalid, device=mem == "device")
-    scale = None if r_star is None else omgw0_scale(vw, an, r_star, g_star, gs_star, suppression, device=mem == "device")
+    if mem == "device":
+        # the preparation runs on its own stream: its host reads must not wait for a previous sweep still in flight
+        main, prep = torch.cuda.current_stream(), engine.prep_stream()
+        with torch.cuda.stream(prep):
+            pt = bub.point_table(model, vw, an, sol_type=sol_type, allow_invalid=allow_invalid, device=True)
+            scale = None if r_star is None else omgw0_scale(vw, an, r_star, g_star, gs_star, suppression, device=True)
+            vw_out, an_out = pt.pg[:, 0].contiguous(), pt.pg[:, 1].contiguous()
+            codes = pt.pg[:, 2].to(torch.int32)
+        main.wait_stream(prep)
+        for t in (pt.pg, pt.pm, scale, vw_out, an_out, codes):
+            if t is not None:
+                t.record_stream(main)
+    else:
+        pt = bub.point_table(model, vw, an, sol_type=sol_type, allow_invalid=allow_invalid, device=False)
+        scale = None if r_star is None else omgw0_scale(vw, an, r_star, g_star, gs_star, suppression, device=False)
+        vw_out, an_out, codes = vw, an, pt.codes
     snr_w = None
     if snr:
         if r_star is None:
@@ -187,13 +201,6 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
     want = (("pow_v",) if want_pow_v else ()) + (("pow_gw",) if want_pow_gw or scale is None else ()) + \
         (("omgw0",) if scale is not None else ())
     pg_in, pm_in, sc_in = pt.pg, pt.pm, scale
-    if mem == "host":
-        vw_out, an_out, codes = vw, an, pt.codes
-    else:
-        # before the call: with device tables the sweep returns with its last chunks in flight, and an upload from
-        # pageable memory after it would wait for them
-        vw_out, an_out = pt.pg[:, 0].contiguous(), pt.pg[:, 1].contiguous()
-        codes = pt.pg[:, 2].to(torch.int32)
     res = engine.sweep_c(plan, pg_in, pm_in, sc_in, n_xi=n_xi, r_star=r_star, lifetime_multiplier=lifetime_multiplier,
                          chunk=chunk, shell_chunk=shell_chunk or 0, want=want, rows=keep_bubbles, mem=mem,
                          on_chunk=on_chunk, timing=timing, out=out, snr_weights=snr_w, table_rows=table_rows,
