@@ -31,6 +31,9 @@ __global__ void __launch_bounds__(64) generic_solve_kernel(
     int* __restrict__ status) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+#ifdef PTT_K3_CLOCKS
+    const long long clk0 = clock64();      // diagnostics (tools/k3_clocks.py): cycles this lane's warp spent until it was done
+#endif
     const double* q = pg + (size_t)i * GEN_PARAMS;
     RowOut row;
     row.v = rows_v + (size_t)i * row_stride;
@@ -74,6 +77,9 @@ __global__ void __launch_bounds__(64) generic_solve_kernel(
     sc[0] = o.vp; sc[1] = o.vm; sc[2] = o.vp_tilde; sc[3] = o.vm_tilde; sc[4] = o.v_sh; sc[5] = o.vm_sh;
     sc[6] = o.vm_tilde_sh; sc[7] = o.wp; sc[8] = o.wm; sc[9] = o.wm_sh; sc[10] = o.v_cj; sc[11] = o.wn;
     sc[12] = o.wn_estimate; sc[13] = (double)o.solver_failed; sc[14] = (double)o.n_resid; sc[15] = 0.0;
+#ifdef PTT_K3_CLOCKS
+    sc[15] = (double)(clock64() - clk0);
+#endif
     status[i] = o.solver_failed ? ST_SOLVER_FAILED : ST_OK;
 }
 
