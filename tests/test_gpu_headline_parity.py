@@ -37,8 +37,14 @@ def _audit(name, model, d, prefix, spectrum_kwargs, audit):
     bb = res.bubbles
     r = res.numpy()
     err, flags, noise = d[f"{prefix}err"], d[f"{prefix}flags"], d[f"{prefix}noise"]
+    validity = bb.validity()          # the flags Bubble.solve sets (bubble.py:290-352), for the whole sweep
+    # fixture flags: sol_type, solver_failed, no_solution_found, numerical_error, unphysical_alpha_plus,
+    # negative_entropy_flux, negative_net_entropy_change, number of samples
+    VALIDITY = ((3, "numerical_error"), (4, "unphysical_alpha_plus"), (5, "negative_entropy_flux"),
+                (6, "negative_net_entropy_change"))
     entry = {"points": int(len(pts)), "reference_rejects": int((err == 1).sum()), "reference_no_solution": int((err == 2).sum()),
-             "flag_mismatches": [], "both_solver_failed": 0, "npts_mismatches": [], "over_bar_within_2x_noise": [], "violations": [],
+             "flag_mismatches": [], "validity_flags_compared": 0, "validity_flags_set_in_reference": 0,
+             "both_solver_failed": 0, "npts_mismatches": [], "over_bar_within_2x_noise": [], "violations": [],
              "worst": {"curve_v": 0.0, "curve_w": 0.0, "scalar": 0.0, "pow_v": 0.0, "pow_gw": 0.0, "omgw0": 0.0}}
 
     def check(i, what, dev, tol, ns):
@@ -69,6 +75,13 @@ def _audit(name, model, d, prefix, spectrum_kwargs, audit):
             entry["flag_mismatches"].append({"point": [float(vw), float(an)], "ours_solver_failed": bool(r.status[i] == 5),
                                              "reference_solver_failed": bool(fl[1])})
             continue
+        assert not bool(fl[2]) and not validity["no_solution_found"][i]
+        for col, nm in VALIDITY:
+            entry["validity_flags_compared"] += 1
+            entry["validity_flags_set_in_reference"] += int(bool(fl[col]))
+            if bool(fl[col]) != bool(validity[nm][i]):
+                entry["flag_mismatches"].append({"point": [float(vw), float(an)], "flag": nm, "ours": bool(validity[nm][i]),
+                                                 "reference": bool(fl[col])})
         if bool(fl[1]):
             # solver_failed in the reference AND here: the root search did not converge, the returned profile is the
             # last iterate of whatever path the root finder took (Bubble.solver_failed, bubble.py:123-131) -- the flag
