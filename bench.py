@@ -41,6 +41,11 @@ WORKLOADS = {
                 "1000); per point Bubble(model, v_wall, alpha_n) [model-independent solver, n_xi=5000, t_end=50] + "
                 "Spectrum(bubble, r_star=0.1) [y=logspace(-1,3,1000), nt=10^4, n_z_lookup=10^4, nxi=2000] -> pow_v, pow_gw, "
                 "omgw0"),
+    # config 5: the same per-point work, the whole grid as ONE sweep per step
+    "config5": ("config5: the full grid v_wall=linspace(0.05,0.95,1000) x alpha_n=linspace(0.005,0.5,1000) "
+                "(BagModel(alpha_n_min=0.005)) in ONE call of sweep.sweep_omgw0_distributed per step -> Omega_gw,0 table "
+                "[10^6, 1000] on rank 0; per point Bubble [n_xi=5000] + Spectrum(r_star=0.1) at the reference's default "
+                "sizes; a step = one time-to-solution"),
     # the reference's old bag API
     "bag": ("config2: BagModel grid v_wall=linspace(0.05,0.95,1000) x alpha_n=linspace(0.005,0.5,1000); per point "
             "sound_shell_bag(n_xi=2000) + power_gw_scaled_bag(z=logspace(-1,3,1000), npt=(2000,10000,10000))"),
@@ -344,6 +349,13 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    full_grid = args.workload == "config5"
+    if full_grid:
+        # BASELINE.json config 5: the WHOLE 1000 x 1000 grid in one product call per step, sharded over the ranks
+        # (strong scaling: the work of a step does not depend on N)
+        if (GRID_N * GRID_N) % world:
+            sys.exit("config5 needs a number of GPUs that divides 10^6")
+        args.batch = GRID_N * GRID_N // world
     B = args.batch
     from pttools_b200.models import BagModel
     from pttools_b200 import fluid_reference
@@ -357,24 +369,34 @@ def gpu_arm(args):
     def step_points(s):
         """The points of step s for ALL ranks (the product API shards them: whole v_wall rows per rank).  Synthetic
         input: generated before the timed regions (the inputs of a step are resident in host memory when it starts)."""
+        if full_grid:
+            s = 0                        # every step is the same sweep: the full grid, v_wall-major
         if s not in points_cache:
-            parts = [batch_points(s, r, world, B) for r in range(world)]
-            points_cache[s] = (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]))
+            if full_grid:
+                v_walls, alpha_ns = np.linspace(0.05, 0.95, GRID_N), np.linspace(0.005, 0.5, GRID_N)
+                points_cache[s] = (np.repeat(v_walls, GRID_N), np.tile(alpha_ns, GRID_N))
+            else:
+                parts = [batch_points(s, r, world, B) for r in range(world)]
+                points_cache[s] = (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]))
         return points_cache[s]
 
     # the result table of a step: on rank 0, written by all ranks (CUDA IPC, peer stores over NVLink); allocated once
-    shared = sweep.SharedTable(B * world, Y.size) if world > 1 else None
+    # two of them, used alternately: a step's table stays untouched while the next step runs (a consumer on rank 0 has a
+    # whole step to read it), so consecutive sweeps need no barrier between them
+    shared = [sweep.SharedTable(B * world, Y.size) for _ in range(1 if full_grid else 2)] if world > 1 else None
 
     def device_step(s):
         """One pass of the hot path through the product's sweep API: rank 0 ends with the Omega_gw,0 table of all
         world x B points in HBM, in the order of the input points (config 5 of BASELINE.json)."""
         vw, an = step_points(s)
         return sweep.sweep_omgw0_distributed(model, vw, an, y=Y, r_star=R_STAR, n_xi=N_XI, chunk=args.chunk, plan=plan,
-                                             timing=True, shared=shared)
+                                             timing=True, shared=None if shared is None else shared[s % len(shared)],
+                                             wait=full_grid or world == 1)
 
     def barrier():
+        torch.cuda.synchronize()      # this rank's rows are in the tables on rank 0 ...
         if world > 1:
-            dist.barrier()
+            dist.barrier()            # ... and so are everybody else's
         torch.cuda.synchronize()
 
     total_steps = args.warmup + args.steps
@@ -433,12 +455,27 @@ def gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms = float(t[0]), float(t[1])
+    grid_check = None
+    if full_grid and rank == 0:
+        # the gathered table against a single-GPU sweep of three of its v_wall rows
+        vw_all, an_all = step_points(0)
+        rows = [137, 577, 902]
+        sel = np.concatenate([np.arange(r * GRID_N, (r + 1) * GRID_N) for r in rows])
+        local = sweep.sweep_spectra(model, vw_all[sel], an_all[sel], y=Y, r_star=R_STAR, n_xi=N_XI, chunk=args.chunk, plan=plan,
+                                    want_pow_v=False, want_pow_gw=False)
+        got = table[torch.as_tensor(sel, device="cuda")]
+        fin = torch.isfinite(local.omgw0)
+        dev = float(((got[fin] / local.omgw0[fin]) - 1).abs().max()) if bool(fin.any()) else 0.0
+        grid_check = {"v_wall_rows": rows, "max_rel_dev_vs_single_gpu_sweep": dev,
+                      "nan_pattern_equal": bool(torch.equal(fin, torch.isfinite(got))),
+                      "finite_rows_in_table": int(torch.isfinite(table[:, 0]).sum())}
+        del local, got
     del table
 
     # ---- end-to-end: host buffers in, host result table out, through the reference-facing call
     # (analysis.create_spectra semantics at N = 1; at N > 1 every rank delivers its shard of the table to pinned host
     # memory, streamed out chunk by chunk under the compute)
-    e2e_steps = args.steps
+    e2e_steps = min(args.steps, 2) if full_grid else args.steps
 
     def e2e_step(s):
         vw, an = step_points(1000 + s)
@@ -515,13 +552,18 @@ def gpu_arm(args):
         out = {
             "metric": "bubble+GW spectra/sec", "value": value, "unit": "spectra/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS["generic"], "batch_per_step": B * world, "batch_per_gpu_per_step": B,
+            "higher_is_better": True, "scaling": "strong" if full_grid else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": (WORKLOADS["config5"] if full_grid else WORKLOADS["generic"]),
+                       "batch_per_step": B * world, "batch_per_gpu_per_step": B,
                        "chunk": args.chunk, "api": "sweep.sweep_omgw0_distributed -> ptt_sweep_spectra (one C call per rank and "
                        "step); whole v_wall rows per rank; every rank writes its rows into the table on rank 0 (CUDA IPC, peer "
-                       "stores over NVLink) chunk by chunk as they are produced",
+                       "stores over NVLink) chunk by chunk as they are produced" +
+                       ("" if full_grid or world == 1 else "; consecutive steps write two tables alternately and are not separated "
+                        "by a barrier (wait=False; the timed region ends with stream synchronisation + barrier)"),
                        "l2": "per-step working set (profiles + A2 + lookup tables, ~1 MB per point) exceeds the 126 MB L2; "
                              "every step uses fresh points",
+                       **({"table_check": grid_check} if grid_check is not None else {}),
                        "valid_points_in_timed_region_rank0": n_ok, "per_step_ms": per_step_ms,
                        "wall_ms_per_step": wall_ms / args.steps, "stage_ms_by_step_rank0": step_stages,
                        "retried_points_rank0": agg["retried"],
@@ -541,8 +583,8 @@ def gpu_arm(args):
         print(json.dumps(out), file=RESULT, flush=True)
     if world > 1:
         dist.barrier()
-        if shared is not None:
-            shared.close()
+        for sh in shared or ():
+            sh.close()
         dist.destroy_process_group()
 
 
@@ -873,7 +915,7 @@ if __name__ == "__main__":
     ap.add_argument("--chunk", type=int, default=8000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="generic", choices=["generic"])
-    ap.add_argument("--workload", default="headline", choices=["headline", "config3", "config2-shells", "config4"],
+    ap.add_argument("--workload", default="headline", choices=["headline", "config5", "config3", "config2-shells", "config4"],
                     help="headline = configs 2/5 of BASELINE.json (the metric's configuration); the others are extra lines")
     ap.add_argument("--pow-v", action="store_true", help="also compute pow_v (the y pass of spec_den_v)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -883,7 +925,7 @@ if __name__ == "__main__":
     RESULT = _claim_stdout()
     if a.impl == "reference":
         reference_arm(a)
-    elif a.workload == "headline":
+    elif a.workload in ("headline", "config5"):
         gpu_arm(a)
     else:
         if int(os.environ.get("WORLD_SIZE", "1")) > 1:

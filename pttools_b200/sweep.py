@@ -460,14 +460,25 @@ class SharedTable:
             pass
 
 
+def wait_distributed():
+    """Completes sweep_omgw0_distributed(..., wait=False) calls: this rank's rows are in the table on `dst` and so are
+    everybody else's (stream synchronisation + one barrier)."""
+    import torch.distributed as dist
+    engine._torch().cuda.current_stream().synchronize()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
 def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, chunk=8000, dst=0, table="omgw0", mem="device",
-                            shared: tp.Optional[SharedTable] = None, transport: str = "auto", **kw):
+                            shared: tp.Optional[SharedTable] = None, transport: str = "auto", wait: bool = True, **kw):
     """The 10^6-point sweep of BASELINE.json config 5, sharded over the ranks of torch.distributed (one process per
     GPU): Omega_gw,0(f) table [n, n_y] on rank `dst` with rows in the order of the input points (None on the other
     ranks).  Whole v_wall rows per rank (shard_rows); every rank's sweep writes its rows STRAIGHT INTO the table on
     `dst`, chunk by chunk as they are produced: the table is shared through CUDA IPC (SharedTable) and the rows travel as
     peer stores over NVLink / NVSwitch under the compute of the next chunk -- no collective, no SM of the receiving GPU
-    involved; one barrier at the end.  shared: a SharedTable([n, n_y]) to write into (reuse it across sweeps of one
+    involved; one barrier at the end.  wait=False (needs `shared`): returns as soon as this rank's work is queued, like a
+    single-GPU sweep does; the table is complete after wait_distributed() -- for back-to-back sweeps into different
+    tables, whose host preparation then overlaps the previous sweep's tail.  shared: a SharedTable([n, n_y]) to write into (reuse it across sweeps of one
     shape; without it a table is allocated and mapped per call).  transport="sendrecv": point-to-point messages of
     torch.distributed instead (distributed_table; what the CPU tests run over gloo).
     mem="host": no exchange; every rank returns (indices of its shard, its [n_shard, n_y] block in pinned host memory),
@@ -510,6 +521,10 @@ def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, chunk=80
         raise ValueError(f"shared table has shape {shared.shape}, the sweep needs {(vw.size, y.size)}")
     if len(idx):
         LAST_LOCAL["result"] = sweep_spectra(m, vw[idx], an[idx], out={table: shared.tensor}, table_rows=idx, **common)
+    if not wait:
+        if own:
+            raise ValueError("wait=False needs a SharedTable that outlives the call")
+        return shared.tensor if rank == dst else None
     torch.cuda.current_stream().synchronize()      # this rank's rows are in the table on `dst`
     dist.barrier()
     result = shared.tensor if rank == dst else None

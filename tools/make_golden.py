@@ -435,7 +435,42 @@ def noise_snr():
     np.savez_compressed(os.path.join(OUT, "ref_noise_snr.npz"), **d)
 
 
-TASKS.update({"headline_grid": headline_grid, "config3_grid": config3_grid, "noise_snr": noise_snr})
+def bag_solver_bubbles():
+    """Bubble(BagModel, v_wall, alpha_n, use_bag_solver=True): the reference's Bubble on top of its OLD bag solver
+    (fluid.py:892-918: sound_shell_bag, w scaled by wn, props.v_and_w_from_solution; v_sh, vm_sh, vm_tilde_sh are NaN;
+    alpha_n within 0.05 of alpha_n_max_deflagration_bag: NaN arrays with solver_failed).  Profiles decimated; scalars
+    in full."""
+    from pttools.models import BagModel
+    from pttools.bubble import Bubble
+    from pttools.bubble.boundary import SolutionType
+    codes = {SolutionType.SUB_DEF: 0, SolutionType.HYBRID: 1, SolutionType.DETON: 2, SolutionType.ERROR: -1}
+    model = BagModel(a_s=1.1, a_b=1, V_s=1)
+    pts = [(0.3, 0.05), (0.5, 0.1), (0.44, 0.04), (0.62, 0.1), (0.7, 0.15), (0.8, 0.05), (0.92, 0.2), (0.55, 0.3),
+           (0.4, 0.33)]
+    from pttools.bubble.alpha import alpha_n_max_deflagration_bag
+    pts.append((0.3, float(alpha_n_max_deflagration_bag(0.3)) - 0.02))      # "high alpha_n": NaN arrays, solver_failed
+    names = ["wn", "vp", "vm", "vp_tilde", "vm_tilde", "wp", "wm", "wm_sh", "v_cj", "kappa", "omega", "kinetic_energy_fraction",
+             "kinetic_energy_density", "thermal_energy_density", "va_enthalpy_density", "ubarf2", "wbar", "ebar",
+             "va_trace_anomaly_diff", "va_thermal_energy_density_diff", "va_entropy_density_diff", "mean_adiabatic_index"]
+    d = {"points": np.array(pts), "scalar_names": np.array(names),
+         "model": np.array([model.a_s, model.a_b, model.V_s, model.V_b])}
+    for i, (vw, an) in enumerate(pts):
+        b = Bubble(model, vw, an, use_bag_solver=True)
+        d[f"flags_{i}"] = np.array([codes[b.sol_type], b.solved, b.solver_failed, b.no_solution_found, b.numerical_error,
+                                    b.unphysical_alpha_plus, b.negative_entropy_flux, b.negative_net_entropy_change,
+                                    b.v.size], dtype=float)
+        if b.solved and not b.solver_failed:
+            idx = _decimate(b.v)
+            d[f"v_{i}"], d[f"w_{i}"], d[f"xi_{i}"] = b.v[idx], b.w[idx], b.xi[idx]
+            d[f"scal_{i}"] = np.array([float(getattr(b, k)) for k in names])
+            d[f"nan_scal_{i}"] = np.array([float(b.v_sh), float(b.vm_sh), float(b.vm_tilde_sh)])
+        print(i, vw, an, b.sol_type, "solved", b.solved, "failed", b.solver_failed, b.v.size)
+    np.savez_compressed(os.path.join(OUT, "ref_bag_solver_bubbles.npz"), **d)
+    print("ref_bag_solver_bubbles.npz")
+
+
+TASKS.update({"headline_grid": headline_grid, "config3_grid": config3_grid, "noise_snr": noise_snr,
+              "bag_solver_bubbles": bag_solver_bubbles})
 
 
 if __name__ == "__main__":
