@@ -162,12 +162,12 @@ def create_bubbles(model: Model, v_walls: np.ndarray, alpha_ns: np.ndarray, func
     v_walls, alpha_ns = np.asarray(v_walls, dtype=float), np.asarray(alpha_ns, dtype=float)
     kwargs = dict(kwargs or {})
     allow_bubble_failure = bool(kwargs.pop("allow_bubble_failure", allow_bubble_failure))
-    if kwargs.pop("use_bag_solver", False):
-        raise NotImplementedError("use_bag_solver is outside the hot path")
+    use_bag_solver = bool(kwargs.pop("use_bag_solver", False))
     vw, an = np.meshgrid(v_walls, alpha_ns)                     # params[i_alpha, i_vw], parallel.py:126-130
     bk = bubble_kwargs or {}
     batch = bub.sweep_bubbles(model, vw.ravel(), an.ravel(), n_xi=bk.get("n_xi", bub.N_XI_DEFAULT),
-                              t_end=bk.get("t_end", bub.T_END_DEFAULT), allow_invalid=bk.get("allow_invalid", False))
+                              t_end=bk.get("t_end", bub.T_END_DEFAULT), allow_invalid=bk.get("allow_invalid", False),
+                              use_bag_solver=use_bag_solver or bool(bk.get("use_bag_solver", False)))
     flat = _bubble_objects(model, batch, vw.shape, allow_bubble_failure)
     objs = flat.reshape(vw.shape)
     if func is None:
@@ -221,9 +221,9 @@ class BubbleGridVWAlpha:
 
     def __init__(self, model: Model, v_walls: np.ndarray, alpha_ns: np.ndarray, func: callable = None,
                  use_bag_solver: bool = False, **kw):
-        if use_bag_solver:
-            raise NotImplementedError("use_bag_solver is outside the hot path")
         self.model, self.v_walls, self.alpha_ns = model, v_walls, alpha_ns
+        kw = dict(kw)
+        kw["kwargs"] = {**(kw.get("kwargs") or {}), "use_bag_solver": use_bag_solver}        # bubble_grid.py:66-69
         out = create_bubbles(model, v_walls, alpha_ns, func, allow_bubble_failure=True, **kw)
         if isinstance(out, tuple):
             self.bubbles = out[0]

@@ -309,14 +309,18 @@ def point_table(model, v_wall, alpha_n, sol_type=None, allow_invalid=False, devi
 
 def sweep_bubbles(model, v_wall, alpha_n, sol_type=None, n_xi=N_XI_DEFAULT, t_end=T_END_DEFAULT,
                   thin_shell_limit=THIN_SHELL_T_POINTS_MIN, wn_rtol=1e-4, thermo=True, retry="sync",
-                  allow_invalid=False) -> BubbleBatch:
+                  allow_invalid=False, use_bag_solver=False) -> BubbleBatch:
     """Bubble(model, v_wall, alpha_n).solve() for every point of a sweep (bubble.py:232-352, fluid.py:848-1052) through
     ptt_sweep_spectra (shells, retries, thermodynamic scalars; no spectra).  `model` is one Model or a sequence with
     one Model per point.  retry: "sync" = the reference's retries (fsolve_vary, backup scan) for the points whose first
-    root search fails; "off" = report them as solver failures.  Profiles stay on the device (`shells`)."""
+    root search fails; "off" = report them as solver failures.  Profiles stay on the device (`shells`).
+    use_bag_solver: for a BagModel the reference's OLD solver (sound_shell_bag) under the Bubble interface
+    (fluid.py:892-918); ignored for other models, as in the reference."""
     torch = engine._torch()
     if retry not in ("sync", "off"):
         raise ValueError(f"retry={retry!r}")
+    if use_bag_solver and isinstance(model, Model) and model.name == "bag":
+        return _sweep_bubbles_bag_solver(model, v_wall, alpha_n, allow_invalid)
     pt = point_table(model, v_wall, alpha_n, sol_type, allow_invalid)
     n = pt.wn.size
     out = engine.sweep_c(None, engine.dev_f64(pt.pg), engine.dev_f64(pt.pm), n_xi=n_xi, t_end=t_end,
@@ -330,6 +334,79 @@ def sweep_bubbles(model, v_wall, alpha_n, sol_type=None, n_xi=N_XI_DEFAULT, t_en
     pp = engine.point_params(pg[:, 0], torch.sqrt(pg[:, 10]), 1 - 1 / mu_s, 1 - 1 / mu_b, pg[:, 11], pg[:, 12])
     return BubbleBatch(model, shells, shells.v_wall, shells.alpha_n, engine.dev_f64(pt.wn), sol, out.status, scal, pp,
                        n_xi, invalid=pt.invalid)
+
+
+def _sweep_bubbles_bag_solver(model: Model, v_wall, alpha_n, allow_invalid=False) -> BubbleBatch:
+    """Bubble(BagModel, v_wall, alpha_n, use_bag_solver=True).solve() for every point (fluid.py:892-918, bubble.py:250-
+    352): sound_shell_bag(v_wall, alpha_n) at its default n_xi with w scaled by wn, the wall values of
+    props.v_and_w_from_solution (:51-87, including its wm_sh = w[argmax(flip(w) > wn)]), v_sh / vm_sh / vm_tilde_sh = NaN
+    (and with them the quantities that need v_sh), the thermodynamic integrals of the scaled profile.  Points within 0.05
+    of alpha_n_max_deflagration_bag ("high alpha_n", bubble.py:253) come back as the reference returns them: solved with
+    solver_failed and a one-sample NaN profile."""
+    torch = engine._torch()
+    pt = point_table(model, v_wall, alpha_n, None, allow_invalid)
+    vw, an = engine.dev_f64(pt.pg[:, 0].copy()), engine.dev_f64(pt.pg[:, 1].copy())
+    n = pt.wn.size
+    wn = engine.dev_f64(pt.wn)
+    an_max, _ = engine.bag_alpha_n_max_unique(vw)
+    shells = engine.sweep_shells_bag(vw, an, n_xi=N_XI_DEFAULT, an_max=an_max)
+    shells.rows_w.mul_(wn[:, None])                                   # the old solver works at wn = 1
+    high = (an_max - an) < 0.05
+    shells.sol_type[high] = -1                                         # fluid.py:893-897: SolutionType.ERROR
+    invalid = torch.as_tensor(pt.invalid, device="cuda")
+    failed = high | (shells.status != 0)
+    wall = engine.shell_wall_values(shells)                           # vp, vm, vp_tilde, vm_tilde, wp, wm, w[-1]
+    # wm_sh as the reference computes it: index of the first w > w[-1] in the FLIPPED array, used in the unflipped one
+    cap = shells.rows_w.shape[1]
+    off, npts = shells.off.long(), shells.npts.long()
+    last = (off + npts - 1).clamp(0, cap - 1)
+    rows = torch.arange(n, device="cuda")
+    w_last = shells.rows_w[rows, last]
+    wm_sh = torch.empty(n, dtype=torch.float64, device="cuda")
+    col = torch.arange(cap, device="cuda")[None, :]
+    for a in range(0, n, 2048):
+        b = min(n, a + 2048)
+        w = shells.rows_w[a:b]
+        inside = (col >= off[a:b, None]) & (col <= last[a:b, None]) & (w > w_last[a:b, None])
+        p_max = torch.where(inside, col, -1).max(dim=1).values
+        j = torch.where(p_max >= 0, last[a:b] - p_max, torch.zeros_like(p_max))
+        wm_sh[a:b] = w[torch.arange(b - a, device="cuda"), (off[a:b] + j).clamp(0, cap - 1)]
+    mu_s, mu_b = 1 + 1 / model.css2, 1 + 1 / model.csb2
+    pp2 = torch.zeros((n, 12), dtype=torch.float64, device="cuda")
+    pp2[:, 0] = vw
+    for k, c in enumerate((mu_s, mu_b, model.V_s, model.V_b, model.a_s, model.a_b, model.T_ref, 1.0)):
+        pp2[:, 1 + k] = c
+    I = engine.profile_integrals(shells, pp2)
+    # thermo.py:42-221 from the integrals (the algebra of the sweep driver's thermo_finish_kernel); v_sh is NaN here
+    nan = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    four_pi_3, vw3 = 4 * np.pi / 3, vw ** 3
+    va_kin, va_trace, va_thd, va_s, wbar = four_pi_3 * I[:, 0], four_pi_3 * I[:, 1], four_pi_3 * 0.75 * I[:, 2], \
+        four_pi_3 * I[:, 3], I[:, 4]
+    ebar = (1 - 1 / mu_s) * wn + model.V_s
+    ked = 3 / (4 * np.pi * vw3) * va_kin
+    kef = ked / ebar
+    v_cj = engine.dev_f64(np.asarray(model.v_chapman_jouguet(pt.pg[:, 1], pt.wn), dtype=float).reshape(-1))
+    cols = [wall[:, 0], wall[:, 1], wall[:, 2], wall[:, 3], nan, nan, nan, wall[:, 4], wall[:, 5], wm_sh, v_cj, wn,
+            wall[:, 6], failed.double(), va_kin, va_trace, va_thd, va_s, wbar, ebar, ked, kef, nan, nan, nan,
+            va_kin / va_trace.abs(), va_thd / va_trace.abs(), ked / I[:, 7], wbar / ebar, nan, nan, shells.npts.double()]
+    table = torch.stack(cols, dim=1)
+    assert table.shape[1] == len(_lib.SWEEP_SCALARS)
+    table[failed | invalid] = float("nan")
+    table[:, 13] = failed.double()
+    status = torch.where(invalid, torch.full_like(shells.status, 4), torch.where(failed, torch.full_like(shells.status, 5),
+                                                                                  torch.zeros_like(shells.status)))
+    # failed points carry a one-sample NaN profile (const.nan_arr)
+    bad = failed | invalid
+    shells.off[bad] = 0
+    shells.npts[bad] = 1
+    for r in (shells.rows_v, shells.rows_w, shells.rows_xi):
+        r[bad, 0] = float("nan")
+    shells.status = status
+    scal = {name: table[:, k] for k, name in enumerate(_lib.SWEEP_SCALARS)}
+    cs_b = torch.full((n,), float(np.sqrt(model.csb2)), dtype=torch.float64, device="cuda")
+    pp = engine.point_params(vw, cs_b, 1 - 1 / mu_s, 1 - 1 / mu_b, model.V_s, model.V_b)
+    shells.scalars = table
+    return BubbleBatch(model, shells, vw, an, wn, shells.sol_type, status, scal, pp, N_XI_DEFAULT, invalid=pt.invalid)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -350,8 +427,9 @@ class Bubble:
                  thin_shell_t_points_min: int = THIN_SHELL_T_POINTS_MIN, use_bag_solver: bool = False,
                  use_giese_solver: bool = False, log_success: bool = False, allow_invalid: bool = False,
                  log_invalid: bool = True):
-        if use_bag_solver or use_giese_solver or theta_bar:
-            raise NotImplementedError("use_bag_solver / use_giese_solver / theta_bar are outside the hot path")
+        if use_giese_solver or theta_bar:
+            raise NotImplementedError("use_giese_solver / theta_bar are outside the hot path")
+        self.use_bag_solver = bool(use_bag_solver)
         if v_wall < 0 or v_wall > 1:
             raise ValueError(f"Invalid v_wall={v_wall}")
         model.validate_alpha_n(alpha_n, allow_invalid=allow_invalid, log_invalid=log_invalid)
@@ -382,11 +460,14 @@ class Bubble:
         if solve:
             self.solve()
 
-    def solve(self, sum_rtol_warning: float = 1.5e-2, sum_rtol_error: float = 5e-2, **_):
+    def solve(self, sum_rtol_warning: float = 1.5e-2, sum_rtol_error: float = 5e-2, use_bag_solver: bool = False, **_):
         batch = sweep_bubbles(self.model, [self.v_wall], [self.alpha_n], [SOL_CODE[self.sol_type]], self.n_xi,
-                              self.t_end, self.thin_shell_t_points_min)
+                              self.t_end, self.thin_shell_t_points_min,
+                              use_bag_solver=self.use_bag_solver or use_bag_solver)
         self._batch = batch
         st = int(batch.status[0])
+        if int(batch.sol_type[0]) < 0:
+            self.sol_type = SolutionType.ERROR         # the old bag solver's answer to "high alpha_n" (fluid.py:893-897)
         if st not in (0, 5):
             self.no_solution_found = True              # bubble.py:290-295 (IndexError / RuntimeError in the solver)
             return

@@ -128,6 +128,64 @@ def test_bubble_constructor_errors():
     assert data["v_wall"] == 0.5 and data["model"]["css2"] == 0.25
 
 
+def test_bubble_on_the_old_bag_solver_matches_the_reference():
+    """Bubble(BagModel, v_wall, alpha_n, use_bag_solver=True) (fluid.py:892-918, bubble.py:250-352): the reference's own
+    objects at ten points (tools/make_golden.py::bag_solver_bubbles): flags, solution type, curves 1e-6, wall values and
+    thermodynamic scalars 1e-6 -- or twice the reference's own LSODA noise on that quantity, measured with the oracle's
+    restatement of the same branch run at tight tolerances -- NaN where the reference has NaN (v_sh and what needs it),
+    the "high alpha_n" point as solver_failed with a NaN profile; also through create_bubbles / BubbleGridVWAlpha."""
+    from pttools_b200 import analysis
+    from pttools_b200.bubble import Bubble, SOL_CODE
+    from pttools_b200.models import BagModel
+    from oracle import models as omodels, shell_bag as sb, shell_generic as sg
+    from util_compare import curve_errors
+    d = np.load(os.path.join(GOLDEN, "ref_bag_solver_bubbles.npz"))
+    model = BagModel(a_s=1.1, a_b=1, V_s=1)
+    omodel = omodels.bag_model(1.1, 1, 1)
+    names = list(d["scalar_names"])
+    n_checked = 0
+    for i, (vw, an) in enumerate(d["points"]):
+        fl = d[f"flags_{i}"]        # code, solved, solver_failed, no_solution_found, 4 validity flags, samples
+        b = Bubble(model, float(vw), float(an), use_bag_solver=True)
+        assert (b.solved, b.solver_failed, b.no_solution_found) == (bool(fl[1]), bool(fl[2]), bool(fl[3])), (vw, an)
+        if fl[2]:
+            assert b.v.size == 1 and np.isnan(b.v[0]) and np.isnan(b.w[0])                  # const.nan_arr
+            continue
+        assert SOL_CODE[b.sol_type] == int(fl[0])
+        assert (b.numerical_error, b.unphysical_alpha_plus, b.negative_entropy_flux, b.negative_net_entropy_change) == \
+            tuple(bool(x) for x in fl[4:8])
+        ev, ew = curve_errors(b.xi, b.v, b.w, d[f"xi_{i}"], d[f"v_{i}"], d[f"w_{i}"], vw)
+        assert ev < 1e-6 and ew < 1e-6, (vw, an, ev, ew)
+        assert np.isnan(b.v_sh) and np.isnan(b.vm_sh) and np.isnan(b.vm_tilde_sh) and np.all(np.isnan(d[f"nan_scal_{i}"]))
+        # the reference's own noise: the same branch with tight LSODA tolerances (oracle pinned to the reference)
+        wn = float(omodel.wn(an))
+        with sb.lsoda_tolerances(1e-12, 1e-13):
+            vt, wt, xt = sb.sound_shell_bag(vw, an)
+        st = sb.identify_solution_type(vw, an)
+        tv = sg.v_and_w_from_solution(vt, wt * wn, xt, vw, st)
+        tight = dict(zip(("vp", "vm", "vp_tilde", "vm_tilde", "wp", "wm"), tv))
+        tight.update(sg.bubble_scalars(omodel, dict(v=vt, w=wt * wn, xi=xt, wn=wn, v_sh=np.nan), vw))
+        ref = dict(zip(names, d[f"scal_{i}"]))
+        for nm in names:
+            got = float(getattr(b, nm))
+            if np.isnan(ref[nm]):
+                assert np.isnan(got), nm
+                continue
+            if ref[nm] == 0:
+                assert abs(got) < 1e-12, nm
+                continue
+            dev = abs(got / ref[nm] - 1)
+            noise = abs(tight[nm] / ref[nm] - 1) if nm in tight and np.isfinite(tight[nm]) else 0.0
+            assert dev <= max(1e-6, 2 * noise), (nm, vw, an, got, ref[nm], dev, noise)
+        n_checked += 1
+    assert n_checked >= 8
+    # the same through the grid facade (bubble_grid.py:57-80 passes use_bag_solver to every Bubble)
+    grid = analysis.BubbleGridVWAlpha(model, np.array([0.5, 0.8]), np.array([0.05, 0.1]), use_bag_solver=True)
+    one = Bubble(model, 0.8, 0.05, use_bag_solver=True)
+    np.testing.assert_allclose(grid.kappa()[0, 1], one.kappa, rtol=1e-12)
+    assert np.isnan(grid.get_value("v_sh", dtype=np.float64)[0, 1])
+
+
 def test_suppression_ssm_tables_through_the_sweep_operator():
     """The reference's stored calc_sup_ssm results (reference test tests/omgw0/test_suppression.py:32-59): integrals of
     power_gw_scaled_bag over ln z with npt = (2000, 200, 320) and get_ubarf2_bag for all 103 simulation points.
