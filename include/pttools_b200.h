@@ -210,6 +210,12 @@ int ptt_spec_den_v_batch(const ptt_sdv_plan_t* plan, int P, const double* a2, in
  * omega: device scratch of n_tiles*128*kw + 2 n_q doubles.  out[p, i], like ptt_spec_den_v_batch. */
 int ptt_spec_den_v_group(const ptt_sdv_plan_t* plan, int n_p, const double* a2, int64_t a2_stride, double v_wall,
                          int kw, const int32_t* e_base, double* omega, double* out, int64_t out_stride, void* stream);
+/* The same with flags.  PTT_SDV_ALIGNED_BAND: the caller promises that a2 + e_base[t] lies on a 16-byte boundary for every
+ * row tile t (e_base[t] may then be -1: a knot before the table, weight 0) and that a2_stride is even; the operands are then
+ * moved by tensor-map copies (TMA) into a shared-memory ring instead of through registers. */
+#define PTT_SDV_ALIGNED_BAND 1
+int ptt_spec_den_v_group_ex(const ptt_sdv_plan_t* plan, int n_p, const double* a2, int64_t a2_stride, double v_wall, int kw,
+                            const int32_t* e_base, double* omega, double* out, int64_t out_stride, int flags, void* stream);
 
 typedef struct ptt_gw_plan {
     int32_t n_zl;         /* size of z_lookup */

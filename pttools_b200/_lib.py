@@ -87,6 +87,7 @@ SWEEP_SCALARS = ("vp", "vm", "vp_tilde", "vm_tilde", "v_sh", "vm_sh", "vm_tilde_
                  "kappa", "omega", "ubarf2", "mean_adiabatic_index", "nu_gdh2024", "source_lifetime_factor", "npts")
 SWEEP_TIMING, SWEEP_NO_RETRY = 1, 2
 PLAN_ONLY_FIRST_PASS, PLAN_ONLY_LOOKUP_PASS, PLAN_FORCE_DIRECT, PLAN_NO_GW_CELLS = 1, 2, 4, 8
+SDV_ALIGNED_BAND = 1
 
 
 class SweepStats(C.Structure):
@@ -127,6 +128,8 @@ SIGNATURES = {
                                        C.c_int64, C.c_void_p]),
     "ptt_spec_den_v_group": (C.c_int, [C.POINTER(SdvPlan), C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ptt_spec_den_v_group_ex": (C.c_int, [C.POINTER(SdvPlan), C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ptt_spec_den_gw_batch": (C.c_int, [C.POINTER(GwPlan), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ptt_spec_den_gw_general_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

@@ -101,4 +101,9 @@ private:
     std::vector<Back> backs_;
 };
 
+// ptt_a2_batch with an explicit row stride of the A^2 table (ptt_ssm.cu); used by the sweep driver
+int a2_batch_strided(const ptt_a2_plan_t* plan, int P, const double* rows_v, const double* rows_w, const double* rows_xi,
+                     int64_t row_stride, const int32_t* off, const int32_t* npts, const double* pp, double* work,
+                     int64_t work_stride, double* a2, int64_t a2_stride, double* fp2_2, double* lam2, void* stream);
+
 }  // namespace ptt

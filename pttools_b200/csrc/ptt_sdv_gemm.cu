@@ -9,6 +9,8 @@
 // same index arithmetic as the gather kernel) and multiplied with the A2 table by an FP64 tensor-core GEMM
 // (mma.sync m8n8k4 f64 -- there is no tcgen05 kind for FP64).  Identical linear-interpolation weights, different
 // summation order; the gather kernel (ptt_ssm.cu) remains for profiles that do not share v_w.
+#include <cuda.h>              // CUtensorMap (types only: the encoder is fetched through the runtime, no -lcuda)
+
 #include "ptt_host.cuh"
 
 namespace ptt {
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(GM_THREADS) sdv_gemm_kernel(
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int k = eb + k0 + lk + q;
-            rb[q] = (p_ok && k < n_q && k0 + lk + q < kw) ? Bg[k] : 0.0;
+            rb[q] = (p_ok && k >= 0 && k < n_q && k0 + lk + q < kw) ? Bg[k] : 0.0;
         }
     };
     auto store_smem = [&](const int buf) {
@@ -220,6 +222,184 @@ __global__ void __launch_bounds__(GM_THREADS) sdv_gemm_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same product with the operands moved by the TMA.  Per 16-knot step one thread issues two tensor-map copies
+// (cp.async.bulk.tensor.2d: the 128 x 16 tile of Omega and the 128 x 16 tile of A^2, 16 KB each, 128-byte swizzle)
+// into a ring of GT_STAGES stages, GT_STAGES - 1 steps ahead; the 16 warps (4 x 4, warp tile 32 x 32, as above) wait on
+// the stage's "full" mbarrier, load their fragments conflict-free from the swizzled tiles, issue the DMMAs and release
+// the stage on its "empty" mbarrier (the issuing thread refills the stage the CTA consumed one step earlier, so it only
+// ever waits for the skew between warps).  No register staging, no shared-memory stores by the SMs, no CTA-wide barrier
+// in the loop.  (A seventeenth, producer-only warp puts five warps on one scheduler and caps the kernel at 96 registers.)
+// Out-of-range parts of a box (knots beyond the band or the table, profiles beyond n_p) are zero-filled by the TMA,
+// which is what the predicated loads of the kernel above do.  Needs 16-byte aligned rows of A^2 (even row stride).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GT_STAGES = 4;
+constexpr int GT_CONSUMERS = 16;                          // warps
+constexpr int GT_THREADS = GT_CONSUMERS * 32;
+constexpr int GT_TILE_BYTES = GM_BM * GM_BK * 8;          // 16 KB: one operand tile of one stage
+constexpr int GT_SMEM = GT_STAGES * 2 * GT_TILE_BYTES + 1024 /* alignment */ + 2 * GT_STAGES * 8;
+
+__device__ __forceinline__ uint32_t gt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gt_mbar_init(uint64_t* bar, const int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gt_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_expect_tx(uint64_t* bar, const uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gt_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gt_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_wait(uint64_t* bar, const uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(gt_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// box (c0 = fastest coordinate, c1) of a 2-D tensor map -> shared memory, completion on the mbarrier
+__device__ __forceinline__ void gt_tma_load_2d(void* dst, const CUtensorMap* map, const int c0, const int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(gt_smem_u32(dst)), "l"(map), "r"(gt_smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// map_om: Omega scratch as [rows = n_tiles * 128][kw] doubles; map_a2: the A^2 table as [n_p][row stride] doubles with
+// its first k_off columns belonging to somebody else (column offset of this pass + alignment).
+__global__ void __launch_bounds__(GT_THREADS, 1) sdv_gemm_tma_kernel(
+    const __grid_constant__ CUtensorMap map_om, const __grid_constant__ CUtensorMap map_a2, const int n_z, const int n_p,
+    const int kw, const int n_tn, const int k_off, const int* __restrict__ e_base, const double factor,
+    double* __restrict__ out, const long long out_stride) {
+    extern __shared__ unsigned char gt_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gt_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + GT_STAGES * 2 * GT_TILE_BYTES);
+    uint64_t* empty = full + GT_STAGES;
+    const int tile_m = blockIdx.x / n_tn, tile_n = blockIdx.x % n_tn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_k = (kw + GM_BK - 1) / GM_BK;
+    if (tid == 0) {
+        for (int s = 0; s < GT_STAGES; ++s) { gt_mbar_init(full + s, 1); gt_mbar_init(empty + s, GT_CONSUMERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int eb = e_base[tile_m] + k_off;
+    auto issue = [&](const int kt) {          // thread 0: the two tiles of step kt into stage kt % GT_STAGES
+        const int st = kt % GT_STAGES;
+        gt_mbar_expect_tx(full + st, 2 * GT_TILE_BYTES);
+        gt_tma_load_2d(base + (size_t)st * 2 * GT_TILE_BYTES, &map_om, kt * GM_BK, tile_m * GM_BM, full + st);
+        gt_tma_load_2d(base + (size_t)st * 2 * GT_TILE_BYTES + GT_TILE_BYTES, &map_a2, eb + kt * GM_BK, tile_n * GM_BN, full + st);
+    };
+    if (tid == 0)
+        for (int kt = 0; kt < min(GT_STAGES - 1, n_k); ++kt) issue(kt);
+    // ---- consumers
+    const int wm = warp & 3, wn = warp >> 2;          // 4 x 4 warps; warp tile 32 (m) x 32 (n)
+    const int nb = min(4, max(0, (n_p - (tile_n * GM_BN + wn * 32) + 7) >> 3));      // 8-profile fragments with profiles
+    const int fr = lane >> 2, fk = lane & 3;
+    // element (row r, knot c) of a tile sits at r * 128 + (((c >> 1) ^ (r & 7)) << 4) + (c & 1) * 8 bytes (128-byte
+    // swizzle); r & 7 == fr for every fragment row of this lane
+    int koff[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) koff[q] = ((((4 * q + fk) >> 1) ^ fr) << 4) + ((fk & 1) << 3);
+    const int row_a = (wm * 32 + fr) * 128, row_b = (wn * 32 + fr) * 128;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kt = 0; kt < n_k; ++kt) {
+        if (tid == 0) {
+            const int nk = kt + GT_STAGES - 1;          // refill the stage consumed in step kt - 1
+            if (nk < n_k) {
+                if (nk >= GT_STAGES) gt_mbar_wait(empty + nk % GT_STAGES, (uint32_t)((nk / GT_STAGES - 1) & 1));
+                issue(nk);
+            }
+        }
+        __syncwarp();
+        gt_mbar_wait(full + s, ph);
+        const unsigned char* As = base + (size_t)s * 2 * GT_TILE_BYTES + row_a;
+        const unsigned char* Bs = base + (size_t)s * 2 * GT_TILE_BYTES + GT_TILE_BYTES + row_b;
+        if (nb > 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double af[4], bf[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) af[a] = *reinterpret_cast<const double*>(As + a * 8 * 128 + koff[q]);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) bf[b] = *reinterpret_cast<const double*>(Bs + b * 8 * 128 + koff[q]);
+                if (nb == 4) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        if (b < nb) {
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) gt_mbar_arrive(empty + s);
+        if (++s == GT_STAGES) { s = 0; ph ^= 1u; }
+    }
+    // C fragment: row = lane / 4, cols = 2 * (lane % 4) + {0, 1}
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = tile_m * GM_BM + wm * 32 + a * 8 + fr;
+        if (i >= n_z) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int p0 = tile_n * GM_BN + wn * 32 + b * 8 + 2 * fk;
+            if (p0 < n_p) out[(long long)p0 * out_stride + i] = factor * acc[a][b][0];
+            if (p0 + 1 < n_p) out[(long long)(p0 + 1) * out_stride + i] = factor * acc[a][b][1];
+        }
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*gt_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static gt_encode_fn gt_encoder() {
+    static gt_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<gt_encode_fn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+// [rows][cols] doubles, row stride ld doubles, box 16 (cols) x 128 (rows), 128-byte swizzle, zero fill outside
+static bool gt_make_map(CUtensorMap* m, const double* base, const uint64_t cols, const uint64_t rows, const uint64_t ld) {
+    gt_encode_fn enc = gt_encoder();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (ld & 1) || cols == 0 || rows == 0) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * sizeof(double)};
+    const cuuint32_t box[2] = {GM_BK, GM_BM};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace ptt
 
 using namespace ptt;
@@ -229,6 +409,12 @@ using namespace ptt;
 extern "C" int ptt_spec_den_v_group(const ptt_sdv_plan_t* plan, int n_p, const double* a2, int64_t a2_stride,
                                     double v_wall, int kw, const int32_t* e_base, double* omega, double* out,
                                     int64_t out_stride, void* stream_) {
+    return ptt_spec_den_v_group_ex(plan, n_p, a2, a2_stride, v_wall, kw, e_base, omega, out, out_stride, 0, stream_);
+}
+
+extern "C" int ptt_spec_den_v_group_ex(const ptt_sdv_plan_t* plan, int n_p, const double* a2, int64_t a2_stride,
+                                       double v_wall, int kw, const int32_t* e_base, double* omega, double* out,
+                                       int64_t out_stride, int flags, void* stream_) {
     if (n_p == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
     if (!plan || n_p < 0 || !a2 || !e_base || !omega || !out || kw < 2)
         return set_error(PTT_E_ARG, "ptt_spec_den_v_group: null pointer or bad size");
@@ -248,6 +434,25 @@ extern "C" int ptt_spec_den_v_group(const ptt_sdv_plan_t* plan, int n_p, const d
     const double factor = 2.0 / (bv * bv * bv * bv * bv * bv);
     const int n_tn = (n_p + GM_BN - 1) / GM_BN;
     dim3 grid(n_tiles * n_tn);
+#ifndef PTT_GEMM_NO_TMA
+    if (flags & PTT_SDV_ALIGNED_BAND) {
+        // operands by tensor-map copies: the caller has aligned every tile's band start (a box of doubles must start on
+        // a 16-byte boundary: an odd start coordinate is an illegal instruction) and padded the row stride; a2 itself
+        // may start one double past an aligned address (the lookup pass follows the y pass in the table)
+        const int k_off = (reinterpret_cast<uintptr_t>(a2) & 15) ? 1 : 0;
+        CUtensorMap map_om, map_a2;
+        if (gt_make_map(&map_om, omega, (uint64_t)kw, (uint64_t)n_tiles * GM_BM, (uint64_t)kw) &&
+            gt_make_map(&map_a2, a2 - k_off, (uint64_t)plan->n_q + k_off, (uint64_t)n_p, (uint64_t)a2_stride)) {
+            const cudaError_t ea = cudaFuncSetAttribute(sdv_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+            if (ea != cudaSuccess) return set_cuda_error("sdv_gemm_tma_kernel smem", ea);
+            sdv_gemm_tma_kernel<<<grid, GT_THREADS, GT_SMEM, stream>>>(map_om, map_a2, plan->n_z, n_p, kw, n_tn, k_off, e_base,
+                                                                     factor, out, out_stride);
+            const cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return set_cuda_error("sdv_gemm_tma_kernel", e);
+            return PTT_OK;
+        }
+    }
+#endif
     const int smem = 2 * (GM_BM + GM_BN) * GM_PITCH * (int)sizeof(double);
     {
         const cudaError_t e = cudaFuncSetAttribute(sdv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -653,7 +653,8 @@ constexpr int A2F_PPT = 8;      // profiles per thread: the stencil and 1/dz of 
 __global__ void __launch_bounds__(256) a2_finish_kernel(
     const int P, const int n_z, const int n_seg, const int* __restrict__ seg, const double* __restrict__ z,
     const double* __restrict__ work, const long long work_stride, const long long offF, const long long offL,
-    const double* __restrict__ pp, double* __restrict__ a2, double* __restrict__ fp2_2, double* __restrict__ lam2) {
+    const double* __restrict__ pp, double* __restrict__ a2, const long long a2_stride, double* __restrict__ fp2_2,
+    double* __restrict__ lam2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_z) return;
     int s0 = 0, s1 = n_z;
@@ -676,7 +677,7 @@ __global__ void __launch_bounds__(256) a2_finish_kernel(
         const double cs = pp[8 * p + 1];
         const double cl = cs * L[i];
         const long long o = (long long)p * n_z + i;
-        a2[o] = 0.25 * (v_ft * v_ft + cl * cl);
+        a2[(long long)p * a2_stride + i] = 0.25 * (v_ft * v_ft + cl * cl);
         if (fp2_2) fp2_2[o] = v_ft * v_ft / 2.0;
         if (lam2) lam2[o] = cl * cl / 2.0;
     }
@@ -999,15 +1000,25 @@ extern "C" int ptt_a2_batch(const ptt_a2_plan_t* plan, int P, const double* rows
                             const double* rows_xi, int64_t row_stride, const int32_t* off, const int32_t* npts,
                             const double* pp, double* work, int64_t work_stride, double* a2, double* fp2_2,
                             double* lam2, void* stream_) {
+    return ptt::a2_batch_strided(plan, P, rows_v, rows_w, rows_xi, row_stride, off, npts, pp, work, work_stride, a2,
+                                 plan ? plan->n_z : 0, fp2_2, lam2, stream_);
+}
+
+// ptt_a2_batch with a row stride of its own for the A^2 table (the sweep driver pads it to an even number of doubles:
+// rows that start on 16-byte boundaries can be fetched by the tensor-map copies of K6').  fp2_2 / lam2: stride n_z.
+int ptt::a2_batch_strided(const ptt_a2_plan_t* plan, int P, const double* rows_v, const double* rows_w,
+                          const double* rows_xi, int64_t row_stride, const int32_t* off, const int32_t* npts,
+                          const double* pp, double* work, int64_t work_stride, double* a2, int64_t a2_stride,
+                          double* fp2_2, double* lam2, void* stream_) {
     if (P == 0) return PTT_OK;      // an empty batch is valid, whatever the pointers
-    if (!plan || P < 0 || !rows_v || !rows_w || !rows_xi || !off || !npts || !pp || !work || !a2)
+    if (!plan || P < 0 || !rows_v || !rows_w || !rows_xi || !off || !npts || !pp || !work || !a2 || a2_stride < plan->n_z)
         return set_error(PTT_E_ARG, "ptt_a2_batch: null pointer or bad size");
     for (int p0 = 0; P > MAX_BATCH_SLICE && p0 < P; p0 += MAX_BATCH_SLICE) {
         const size_t o = (size_t)p0;
-        const int rc = ptt_a2_batch(plan, min(MAX_BATCH_SLICE, P - p0), rows_v + o * row_stride, rows_w + o * row_stride,
-                                    rows_xi + o * row_stride, row_stride, off + p0, npts + p0, pp + o * 8,
-                                    work + o * work_stride, work_stride, a2 + o * plan->n_z,
-                                    fp2_2 ? fp2_2 + o * plan->n_z : nullptr, lam2 ? lam2 + o * plan->n_z : nullptr, stream_);
+        const int rc = a2_batch_strided(plan, min(MAX_BATCH_SLICE, P - p0), rows_v + o * row_stride, rows_w + o * row_stride,
+                                        rows_xi + o * row_stride, row_stride, off + p0, npts + p0, pp + o * 8,
+                                        work + o * work_stride, work_stride, a2 + o * a2_stride, a2_stride,
+                                        fp2_2 ? fp2_2 + o * plan->n_z : nullptr, lam2 ? lam2 + o * plan->n_z : nullptr, stream_);
         if (rc != PTT_OK || p0 + MAX_BATCH_SLICE >= P) return rc;
     }
     if (P == 0) return PTT_OK;
@@ -1036,7 +1047,7 @@ extern "C" int ptt_a2_batch(const ptt_a2_plan_t* plan, int P, const double* rows
     }
     dim3 grid2((plan->n_z + 255) / 256, (P + A2F_PPT - 1) / A2F_PPT);
     a2_finish_kernel<<<grid2, 256, 0, stream>>>(P, plan->n_z, plan->n_seg, plan->seg, plan->z, work, work_stride, lay.F(),
-                                                lay.L(), pp, a2, fp2_2, lam2);
+                                                lay.L(), pp, a2, a2_stride, fp2_2, lam2);
     return check_launch("ptt_a2_batch");
 }
 

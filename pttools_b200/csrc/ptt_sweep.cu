@@ -291,6 +291,9 @@ static ptt_sweep_stats_t g_stats;
 
 // First knot of every 128-row tile and the common band width of K6' for one wall speed (host side of
 // ptt_spec_den_v_group).
+// Every tile's first knot is given the parity of the pass' first column in the A^2 table (one knot earlier where needed;
+// -1 = a knot before the table, weight 0): with the even row stride of the table its entries then start on a 16-byte
+// boundary, which the tensor-map copies of K6' need (PTT_SDV_ALIGNED_BAND).
 static int group_band(const ptt_sweep_plan_t& pl, const int ip, const double v_wall, int32_t* e_base) {
     const ptt_sdv_plan_t& sp = pl.sdv[ip];
     const double* zterm = pl.h_zterm[ip];
@@ -303,7 +306,8 @@ static int group_band(const ptt_sweep_plan_t& pl, const int ip, const double v_w
     for (int t = 0; t < n_tiles; ++t) {
         const int i0 = t * SW_GM_BM, i1 = std::min(i0 + SW_GM_BM, n_z) - 1;
         const long long e_first = (long long)floor(zterm[i0] + pl.lt_first[ip] + shift) - 1;
-        const long long eb = std::min(std::max(e_first, 0LL), hi);
+        long long eb = std::min(std::max(e_first, 0LL), hi);
+        eb -= (eb + pl.seg[ip]) & 1;
         long long e_last = (long long)floor(zterm[i1] + pl.lt_last[ip] + shift) + 1;
         e_last = std::min(std::max(e_last, 0LL), hi) + 1;
         e_base[t] = (int32_t)eb;
@@ -368,6 +372,7 @@ struct Sweep {
 
     long long n = 0, shell_chunk = 0, n_shell_chunks = 0, C = 0, cap = 0;
     int n_xi = 5000, thin = 100, chunk = 8000, group_min = SW_GROUP_MIN, n_pass = 0, n_y = 0, n_zl = 0, n_a2 = 0, ws_stride = 0;
+    long long a2_ld = 0;             // row stride of the A^2 table: n_a2 padded to an even number (16-byte aligned rows for K6')
     double t_end = 50.0, wn_rtol = 1e-4;
     bool sorted = true, want_spec = false, want_rows = false, use_cells = false, retry = true;
     double* h_pg = nullptr;
@@ -503,7 +508,8 @@ int Sweep::setup(const long long n_, const double* pg, const double* pm, const d
         n_y = plan->gw.n_y; n_zl = plan->gw.n_zl; n_a2 = plan->a2.n_z;
         ws_stride = ptt_a2_work_stride((int)cap, plan->a2.nxi, n_a2);
         use_cells = plan->cells.cap > 0;
-        d_a2 = ws.a2.get<double>((size_t)C * n_a2); SW_ALLOC(d_a2);
+        a2_ld = (n_a2 + 1) / 2 * 2;
+        d_a2 = ws.a2.get<double>((size_t)C * a2_ld); SW_ALLOC(d_a2);
         d_work = ws.work.get<double>((size_t)C * ws_stride); SW_ALLOC(d_work);
         d_pvl = ws.pv_l.get<double>((size_t)C * n_zl); SW_ALLOC(d_pvl);
         if (n_pass == 2 && plan->has_y_pass) { d_pvy = ws.pv_y.get<double>((size_t)C * plan->sdv[0].n_z); SW_ALLOC(d_pvy); }
@@ -707,7 +713,7 @@ int Sweep::sdv_pass(const int ip, const long long c, const long long s, const lo
         SW_ALLOC(vw_c);
         SW_CUDA(cudaMemcpy2DAsync(vw_c, sizeof(double), sl.pp.as<double>() + (size_t)(sm.first - s0) * 8, 8 * sizeof(double),
                                   sizeof(double), (size_t)m, cudaMemcpyDeviceToDevice, s_main));
-        SW_RC(ptt_spec_den_v_batch(&sp, (int)m, a2p + (size_t)(sm.first - s) * n_a2, n_a2, vw_c,
+        SW_RC(ptt_spec_den_v_batch(&sp, (int)m, a2p + (size_t)(sm.first - s) * a2_ld, a2_ld, vw_c,
                                    out_pv + (size_t)(sm.first - s) * n_z, n_z, s_main));
         stats.launches += 1;
     }
@@ -728,9 +734,9 @@ int Sweep::sdv_pass(const int ip, const long long c, const long long s, const lo
             const size_t need = (size_t)n_tiles[ip] * SW_GM_BM * kw + 2 * (size_t)sp.n_q;
             double* om = ws.omega[side].get<double>(need);
             SW_ALLOC(om);
-            SW_RC(ptt_spec_den_v_group(&sp, (int)(g.b - g.a), a2p + (size_t)(g.a - s) * n_a2, n_a2, hq(g.a, 0), kw,
-                                       d_ebase + eb_off[ip] + g.run * n_tiles[ip], om, out_pv + (size_t)(g.a - s) * n_z,
-                                       n_z, ws.s_side[side]));
+            SW_RC(ptt_spec_den_v_group_ex(&sp, (int)(g.b - g.a), a2p + (size_t)(g.a - s) * a2_ld, a2_ld, hq(g.a, 0), kw,
+                                          d_ebase + eb_off[ip] + g.run * n_tiles[ip], om, out_pv + (size_t)(g.a - s) * n_z,
+                                          n_z, PTT_SDV_ALIGNED_BAND, ws.s_side[side]));
             stats.launches += 2;
             if (ip == n_pass - 1) {
                 stats.group_profiles += g.b - g.a;
@@ -758,9 +764,9 @@ int Sweep::spectra_chunk(const long long c, const long long s, const long long e
     // the output slot's previous tenant has been delivered
     if (out_used[b]) SW_CUDA(cudaStreamWaitEvent(s_main, ws.out_free[b], 0));
     cudaEvent_t t0 = timer.begin(s_main);
-    SW_RC(ptt_a2_batch(&plan->a2, P, sl.rows[0].as<double>() + lo * cap, sl.rows[1].as<double>() + lo * cap,
-                       sl.rows[2].as<double>() + lo * cap, cap, sl.off.as<int32_t>() + lo, sl.npts.as<int32_t>() + lo,
-                       sl.pp.as<double>() + lo * 8, d_work, ws_stride, d_a2, nullptr, nullptr, s_main));
+    SW_RC(a2_batch_strided(&plan->a2, P, sl.rows[0].as<double>() + lo * cap, sl.rows[1].as<double>() + lo * cap,
+                           sl.rows[2].as<double>() + lo * cap, cap, sl.off.as<int32_t>() + lo, sl.npts.as<int32_t>() + lo,
+                           sl.pp.as<double>() + lo * 8, d_work, ws_stride, d_a2, a2_ld, nullptr, nullptr, s_main));
     timer.end(PTT_STAGE_A2, t0, s_main);
     stats.launches += 3;
     stats.a2_profiles += P;

@@ -936,8 +936,10 @@ GROUP_MIN = 24          # smallest run of equal v_wall worth the banded matrix p
 USE_GROUPED_SDV = True
 
 
-def _group_band(p: SdvPass, v_wall: float):
-    """First knot of every 128-row tile and the common band width for one wall speed (host side of K6')."""
+def _group_band(p: SdvPass, v_wall: float, parity=None):
+    """First knot of every 128-row tile and the common band width for one wall speed (host side of K6').  parity (0 or
+    1): every tile's first knot gets this parity (one knot earlier where needed; -1 = a knot before the table, weight
+    0), so that its A^2 entries start on a 16-byte boundary (PTT_SDV_ALIGNED_BAND)."""
     b_r = (8.0 * np.pi) ** (1.0 / 3.0)
     shift = -np.log10(b_r * v_wall) / p.dl
     n_z, n_q = p.z.size, p.qT.size
@@ -945,6 +947,8 @@ def _group_band(p: SdvPass, v_wall: float):
     i1 = np.minimum(i0 + 128, n_z) - 1
     e_first = np.floor(p.zterm[i0] + p.LT[0] + shift).astype(np.int64) - 1
     e_base = np.clip(e_first, 0, max(n_q - 2, 0))
+    if parity is not None:
+        e_base = e_base - ((e_base + int(parity)) & 1)
     e_last = np.clip(np.floor(p.zterm[i1] + p.LT[-1] + shift).astype(np.int64) + 1, 0, n_q - 2) + 1
     kw = int((e_last - e_base).max()) + 3
     kw = ((kw + 15) // 16) * 16
@@ -958,7 +962,10 @@ def spec_den_v_group(plan: SsmPlan, ipass: int, a2, v_wall: float, out, slot: in
     torch = _torch()
     lib = _lib.load()
     sp, p = plan.sdv_plans[ipass], plan.passes[ipass]
-    e_base, kw = _group_band(p, v_wall)
+    # rows of A^2 on 16-byte boundaries: the band of every tile can be aligned too, and the operands go by TMA
+    a2_addr = a2.data_ptr() + 8 * int(plan.seg[ipass])
+    aligned = a2.stride(0) % 2 == 0 and a2.data_ptr() % 16 == 0
+    e_base, kw = _group_band(p, v_wall, parity=(a2_addr >> 3) & 1 if aligned else None)
     n_tiles = e_base.size
     key = ("omega", ipass, slot)
     need = n_tiles * 128 * kw + 2 * p.qT.size
@@ -967,10 +974,11 @@ def spec_den_v_group(plan: SsmPlan, ipass: int, a2, v_wall: float, out, slot: in
         buf = torch.empty(int(need * 1.02) + 1024, dtype=torch.float64, device=a2.device)
         plan._t[key] = buf
     eb = torch.as_tensor(e_base, device=a2.device)
-    a2_ptr = C.c_void_p(a2.data_ptr() + 8 * int(plan.seg[ipass]))
-    call = lambda: _lib.check(lib.ptt_spec_den_v_group(C.byref(sp), a2.shape[0], a2_ptr, a2.stride(0), float(v_wall), kw,
-                                                       _ptr(eb), _ptr(buf), _ptr(out), out.stride(0), _stream_ptr(torch)),
-                              "ptt_spec_den_v_group")
+    a2_ptr = C.c_void_p(a2_addr)
+    call = lambda: _lib.check(lib.ptt_spec_den_v_group_ex(C.byref(sp), a2.shape[0], a2_ptr, a2.stride(0), float(v_wall), kw,
+                                                          _ptr(eb), _ptr(buf), _ptr(out), out.stride(0),
+                                                          _lib.SDV_ALIGNED_BAND if aligned else 0, _stream_ptr(torch)),
+                              "ptt_spec_den_v_group_ex")
     if timed:
         with STAGES.stage(_group_stage_name(plan, ipass), 2):
             call()
