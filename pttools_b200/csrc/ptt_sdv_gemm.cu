@@ -233,7 +233,10 @@ __global__ void __launch_bounds__(GM_THREADS) sdv_gemm_kernel(
 // Out-of-range parts of a box (knots beyond the band or the table, profiles beyond n_p) are zero-filled by the TMA,
 // which is what the predicated loads of the kernel above do.  Needs 16-byte aligned rows of A^2 (even row stride).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int GT_STAGES = 4;
+#ifndef PTT_GT_STAGES
+#define PTT_GT_STAGES 4
+#endif
+constexpr int GT_STAGES = PTT_GT_STAGES;
 constexpr int GT_CONSUMERS = 16;                          // warps
 constexpr int GT_THREADS = GT_CONSUMERS * 32;
 constexpr int GT_TILE_BYTES = GM_BM * GM_BK * 8;          // 16 KB: one operand tile of one stage
@@ -303,10 +306,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) sdv_gemm_tma_kernel(
     const int nb = min(4, max(0, (n_p - (tile_n * GM_BN + wn * 32) + 7) >> 3));      // 8-profile fragments with profiles
     const int fr = lane >> 2, fk = lane & 3;
     // element (row r, knot c) of a tile sits at r * 128 + (((c >> 1) ^ (r & 7)) << 4) + (c & 1) * 8 bytes (128-byte
-    // swizzle); r & 7 == fr for every fragment row of this lane
+    // swizzle); r & 7 == fr for every fragment row of this lane.  The four knots of DMMA step q are the columns
+    // {2q, 2q + 1, 2q + 8, 2q + 9} of the tile (the order of the 16 knots inside a tile is free): the 16-byte chunks of a
+    // half-warp, (q ^ fr) and (q ^ fr) ^ 4 for fr = 0..3, are then all different and a fragment load touches every bank
+    // once (with the columns {4q .. 4q + 3} rows fr and fr ^ 1 share their chunk positions: 2-way conflicts).
     int koff[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) koff[q] = ((((4 * q + fk) >> 1) ^ fr) << 4) + ((fk & 1) << 3);
+    for (int q = 0; q < 4; ++q) koff[q] = (((q + 4 * (fk >> 1)) ^ fr) << 4) + ((fk & 1) << 3);
     const int row_a = (wm * 32 + fr) * 128, row_b = (wn * 32 + fr) * 128;
     double acc[4][4][2];
 #pragma unroll

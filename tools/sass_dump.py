@@ -4,7 +4,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pttools_b200", "libpttools_b200.so")
 out_dir, tag = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "r02")
-HOT = ("sdv_gemm_kernel", "spec_den_gw_cells_kernel", "sin_transform_moments_kernel", "a2_moments_kernel", "sdv_weights_kernel")
+HOT = ("sdv_gemm_tma_kernel", "sdv_gemm_kernel", "spec_den_gw_cells_kernel", "sin_transform_moments_kernel", "a2_moments_kernel", "sdv_weights_kernel")
 txt = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 kernels, cur = collections.OrderedDict(), None
 for ln in txt.splitlines():
