@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpttools_b200.so")
+LIB_PATH = os.environ.get("PTT_B200_LIB") or os.path.join(HERE, "libpttools_b200.so")   # override: instrumented builds (tools/)
 
 MEM_HOST, MEM_DEVICE = 0, 1
 ST_OK, ST_NO_SOLUTION, ST_INTEGRATION_FAILED, ST_ROOT_NOT_CONVERGED, ST_INVALID_INPUT, ST_SOLVER_FAILED = range(6)

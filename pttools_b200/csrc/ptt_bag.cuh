@@ -109,6 +109,30 @@ struct ShockLocator {
     }
     PTT_HD static bool crossed(const State& y) { return y.v <= v_shock_bag(y.xi); }   // NaN compares false
     PTT_HD bool skip(const State& y_end) const { return !full && !zero_hit && !crossed(y_end); }
+    // The crossing inside one integrator step by bisection (see integrate_grid): on thin shells one step holds thousands
+    // of tau-grid samples.  Same assumption as skip(): within a step the curve crosses the shock curve once.
+    template <class Sampler>
+    PTT_HD int search(const int i_lo, const int i_hi, const Sampler& sample) {
+        if (full || zero_hit || last_i != i_lo - 1) return -1;
+        const State y_hi = sample(i_hi);
+        if (!crossed(y_hi)) return (i_lo > 1) ? -2 : -1;
+        if (crossed(prev)) return -1;
+        int lo = i_lo - 1, hi = i_hi;
+        State y_found = y_hi;
+        while (hi - lo > 1) {
+            const int mid = lo + ((hi - lo) >> 1);
+            const State y = sample(mid);
+            if (crossed(y)) { hi = mid; y_found = y; } else { lo = mid; }
+        }
+        if (i_lo == 1) y1 = (hi == 1) ? y_found : sample(1);
+        if (hi - 1 >= i_lo) {
+            const State p1 = sample(hi - 1);
+            prev2 = (hi - 2 >= i_lo) ? sample(hi - 2) : prev;
+            prev = p1;
+        }
+        found = hi; cur = y_found; last_i = hi - 1;
+        return hi;
+    }
     PTT_HD bool visit(const int i, const State& y) {
         if (i == 1) y1 = y;
         if (i == 0) {
@@ -454,6 +478,10 @@ struct BagVisitor {
     ForwardEmitter fe;
     BackwardEmitter be;
     PTT_HD bool skip(const State& y_end) const { return kind == BJ_LOCATE && loc.skip(y_end); }
+    template <class Sampler>
+    PTT_HD int search(const int i_lo, const int i_hi, const Sampler& sample) {
+        return (kind == BJ_LOCATE) ? loc.search(i_lo, i_hi, sample) : -1;
+    }
     PTT_HD bool visit(const int i, const State& y) {
         if (kind == BJ_LOCATE) return loc.visit(i, y);
         if (kind == BJ_EMIT_FWD) return fe.visit(i, y);

@@ -95,7 +95,42 @@ struct GenericShockLocator {
         return fabs(y.xi - c) <= 1e-8 + 1e-5 * fabs(c) && fabs(y.v) <= 1e-8;
     }
     PTT_HD bool skip(const State& y_end) const {
+        // (near the fixed point (cs, 0) every sample is looked at: the index at which rounding lifts xi to cs there -
+        // it fixes v_sh = cs to 1e-14, as the reference's result has it - cannot be found any other way)
         return !full && !behind(y_end) && !near_cs(y_end) && (last_i < 0 || y_end.xi > prev.xi);
+    }
+    // The first sample behind the shock curve inside one integrator step, by bisection instead of the ordered walk:
+    // on thin shells a single step holds thousands of tau-grid samples (the step is set by the accuracy of the curve,
+    // the grid by n_xi).  Taken only in the clean case - the curve moves outwards over the step, away from the fixed
+    // point (cs, 0), the last sample of the step is behind the shock curve and the sample before the step is not - and
+    // with the assumption skip() already makes: within one step the curve crosses the shock curve once.  Leaves the
+    // locator as the ordered walk would (found, cur, prev, prev2, last_i).
+    template <class Sampler>
+    PTT_HD int search(const int i_lo, const int i_hi, const Sampler& sample) {
+        if (full || last_i != i_lo - 1) return -1;
+        const double v_clear = 1e-6;                                        // near_cs() needs |v| <= 1e-8
+        const State y_hi = sample(i_hi);
+        if (i_lo == 1 && skip(y_hi)) return -2;                             // (the walk applies skip() from the second step on)
+        if (!(prev.v > v_clear) || !(y_hi.v > v_clear) || !(y_hi.xi > prev.xi)) return -1;
+        if (!behind(y_hi) || behind(prev)) return -1;
+        int lo = i_lo - 1, hi = i_hi;                                       // not behind / behind
+        State y_found = y_hi;
+        while (hi - lo > 1) {
+            const int mid = lo + ((hi - lo) >> 1);
+            const State y = sample(mid);
+            if (!(y.v > v_clear)) return -1;
+            if (behind(y)) { hi = mid; y_found = y; } else { lo = mid; }
+        }
+        // samples hi - 2, hi - 1 as the walk would hold them (first_above is not read once the shock is found)
+        if (hi - 1 >= i_lo) {
+            const State y1 = sample(hi - 1);
+            const State y2 = (hi - 2 >= i_lo) ? sample(hi - 2) : prev;
+            if (!m.bag_name && !(y1.xi >= y2.xi && y_found.xi >= y1.xi)) return -1;        // a turning curve: ordered walk
+            prev2 = y2;
+            prev = y1;
+        }
+        found = hi; cur = y_found; last_i = hi - 1;
+        return hi;
     }
     PTT_HD bool visit(const int i, const State& y) {
         if (first_above < 0 && y.xi > cs_n) first_above = i;                // i_cs_n = argmax(xi > cs_n), shock.py:112
@@ -169,6 +204,10 @@ struct JobVisitor {
     OffsetEmitter oe;
     CsTrimEmitter ce;
     PTT_HD bool skip(const State& y_end) const { return kind == JOB_LOCATE && loc.skip(y_end); }
+    template <class Sampler>
+    PTT_HD int search(const int i_lo, const int i_hi, const Sampler& sample) {
+        return (kind == JOB_LOCATE) ? loc.search(i_lo, i_hi, sample) : -1;
+    }
     PTT_HD bool visit(const int i, const State& y) {
         if (kind == JOB_LOCATE) return loc.visit(i, y);
         if (kind == JOB_EMIT) return oe.visit(i, y);

@@ -17,6 +17,14 @@
 #define PTT_HD inline
 #endif
 
+// test-only hook of the host emulation (step statistics); empty in the product
+#ifndef PTT_ODE_STEP_HOOK
+#define PTT_ODE_STEP_HOOK(accepted)
+#endif
+#ifndef PTT_ODE_SAMPLE_HOOK
+#define PTT_ODE_SAMPLE_HOOK(searched)
+#endif
+
 namespace ptt {
 
 // Equation of state seen by the fluid equations: both in-scope models have a piecewise-constant sound speed,
@@ -144,16 +152,17 @@ struct Dopri5 {
             const double sv = ATOL + RTOL * fmax(fabs(y.v), fabs(y1.v));
             const double sw = ATOL + RTOL * fmax(fabs(y.w), fabs(y1.w));
             const double sx = ATOL + RTOL * fmax(fabs(y.xi), fabs(y1.xi));
-            const double err = sqrt(((ev / sv) * (ev / sv) + (ew / sw) * (ew / sw) + (ex / sx) * (ex / sx)) / 3.0);
-            if (!(err == err)) {           // NaN: the trajectory left the domain (v -> 1 or xi*v -> 1)
+            // err^2 (the RMS norm squared): the accept test and the step-size factor need no square root
+            const double err2 = ((ev / sv) * (ev / sv) + (ew / sw) * (ew / sw) + (ex / sx) * (ex / sx)) * (1.0 / 3.0);
+            if (!(err2 == err2)) {         // NaN: the trajectory left the domain (v -> 1 or xi*v -> 1)
                 failed = true;
                 return false;
             }
             // step-size factor 0.9 err^(-1/5): single precision is plenty for a step-size heuristic
-            double fac = (err > 0.0) ? 0.9 * (double)powf((float)fmin(fmax(err, 1e-30), 1e30), -0.2f) : 5.0;
+            double fac = (err2 > 0.0) ? 0.9 * (double)powf((float)fmin(fmax(err2, 1e-30), 1e30), -0.1f) : 5.0;
             if (fac < 0.2) fac = 0.2;
             if (fac > 5.0) fac = 5.0;
-            if (err <= 1.0) {
+            if (err2 <= 1.0) {
                 // accept; build the continuous extension (Hairer's contd5)
                 t0 = t;
                 hd = hs;
@@ -171,10 +180,12 @@ struct Dopri5 {
                 nrej = 0;
                 h = hs * fac;
                 ++nsteps;
+                PTT_ODE_STEP_HOOK(true)
                 return true;
             }
             // reject
             ++nrej;
+            PTT_ODE_STEP_HOOK(false)
             h = hs * fac;
             if (fabs(h) < 1e-15 * fmax(1.0, fabs(t))) {
                 failed = true;
@@ -186,8 +197,9 @@ struct Dopri5 {
     }
 
     // Continuous extension inside the last accepted step.
-    PTT_HD State dense(const double tq) const {
-        const double th = (tq - t0) / hd;
+    // inv_hd = 1 / hd, computed once per step by the caller
+    PTT_HD State dense(const double tq, const double inv_hd) const {
+        const double th = (tq - t0) * inv_hd;
         const double th1 = 1.0 - th;
         State o;
         o.v = r1.v + th * (r2.v + th1 * (r3.v + th * (r4.v + th1 * r5.v)));
@@ -196,6 +208,30 @@ struct Dopri5 {
         return o;
     }
 };
+
+// Grid samples inside the last accepted step: sample(k) is what the ordered walk below hands to visit(k, .).
+struct StepSampler {
+    const Dopri5& s;
+    double dt, t_end, inv_hd;
+    int n;
+    PTT_HD State operator()(const int k) const {
+        const double tk = (k >= n - 1) ? t_end : (double)k * dt;
+        return (tk == s.t) ? s.y : s.dense(tk, inv_hd);
+    }
+};
+
+// Optional member of a visitor:
+//   int search(int i_lo, int i_hi, const StepSampler& sample)
+// called for a step that holds the grid samples i_lo..i_hi (more than one) and was not skipped.  A visitor that can find
+// its stopping sample without seeing every sample in order (bisection) does so and returns its index (it then has the
+// state visit() would have left behind); -1 = walk the samples one by one; -2 = only the last one, i_hi, needs to be seen.
+template <class Visitor>
+PTT_HD auto visitor_search(Visitor& v, const int i_lo, const int i_hi, const StepSampler& sm, int)
+    -> decltype(v.search(i_lo, i_hi, sm)) {
+    return v.search(i_lo, i_hi, sm);
+}
+template <class Visitor>
+PTT_HD int visitor_search(Visitor&, const int, const int, const StepSampler&, long) { return -1; }
 
 // Walks the tau-grid t_i = linspace(0, t_end, n)[i] in order and hands samples to a visitor:
 //   bool visit(int i, const State& y)   -- return false to stop early
@@ -216,26 +252,34 @@ PTT_HD int integrate_grid(const double cs2, const State& y0, const double t_end,
     Dopri5 s;
     s.init(cs2, y0, t_end);
     const double sgn = (t_end < 0.0) ? -1.0 : 1.0;
-    const double dt = t_end / (double)(n - 1);
+    const double dt = t_end / (double)(n - 1);          // grid_time(t_end, n, k) = k * dt below the last sample
+    const double inv_dt = 1.0 / dt;
     int i = 1;
     while (i < n) {
         if (!s.step()) return -1;
-        // last grid index inside (t0, t]
+        // last grid index inside (t0, t]: an estimate, then made exact against the grid times themselves
         int i_hi;
         if (s.t == t_end) {
             i_hi = n - 1;
         } else {
-            i_hi = (int)(s.t / dt);
+            i_hi = (int)(s.t * inv_dt);
             if (i_hi > n - 1) i_hi = n - 1;
-            while (i_hi + 1 < n && (grid_time(t_end, n, i_hi + 1) - s.t) * sgn <= 0.0) ++i_hi;
-            while (i_hi >= i && (grid_time(t_end, n, i_hi) - s.t) * sgn > 0.0) --i_hi;
+            while (i_hi + 1 < n && (((i_hi + 1 >= n - 1) ? t_end : (double)(i_hi + 1) * dt) - s.t) * sgn <= 0.0) ++i_hi;
+            while (i_hi >= i && (((i_hi >= n - 1) ? t_end : (double)i_hi * dt) - s.t) * sgn > 0.0) --i_hi;
         }
         if (i_hi < i) continue;
         if (i > 1 && i_hi > i && visit.skip(s.y)) i = i_hi;
+        const StepSampler sample{s, dt, t_end, 1.0 / s.hd, n};
+#ifndef PTT_NO_STEP_SEARCH      // (test switch: the ordered walk everywhere)
+        if (i_hi > i) {
+            const int i_stop = visitor_search(visit, i, i_hi, sample, 0);
+            if (i_stop >= 0) { PTT_ODE_SAMPLE_HOOK(true) return i_stop + 1; }
+            if (i_stop == -2) i = i_hi;
+        }
+#endif
         for (; i <= i_hi; ++i) {
-            const double ti = grid_time(t_end, n, i);
-            const State yi = (ti == s.t) ? s.y : s.dense(ti);
-            if (!visit.visit(i, yi)) return i + 1;
+            PTT_ODE_SAMPLE_HOOK(false)
+            if (!visit.visit(i, sample(i))) return i + 1;
         }
     }
     return n;

@@ -1,6 +1,8 @@
 """Where the shell solver (generic_solve_kernel) spends its time on a bench step: per-point cycle counts (build with
 -DPTT_K3_CLOCKS), by solution type, and a simulation of the warp schedule in the current order against slow-first orders.
-Usage (GPU box): PTT_NVCC_EXTRA=-DPTT_K3_CLOCKS python pttools_b200/build.py --force && python tools/k3_clocks.py"""
+Usage (GPU box): PTT_NVCC_EXTRA=-DPTT_K3_CLOCKS python pttools_b200/build.py --force && python tools/k3_clocks.py
+(or PTT_B200_LIB=<an instrumented build of the library> python tools/k3_clocks.py); per-point arrays go to
+gpurun_out/k3_clocks.npz."""
 import sys, heapq
 import numpy as np
 import torch
@@ -21,6 +23,9 @@ print("kernel ms", ev0.elapsed_time(ev1))
 sc = sh.scalars.cpu().numpy()
 clk, nres = sc[:, 15], sc[:, 14]
 codes = pt.codes
+import os
+os.makedirs("gpurun_out", exist_ok=True)
+np.savez_compressed("gpurun_out/k3_clocks.npz", vw=vw, an=an, codes=codes, clk=clk, n_resid=nres)
 ok = np.isfinite(clk) & (clk > 0)
 print("points with a profile", ok.sum(), "of", clk.size)
 for c, name in ((0, "sub_def"), (1, "hybrid"), (2, "deton")):
