@@ -370,6 +370,12 @@ typedef struct ptt_sweep_opts {
     double wn_rtol;            /* 0 -> 1e-4 (fluid.py:650) */
     double r_star;             /* <= 0: Spectrum without r_star (lifetime factor 1/(1+2 nu) only) */
     double lifetime_multiplier;/* spectrum.py:123-136; may be +inf */
+    /* Optional, PTT_MEM_DEVICE only: HOST copies of v_wall (pg column 0) and of the solution type (pg column 2), [n] each,
+     * in the order of pg.  The driver groups the points by wall speed on the host; with these it does not have to fetch pg
+     * from the device and wait for `stream` to get there, so a sweep can be queued while the previous one is still running
+     * on the same stream (its shell solve then starts the moment the previous sweep ends).  Both or neither. */
+    const double* host_v_wall;
+    const int32_t* host_sol_type;
 } ptt_sweep_opts_t;
 
 typedef struct ptt_sweep_out {
@@ -427,11 +433,16 @@ typedef struct ptt_sweep_stats {
     int64_t chunks_before_fold, chunks_after_fold;   /* spectrum chunks queued before / after the retries were folded in */
     double host_wait_retry_ms;         /* host time spent waiting for the retry search (the device may idle meanwhile) */
     double host_wait_shells_ms;        /* host time spent waiting for the status of a shell chunk */
+    int64_t timing_serial;             /* number of this sweep in the process (1, 2, ...), see ptt_sweep_timing_collect */
 } ptt_sweep_stats_t;
 int ptt_sweep_last_stats(ptt_sweep_stats_t* out);
 /* With PTT_MEM_DEVICE a timed sweep (PTT_SWEEP_TIMING) returns with its last chunks in flight and stage_ms not yet read
- * from the events: this waits for them and completes the stats ptt_sweep_last_stats returns (the next sweep does it too). */
+ * from the events.  ptt_sweep_timing_sync waits for every sweep queued so far and completes the stats
+ * ptt_sweep_last_stats returns.  ptt_sweep_timing_collect waits for ONE sweep (its timing_serial) and returns its completed
+ * stats: a caller that queues sweeps back to back reads sweep k's times while sweep k+1 runs, without waiting for k+1
+ * (the stage events alternate between two sets; the last eight completed sweeps are kept). */
 int ptt_sweep_timing_sync(void);
+int ptt_sweep_timing_collect(int64_t timing_serial, ptt_sweep_stats_t* out);
 /* frees the device / pinned workspace the sweep driver keeps between calls */
 int ptt_sweep_release(void);
 /* Device buffers that other processes of the box can map (CUDA IPC): the result table of a sharded sweep lives on one

@@ -65,7 +65,8 @@ class PlanDesc(C.Structure):
 class SweepOpts(C.Structure):
     _fields_ = [("n_xi", C.c_int32), ("thin_shell_limit", C.c_int32), ("chunk", C.c_int32), ("shell_chunk", C.c_int32),
                 ("flags", C.c_int32), ("group_min", C.c_int32), ("t_end", C.c_double), ("wn_rtol", C.c_double),
-                ("r_star", C.c_double), ("lifetime_multiplier", C.c_double)]
+                ("r_star", C.c_double), ("lifetime_multiplier", C.c_double), ("host_v_wall", C.c_void_p),
+                ("host_sol_type", C.c_void_p)]
 
 
 class SweepOut(C.Structure):
@@ -95,7 +96,7 @@ class SweepStats(C.Structure):
                 ("retried", C.c_int64), ("rescued", C.c_int64), ("group_profiles", C.c_int64), ("group_count", C.c_int64),
                 ("group_kw_sum", C.c_int64), ("group_macs", C.c_int64), ("a2_profiles", C.c_int64), ("gw_profiles", C.c_int64),
                 ("chunks_before_fold", C.c_int64), ("chunks_after_fold", C.c_int64), ("host_wait_retry_ms", C.c_double),
-                ("host_wait_shells_ms", C.c_double)]
+                ("host_wait_shells_ms", C.c_double), ("timing_serial", C.c_int64)]
 
 
 CHUNK_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p)
@@ -171,6 +172,7 @@ SIGNATURES = {
     "ptt_ipc_free": (C.c_int, [C.c_void_p]),
     "ptt_sweep_last_stats": (C.c_int, [C.POINTER(SweepStats)]),
     "ptt_sweep_timing_sync": (C.c_int, []),
+    "ptt_sweep_timing_collect": (C.c_int, [C.c_int64, C.POINTER(SweepStats)]),
     "ptt_sweep_release": (C.c_int, []),
     "ptt_sweep_shell_chunk": (C.c_int64, [C.c_int, C.c_int64]),
     "ptt_suppression_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double,

@@ -108,6 +108,27 @@ struct GenericShockLocator {
     template <class Sampler>
     PTT_HD int search(const int i_lo, const int i_hi, const Sampler& sample) {
         if (full || last_i != i_lo - 1) return -1;
+        if (m.bag_name && first_close >= 0) {
+            // Bag model, the curve creeping into the fixed point (cs, 0) after its first close sample has been noted.
+            // Nothing but a sample behind the shock curve is looked for any more, and that needs xi >= cs (v_shock is
+            // NaN below, shock.py:63-66).  The index that is finally taken is the one at which the noise of the
+            // continuous extension lifts xi to cs (it fixes v_sh = cs to 1e-13, as the reference's result has it): every
+            // sample has to be looked at, but only its xi - and not even that in a step that stays below cs.
+            const double cs = cs0();
+            if (sample.xi_upper_bound() < cs - 1e-14) return -2;
+            for (int k = i_lo; k <= i_hi; ++k) {
+                if (sample.xi(k) < cs) continue;
+                const State y = sample(k);
+                if (behind(y)) {
+                    if (k - 1 >= i_lo) prev = sample(k - 1);
+                    found = k; cur = y; last_i = k - 1;
+                    return k;
+                }
+            }
+            prev = sample(i_hi);
+            last_i = i_hi;
+            return -3;
+        }
         const double v_clear = 1e-6;                                        // near_cs() needs |v| <= 1e-8
         const State y_hi = sample(i_hi);
         if (i_lo == 1 && skip(y_hi)) return -2;                             // (the walk applies skip() from the second step on)

@@ -207,6 +207,16 @@ struct Dopri5 {
         o.xi = r1.xi + th * (r2.xi + th1 * (r3.xi + th * (r4.xi + th1 * r5.xi)));
         return o;
     }
+    // xi alone (the same expression as in dense())
+    PTT_HD double dense_xi(const double tq, const double inv_hd) const {
+        const double th = (tq - t0) * inv_hd;
+        const double th1 = 1.0 - th;
+        return r1.xi + th * (r2.xi + th1 * (r3.xi + th * (r4.xi + th1 * r5.xi)));
+    }
+    // Upper bound of xi over the last accepted step: theta (1 - theta) <= 1/4 on [0, 1].
+    PTT_HD double xi_upper_bound() const {
+        return r1.xi + fmax(r2.xi, 0.0) + 0.25 * (fabs(r3.xi) + fabs(r4.xi) + fabs(r5.xi));
+    }
 };
 
 // Grid samples inside the last accepted step: sample(k) is what the ordered walk below hands to visit(k, .).
@@ -218,13 +228,19 @@ struct StepSampler {
         const double tk = (k >= n - 1) ? t_end : (double)k * dt;
         return (tk == s.t) ? s.y : s.dense(tk, inv_hd);
     }
+    PTT_HD double xi(const int k) const {
+        const double tk = (k >= n - 1) ? t_end : (double)k * dt;
+        return (tk == s.t) ? s.y.xi : s.dense_xi(tk, inv_hd);
+    }
+    PTT_HD double xi_upper_bound() const { return s.xi_upper_bound(); }
 };
 
 // Optional member of a visitor:
 //   int search(int i_lo, int i_hi, const StepSampler& sample)
 // called for a step that holds the grid samples i_lo..i_hi (more than one) and was not skipped.  A visitor that can find
 // its stopping sample without seeing every sample in order (bisection) does so and returns its index (it then has the
-// state visit() would have left behind); -1 = walk the samples one by one; -2 = only the last one, i_hi, needs to be seen.
+// state visit() would have left behind); -1 = walk the samples one by one; -2 = only the last one, i_hi, needs to be seen;
+// -3 = the visitor has seen i_lo..i_hi itself and goes on.
 template <class Visitor>
 PTT_HD auto visitor_search(Visitor& v, const int i_lo, const int i_hi, const StepSampler& sm, int)
     -> decltype(v.search(i_lo, i_hi, sm)) {
@@ -275,6 +291,7 @@ PTT_HD int integrate_grid(const double cs2, const State& y0, const double t_end,
             const int i_stop = visitor_search(visit, i, i_hi, sample, 0);
             if (i_stop >= 0) { PTT_ODE_SAMPLE_HOOK(true) return i_stop + 1; }
             if (i_stop == -2) i = i_hi;
+            if (i_stop == -3) { i = i_hi + 1; continue; }
         }
 #endif
         for (; i <= i_hi; ++i) {

@@ -210,9 +210,16 @@ struct Workspace {
     PinBuf h_pg, h_ebase, h_scal, h_status;
     cudaEvent_t out_free[2] = {nullptr, nullptr}, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_tmp = nullptr,
                 ev_emit = nullptr;
-    std::vector<cudaEvent_t> timing;
+    // Stage events come in two sets used by alternate sweeps: a device-table sweep returns with its tail in flight and
+    // its events unread, and the next sweep - queued behind it without waiting - needs events of its own.
+    std::vector<cudaEvent_t> timing[2];
     size_t timing_used = 0;
-    std::vector<TimingRec> pending_timing;      // stage events of the last device-table sweep, not read yet
+    int tset = 0;                                // the set of the sweep that runs (or ran last)
+    struct Pending { std::vector<TimingRec> recs; ptt_sweep_stats_t stats; int64_t serial = 0; };
+    Pending pending[2];                          // per set: events not read yet, with the stats they complete
+    std::vector<ptt_sweep_stats_t> done;         // completed stats of earlier timed sweeps (serial inside), newest last
+    int64_t serial = 0;
+    PinBuf h_trows;
 
     std::vector<cudaStream_t*> streams() { return {&s_shell, &s_retry, &s_copy, &s_side[0], &s_side[1]}; }
     std::vector<cudaEvent_t*> events() {
@@ -240,12 +247,13 @@ struct Workspace {
         return PTT_OK;
     }
     cudaEvent_t timing_event() {
-        if (timing_used == timing.size()) {
+        std::vector<cudaEvent_t>& t = timing[tset];
+        if (timing_used == t.size()) {
             cudaEvent_t e = nullptr;
             if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
-            timing.push_back(e);
+            t.push_back(e);
         }
-        return timing[timing_used++];
+        return t[timing_used++];
     }
     void release() {
         if (device < 0) return;
@@ -258,10 +266,13 @@ struct Workspace {
         h_pg.release(); h_ebase.release(); h_scal.release(); h_status.release();
         for (cudaStream_t* s : streams()) { cudaStreamDestroy(*s); *s = nullptr; }
         for (cudaEvent_t* e : events()) { cudaEventDestroy(*e); *e = nullptr; }
-        for (cudaEvent_t e : timing) cudaEventDestroy(e);
-        timing.clear();
+        for (int k = 0; k < 2; ++k) {
+            for (cudaEvent_t e : timing[k]) cudaEventDestroy(e);
+            timing[k].clear();
+            pending[k].recs.clear();
+        }
+        h_trows.release();
         timing_used = 0;
-        pending_timing.clear();
         device = -1;
     }
 };
@@ -432,7 +443,13 @@ int Sweep::setup(const long long n_, const double* pg, const double* pm, const d
     // ---- inputs on the host: grouping needs v_wall, the retry filter the solution type
     h_pg = ws.h_pg.get<double>(nn * SW_PG); SW_ALLOC(h_pg);
     if (host) memcpy(h_pg, pg, nn * SW_PG * sizeof(double));
-    else {
+    else if (opts.host_v_wall && opts.host_sol_type) {
+        // the two columns the host looks at (hq(i, 0), hq(i, 2)) come from the caller: nothing to wait for
+        for (size_t i = 0; i < nn; ++i) {
+            h_pg[i * SW_PG] = opts.host_v_wall[i];
+            h_pg[i * SW_PG + 2] = (double)opts.host_sol_type[i];
+        }
+    } else {
         SW_CUDA(cudaMemcpyAsync(h_pg, pg, nn * SW_PG * sizeof(double), cudaMemcpyDeviceToHost, s_main));
         SW_CUDA(cudaStreamSynchronize(s_main));
     }
@@ -522,11 +539,12 @@ int Sweep::setup(const long long n_, const double* pg, const double* pm, const d
         }
     }
     if (out.table_rows && want_spec) {
-        std::vector<long long> tr(nn);
+        // (pinned staging of the workspace: the copy is over when the first shell solve of this sweep is, and the call
+        // does not return before that)
+        long long* tr = ws.h_trows.get<long long>(nn); SW_ALLOC(tr);
         for (size_t i = 0; i < nn; ++i) tr[i] = (long long)out.table_rows[sorted ? i : (size_t)perm[i]];
         d_trows = ws.trows.get<long long>(nn); SW_ALLOC(d_trows);
-        SW_CUDA(cudaMemcpyAsync(d_trows, tr.data(), nn * sizeof(long long), cudaMemcpyHostToDevice, s_main));
-        SW_CUDA(cudaStreamSynchronize(s_main));      // tr is a local
+        SW_CUDA(cudaMemcpyAsync(d_trows, tr, nn * sizeof(long long), cudaMemcpyHostToDevice, s_main));
     }
     if (out.snr && want_spec) { d_snr = ws.snr.get<double>(nn * out.n_snr); SW_ALLOC(d_snr); }
     if (host && !sorted) {
@@ -942,7 +960,7 @@ int Sweep::run() {
     } else if (timer.on) {
         // device tables: the call returns with its last chunks still in flight (the caller's next host work overlaps
         // them); the stage times are read from the events when somebody asks (ptt_sweep_timing_sync, or the next sweep)
-        ws.pending_timing.swap(timer.recs);
+        ws.pending[ws.tset].recs.swap(timer.recs);
     }
     return PTT_OK;
 }
@@ -996,21 +1014,42 @@ extern "C" int ptt_sweep_release(void) {
     return PTT_OK;
 }
 
-// stage times of a device-table sweep are read from its events on demand: waits for the sweep to finish
-static int timing_sync_locked() {
-    if (g_ws.pending_timing.empty()) return PTT_OK;
-    for (const TimingRec& r : g_ws.pending_timing) {
+// Stage times of a device-table sweep are read from its events on demand: waits for that sweep to finish.  The completed
+// stats go to the list of finished sweeps (and to g_stats if it was the last sweep).
+static int timing_complete_locked(const int set) {
+    Workspace::Pending& p = g_ws.pending[set];
+    if (p.recs.empty()) return PTT_OK;
+    for (const TimingRec& r : p.recs) {
         const cudaError_t e = cudaEventSynchronize(r.b);
-        if (e != cudaSuccess) { g_ws.pending_timing.clear(); return set_cuda_error("ptt_sweep_timing_sync", e); }
+        if (e != cudaSuccess) { p.recs.clear(); return set_cuda_error("ptt_sweep_timing_sync", e); }
     }
-    Timer::collect_recs(g_ws.pending_timing, g_stats);
-    g_ws.pending_timing.clear();
+    Timer::collect_recs(p.recs, p.stats);
+    p.recs.clear();
+    if (g_stats.timing_serial == p.stats.timing_serial) g_stats = p.stats;
+    g_ws.done.push_back(p.stats);
+    if (g_ws.done.size() > 8) g_ws.done.erase(g_ws.done.begin());
     return PTT_OK;
+}
+static int timing_sync_locked() {
+    const int older = 1 - g_ws.tset;
+    SW_RC(timing_complete_locked(older));
+    return timing_complete_locked(g_ws.tset);
 }
 
 extern "C" int ptt_sweep_timing_sync(void) {
     std::lock_guard<std::mutex> lock(g_ws.mu);
     return timing_sync_locked();
+}
+
+extern "C" int ptt_sweep_timing_collect(int64_t serial, ptt_sweep_stats_t* out) {
+    if (!out) return set_error(PTT_E_ARG, "ptt_sweep_timing_collect: null pointer");
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    for (int k = 0; k < 2; ++k)
+        if (!g_ws.pending[k].recs.empty() && g_ws.pending[k].stats.timing_serial == serial) SW_RC(timing_complete_locked(k));
+    for (const ptt_sweep_stats_t& st : g_ws.done)
+        if (st.timing_serial == serial) { *out = st; return PTT_OK; }
+    if (g_stats.timing_serial == serial) { *out = g_stats; return PTT_OK; }      // a sweep that had nothing pending
+    return set_error(PTT_E_ARG, "ptt_sweep_timing_collect: no sweep with this serial among the last eight timed ones");
 }
 
 extern "C" int ptt_sweep_last_stats(ptt_sweep_stats_t* out) {
@@ -1056,15 +1095,20 @@ extern "C" int ptt_sweep_spectra(const ptt_sweep_plan_t* plan, const ptt_sweep_o
         return set_error(PTT_E_ARG, "ptt_sweep_spectra: table_rows needs device tables");
     std::lock_guard<std::mutex> lock(g_ws.mu);
     SW_RC(g_ws.init());
-    SW_RC(timing_sync_locked());      // the events are reused: read the previous sweep's first (it has to be over anyway)
+    // the other set of stage events: whatever is still unread there belongs to the sweep before the last one, which is over
+    g_ws.tset = 1 - g_ws.tset;
+    SW_RC(timing_complete_locked(g_ws.tset));
     g_ws.timing_used = 0;
     Sweep sw(g_ws, plan, *opts, *out, cb, user, mem, (cudaStream_t)stream_);
     int rc = sw.setup(n, pg, pm, scale);
     if (rc == PTT_OK) rc = sw.run();
     if (rc != PTT_OK) {
         cudaDeviceSynchronize();      // leave no work in flight that references the workspace
+        g_ws.pending[0].recs.clear(); g_ws.pending[1].recs.clear();
         return rc;
     }
+    sw.stats.timing_serial = ++g_ws.serial;
     g_stats = sw.stats;
+    g_ws.pending[g_ws.tset].stats = sw.stats;
     return PTT_OK;
 }

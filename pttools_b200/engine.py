@@ -344,12 +344,14 @@ _LIVE_CALLBACKS = []
 def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_shell_limit=100, wn_rtol=1e-4, r_star=None,
             lifetime_multiplier=1.0, chunk=8000, shell_chunk=0, want=("pow_v", "pow_gw", "omgw0"), scalars=True,
             rows=False, mem="device", retry=True, timing=False, on_chunk=None, out=None, snr_weights=None,
-            table_rows=None, out_rows=None) -> SweepOutput:
+            table_rows=None, out_rows=None, host_cols=None) -> SweepOutput:
     """The whole sweep in one C call (ptt_sweep_spectra, csrc/ptt_sweep.cu): shells, the reference's retries,
     thermodynamic scalars, A^2, spec_den_v, spec_den_gw, pow_gw, omgw0.  pg[n,16], pm[n,4] as in the C header (host
     numpy arrays or device tensors according to `mem`); plan: SsmPlan / CPlan or None (shells only).
     on_chunk(row0, row1, cuda_stream_ptr) is called as chunks are queued for delivery; out: dict of preallocated
-    destination tables (same kind as `mem`) to write into instead of fresh ones."""
+    destination tables (same kind as `mem`) to write into instead of fresh ones.  host_cols = (v_wall, sol_type codes) on
+    the host, in the order of pg (device mode): saves the driver the device->host copy of pg and the wait for the stream
+    that goes with it, so that this sweep is queued while the previous one still runs (ptt_sweep_opts_t.host_v_wall)."""
     torch = _torch()
     lib = _lib.load()
     host = mem == "host"
@@ -429,10 +431,17 @@ def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_she
                           group_min=int(GROUP_MIN) if USE_GROUPED_SDV else 1 << 30,
                           t_end=float(t_end), wn_rtol=float(wn_rtol), r_star=-1.0 if r_star is None else float(r_star),
                           lifetime_multiplier=float(lifetime_multiplier))
+    if host_cols is not None and not host:
+        hv = np.ascontiguousarray(host_cols[0], dtype=np.float64).reshape(-1)
+        hc = np.ascontiguousarray(host_cols[1], dtype=np.int32).reshape(-1)
+        if hv.size != n or hc.size != n:
+            raise ValueError("host_cols: one v_wall and one solution type per point")
+        res._keep += [hv, hc]
+        opts.host_v_wall, opts.host_sol_type = C.c_void_p(hv.ctypes.data), C.c_void_p(hc.ctypes.data)
     cb = None
     if on_chunk is not None:
         cb = _lib.CHUNK_CB(lambda user, r0, r1, stream: on_chunk(int(r0), int(r1), stream))
-    finish_timing()
+    finish_timing(keep_last=True)
     rc = lib.ptt_sweep_spectra(C.byref(view) if view is not None else None, C.byref(opts), n, ptr(pg_a), ptr(pm_a),
                                ptr(sc_a), C.byref(o), C.cast(cb, C.c_void_p) if cb is not None else None, None,
                                _lib.MEM_HOST if host else _lib.MEM_DEVICE, _stream_ptr(torch))
@@ -446,7 +455,7 @@ def sweep_c(plan, pg, pm, scale=None, *, n_xi=N_XI_DEFAULT, t_end=50.0, thin_she
             _add_stage_times(st)
         else:
             # device tables: the call has returned with its last chunks in flight; the stage times are read from the
-            # events when somebody asks for them (finish_timing) or when the next sweep starts
+            # events when somebody asks for them (finish_timing) or when the sweep after the next one starts
             res.stats_box = _StatsBox(res)
             _PENDING_TIMING.append(res.stats_box)
     res._keep += [pg_a, pm_a, sc_a]
@@ -472,14 +481,14 @@ def _add_stage_times(st):
             d["n"] += int(st.stage_calls[i])
 
 
-def finish_timing():
-    """Completes the stage times of the last timed device-table sweep (waits for it to finish)."""
-    while _PENDING_TIMING:
-        box = _PENDING_TIMING.pop()
+def finish_timing(keep_last=False):
+    """Completes the stage times of the timed device-table sweeps queued so far (waits for them to finish).
+    keep_last: all but the most recent one - what a new sweep does before it is queued behind that one."""
+    while len(_PENDING_TIMING) > (1 if keep_last else 0):
+        box = _PENDING_TIMING.pop(0)
         lib = _lib.load()
-        _lib.check(lib.ptt_sweep_timing_sync(), "ptt_sweep_timing_sync")
         st = _lib.SweepStats()
-        lib.ptt_sweep_last_stats(C.byref(st))
+        _lib.check(lib.ptt_sweep_timing_collect(int(box.stats.timing_serial), C.byref(st)), "ptt_sweep_timing_collect")
         box.stats = st
         res = box._res()
         if res is not None:

@@ -204,7 +204,7 @@ def sweep_spectra(model, v_wall, alpha_n, y=None, r_star=None, lifetime_multipli
     res = engine.sweep_c(plan, pg_in, pm_in, sc_in, n_xi=n_xi, r_star=r_star, lifetime_multiplier=lifetime_multiplier,
                          chunk=chunk, shell_chunk=shell_chunk or 0, want=want, rows=keep_bubbles, mem=mem,
                          on_chunk=on_chunk, timing=timing, out=out, snr_weights=snr_w, table_rows=table_rows,
-                         out_rows=out_rows)
+                         out_rows=out_rows, host_cols=(vw, pt.codes) if mem == "device" else None)
     from . import _lib
     scal = {name: res.scalars[:, k] for k, name in enumerate(_lib.SWEEP_SCALARS)}
     out_ = SweepResult(vw_out, an_out, codes, res.status, None, y, pow_gw=res.pow_gw, pow_v=res.pow_v,

@@ -204,3 +204,41 @@ def test_sweep_argument_errors():
                                _lib.MEM_HOST, None)
     assert rc == -1 and b"plan" in lib.ptt_last_error()
     assert lib.ptt_sweep_release() == 0
+
+
+def test_sweeps_queued_back_to_back_and_their_stage_times():
+    """Device-table sweeps given the host copies of v_wall and the solution type (ptt_sweep_opts_t.host_v_wall /
+    host_sol_type) are queued behind one another without waiting; the stage times of sweep k are read with
+    ptt_sweep_timing_collect(serial) while later sweeps are in flight.  Same tables as the sweep that fetches pg itself."""
+    import torch
+    from pttools_b200 import _lib, bubble, engine
+    from pttools_b200.sweep import omgw0_scale
+    model = _bag()
+    vw, an = _points(n_rows=4, per_row=30, seed=3)
+    plan = engine.SsmPlan(SMALL["y"], cs=float(np.sqrt(model.csb2)), nt=SMALL["nt"], n_z_lookup=SMALL["n_z_lookup"],
+                          mode="ssm", only_lookup_pass=True)
+    pt = bubble.point_table(model, vw, an, device=True)
+    scale = engine.dev_f64(omgw0_scale(vw, an, 0.1))
+    kw = dict(n_xi=SMALL["n_xi"], r_star=0.1, want=("pow_gw", "omgw0"), timing=True)
+    plain = engine.sweep_c(plan, pt.pg, pt.pm, scale, **kw)
+    queued = [engine.sweep_c(plan, pt.pg, pt.pm, scale, host_cols=(vw, pt.codes), **kw) for _ in range(3)]
+    serials = [int(q.stats.timing_serial) for q in queued]
+    assert serials == list(range(serials[0], serials[0] + 3)) and int(plain.stats.timing_serial) == serials[0] - 1
+    lib = _lib.load()
+    st = _lib.SweepStats()
+    # the middle one, while the last one may still be running; then everything
+    _lib.check(lib.ptt_sweep_timing_collect(serials[1], C.byref(st)), "ptt_sweep_timing_collect")
+    assert int(st.timing_serial) == serials[1] and st.stage_ms[0] > 0 and st.stage_calls[0] == 1
+    engine.finish_timing()
+    for q in queued + [plain]:
+        assert q.stats.stage_ms[0] > 0 and int(q.stats.stage_calls[0]) == 1
+    torch.cuda.synchronize()
+    for q in queued:
+        assert torch.equal(q.status, plain.status)
+        assert torch.equal(torch.isnan(q.omgw0), torch.isnan(plain.omgw0))
+        # (the moment sums of the sine transform are accumulated with shared-memory atomics: equal to rounding)
+        np.testing.assert_allclose(torch.nan_to_num(q.omgw0).cpu().numpy(), torch.nan_to_num(plain.omgw0).cpu().numpy(),
+                                   rtol=1e-11)
+    assert lib.ptt_sweep_timing_collect(10 ** 9, C.byref(st)) != 0            # unknown serial: an error, not a hang
+    with pytest.raises(ValueError):
+        engine.sweep_c(plan, pt.pg, pt.pm, scale, host_cols=(vw[:-1], pt.codes), **kw)
