@@ -1,11 +1,15 @@
 """Per-source-line instruction counts and active lanes of one kernel: joins `ncu --page source --csv` (SASS view) with
-the line table of the cubin (`nvdisasm -g`).  usage: ncu_lines.py <src.csv> <disasm> <kernel-substring> [raw.csv]"""
+the line table of the cubin (`cuobjdump -xelf <name> lib.so; nvdisasm --print-line-info <cubin>`; `ncu -i rep --page source --csv --print-source sass`).  usage: ncu_lines.py <src.csv> <disasm> <kernel-substring> [raw.csv]"""
 import csv, re, sys
 src, dis, kern = sys.argv[1:4]
 amap, cur, inkern = {}, None, False
 for ln in open(dis):
-    if ln.startswith('.text.'):
+    m = re.match(r'\s*\.section\s+\.text\.(\S+?),', ln)          # nvdisasm --print-line-info of a cubin
+    if m or ln.startswith('.text.'):
         inkern = kern in ln
+        continue
+    if ln.lstrip().startswith('.section'):
+        inkern = False
         continue
     if not inkern:
         continue
