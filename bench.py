@@ -389,8 +389,8 @@ def gpu_arm(args):
         """One pass of the hot path through the product's sweep API: rank 0 ends with the Omega_gw,0 table of all
         world x B points in HBM, in the order of the input points (config 5 of BASELINE.json)."""
         vw, an = step_points(s)
-        return sweep.sweep_omgw0_distributed(model, vw, an, y=Y, r_star=R_STAR, n_xi=N_XI, chunk=args.chunk, plan=plan,
-                                             timing=True, shared=None if shared is None else shared[s % len(shared)],
+        return sweep.sweep_omgw0_distributed(model, vw, an, y=Y, r_star=R_STAR, n_xi=N_XI, chunk=args.chunk,
+                                             shell_chunk=args.shell_chunk or None, plan=plan, timing=True, shared=None if shared is None else shared[s % len(shared)],
                                              wait=full_grid or world == 1)
 
     def barrier():
@@ -480,7 +480,7 @@ def gpu_arm(args):
     def e2e_step(s):
         vw, an = step_points(1000 + s)
         shard, host_table = sweep.sweep_omgw0_distributed(model, vw, an, y=Y, r_star=R_STAR, n_xi=N_XI, chunk=args.chunk,
-                                                          plan=plan, mem="host")
+                                                          shell_chunk=args.shell_chunk or None, plan=plan, mem="host")
         return float(np.nanmax(host_table[:, 0])) if len(shard) else 0.0
 
     # warm-up: TWO calls -- the pinned result table of a call is released when the next call has returned, so the host
@@ -913,6 +913,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64000)
     ap.add_argument("--chunk", type=int, default=8000)
+    ap.add_argument("--shell-chunk", type=int, default=0, help="points per shell solve (0: from the free device memory)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="generic", choices=["generic"])
     ap.add_argument("--workload", default="headline", choices=["headline", "config5", "config3", "config2-shells", "config4"],

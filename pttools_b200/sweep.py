@@ -496,7 +496,8 @@ def sweep_omgw0_distributed(model, v_wall, alpha_n, y=None, r_star=0.1, chunk=80
     torch = engine._torch()
     # shell chunks that are multiples of the spectrum chunk keep every delivered range inside one block of `chunk` rows
     from . import _lib
-    sc = int(_lib.load().ptt_sweep_shell_chunk(kw.get("n_xi", engine.N_XI_DEFAULT), int(torch.cuda.mem_get_info()[0])))
+    sc = kw.pop("shell_chunk", None) or \
+        int(_lib.load().ptt_sweep_shell_chunk(kw.get("n_xi", engine.N_XI_DEFAULT), int(torch.cuda.mem_get_info()[0])))
     sc = max(chunk, sc // chunk * chunk)
     idx = shards[rank]
     m = model if single else [model[i] for i in idx]
