@@ -9,32 +9,49 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libhostemu.so")
 
 
-def build(force=False):
+def build(force=False, defines=(), so=None):
+    """defines: extra -D switches of the device headers (e.g. PTT_NO_STEP_SEARCH), built into a library of their own."""
+    so = so or _SO
     src = os.path.join(_HERE, "hostemu.cpp")
     hdrs = [os.path.join(_HERE, "..", "..", "pttools_b200", "csrc", h) for h in os.listdir(
         os.path.join(_HERE, "..", "..", "pttools_b200", "csrc")) if h.endswith(".cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", _SO, src])
-    return _SO
+    if force or not os.path.exists(so) or os.path.getmtime(so) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC"] +
+                              [f"-D{d}" for d in defines] + ["-o", so, src])
+    return so
 
 
 _lib = None
+_variants = {}
+
+
+def use_variant(*defines):
+    """Switches the module to a build of the emulation with the given -D switches (no arguments: the plain build)."""
+    global _lib
+    key = tuple(sorted(defines))
+    if key not in _variants:
+        so = _SO if not key else os.path.join(_HERE, "libhostemu_" + "_".join(k.lower() for k in key) + ".so")
+        _variants[key] = _declare(C.CDLL(build(defines=key, so=so)))
+    _lib = _variants[key]
 
 
 def lib():
-    global _lib
     if _lib is None:
-        _lib = C.CDLL(build())
-        d, i, pd, pi = C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)
-        _lib.emu_integrate.argtypes = [d, d, d, d, d, i, pd, pd, pd]
-        _lib.emu_anmax.argtypes = [d, pi]
-        _lib.emu_anmax.restype = d
-        _lib.emu_bag_forward.argtypes = [d, d, i, i, pd]
-        _lib.emu_bag_find_alpha_plus.argtypes = [d, d, i, d, pd, pi, pi]
-        _lib.emu_bag_profile.argtypes = [d, d, i, i, d, pd, pd, pd, pi, pi, pi]
-        _lib.emu_generic_solve.argtypes = [pd, d, d, i, d, d, pd, i, d, i, d, pd, pd, pd, pi, pi, pd]
-        _lib.emu_generic_rescue.argtypes = [pd, d, d, i, d, d, pd, i, d, i, d, pd, pd, pd, pi, pi, pd, pi]
+        use_variant()
+    return _lib
+
+
+def _declare(_lib):
+    d, i, pd, pi = C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    _lib.emu_integrate.argtypes = [d, d, d, d, d, i, pd, pd, pd]
+    _lib.emu_anmax.argtypes = [d, pi]
+    _lib.emu_anmax.restype = d
+    _lib.emu_bag_forward.argtypes = [d, d, i, i, pd]
+    _lib.emu_bag_find_alpha_plus.argtypes = [d, d, i, d, pd, pi, pi]
+    _lib.emu_bag_profile.argtypes = [d, d, i, i, d, pd, pd, pd, pi, pi, pi]
+    _lib.emu_generic_solve.argtypes = [pd, d, d, i, d, d, pd, i, d, i, d, pd, pd, pd, pi, pi, pd]
+    _lib.emu_generic_rescue.argtypes = [pd, d, d, i, d, d, pd, i, d, i, d, pd, pd, pd, pi, pi, pd, pi]
     return _lib
 
 

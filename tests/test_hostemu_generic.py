@@ -167,3 +167,59 @@ def test_oracle_reproduces_reference_retries():
     for vw, an, n_ref in ((0.7364864864864865, 0.05554054054054054, 5005), (0.8806306306306306, 0.4167567567567568, 5166)):
         sol = sg.sound_shell_generic(mo, vw, an, ref)
         assert sol["solver_failed"] and sol["v"].size == n_ref
+
+
+def test_shock_search_inside_a_step_is_the_ordered_walk(fixtures):
+    """integrate_grid lets the shock locators find their sample inside an integrator step by bisection (and walk the
+    approach to the fixed point (cs, 0) on xi alone) instead of visiting every tau-grid sample in order.  Same decisions,
+    same samples: bit-identical profiles and scalars against the build with -DPTT_NO_STEP_SEARCH, on thin hybrids next to
+    v_CJ, slow walls with vanishing shocks, ordinary points of all three types, for the bag and a ConstCS model, and for the
+    old bag solver's machine."""
+    _, ref = fixtures
+    rng = np.random.default_rng(5)
+    cases = []
+    for mname in ("bag", "cs_third_quarter"):
+        m = MODELS[mname]
+        pts = [(vw, an) for vw in (0.06, 0.1266, 0.2977, 0.45, 0.56, 0.62, 0.7, 0.8113, 0.9) for an in (0.0055, 0.05, 0.1601, 0.2993, 0.45)]
+        pts += list(zip(rng.uniform(0.05, 0.95, 40), rng.uniform(0.005, 0.5, 40)))
+        for vw, an in pts:
+            wn = m.wn(an)
+            if not np.isfinite(wn):
+                continue
+            try:
+                st = int(sg.solution_type(m, vw, an, wn))
+            except Exception:
+                continue
+            if st < 0:
+                continue
+            g = ref.get(vw, an, st)
+            wm_g = g[5] * wn if np.isfinite(g[5]) else 0.3 * wn
+            cases.append(((m.css2, m.csb2, m.V_s, m.V_b, m.kind == "bag"), vw, an, st, wn,
+                          sg.v_chapman_jouguet(m, an, wn), (g[0], g[2], g[4] * wn, wm_g)))
+    bag_pts = [(vw, an) for vw in (0.3, 0.5, 0.62, 0.75, 0.9) for an in (0.01, 0.1, 0.3)]
+    out = {}
+    try:
+        for variant in ((), ("PTT_NO_STEP_SEARCH",)):
+            emu.use_variant(*variant)
+            res = [emu.generic_solve(*c) for c in cases]
+            bag = []
+            for vw, an in bag_pts:
+                am, _ = emu.anmax(vw)
+                bag.append(emu.bag_machine(vw, an, 5000, am))
+            out[variant] = (res, bag)
+    finally:
+        emu.use_variant()
+    (a, abag), (b, bbag) = out[()], out[("PTT_NO_STEP_SEARCH",)]
+    assert len(a) > 120 and sum(r[0] == 0 for r in a) > 100
+    for (rc0, v0, w0, x0, s0), (rc1, v1, w1, x1, s1) in zip(a, b):
+        assert rc0 == rc1
+        for p, q in ((v0, v1), (w0, w1), (x0, x1)):
+            assert p.shape == q.shape and np.array_equal(p, q, equal_nan=True)
+        for k in s0:
+            assert s0[k] == s1[k] or (np.isnan(s0[k]) and np.isnan(s1[k]))
+    for r0, r1 in zip(abag, bbag):
+        for p, q in zip(r0, r1):
+            if isinstance(p, np.ndarray):
+                assert p.shape == q.shape and np.array_equal(p, q, equal_nan=True)
+            else:
+                assert p == q or (np.isnan(p) and np.isnan(q))
