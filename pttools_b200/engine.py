@@ -41,12 +41,14 @@ class _Stages:
         self.launches = 0
         self._ev = []
         self.c_stage_ms = {}        # stage times reported by the C sweep driver (ptt_sweep_last_stats)
+        self.c_counts = {}          # what those stages processed (multiply-adds of the matrix products, profiles ...)
 
     def enable(self, on: bool):
         finish_timing()
         self.enabled = on
         self._ev = []
         self.c_stage_ms = {}
+        self.c_counts = {}
 
     class _Ctx:
         def __init__(self, outer, name, launches):
@@ -479,6 +481,8 @@ def _add_stage_times(st):
             d = STAGES.c_stage_ms.setdefault(name, {"ms": 0.0, "n": 0})
             d["ms"] += st.stage_ms[i]
             d["n"] += int(st.stage_calls[i])
+    for k in ("group_macs", "group_profiles", "group_count", "a2_profiles", "gw_profiles"):
+        STAGES.c_counts[k] = STAGES.c_counts.get(k, 0) + int(getattr(st, k))
 
 
 def finish_timing(keep_last=False):

@@ -189,6 +189,12 @@ class Model:
             out = self.bag_wn_const / (alpha_n + (4 / self.mu_s - 1) / 3)
             out = np.where(out < 0, np.nan, out)
         else:
+            if alpha_n.size > 64:
+                # grids repeat the same alpha_n for every wall speed: solve each distinct value once (the iteration below
+                # stops when ALL its values have converged, and the set of values is the same: identical results)
+                uniq, inv = np.unique(alpha_n.ravel(), return_inverse=True)
+                if uniq.size < alpha_n.size:
+                    return np.asarray(self.wn(uniq))[inv.ravel()].reshape(alpha_n.shape)
             # alpha_n(wn) is monotonic below w_crit: safeguarded Newton on log(wn) (the reference: fsolve, model.py:856-922)
             lo = np.full(alpha_n.shape, np.log(self.w_min))
             hi = np.full(alpha_n.shape, np.log(self.w_crit))

@@ -37,12 +37,20 @@ class SweepResult:
 
     def take(self, rows):
         """The given rows (host int array) as a SweepResult of their own."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        on_device = {}
+
         def tk(x):
             if x is None:
                 return None
             if hasattr(x, "cpu"):
                 import torch
-                return x[torch.as_tensor(np.asarray(rows), device=x.device, dtype=torch.int64)]
+                if x.device not in on_device:
+                    # ONE upload of the row list, from pinned memory and without waiting: a pageable copy would hold the
+                    # host until the stream gets there, i.e. until the sweep that is filling these tables has finished
+                    idx = torch.from_numpy(rows)
+                    on_device[x.device] = idx.pin_memory().to(x.device, non_blocking=True) if x.is_cuda else idx
+                return x[on_device[x.device]]
             return np.asarray(x)[rows]
         r = SweepResult(tk(self.v_wall), tk(self.alpha_n), tk(self.sol_type), tk(self.status), tk(self.alpha_plus), self.y,
                         pow_gw=tk(self.pow_gw), pow_v=tk(self.pow_v), omgw0=tk(self.omgw0),
