@@ -86,3 +86,28 @@ def test_constcs_critical_temp_rejects_what_the_reference_rejects():
         ConstCSModel(0.3, 0.28, a_s=2.0, a_b=1.0, V_s=0.5, V_b=1.0)      # V_s < V_b
     m = ConstCSModel(0.3, 0.28, a_s=0.5, a_b=1.0, V_s=1.0, allow_invalid=True)
     assert m.T_crit > 0
+
+
+def test_wn_on_a_grid_solves_each_distinct_alpha_n_once():
+    """ConstCSModel.wn(alpha_n) is an iterative solve; on a (v_wall, alpha_n) grid every alpha_n repeats for every wall
+    speed and is solved once.  The iteration stops when all its values have converged and the set of values is the same,
+    so the result equals the plain solve of the full array bit for bit."""
+    import logging
+    import pttools_b200.models as M
+    logging.disable(logging.CRITICAL)
+    try:
+        m = M.ConstCSModel(css2=0.3, csb2=0.28, a_s=5, a_b=1, V_s=1, alpha_n_min=0.05)
+    finally:
+        logging.disable(logging.NOTSET)
+    an = np.tile(np.linspace(0.05, 0.5, 97), 13).reshape(13, 97)
+    got = m.wn(an)
+    plain_unique = M.np.unique
+    M.np.unique = lambda a, return_inverse=False: (a, np.arange(a.size)) if return_inverse else a     # no duplicates found
+    try:
+        want = m.wn(an)
+    finally:
+        M.np.unique = plain_unique
+    ok = np.isfinite(got)                                   # NaN below the model's own alpha_n_min
+    assert got.shape == an.shape and ok.sum() > an.size // 2
+    assert np.array_equal(got, want, equal_nan=True)
+    np.testing.assert_allclose(m.alpha_n(got[ok]), an[ok], rtol=1e-9)
