@@ -604,26 +604,30 @@ def cpu_baseline_leg(B, cores, args):
 # The other configurations of BASELINE.json (1 GPU): --workload config3 | config2-shells | config4
 # ---------------------------------------------------------------------------------------------------------------
 
-def _timed(step, steps, warmup):
-    """warmup untimed calls of step(s), then `steps` timed ones: device ms (CUDA events on the launching stream) and wall ms.
-    (Every step ends with a synchronisation: without it the shells-only sweeps measured slower, 36.7 against 24.5 ms per
-    step, gpurun_out/bench_final3_*.)"""
+def _timed(step, steps, warmup, sync_each=True):
+    """warmup untimed calls of step(s), then `steps` timed ones: device ms (CUDA events on the launching stream), wall ms and
+    the time of every step.  sync_each: every step ends with a synchronisation (per-step wall times); without it the host
+    preparation of a step overlaps the device work of the previous one and the per-step times are device times between
+    events.  (The shells-only sweeps measured slower without it, 36.7 against 24.5 ms per step, gpurun_out/bench_final3_*.)"""
     import torch
     for s in range(warmup):
         step(s)
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     t0 = time.perf_counter()
-    a.record()
+    ev[0].record()
     per = []
-    for s in range(warmup, warmup + steps):
+    for k, s in enumerate(range(warmup, warmup + steps)):
         t1 = time.perf_counter()
         step(s)
-        torch.cuda.synchronize()
-        per.append(1e3 * (time.perf_counter() - t1))
-    b.record()
+        if sync_each:
+            torch.cuda.synchronize()
+            per.append(1e3 * (time.perf_counter() - t1))
+        ev[k + 1].record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b), 1e3 * (time.perf_counter() - t0), per
+    if not sync_each:
+        per = [a.elapsed_time(b) for a, b in zip(ev[:-1], ev[1:])]
+    return ev[0].elapsed_time(ev[-1]), 1e3 * (time.perf_counter() - t0), per
 
 
 def _peaks(engine):
@@ -686,7 +690,8 @@ def workload_config3(args):
         step(s)
     sampler.mark_start()
     engine.STAGES.enable(True)          # resets the stage times of the warm-up
-    dev_ms, wall_ms, per = _timed(lambda s: step(s + args.warmup), args.steps, 0)
+    # sweeps queue behind one another (device tables): no synchronisation between the steps
+    dev_ms, wall_ms, per = _timed(lambda s: step(s + args.warmup), args.steps, 0, sync_each=False)
     stage_ms = engine.STAGES.summary()
     macs = int(engine.STAGES.c_counts.get("group_macs", 0))
     engine.STAGES.enable(False)
